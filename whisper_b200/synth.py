@@ -1,0 +1,202 @@
+"""Synthetic inputs for parity tests and bench.py: ggml model files and 16 kHz PCM.
+
+There are no real `ggml-*.bin` files and no network in this environment, so every
+correctness and performance run uses model files written here in the reference's exact on-disk format
+(reader: /root/reference/Whisper/source/whisper.cpp:451-1072, Whisper/Whisper/WhisperModel.cpp:434-492;
+layout summarised in SURVEY.md Appendix A).  Real model files load through the same path unchanged.
+
+Both the CPU oracle and the CUDA engine read the *same file bytes*, and both get the *same PCM bytes*.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+GGML_MAGIC = 0x67676D6C  # whisper.cpp:466
+
+
+@dataclass(frozen=True)
+class HParams:
+    """whisper_hparams in file order (whisper.cpp:248-260, :477-487)."""
+
+    n_vocab: int = 51864
+    n_audio_ctx: int = 1500
+    n_audio_state: int = 384
+    n_audio_head: int = 6
+    n_audio_layer: int = 4
+    n_text_ctx: int = 448
+    n_text_state: int = 384
+    n_text_head: int = 6
+    n_text_layer: int = 4
+    n_mels: int = 80
+    f16: int = 1
+
+    def as_list(self):
+        return [self.n_vocab, self.n_audio_ctx, self.n_audio_state, self.n_audio_head, self.n_audio_layer,
+                self.n_text_ctx, self.n_text_state, self.n_text_head, self.n_text_layer, self.n_mels, self.f16]
+
+
+def _hp(d, h, l, vocab):
+    return HParams(n_vocab=vocab, n_audio_state=d, n_audio_head=h, n_audio_layer=l,
+                   n_text_state=d, n_text_head=h, n_text_layer=l)
+
+
+# Model shapes.  "micro" is a test-only shape: the reference loader sizes its arenas by
+# n_audio_layer ∈ {4,6,12,24,32} (whisper.cpp:490-508), so a 4-layer model with a small state loads in the oracle.
+MODELS = {
+    "micro.en": _hp(128, 2, 4, 51864),
+    "micro": _hp(128, 2, 4, 51865),
+    "tiny.en": _hp(384, 6, 4, 51864),
+    "tiny": _hp(384, 6, 4, 51865),
+    "base.en": _hp(512, 8, 6, 51864),
+    "base": _hp(512, 8, 6, 51865),
+    "small": _hp(768, 12, 12, 51865),
+    "medium": _hp(1024, 16, 24, 51865),
+    "large": _hp(1280, 20, 32, 51865),
+}
+
+
+def tensor_list(hp: HParams):
+    """(name, ne[], is_f16, kind) for every tensor the loader requires (whisper.cpp:772-945).
+    ne[0] is the fastest axis.  kind drives the synthetic distribution."""
+    d, dt = hp.n_audio_state, hp.n_text_state
+    out = []
+    out.append(("encoder.positional_embedding", [d, hp.n_audio_ctx], False, "pos"))
+    out.append(("encoder.conv1.weight", [3, hp.n_mels, d], True, "mat"))
+    out.append(("encoder.conv1.bias", [1, d], False, "bias"))
+    out.append(("encoder.conv2.weight", [3, d, d], True, "mat"))
+    out.append(("encoder.conv2.bias", [1, d], False, "bias"))
+    out.append(("encoder.ln_post.weight", [d], False, "gamma"))
+    out.append(("encoder.ln_post.bias", [d], False, "bias"))
+    for i in range(hp.n_audio_layer):
+        p = f"encoder.blocks.{i}."
+        out += [
+            (p + "mlp_ln.weight", [d], False, "gamma"), (p + "mlp_ln.bias", [d], False, "bias"),
+            (p + "mlp.0.weight", [d, 4 * d], True, "mat"), (p + "mlp.0.bias", [4 * d], False, "bias"),
+            (p + "mlp.2.weight", [4 * d, d], True, "mat"), (p + "mlp.2.bias", [d], False, "bias"),
+            (p + "attn_ln.weight", [d], False, "gamma"), (p + "attn_ln.bias", [d], False, "bias"),
+            (p + "attn.query.weight", [d, d], True, "mat"), (p + "attn.query.bias", [d], False, "bias"),
+            (p + "attn.key.weight", [d, d], True, "mat"),
+            (p + "attn.value.weight", [d, d], True, "mat"), (p + "attn.value.bias", [d], False, "bias"),
+            (p + "attn.out.weight", [d, d], True, "mat"), (p + "attn.out.bias", [d], False, "bias"),
+        ]
+    out.append(("decoder.positional_embedding", [dt, hp.n_text_ctx], False, "pos"))
+    out.append(("decoder.token_embedding.weight", [dt, hp.n_vocab], True, "emb"))
+    out.append(("decoder.ln.weight", [dt], False, "gamma"))
+    out.append(("decoder.ln.bias", [dt], False, "bias"))
+    for i in range(hp.n_text_layer):
+        p = f"decoder.blocks.{i}."
+        out += [
+            (p + "mlp_ln.weight", [dt], False, "gamma"), (p + "mlp_ln.bias", [dt], False, "bias"),
+            (p + "mlp.0.weight", [dt, 4 * dt], True, "mat"), (p + "mlp.0.bias", [4 * dt], False, "bias"),
+            (p + "mlp.2.weight", [4 * dt, dt], True, "mat"), (p + "mlp.2.bias", [dt], False, "bias"),
+            (p + "attn_ln.weight", [dt], False, "gamma"), (p + "attn_ln.bias", [dt], False, "bias"),
+            (p + "attn.query.weight", [dt, dt], True, "mat"), (p + "attn.query.bias", [dt], False, "bias"),
+            (p + "attn.key.weight", [dt, dt], True, "mat"),
+            (p + "attn.value.weight", [dt, dt], True, "mat"), (p + "attn.value.bias", [dt], False, "bias"),
+            (p + "attn.out.weight", [dt, dt], True, "mat"), (p + "attn.out.bias", [dt], False, "bias"),
+            (p + "cross_attn_ln.weight", [dt], False, "gamma"), (p + "cross_attn_ln.bias", [dt], False, "bias"),
+            (p + "cross_attn.query.weight", [dt, dt], True, "mat"), (p + "cross_attn.query.bias", [dt], False, "bias"),
+            (p + "cross_attn.key.weight", [dt, dt], True, "mat"),
+            (p + "cross_attn.value.weight", [dt, dt], True, "mat"), (p + "cross_attn.value.bias", [dt], False, "bias"),
+            (p + "cross_attn.out.weight", [dt, dt], True, "mat"), (p + "cross_attn.out.bias", [dt], False, "bias"),
+        ]
+    return out
+
+
+def _mel_filters(n_mel=80, n_fft=201, seed=7):
+    """Triangular-ish non-negative filterbank.  The values are free parameters of the file (the reference reads
+    them from the model, whisper.cpp:531-538); a banded bank keeps the log-mel dynamic range realistic."""
+    f = np.zeros((n_mel, n_fft), np.float32)
+    # mel-like warping: denser at low frequencies
+    centres = np.expm1(np.linspace(0, np.log1p(n_fft - 2.0), n_mel))
+    centres = np.maximum(centres, np.arange(n_mel) * 0.9 + 0.5)
+    width = np.maximum(np.gradient(centres), 1.0) * 1.5
+    k = np.arange(n_fft, dtype=np.float64)
+    for j in range(n_mel):
+        tri = np.maximum(0.0, 1.0 - np.abs(k - centres[j]) / width[j])
+        s = tri.sum()
+        f[j] = (tri / max(s, 1e-9) * 0.05).astype(np.float32)
+    return f
+
+
+def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0) -> HParams:
+    """Write a synthetic ggml model file.  Matrices ~ N(0, 1/fan_in) stored f16; LN gamma = 1 + N(0, 0.01);
+    biases N(0, 0.01); positional embeddings N(0, 0.01); the token embedding is scaled by
+    `emb_scale` so that greedy decisions are not near-ties on random weights (SURVEY.md §7 "Parity definition")."""
+    hp = MODELS[name_or_hp] if isinstance(name_or_hp, str) else name_or_hp
+    rng = np.random.default_rng(seed)
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(struct.pack("<I", GGML_MAGIC))
+        f.write(struct.pack("<11i", *hp.as_list()))
+        filt = _mel_filters(hp.n_mels, 201)
+        f.write(struct.pack("<2i", hp.n_mels, 201))
+        f.write(filt.astype("<f4").tobytes())
+        n_words = 50257  # as in real files; the loader synthesises the remaining special tokens (whisper.cpp:585-607)
+        f.write(struct.pack("<i", n_words))
+        chunks = []
+        for i in range(n_words):
+            w = (" t%d" % i).encode() if i != 50256 else b""
+            chunks.append(struct.pack("<I", len(w)) + w)
+        f.write(b"".join(chunks))
+        for name, ne, is_f16, kind in tensor_list(hp):
+            n = int(np.prod(ne))
+            if kind == "mat":
+                fan_in = ne[0] if len(ne) == 2 else ne[0] * ne[1]
+                data = rng.standard_normal(n, dtype=np.float32) * np.float32(1.0 / np.sqrt(fan_in))
+            elif kind == "emb":
+                data = rng.standard_normal(n, dtype=np.float32) * np.float32(emb_scale / np.sqrt(ne[0]))
+            elif kind == "gamma":
+                data = 1.0 + rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
+            elif kind == "pos":
+                data = rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
+            else:
+                data = rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
+            nb = name.encode()
+            f.write(struct.pack("<3i", len(ne), len(nb), 1 if is_f16 else 0))
+            f.write(struct.pack("<%di" % len(ne), *ne))
+            f.write(nb)
+            f.write(data.astype("<f2" if is_f16 else "<f4").tobytes())
+    os.replace(tmp, path)
+    return hp
+
+
+def model_path(name: str, seed: int = 1234, cache_dir: str | None = None) -> str:
+    """Return (creating on first use) the cached synthetic model file for `name`."""
+    cache_dir = cache_dir or os.environ.get("WSP_MODEL_CACHE", "/tmp/wsp_models")
+    os.makedirs(cache_dir, exist_ok=True)
+    p = os.path.join(cache_dir, "ggml-%s-synth%d.bin" % (name, seed))
+    if not os.path.exists(p):
+        write_model(p, name, seed)
+    return p
+
+
+def lcg_u32(seed: int, n: int) -> np.ndarray:
+    """x_{k+1} = x_k * 1664525 + 1013904223 (mod 2^32), vectorised by doubling.  Returns x_1..x_n."""
+    A = np.array([1664525], np.uint64)
+    C = np.array([1013904223], np.uint64)
+    M = np.uint64(0xFFFFFFFF)
+    while A.size < n:
+        Am, Cm = A[-1], C[-1]
+        A2 = (A * Am) & M
+        C2 = ((A * Cm) & M) + C & M
+        A = np.concatenate([A, A2])
+        C = np.concatenate([C, C2 & M])
+    A, C = A[:n], C[:n]
+    x = ((A * np.uint64(seed & 0xFFFFFFFF)) & M) + C & M
+    return x.astype(np.uint32)
+
+
+def synth_pcm(chunk_id: int = 0, n_samples: int = 480000, seed: int = 12345) -> np.ndarray:
+    """30 s of 16 kHz mono f32: 0.3*sin(2*pi*440*i/16000) + a slow chirp + 0.05*U(-0.5,0.5)  (SURVEY.md §8(d))."""
+    i = np.arange(n_samples, dtype=np.float64)
+    u = lcg_u32(seed + chunk_id, n_samples).astype(np.float64) / 4294967296.0 - 0.5
+    f2 = 180.0 + 40.0 * chunk_id
+    x = 0.3 * np.sin(2 * np.pi * 440.0 * i / 16000.0) + 0.1 * np.sin(2 * np.pi * (f2 + i * (900.0 / n_samples)) * i / 16000.0) + 0.05 * u
+    # amplitude envelope so frames differ (speech-like energy bursts)
+    env = 0.55 + 0.45 * np.sin(2 * np.pi * i / 16000.0 * (0.7 + 0.13 * chunk_id))
+    return (x * env).astype(np.float32)
