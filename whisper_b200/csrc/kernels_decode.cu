@@ -1,0 +1,604 @@
+// Decoder per-token kernels (weight/KV streaming, HBM-bound): skinny GEMM, self/cross attention over f16 KV, sampler.
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include <math.h>
+
+namespace kern
+{
+	__device__ __forceinline__ float warpSumD( float v )
+	{
+		for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+		return v;
+	}
+	__device__ __forceinline__ float warpMaxD( float v )
+	{
+		for( int o = 16; o > 0; o >>= 1 ) v = fmaxf( v, __shfl_xor_sync( 0xffffffffu, v, o ) );
+		return v;
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// Skinny GEMM: out[col][n] = sum_k W[n][k] * x[col][k] for a handful of columns (decoder tokens x chunks).
+	//
+	// Replaces mulMatByRowTiled.hlsl (32 % of the reference's GPU time, ComputeShaders/mulMatByRowTiled.hlsl:42-169) and the N=1
+	// case of ggml_compute_forward_mul_mat_f16_f32 (ggml.c:4447-4749).  The op is pure weight streaming, so the design goal is
+	// HBM rate: each lane issues 16-byte loads covering 64 contiguous bytes of a weight row per quad, several in flight; the f16
+	// activations (optionally LayerNorm-ed on the fly) sit in shared memory; products go through mma.sync.m16n8k16 (f16 x f16
+	// -> f32, the oracle's arithmetic) because 8..16 columns exactly fill the n dimension and the tensor pipe is idle otherwise.
+	// The k index is permuted identically for A and B fragments so that every fragment load is one 128-bit access.
+	//
+	// CTA = 16 weight rows x (up to 16 columns); 8 warps split K; cross-warp reduction through shared memory; fused epilogue.
+	constexpr int SK_ROWS = 16;
+	constexpr int SK_COLS = 16;      // columns per CTA pass (2 n-tiles of 8)
+	constexpr int SK_WARPS = 8;
+	constexpr int SK_PAD = 32;       // halves of padding per activation row: row stride = 64 (mod 128) bytes -> conflict-free LDS.128
+
+	__device__ __forceinline__ void mma16816( float* c, const uint32_t* a, uint32_t b0, uint32_t b1 )
+	{
+		asm volatile(
+			"mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+			: "+f"( c[ 0 ] ), "+f"( c[ 1 ] ), "+f"( c[ 2 ] ), "+f"( c[ 3 ] )
+			: "r"( a[ 0 ] ), "r"( a[ 1 ] ), "r"( a[ 2 ] ), "r"( a[ 3 ] ), "r"( b0 ), "r"( b1 ) );
+	}
+
+	__device__ __forceinline__ uint4 ldg_stream( const uint4* p )
+	{
+		uint4 r;
+		asm volatile( "ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( r.x ), "=r"( r.y ), "=r"( r.z ), "=r"( r.w ) : "l"( p ) );
+		return r;
+	}
+
+	__global__ void __launch_bounds__( SK_WARPS * 32 )
+		skinny_gemm_kernel( SkinnyArgs a )
+	{
+		extern __shared__ __align__( 16 ) uint8_t sk_smem[];
+		const int K = a.K;
+		const int rowStride = K + SK_PAD;   // halves
+		__half* sx = reinterpret_cast<__half*>( sk_smem );                       // [SK_COLS][rowStride]
+		float* red = reinterpret_cast<float*>( sx + (size_t)SK_COLS * rowStride ); // [SK_WARPS][SK_ROWS][SK_COLS]
+
+		const int tid = threadIdx.x;
+		const int warp = tid >> 5;
+		const int lane = tid & 31;
+		const int row0 = blockIdx.x * SK_ROWS;
+		const int col0 = blockIdx.y * SK_COLS;
+		const int ncols = min( SK_COLS, a.nCols - col0 );
+
+		// ---- stage activations as f16 (LayerNorm fused when gamma is given) ----
+		for( int c = warp; c < SK_COLS; c += SK_WARPS )
+		{
+			__half* dst = sx + (size_t)c * rowStride;
+			if( c >= ncols )
+			{
+				for( int k = lane; k < K; k += 32 ) dst[ k ] = __float2half_rn( 0.0f );
+				continue;
+			}
+			if( a.xF32 )
+			{
+				const float* src = a.xF32 + (size_t)( col0 + c ) * a.xStride;
+				if( a.gamma )
+				{
+					// oracle: ggml_norm (ggml.c:4098-4156) + gamma/beta, then f16 conversion at the mul_mat (ggml.c:4592-4603)
+					float s = 0.0f;
+					for( int k = lane; k < K; k += 32 ) s += src[ k ];
+					const float mean = warpSumD( s ) / (float)K;
+					float sq = 0.0f;
+					for( int k = lane; k < K; k += 32 ) { const float v = src[ k ] - mean; sq += v * v; }
+					const float rstd = 1.0f / sqrtf( warpSumD( sq ) / (float)K + 1e-5f );
+					for( int k = lane; k < K; k += 32 )
+						dst[ k ] = __float2half_rn( ( src[ k ] - mean ) * rstd * a.gamma[ k ] + a.beta[ k ] );
+				}
+				else
+					for( int k = lane; k < K; k += 32 ) dst[ k ] = __float2half_rn( src[ k ] );
+			}
+			else
+			{
+				const uint4* src = reinterpret_cast<const uint4*>( a.xF16 + (size_t)( col0 + c ) * a.xStride );
+				uint4* d4 = reinterpret_cast<uint4*>( dst );
+				for( int k = lane; k < K / 8; k += 32 ) d4[ k ] = src[ k ];
+			}
+		}
+		__syncthreads();
+
+		// ---- main loop: 32 k per step, steps interleaved across the 8 warps (8 warps x 64 B = 512 contiguous bytes per row) ----
+		const int g = lane >> 2, t = lane & 3;
+		const int rA = min( row0 + g, a.nOut - 1 );
+		const int rB = min( row0 + g + 8, a.nOut - 1 );
+		const uint4* wA = reinterpret_cast<const uint4*>( a.W + (size_t)rA * K + 8 * t );
+		const uint4* wB = reinterpret_cast<const uint4*>( a.W + (size_t)rB * K + 8 * t );
+		const __half* xb0 = sx + (size_t)g * rowStride + 8 * t;         // n-tile 0: column g
+		const __half* xb1 = sx + (size_t)( g + 8 ) * rowStride + 8 * t; // n-tile 1: column g+8
+		float acc0[ 4 ] = { 0, 0, 0, 0 }, acc1[ 4 ] = { 0, 0, 0, 0 };
+		const int steps = K / 32;
+		constexpr int U = 4;
+		for( int s0 = warp; s0 < steps; s0 += SK_WARPS * U )
+		{
+			uint4 va[ U ], vb[ U ];
+#pragma unroll
+			for( int u = 0; u < U; u++ )
+			{
+				const int st = s0 + u * SK_WARPS;
+				if( st < steps )
+				{
+					va[ u ] = ldg_stream( wA + st * 4 );   // 32 halves = 4 uint4 per step
+					vb[ u ] = ldg_stream( wB + st * 4 );
+				}
+			}
+#pragma unroll
+			for( int u = 0; u < U; u++ )
+			{
+				const int st = s0 + u * SK_WARPS;
+				if( st < steps )
+				{
+					const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 32 );
+					const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 32 );
+					const uint32_t a1[ 4 ] = { va[ u ].x, vb[ u ].x, va[ u ].y, vb[ u ].y };
+					const uint32_t a2[ 4 ] = { va[ u ].z, vb[ u ].z, va[ u ].w, vb[ u ].w };
+					mma16816( acc0, a1, x0.x, x0.y );
+					mma16816( acc0, a2, x0.z, x0.w );
+					mma16816( acc1, a1, x1.x, x1.y );
+					mma16816( acc1, a2, x1.z, x1.w );
+				}
+			}
+		}
+
+		// ---- cross-warp reduction ----
+		// c0,c1: (row g, cols 2t, 2t+1); c2,c3: (row g+8, same cols)
+		float* my = red + (size_t)warp * SK_ROWS * SK_COLS;
+		my[ g * SK_COLS + 2 * t + 0 ] = acc0[ 0 ];
+		my[ g * SK_COLS + 2 * t + 1 ] = acc0[ 1 ];
+		my[ ( g + 8 ) * SK_COLS + 2 * t + 0 ] = acc0[ 2 ];
+		my[ ( g + 8 ) * SK_COLS + 2 * t + 1 ] = acc0[ 3 ];
+		my[ g * SK_COLS + 8 + 2 * t + 0 ] = acc1[ 0 ];
+		my[ g * SK_COLS + 8 + 2 * t + 1 ] = acc1[ 1 ];
+		my[ ( g + 8 ) * SK_COLS + 8 + 2 * t + 0 ] = acc1[ 2 ];
+		my[ ( g + 8 ) * SK_COLS + 8 + 2 * t + 1 ] = acc1[ 3 ];
+		__syncthreads();
+
+		// ---- epilogue: thread -> (col = tid / 16, row = tid % 16): consecutive threads write consecutive output features ----
+		const int c = tid >> 4, r = tid & 15;
+		const int n = row0 + r;
+		if( c >= ncols || n >= a.nOut ) return;
+		float v = 0.0f;
+#pragma unroll
+		for( int w = 0; w < SK_WARPS; w++ ) v += red[ ( (size_t)w * SK_ROWS + r ) * SK_COLS + c ];
+		const int col = col0 + c;
+		switch( a.epi )
+		{
+		case SK_QKV:
+		{
+			const int which = n / a.d;
+			const int nn = n - which * a.d;
+			if( which == 0 )
+				a.outF32[ (size_t)col * a.ld + nn ] = ( v + a.bias[ n ] ) * a.scale;
+			else
+			{
+				const int b = col / a.N, i = col - b * a.N;
+				const size_t off = ( (size_t)b * a.nTextCtx + ( *a.dNPast + i ) ) * a.d + nn;
+				if( which == 1 ) a.kCache[ off ] = __float2half_rn( v * a.scale );
+				else a.vCache[ off ] = __float2half_rn( v + a.bias[ n ] );
+			}
+			break;
+		}
+		case SK_BIAS_RESID:
+		{
+			float* p = a.outF32 + (size_t)col * a.ld + n;
+			*p = v + a.bias[ n ] + *p;
+			break;
+		}
+		case SK_Q_SCALE:
+			a.outF32[ (size_t)col * a.ld + n ] = ( v + a.bias[ n ] ) * a.scale;
+			break;
+		case SK_GELU_F16:
+			a.outF16[ (size_t)col * a.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( v + a.bias[ n ] ) );
+			break;
+		default:
+			a.outF32[ (size_t)col * a.ld + n ] = v;
+			break;
+		}
+	}
+
+	static size_t skinnySmem( int K ) { return (size_t)SK_COLS * ( K + SK_PAD ) * sizeof( __half ) + (size_t)SK_WARPS * SK_ROWS * SK_COLS * sizeof( float ); }
+	static size_t g_skinnySmemSet = 0;
+	cudaError_t prepare( int maxK )
+	{
+		const size_t smem = skinnySmem( maxK );
+		if( smem > g_skinnySmemSet )
+		{
+			cudaError_t e = cudaFuncSetAttribute( skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+			if( e != cudaSuccess ) return e;
+			g_skinnySmemSet = smem;
+		}
+		return cudaSuccess;
+	}
+	cudaError_t skinnyGemm( const SkinnyArgs& a, cudaStream_t s )
+	{
+		if( a.K % 32 != 0 ) return cudaErrorInvalidValue;
+		const size_t smem = skinnySmem( a.K );
+		if( smem > g_skinnySmemSet )
+		{
+			cudaError_t e = prepare( a.K );
+			if( e != cudaSuccess ) return e;
+		}
+		dim3 grid( ( a.nOut + SK_ROWS - 1 ) / SK_ROWS, ( a.nCols + SK_COLS - 1 ) / SK_COLS );
+		skinny_gemm_kernel<<<grid, SK_WARPS * 32, smem, s>>>( a );
+		return cudaGetLastError();
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// Decoder self-attention, one CTA per (chunk, head, query).  Oracle: whisper.cpp:1616-1661 — K*Q (Q rounded to f16 by the
+	// mul_mat, ggml.c:4599), causal mask, softmax, V^T * P.  KV cache rows are [b][pos][d] f16.
+	constexpr int SA_THREADS = 128;
+	constexpr int SA_MAXKV = 448;
+
+	__global__ void __launch_bounds__( SA_THREADS )
+		self_attn_decode_kernel( const float* __restrict__ q, const __half* __restrict__ kCache, const __half* __restrict__ vCache, __half* __restrict__ out,
+			int N, int H, int d, int nTextCtx, const int* __restrict__ dNPast )
+	{
+		__shared__ float sq[ 64 ];
+		__shared__ float sp[ SA_MAXKV ];
+		__shared__ float sred[ SA_THREADS / 32 ];
+		__shared__ float so[ 2 ][ 64 ];
+		const int bh = blockIdx.x;
+		const int b = bh / H, h = bh - b * H;
+		const int i = blockIdx.y;
+		const int tid = threadIdx.x;
+		const int nkv = min( *dNPast + i + 1, nTextCtx );
+		const int col = b * N + i;
+		if( tid < 64 )
+			sq[ tid ] = __half2float( __float2half_rn( q[ (size_t)col * d + h * 64 + tid ] ) );
+		__syncthreads();
+		const __half* kb = kCache + (size_t)b * nTextCtx * d + h * 64;
+		const __half* vb = vCache + (size_t)b * nTextCtx * d + h * 64;
+		float lmax = -INFINITY;
+		for( int j = tid; j < nkv; j += SA_THREADS )
+		{
+			const uint4* kr = reinterpret_cast<const uint4*>( kb + (size_t)j * d );
+			float s = 0.0f;
+#pragma unroll
+			for( int c = 0; c < 8; c++ )
+			{
+				const uint4 u = kr[ c ];
+				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+#pragma unroll
+				for( int e = 0; e < 4; e++ )
+				{
+					const float2 f = __half22float2( h2[ e ] );
+					s += f.x * sq[ c * 8 + e * 2 ] + f.y * sq[ c * 8 + e * 2 + 1 ];
+				}
+			}
+			sp[ j ] = s;
+			lmax = fmaxf( lmax, s );
+		}
+		lmax = warpMaxD( lmax );
+		if( ( tid & 31 ) == 0 ) sred[ tid >> 5 ] = lmax;
+		__syncthreads();
+		float mx = sred[ 0 ];
+		for( int w = 1; w < SA_THREADS / 32; w++ ) mx = fmaxf( mx, sred[ w ] );
+		__syncthreads();
+		float lsum = 0.0f;
+		for( int j = tid; j < nkv; j += SA_THREADS )
+		{
+			const float e = expf( sp[ j ] - mx );
+			sp[ j ] = e;
+			lsum += e;
+		}
+		lsum = warpSumD( lsum );
+		if( ( tid & 31 ) == 0 ) sred[ tid >> 5 ] = lsum;
+		__syncthreads();
+		float tot = 0.0f;
+		for( int w = 0; w < SA_THREADS / 32; w++ ) tot += sred[ w ];
+		const float inv = 1.0f / tot;
+		// O[e] = sum_j P[j] V[j][e]: two key-halves x 64 dims
+		const int e = tid & 63, half = tid >> 6;
+		float o = 0.0f;
+		for( int j = half; j < nkv; j += 2 )
+			o += sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
+		so[ half ][ e ] = o;
+		__syncthreads();
+		if( tid < 64 )
+			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( ( so[ 0 ][ tid ] + so[ 1 ][ tid ] ) * inv );
+	}
+	cudaError_t selfAttnDecode( const float* q, const __half* kCache, const __half* vCache, __half* out, int B, int N, int H, int d, int nTextCtx, const int* dNPast, cudaStream_t s )
+	{
+		if( nTextCtx > SA_MAXKV ) return cudaErrorInvalidValue;
+		dim3 grid( B * H, N );
+		self_attn_decode_kernel<<<grid, SA_THREADS, 0, s>>>( q, kCache, vCache, out, N, H, d, nTextCtx, dNPast );
+		return cudaGetLastError();
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// Decoder cross-attention, one CTA per (chunk, head, query); K and V memories are [b][h][T][64] f16, written by the
+	// encoder's cross-KV GEMM epilogue.  Oracle: whisper.cpp:1688-1749 (no mask, K pre-scaled at encode time :1465).
+	// The per-sequence 2*T*d bytes per layer are the dominant per-chunk HBM traffic of a decode step:
+	// every access below is a 16-byte load, 8 lanes per 128-byte row, fully coalesced.
+	constexpr int CA_THREADS = 256;
+	constexpr int CA_MAXT = 1536;
+
+	__global__ void __launch_bounds__( CA_THREADS )
+		cross_attn_decode_kernel( const float* __restrict__ q, const __half* __restrict__ kMem, const __half* __restrict__ vMem, __half* __restrict__ out,
+			int N, int H, int d, int T )
+	{
+		__shared__ float sp[ CA_MAXT ];
+		__shared__ float sred[ CA_THREADS / 32 ];
+		__shared__ float so[ CA_THREADS / 32 ][ 4 ][ 64 ];   // per warp, per row-group partial outputs (8 KB)
+		const int bh = blockIdx.x;
+		const int b = bh / H, h = bh - b * H;
+		const int i = blockIdx.y;
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		const int col = b * N + i;
+		const int sub = lane & 7;        // which 16-byte chunk of the 128-byte row
+		const int rgrp = lane >> 3;      // row within a group of 4
+		float qf[ 8 ];
+#pragma unroll
+		for( int e = 0; e < 8; e++ )
+			qf[ e ] = __half2float( __float2half_rn( q[ (size_t)col * d + h * 64 + sub * 8 + e ] ) );
+		const uint4* K4 = reinterpret_cast<const uint4*>( kMem + (size_t)bh * T * 64 );
+		const uint4* V4 = reinterpret_cast<const uint4*>( vMem + (size_t)bh * T * 64 );
+
+		float lmax = -INFINITY;
+		for( int j0 = warp * 4; j0 < T; j0 += ( CA_THREADS / 32 ) * 4 )
+		{
+			const int j = j0 + rgrp;
+			float s = 0.0f;
+			if( j < T )
+			{
+				const uint4 u = K4[ (size_t)j * 8 + sub ];
+				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+#pragma unroll
+				for( int e = 0; e < 4; e++ )
+				{
+					const float2 f = __half22float2( h2[ e ] );
+					s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
+				}
+			}
+			s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+			s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+			s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+			if( j < T )
+			{
+				if( sub == 0 ) sp[ j ] = s;
+				lmax = fmaxf( lmax, s );
+			}
+		}
+		lmax = warpMaxD( lmax );
+		if( lane == 0 ) sred[ warp ] = lmax;
+		__syncthreads();
+		float mx = sred[ 0 ];
+		for( int w = 1; w < CA_THREADS / 32; w++ ) mx = fmaxf( mx, sred[ w ] );
+		__syncthreads();
+		float lsum = 0.0f;
+		for( int j = tid; j < T; j += CA_THREADS )
+		{
+			const float e = expf( sp[ j ] - mx );
+			sp[ j ] = e;
+			lsum += e;
+		}
+		lsum = warpSumD( lsum );
+		if( lane == 0 ) sred[ warp ] = lsum;
+		__syncthreads();
+		float tot = 0.0f;
+		for( int w = 0; w < CA_THREADS / 32; w++ ) tot += sred[ w ];
+		const float inv = 1.0f / tot;
+
+		float o[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+		for( int j0 = warp * 4; j0 < T; j0 += ( CA_THREADS / 32 ) * 4 )
+		{
+			const int j = j0 + rgrp;
+			if( j < T )
+			{
+				const float p = sp[ j ];
+				const uint4 u = V4[ (size_t)j * 8 + sub ];
+				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+#pragma unroll
+				for( int e = 0; e < 4; e++ )
+				{
+					const float2 f = __half22float2( h2[ e ] );
+					o[ e * 2 ] += p * f.x;
+					o[ e * 2 + 1 ] += p * f.y;
+				}
+			}
+		}
+#pragma unroll
+		for( int e = 0; e < 8; e++ ) so[ warp ][ rgrp ][ sub * 8 + e ] = o[ e ];
+		__syncthreads();
+		if( tid < 64 )
+		{
+			float acc = 0.0f;
+			for( int w = 0; w < CA_THREADS / 32; w++ )
+#pragma unroll
+				for( int r = 0; r < 4; r++ ) acc += so[ w ][ r ][ tid ];
+			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc * inv );
+		}
+	}
+	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, cudaStream_t s )
+	{
+		if( T > CA_MAXT ) return cudaErrorInvalidValue;
+		dim3 grid( B * H, N );
+		cross_attn_decode_kernel<<<grid, CA_THREADS, 0, s>>>( q, kMem, vMem, out, N, H, d, T );
+		return cudaGetLastError();
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// softmax over the vocabulary + greedy sampling with the timestamp rules, one CTA per chunk.
+	// Oracle: ggml_soft_max (ggml.c:5026-5095) then whisper_sample_best (whisper.cpp:1875-1964):
+	//   max_tx = max p(text); if is_initial: p(ts > beg+100) = -inf; sum_ts, max_ts/tid over timestamp tokens;
+	//   if sum_ts > max_tx or force_timestamp: p(text) = -inf;  top-4 by p; skip sot/solm/not among the first three.
+	constexpr int SM_THREADS = 1024;
+
+	struct Top1 { float v; int i; };
+	__device__ __forceinline__ Top1 better( Top1 a, Top1 b ) { return ( b.v > a.v || ( b.v == a.v && b.i < a.i ) ) ? b : a; }
+
+	__device__ Top1 blockArgmax( Top1 x, Top1* sbuf )
+	{
+		for( int o = 16; o > 0; o >>= 1 )
+		{
+			Top1 y;
+			y.v = __shfl_xor_sync( 0xffffffffu, x.v, o );
+			y.i = __shfl_xor_sync( 0xffffffffu, x.i, o );
+			x = better( x, y );
+		}
+		__syncthreads();
+		if( ( threadIdx.x & 31 ) == 0 ) sbuf[ threadIdx.x >> 5 ] = x;
+		__syncthreads();
+		Top1 r = sbuf[ 0 ];
+		for( int w = 1; w < SM_THREADS / 32; w++ ) r = better( r, sbuf[ w ] );
+		return r;
+	}
+	__device__ float blockSumF( float v, float* sbuf )
+	{
+		v = warpSumD( v );
+		__syncthreads();
+		if( ( threadIdx.x & 31 ) == 0 ) sbuf[ threadIdx.x >> 5 ] = v;
+		__syncthreads();
+		float r = 0.0f;
+		for( int w = 0; w < SM_THREADS / 32; w++ ) r += sbuf[ w ];
+		return r;
+	}
+	__device__ float blockMaxF( float v, float* sbuf )
+	{
+		v = warpMaxD( v );
+		__syncthreads();
+		if( ( threadIdx.x & 31 ) == 0 ) sbuf[ threadIdx.x >> 5 ] = v;
+		__syncthreads();
+		float r = sbuf[ 0 ];
+		for( int w = 1; w < SM_THREADS / 32; w++ ) r = fmaxf( r, sbuf[ w ] );
+		return r;
+	}
+	__device__ double blockSumD( double v, double* sbuf )
+	{
+		for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+		__syncthreads();
+		if( ( threadIdx.x & 31 ) == 0 ) sbuf[ threadIdx.x >> 5 ] = v;
+		__syncthreads();
+		double r = 0.0;
+		for( int w = 0; w < SM_THREADS / 32; w++ ) r += sbuf[ w ];
+		return r;
+	}
+
+	__global__ void __launch_bounds__( SM_THREADS )
+		sample_kernel( SampleArgs a )
+	{
+		__shared__ float sf[ SM_THREADS / 32 ];
+		__shared__ double sd[ SM_THREADS / 32 ];
+		__shared__ Top1 st[ SM_THREADS / 32 ];
+		const int b = blockIdx.x;
+		const int tid = threadIdx.x;
+		const int nv = a.nVocab;
+		const float* lg = a.logits + (size_t)b * nv;
+		float* pr = a.probs + (size_t)b * nv;
+		const bool forceTs = a.dForceTs && a.dForceTs[ 0 ] != 0;
+		const bool isInitial = a.dForceTs && a.dForceTs[ 1 ] != 0;
+
+		float mx = -INFINITY;
+		for( int i = tid; i < nv; i += SM_THREADS ) mx = fmaxf( mx, lg[ i ] );
+		mx = blockMaxF( mx, sf );
+		double dsum = 0.0;
+		for( int i = tid; i < nv; i += SM_THREADS )
+		{
+			const float e = expf( lg[ i ] - mx );
+			pr[ i ] = e;
+			dsum += (double)e;
+		}
+		dsum = blockSumD( dsum, sd );
+		const float inv = (float)( 1.0 / dsum );
+		// timestamp bookkeeping on the normalised probabilities
+		const int beg = a.tokenBeg;
+		const int tsEnd = isInitial ? min( beg + 101, nv ) : nv;   // initial timestamp <= 1 s (whisper.cpp:1902-1911)
+		float maxTx = -1.0f;
+		double sumTs = 0.0;
+		Top1 bestTs = { -INFINITY, 0x7fffffff };
+		for( int i = tid; i < nv; i += SM_THREADS )
+		{
+			const float p = pr[ i ] * inv;
+			pr[ i ] = p;
+			if( i < beg ) maxTx = fmaxf( maxTx, p );
+			else if( i < tsEnd )
+			{
+				sumTs += (double)p;
+				bestTs = better( bestTs, Top1{ p, i } );
+			}
+		}
+		maxTx = blockMaxF( maxTx, sf );
+		sumTs = blockSumD( sumTs, sd );
+		bestTs = blockArgmax( bestTs, st );
+		const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
+
+		// top-4 of the (masked) distribution by repeated argmax
+		int topI[ 4 ];
+		float topV[ 4 ];
+		for( int k = 0; k < 4; k++ )
+		{
+			Top1 best = { -INFINITY, 0x7fffffff };
+			for( int i = tid; i < nv; i += SM_THREADS )
+			{
+				bool skip = false;
+				for( int kk = 0; kk < k; kk++ ) skip |= ( topI[ kk ] == i );
+				if( skip ) continue;
+				float p = pr[ i ];
+				if( maskText && i < beg ) p = -INFINITY;
+				if( isInitial && i >= beg + 101 ) p = -INFINITY;
+				best = better( best, Top1{ p, i } );
+			}
+			best = blockArgmax( best, st );
+			topI[ k ] = best.i;
+			topV[ k ] = best.v;
+		}
+		if( tid == 0 )
+		{
+			int res = 0;
+			while( ( topI[ res ] == a.tokenSot || topI[ res ] == a.tokenSolm || topI[ res ] == a.tokenNot ) && res < 3 ) res++;
+			TokenData td;
+			td.id = topI[ res ];
+			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
+			td.p = topV[ res ];
+			td.pt = (float)( (double)bestTs.v / ( sumTs + 1e-10 ) );
+			td.ptsum = (float)sumTs;
+			a.out[ b ] = td;
+			if( a.nextTokens ) a.nextTokens[ b ] = td.id;
+			if( a.history && a.dStep && *a.dStep < a.histCap ) a.history[ (size_t)b * a.histCap + *a.dStep ] = td.id;
+		}
+	}
+
+	__global__ void __launch_bounds__( SM_THREADS )
+		softmax_rows_kernel( const float* __restrict__ logits, float* __restrict__ probs, int n )
+	{
+		__shared__ float sf[ SM_THREADS / 32 ];
+		__shared__ double sd[ SM_THREADS / 32 ];
+		const float* lg = logits + (size_t)blockIdx.x * n;
+		float* pr = probs + (size_t)blockIdx.x * n;
+		const int tid = threadIdx.x;
+		float mx = -INFINITY;
+		for( int i = tid; i < n; i += SM_THREADS ) mx = fmaxf( mx, lg[ i ] );
+		mx = blockMaxF( mx, sf );
+		double dsum = 0.0;
+		for( int i = tid; i < n; i += SM_THREADS )
+		{
+			const float e = expf( lg[ i ] - mx );
+			pr[ i ] = e;
+			dsum += (double)e;
+		}
+		dsum = blockSumD( dsum, sd );
+		const float inv = (float)( 1.0 / dsum );
+		for( int i = tid; i < n; i += SM_THREADS ) pr[ i ] *= inv;
+	}
+	cudaError_t softmaxRows( const float* logits, float* probs, int rows, int n, cudaStream_t s )
+	{
+		softmax_rows_kernel<<<rows, SM_THREADS, 0, s>>>( logits, probs, n );
+		return cudaGetLastError();
+	}
+
+	__global__ void advance_kernel( int* dNPast, int N, int* dForceTs, int* dStep )
+	{
+		if( dNPast ) *dNPast += N;
+		if( dForceTs ) { dForceTs[ 0 ] = 0; dForceTs[ 1 ] = 0; }
+		if( dStep ) *dStep += 1;
+	}
+
+	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s )
+	{
+		sample_kernel<<<a.B, SM_THREADS, 0, s>>>( a );
+		// step-global state is advanced by a separate 1-thread kernel so that no CTA of the sampler races with it
+		advance_kernel<<<1, 1, 0, s>>>( a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );
+		return cudaGetLastError();
+	}
+}
