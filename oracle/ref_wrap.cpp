@@ -95,7 +95,21 @@ extern "C" {
 void ora_set_log_level( int lvl ) { g_logLevel = lvl; }
 const char* ora_system_info() { return whisper_print_system_info(); }
 
-whisper_context* ora_init( const char* path ) { return whisper_init( path ); }
+whisper_context* ora_init( const char* path )
+{
+	whisper_context* c = whisper_init( path );
+	if( c )
+	{
+		// whisper_context leaves these members uninitialised (whisper.cpp:425-431) and only whisper_full() sets them
+		// (:2804-2807, :2836).  whisper_encode/whisper_decode read exp_n_audio_ctx (:1092, :1528), so a caller that drives
+		// encode/decode directly — as this wrapper does — must give them their documented defaults ("0 - use default").
+		c->exp_n_audio_ctx = 0;
+		c->t_beg = 0;
+		c->t_last = 0;
+		c->tid_last = 0;
+	}
+	return c;
+}
 void ora_free( whisper_context* c ) { if( c ) whisper_free( c ); }
 
 // hparams in file order (whisper.cpp:477-487)

@@ -130,15 +130,18 @@ def stage_mel():
 def stage_encoder(model_name="micro.en"):
     from whisper_b200 import synth
     from oracle.ref import RefOracle
-    path, m, e, c = _open(model_name)
-    o = RefOracle(path, threads=4)
+    path = synth.model_path(model_name)
+    o = RefOracle(path, threads=int(os.environ.get("ORA_THREADS", "4")))
     pcm = synth.synth_pcm(0)
     mel = o.pcm_to_mel(pcm)
+    print("  oracle mel done", flush=True)
     o.trace(True)
     o.encode(0)
+    print("  oracle encode done", flush=True)
     tr = o.trace_items()
     o.trace(False)
     print("  oracle trace keys:", list(tr.keys())[:12], flush=True)
+    path, m, e, c = _open(model_name)
     c.set_mel(0, mel)
     d, T = m.n_audio_state, m.n_audio_ctx
     L = m.n_audio_layer
@@ -178,7 +181,10 @@ def stage_decoder(model_name="micro.en"):
     from whisper_b200 import capi, synth
     from oracle.ref import RefOracle
     path, m, e, c = _open(model_name)
-    o = RefOracle(path, threads=1)
+    th = int(os.environ.get("ORA_THREADS", "4"))
+    o = RefOracle(path, threads=th)
+    c.set_reference_threads(th)
+    print("  reference threads = %d" % th, flush=True)
     pcm = synth.synth_pcm(0)
     mel = o.pcm_to_mel(pcm)
     o.encode(0)
@@ -216,7 +222,10 @@ def stage_decoder(model_name="micro.en"):
     # graph on/off consistency + device-token feedback
     toks, st = c.run_chunks([pcm], prompt, 16)
     print("  run_chunks tokens:", toks[0].tolist(), "stage_ms", st.tolist(), flush=True)
-    ref_s, ref_toks, ref_st = o.bench_chunk(pcm, prompt, 16, threads=1)
+    c.set_graph(False)
+    toks2, st2 = c.run_chunks([pcm], prompt, 16)
+    print("  run_chunks (no graph):", "same" if (toks2 == toks).all() else toks2[0].tolist(), st2.tolist(), flush=True)
+    ref_s, ref_toks, ref_st = o.bench_chunk(pcm, prompt, 16, threads=th)
     print("  oracle tokens    :", ref_toks.tolist(), flush=True)
 
 
@@ -266,6 +275,8 @@ STAGES = {
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--stage":
+        import faulthandler
+        faulthandler.enable()
         STAGES[sys.argv[2]]()
         sys.exit(0)
     names = sys.argv[1:] or list(STAGES.keys())

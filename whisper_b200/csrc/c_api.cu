@@ -305,6 +305,14 @@ wsp_status wsp_debug_set_encoder_layers( wsp_context* c, int32_t n )
 	c->c->debugEncLayers = n;
 	return WSP_OK;
 }
+wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	if( n < 0 || n > 16 ) return fail( WSP_E_INVALIDARG, "reference thread count must be in [0, 16]" );
+	if( n != c->c->refThreads && c->c->stepGraph ) { cudaGraphExecDestroy( c->c->stepGraph ); c->c->stepGraph = nullptr; }
+	c->c->refThreads = n;
+	return WSP_OK;
+}
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on )
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );

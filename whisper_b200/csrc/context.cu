@@ -308,7 +308,7 @@ namespace wsp
 			a.epi = kern::SK_QKV; a.bias = W.bqkv; a.scale = qkScale; a.outF32 = c.qd; a.ld = d; a.kCache = kc; a.vCache = vc;
 			a.d = d; a.N = N; a.nTextCtx = nCtx; a.dNPast = c.dNPast;
 			WSP_CUDA( kern::skinnyGemm( a, s ) );
-			WSP_CUDA( kern::selfAttnDecode( c.qd, kc, vc, c.attnD, batch, N, H, d, nCtx, c.dNPast, s ) );
+			WSP_CUDA( kern::selfAttnDecode( c.qd, kc, vc, c.attnD, batch, N, H, d, nCtx, c.dNPast, c.refThreads, s ) );
 			a = kern::SkinnyArgs();
 			a.W = W.wo; a.nOut = d; a.K = d; a.xF16 = c.attnD; a.xStride = d; a.nCols = cols;
 			a.epi = kern::SK_BIAS_RESID; a.bias = W.bo; a.outF32 = c.xd; a.ld = d;
@@ -319,7 +319,7 @@ namespace wsp
 			a.epi = kern::SK_Q_SCALE; a.bias = W.bcq; a.scale = qkScale; a.outF32 = c.qd; a.ld = d;
 			WSP_CUDA( kern::skinnyGemm( a, s ) );
 			const size_t crossOff = (size_t)il * c.maxB * T * d;
-			WSP_CUDA( kern::crossAttnDecode( c.qd, c.crossK + crossOff, c.crossV + crossOff, c.attnD, batch, N, H, d, T, s ) );
+			WSP_CUDA( kern::crossAttnDecode( c.qd, c.crossK + crossOff, c.crossV + crossOff, c.attnD, batch, N, H, d, T, c.refThreads, s ) );
 			a = kern::SkinnyArgs();
 			a.W = W.wco; a.nOut = d; a.K = d; a.xF16 = c.attnD; a.xStride = d; a.nCols = cols;
 			a.epi = kern::SK_BIAS_RESID; a.bias = W.bco; a.outF32 = c.xd; a.ld = d;

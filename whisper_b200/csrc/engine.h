@@ -131,6 +131,7 @@ namespace wsp
 		int histCap = 0;
 		int lastLogitRows = 0;
 		int debugEncLayers = -1;
+		int refThreads = 4;             // reference CPU thread count whose V^T*P arithmetic the decoder reproduces (0 = exact)
 
 		// tensor maps (built once; M of a launch limits the rows touched)
 		CUtensorMap mapMel, mapConv1Even, mapConv1Odd, mapXn, mapAttn, mapH;

@@ -62,10 +62,11 @@ namespace kern
 	};
 	cudaError_t skinnyGemm( const SkinnyArgs& a, cudaStream_t s );
 
+	// refThreads: reproduce the reference's f16-accumulated V^T*P for that many CPU threads (see kernels_decode.cu); 0 = exact f32
 	// self attention over the f16 self-KV cache, causal: query i of chunk b sees keys [0, nPast+i]   (a14)
-	cudaError_t selfAttnDecode( const float* q, const __half* kCache, const __half* vCache, __half* out, int B, int N, int H, int d, int nTextCtx, const int* dNPast, cudaStream_t s );
+	cudaError_t selfAttnDecode( const float* q, const __half* kCache, const __half* vCache, __half* out, int B, int N, int H, int d, int nTextCtx, const int* dNPast, int refThreads, cudaStream_t s );
 	// cross attention over the f16 cross-KV memory [b][h][T][64]                                       (a15)
-	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, cudaStream_t s );
+	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, int refThreads, cudaStream_t s );
 
 	// softmax + greedy sampling with the Whisper timestamp rules (a17 softmax, a18: whisper.cpp:1875-1964)
 	struct TokenData

@@ -225,6 +225,41 @@ namespace kern
 	}
 
 	// ---------------------------------------------------------------------------------------------------------------
+	// V^T * P with the reference's arithmetic.  In the CPU reference this product takes ggml's "mad" path because V is read
+	// transposed (ggml.c:4680-4722): thread ith of nth owns the contiguous key range [ith*dc, (ith+1)*dc), dc = ceil(nkv/nth), and
+	// accumulates y[e] = f16( fma( V[j][e], P[j], f32(y[e]) ) ) key by key in an f16 work row (ggml_vec_mad_f16, ggml.c:871-893, with
+	// AVX2/F16C: f32 FMA then a round-to-nearest-even store to f16); FINALIZE adds the nth partial rows in f32 in thread order
+	// (ggml.c:4613-4640).  With ~1500 keys the f16 running sum swamps the small P[j]*V increments, so the result depends on nth and
+	// differs from the exact sum by several percent — that IS the reference's output, and the greedy token sequence depends on it.
+	// `refThreads` reproduces it for a given thread count (the reference's default is min(4, cores), whisper.cpp:2605; its own
+	// compat shader also "fakes 4 CPU threads", ComputeShaders/mulMatMadMain.hlsl:107).  refThreads = 0 selects exact f32 accumulation.
+	__device__ __forceinline__ float pvChainF16( const float* __restrict__ sp, const __half* __restrict__ v, size_t vStride, int j0, int j1 )
+	{
+		float y = 0.0f;   // always exactly representable in f16
+		int j = j0;
+		for( ; j + 4 <= j1; j += 4 )
+		{
+			const float x0 = __half2float( v[ (size_t)j * vStride ] );
+			const float x1 = __half2float( v[ (size_t)( j + 1 ) * vStride ] );
+			const float x2 = __half2float( v[ (size_t)( j + 2 ) * vStride ] );
+			const float x3 = __half2float( v[ (size_t)( j + 3 ) * vStride ] );
+			y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
+			y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
+			y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
+			y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
+		}
+		for( ; j < j1; j++ )
+			y = __half2float( __float2half_rn( __fmaf_rn( __half2float( v[ (size_t)j * vStride ] ), sp[ j ], y ) ) );
+		return y;
+	}
+	// exp through the reference's f16 table semantics: f32( f16( exp( f16(x) ) ) )  (ggml.c:5075-5077, table :1372-1383)
+	__device__ __forceinline__ float expF16Table( float x )
+	{
+		return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) );
+	}
+	constexpr int PV_MAX_THREADS = 16;
+
+	// ---------------------------------------------------------------------------------------------------------------
 	// Decoder self-attention, one CTA per (chunk, head, query).  Oracle: whisper.cpp:1616-1661 — K*Q (Q rounded to f16 by the
 	// mul_mat, ggml.c:4599), causal mask, softmax, V^T * P.  KV cache rows are [b][pos][d] f16.
 	constexpr int SA_THREADS = 128;
@@ -232,17 +267,18 @@ namespace kern
 
 	__global__ void __launch_bounds__( SA_THREADS )
 		self_attn_decode_kernel( const float* __restrict__ q, const __half* __restrict__ kCache, const __half* __restrict__ vCache, __half* __restrict__ out,
-			int N, int H, int d, int nTextCtx, const int* __restrict__ dNPast )
+			int N, int H, int d, int nTextCtx, const int* __restrict__ dNPast, int refThreads )
 	{
 		__shared__ float sq[ 64 ];
 		__shared__ float sp[ SA_MAXKV ];
 		__shared__ float sred[ SA_THREADS / 32 ];
-		__shared__ float so[ 2 ][ 64 ];
+		__shared__ float so[ PV_MAX_THREADS ][ 64 ];
 		const int bh = blockIdx.x;
 		const int b = bh / H, h = bh - b * H;
 		const int i = blockIdx.y;
 		const int tid = threadIdx.x;
-		const int nkv = min( *dNPast + i + 1, nTextCtx );
+		const int nkv = min( *dNPast + i + 1, nTextCtx );   // causal: keys visible to query i
+		const int nkvAll = min( *dNPast + N, nTextCtx );     // columns of the KQ matrix the reference partitions over its threads
 		const int col = b * N + i;
 		if( tid < 64 )
 			sq[ tid ] = __half2float( __float2half_rn( q[ (size_t)col * d + h * 64 + tid ] ) );
@@ -278,7 +314,7 @@ namespace kern
 		float lsum = 0.0f;
 		for( int j = tid; j < nkv; j += SA_THREADS )
 		{
-			const float e = expf( sp[ j ] - mx );
+			const float e = expF16Table( sp[ j ] - mx );
 			sp[ j ] = e;
 			lsum += e;
 		}
@@ -288,21 +324,43 @@ namespace kern
 		float tot = 0.0f;
 		for( int w = 0; w < SA_THREADS / 32; w++ ) tot += sred[ w ];
 		const float inv = 1.0f / tot;
-		// O[e] = sum_j P[j] V[j][e]: two key-halves x 64 dims
-		const int e = tid & 63, half = tid >> 6;
-		float o = 0.0f;
-		for( int j = half; j < nkv; j += 2 )
-			o += sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
-		so[ half ][ e ] = o;
+		for( int j = tid; j < nkv; j += SA_THREADS ) sp[ j ] *= inv;   // the reference normalises P before V^T*P (ggml.c:5085-5090)
 		__syncthreads();
-		if( tid < 64 )
-			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( ( so[ 0 ][ tid ] + so[ 1 ][ tid ] ) * inv );
+		const int e = tid & 63;
+		if( refThreads > 0 )
+		{
+			// reference arithmetic: refThreads f16 chains over contiguous key ranges, summed in f32 in thread order
+			const int dc = ( nkvAll + refThreads - 1 ) / refThreads;
+			for( int part = tid >> 6; part < refThreads; part += SA_THREADS / 64 )
+			{
+				const int j0 = min( part * dc, nkv ), j1 = min( ( part + 1 ) * dc, nkv );   // masked keys contribute exactly 0
+				so[ part ][ e ] = pvChainF16( sp, vb + e, (size_t)d, j0, j1 );
+			}
+			__syncthreads();
+			if( tid < 64 )
+			{
+				float acc = so[ 0 ][ tid ];
+				for( int k = 1; k < refThreads; k++ ) acc += so[ k ][ tid ];
+				out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc );
+			}
+		}
+		else
+		{
+			const int half = tid >> 6;
+			float o = 0.0f;
+			for( int j = half; j < nkv; j += 2 )
+				o += sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
+			so[ half ][ e ] = o;
+			__syncthreads();
+			if( tid < 64 )
+				out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( so[ 0 ][ tid ] + so[ 1 ][ tid ] );
+		}
 	}
-	cudaError_t selfAttnDecode( const float* q, const __half* kCache, const __half* vCache, __half* out, int B, int N, int H, int d, int nTextCtx, const int* dNPast, cudaStream_t s )
+	cudaError_t selfAttnDecode( const float* q, const __half* kCache, const __half* vCache, __half* out, int B, int N, int H, int d, int nTextCtx, const int* dNPast, int refThreads, cudaStream_t s )
 	{
-		if( nTextCtx > SA_MAXKV ) return cudaErrorInvalidValue;
+		if( nTextCtx > SA_MAXKV || refThreads < 0 || refThreads > PV_MAX_THREADS ) return cudaErrorInvalidValue;
 		dim3 grid( B * H, N );
-		self_attn_decode_kernel<<<grid, SA_THREADS, 0, s>>>( q, kCache, vCache, out, N, H, d, nTextCtx, dNPast );
+		self_attn_decode_kernel<<<grid, SA_THREADS, 0, s>>>( q, kCache, vCache, out, N, H, d, nTextCtx, dNPast, refThreads );
 		return cudaGetLastError();
 	}
 
@@ -316,7 +374,7 @@ namespace kern
 
 	__global__ void __launch_bounds__( CA_THREADS )
 		cross_attn_decode_kernel( const float* __restrict__ q, const __half* __restrict__ kMem, const __half* __restrict__ vMem, __half* __restrict__ out,
-			int N, int H, int d, int T )
+			int N, int H, int d, int T, int refThreads )
 	{
 		__shared__ float sp[ CA_MAXT ];
 		__shared__ float sred[ CA_THREADS / 32 ];
@@ -369,7 +427,7 @@ namespace kern
 		float lsum = 0.0f;
 		for( int j = tid; j < T; j += CA_THREADS )
 		{
-			const float e = expf( sp[ j ] - mx );
+			const float e = expF16Table( sp[ j ] - mx );
 			sp[ j ] = e;
 			lsum += e;
 		}
@@ -379,6 +437,30 @@ namespace kern
 		float tot = 0.0f;
 		for( int w = 0; w < CA_THREADS / 32; w++ ) tot += sred[ w ];
 		const float inv = 1.0f / tot;
+		for( int j = tid; j < T; j += CA_THREADS ) sp[ j ] *= inv;   // normalised P (ggml.c:5085-5090)
+		__syncthreads();
+
+		if( refThreads > 0 )
+		{
+			// reference arithmetic (see pvChainF16): one f16 chain per (reference thread, output dim)
+			float* sof = &so[ 0 ][ 0 ][ 0 ];   // reused as [refThreads][64]
+			const __half* vb = vMem + (size_t)bh * T * 64;
+			const int dc = ( T + refThreads - 1 ) / refThreads;
+			for( int idx = tid; idx < refThreads * 64; idx += CA_THREADS )
+			{
+				const int part = idx >> 6, e = idx & 63;
+				const int j0 = min( part * dc, T ), j1 = min( ( part + 1 ) * dc, T );
+				sof[ idx ] = pvChainF16( sp, vb + e, 64, j0, j1 );
+			}
+			__syncthreads();
+			if( tid < 64 )
+			{
+				float acc = sof[ tid ];
+				for( int k = 1; k < refThreads; k++ ) acc += sof[ k * 64 + tid ];
+				out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc );
+			}
+			return;
+		}
 
 		float o[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 		for( int j0 = warp * 4; j0 < T; j0 += ( CA_THREADS / 32 ) * 4 )
@@ -407,14 +489,14 @@ namespace kern
 			for( int w = 0; w < CA_THREADS / 32; w++ )
 #pragma unroll
 				for( int r = 0; r < 4; r++ ) acc += so[ w ][ r ][ tid ];
-			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc * inv );
+			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc );
 		}
 	}
-	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, cudaStream_t s )
+	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, int refThreads, cudaStream_t s )
 	{
-		if( T > CA_MAXT ) return cudaErrorInvalidValue;
+		if( T > CA_MAXT || refThreads < 0 || refThreads > PV_MAX_THREADS ) return cudaErrorInvalidValue;
 		dim3 grid( B * H, N );
-		cross_attn_decode_kernel<<<grid, CA_THREADS, 0, s>>>( q, kMem, vMem, out, N, H, d, T );
+		cross_attn_decode_kernel<<<grid, CA_THREADS, 0, s>>>( q, kMem, vMem, out, N, H, d, T, refThreads );
 		return cudaGetLastError();
 	}
 
@@ -495,7 +577,7 @@ namespace kern
 		double dsum = 0.0;
 		for( int i = tid; i < nv; i += SM_THREADS )
 		{
-			const float e = expf( lg[ i ] - mx );
+			const float e = expF16Table( lg[ i ] - mx );
 			pr[ i ] = e;
 			dsum += (double)e;
 		}
@@ -573,7 +655,7 @@ namespace kern
 		double dsum = 0.0;
 		for( int i = tid; i < n; i += SM_THREADS )
 		{
-			const float e = expf( lg[ i ] - mx );
+			const float e = expF16Table( lg[ i ] - mx );
 			pr[ i ] = e;
 			dsum += (double)e;
 		}
