@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from oracle/_ref — the reference's own CPU implementation (Whisper/source/{ggml.c,whisper.cpp},
+compiled unmodified by oracle/Makefile).  The reference ships no golden vectors for this path, so these
+fixtures ARE the pin: they are what the numpy restatement (oracle/whisper_np.py) and the CUDA engine are compared with on
+machines where /root/reference (and hence a fresh oracle/_ref build) is not available.
+
+Inputs are fully determined by whisper_b200/synth.py (model seed 1234, PCM chunk ids), so only outputs are stored, and large
+tensors are stored as deterministic sub-samples to keep the fixtures small.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref import RefOracle  # noqa: E402
+from whisper_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# deterministic sub-sampling shared with the tests
+MEL_STEP = 10        # every 10th frame
+ROW_STEP = 25        # every 25th time step of [T][d] tensors
+LOGIT_STEP = 61      # every 61st vocabulary entry
+N_STEPS = 16         # greedy steps stored
+
+
+def logits_sample(lg):
+    idx = np.arange(0, lg.shape[-1], LOGIT_STEP)
+    return lg[..., idx].astype(np.float32)
+
+
+def make(model_name: str, chunk: int, n_samples: int, offset: int, threads_list=(1, 4)):
+    path = synth.model_path(model_name)
+    pcm = synth.synth_pcm(chunk, n_samples)
+    out = {}
+    o = RefOracle(path, threads=1)
+    mel = o.pcm_to_mel(pcm)
+    out["mel_shape"] = np.array(mel.shape, np.int32)
+    out["mel"] = mel[:, ::MEL_STEP].astype(np.float32)
+    o.trace(True)
+    o.encode(offset)
+    tr = o.trace_items()
+    o.trace(False)
+    d, T, L = o.n_audio_state, o.n_audio_ctx, o.n_audio_layer
+    out["enc_temp1"] = tr["enc.temp1"].reshape(d, 3000).T[::ROW_STEP * 2].astype(np.float32)
+    for il in (0, 1):
+        out["enc_layer%d_in" % il] = tr["enc.layer[ %d ].in" % il].reshape(T, d)[::ROW_STEP].astype(np.float32)
+    out["enc_layers"] = tr["enc.layers"].reshape(T, d)[::ROW_STEP].astype(np.float32)
+    out["encode_out"] = tr["encode-out"].reshape(T, d)[::ROW_STEP].astype(np.float32)
+    ck, cv = o.cross_kv()
+    out["cross_k"] = ck[:, ::ROW_STEP].astype(np.float16)
+    out["cross_v"] = cv[:, ::ROW_STEP].astype(np.float16)
+    prompt = [o.special["sot"]]
+    if o.n_vocab == 51865:
+        prompt += [o.special["sot"] + 1, o.special["transcribe"]]
+    out["prompt"] = np.array(prompt, np.int32)
+    for th in threads_list:
+        oo = RefOracle(path, threads=th)
+        oo.set_mel(mel)
+        oo.encode(offset)
+        lg, pr = oo.decode(prompt, 0)
+        out["t%d_prompt_logits" % th] = logits_sample(lg)
+        out["t%d_prompt_logits_max" % th] = lg.max(-1).astype(np.float32)
+        out["t%d_prompt_argmax" % th] = lg.argmax(-1).astype(np.int32)
+        tok = oo.sample(initial=True, force_timestamp=True)
+        toks, ps, step_logits, tids = [tok["id"]], [tok["p"]], [], [tok["tid"]]
+        n_past = len(prompt)
+        for _ in range(N_STEPS - 1):
+            lg, pr = oo.decode([toks[-1]], n_past)
+            n_past += 1
+            step_logits.append(logits_sample(lg[0]))
+            tok = oo.sample()
+            toks.append(tok["id"]); ps.append(tok["p"]); tids.append(tok["tid"])
+        out["t%d_tokens" % th] = np.array(toks, np.int32)
+        out["t%d_tids" % th] = np.array(tids, np.int32)
+        out["t%d_token_p" % th] = np.array(ps, np.float32)
+        out["t%d_step_logits" % th] = np.stack(step_logits)
+    return out
+
+
+CASES = {
+    # name: (model, pcm chunk id, n_samples, mel offset)
+    "micro_en_30s": ("micro.en", 0, 480000, 0),
+    "micro_ml_11s": ("micro", 1, 176000, 0),          # multilingual specials, short clip (zero-padded window)
+    "micro_en_offset": ("micro.en", 2, 640000, 1000),  # 40 s clip, window starting at frame 1000 (ragged tail)
+}
+
+if __name__ == "__main__":
+    for name, (model, chunk, n, off) in CASES.items():
+        data = make(model, chunk, n, off)
+        p = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(p, **data)
+        print(name, "%.0f KB" % (os.path.getsize(p) / 1024))

@@ -1,0 +1,199 @@
+"""Parity of the CUDA hot path with the reference, on a B200, through the C ABI.
+
+Oracle: the committed fixtures tests/golden/*.npz (outputs of oracle/_ref = the reference's unmodified CPU code), plus oracle/_ref
+itself when the prebuilt library travelled to this box.  Nothing here reads /root/reference.
+
+Tolerances (floating point, activations O(1), logits rms ~3):
+  mel 5e-4 · encoder tensors 8e-3 · f16 KV memories 4e-3 · logits 3e-2 (measured: 1e-4, 3e-3, 2e-3, 1e-2).
+Greedy tokens must be IDENTICAL to the reference's for the whole free-running sequence.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.make_golden import CASES, LOGIT_STEP, MEL_STEP, N_STEPS, ROW_STEP
+from whisper_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_MEL, TOL_ENC, TOL_KV, TOL_LOGIT = 5e-4, 8e-3, 4e-3, 3e-2
+
+_cache = {}
+
+
+def open_model(name, batch=1):
+    key = (name, batch)
+    if key not in _cache:
+        m = capi.Model(synth.model_path(name))
+        e = _cache.get(("engine", name)) or capi.Engine(m, 0)
+        _cache[("engine", name)] = e
+        _cache[key] = (m, e, capi.Context(e, batch))
+    return _cache[key]
+
+
+def golden(name):
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_mel(name):
+    model, chunk, n, off = CASES[name]
+    m, e, c = open_model(model)
+    g = golden(name)
+    c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
+    mel = c.get_mel(0)
+    assert mel.shape == tuple(g["mel_shape"])
+    assert np.abs(mel[:, ::MEL_STEP] - g["mel"]).max() < TOL_MEL
+
+
+def test_mel_edge_cases():
+    m, e, c = open_model("micro.en")
+    # shorter than one FFT window, and an empty buffer: n_len = n_samples / 160 frames, zero-padded frames (whisper.cpp:2080, 2105-2109)
+    for n in (0, 100, 160, 399, 400, 16000):
+        c.pcm_to_mel(0, synth.synth_pcm(3, n) if n else np.zeros(0, np.float32))
+        mel = c.get_mel(0)
+        assert mel.shape == (80, n // 160)
+        assert np.isfinite(mel).all()
+    # silence: log10 clamps at 1e-10 -> constant (-10 + 4)/4
+    c.pcm_to_mel(0, np.zeros(32000, np.float32))
+    assert np.allclose(c.get_mel(0), (-10.0 + 4.0) / 4.0)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_encoder_trace_points(name):
+    """Same named intermediates the reference traces (whisper.cpp:1121-1432), layer by layer."""
+    model, chunk, n, off = CASES[name]
+    m, e, c = open_model(model)
+    g = golden(name)
+    d, T, L = m.n_audio_state, m.n_audio_ctx, m.n_audio_layer
+    c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
+    c.set_encoder_layers(0)
+    c.encode(1, [off])
+    conv1 = c.get_tensor("enc.conv1").reshape(3000, d)
+    assert np.abs(conv1[::ROW_STEP * 2] - g["enc_temp1"]).max() < TOL_ENC
+    assert np.abs(c.get_tensor("enc.x").reshape(T, d)[::ROW_STEP] - g["enc_layer0_in"]).max() < TOL_ENC
+    c.set_encoder_layers(1)
+    c.encode(1, [off])
+    assert np.abs(c.get_tensor("enc.x").reshape(T, d)[::ROW_STEP] - g["enc_layer1_in"]).max() < TOL_ENC
+    c.set_encoder_layers(-1)
+    c.encode(1, [off])
+    assert np.abs(c.get_tensor("enc.x").reshape(T, d)[::ROW_STEP] - g["enc_layers"]).max() < TOL_ENC
+    assert np.abs(c.get_tensor("encode-out").reshape(T, d)[::ROW_STEP] - g["encode_out"]).max() < TOL_ENC
+    H, Ld = m.n_audio_head, m.n_text_layer
+    for nm in ("cross_k", "cross_v"):
+        got = c.get_tensor(nm).reshape(Ld, H, T, 64).transpose(0, 2, 1, 3).reshape(Ld, T, d)
+        assert np.abs(got[:, ::ROW_STEP] - g[nm].astype(np.float32)).max() < TOL_KV
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("threads", [1, 4])
+def test_decoder_logits_teacher_forced(name, threads):
+    model, chunk, n, off = CASES[name]
+    m, e, c = open_model(model)
+    g = golden(name)
+    c.set_reference_threads(threads)
+    c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
+    c.encode(1, [off])
+    prompt = g["prompt"].tolist()
+    idx = np.arange(0, m.n_vocab, LOGIT_STEP)
+    c.decode([prompt], 0, 1, capi.DECODE_ALL_LOGITS)
+    lg = c.logits(len(prompt))
+    assert np.abs(lg[:, idx] - g["t%d_prompt_logits" % threads]).max() < TOL_LOGIT
+    assert np.abs(lg.max(-1) - g["t%d_prompt_logits_max" % threads]).max() < TOL_LOGIT
+    pr = c.probs(len(prompt))
+    assert np.allclose(pr.sum(-1), 1.0, atol=1e-4)
+    toks = g["t%d_tokens" % threads]
+    s = c.decode([prompt], 0, 1, capi.DECODE_FORCE_TIMESTAMP | capi.DECODE_INITIAL)[0]
+    assert s["id"] == toks[0] and s["tid"] == g["t%d_tids" % threads][0]
+    assert abs(s["p"] - g["t%d_token_p" % threads][0]) < 1e-3
+    n_past = len(prompt)
+    for i in range(1, N_STEPS):
+        s = c.decode([[int(toks[i - 1])]], n_past, 1, 0)[0]
+        n_past += 1
+        lg = c.logits(1)
+        assert np.abs(lg[0, idx] - g["t%d_step_logits" % threads][i - 1]).max() < TOL_LOGIT, "step %d" % i
+        assert s["id"] == toks[i], "step %d" % i
+        assert abs(s["p"] - g["t%d_token_p" % threads][i]) < 5e-3
+    c.set_reference_threads(4)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("graph", [True, False])
+def test_greedy_tokens_free_running(name, threads, graph):
+    """The measured path (wsp_run_chunks: tokens fed back on the device, CUDA graph per step) reproduces the reference's
+    greedy sequence exactly — when the window starts at frame 0, which is what run_chunks encodes."""
+    model, chunk, n, off = CASES[name]
+    if off != 0:
+        pytest.skip("run_chunks always encodes the window at offset 0")
+    m, e, c = open_model(model)
+    g = golden(name)
+    c.set_reference_threads(threads)
+    c.set_graph(graph)
+    toks, st = c.run_chunks([synth.synth_pcm(chunk, n)], g["prompt"].tolist(), N_STEPS)
+    assert toks[0].tolist() == g["t%d_tokens" % threads].tolist()
+    c.set_graph(True)
+    c.set_reference_threads(4)
+
+
+def test_batch_equals_single():
+    """Independent chunks: a chunk's tokens do not depend on which batch slot it sits in or on its neighbours."""
+    m, e, c1 = open_model("micro.en", 1)
+    _, _, c4 = open_model("micro.en", 4)
+    pcms = [synth.synth_pcm(i, 480000 - 16000 * i) for i in range(4)]
+    prompt = m.prompt_init()
+    t4, _ = c4.run_chunks(pcms, prompt, 12)
+    for i in range(4):
+        t1, _ = c1.run_chunks([pcms[i]], prompt, 12)
+        assert t1[0].tolist() == t4[i].tolist()
+    # permuting the batch permutes the results
+    t4p, _ = c4.run_chunks(pcms[::-1], prompt, 12)
+    assert t4p[::-1].tolist() == t4.tolist()
+    # partial batch on a larger context
+    t2, _ = c4.run_chunks(pcms[:2], prompt, 12)
+    assert t2.tolist() == t4[:2].tolist()
+
+
+def test_live_reference_when_prebuilt():
+    """If oracle/_ref travelled to this box, compare against the reference live on a case that has no committed fixture."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    m, e, c = open_model("tiny.en")
+    o = ref.RefOracle(synth.model_path("tiny.en"), threads=4)
+    pcm = synth.synth_pcm(5)
+    mel_ref = o.pcm_to_mel(pcm)
+    c.pcm_to_mel(0, pcm)
+    assert np.abs(c.get_mel(0) - mel_ref).max() < TOL_MEL
+    o.encode(0)
+    c.encode(1)
+    ck, cv = o.cross_kv()
+    d, T, H, L = m.n_audio_state, m.n_audio_ctx, m.n_audio_head, m.n_text_layer
+    got = c.get_tensor("cross_k").reshape(L, H, T, 64).transpose(0, 2, 1, 3).reshape(L, T, d)
+    assert np.abs(got - ck).max() < TOL_KV
+    prompt = m.prompt_init()
+    ref_s, ref_toks, _ = o.bench_chunk(pcm, prompt, 20)
+    toks, _ = c.run_chunks([pcm], prompt, 20)
+    assert toks[0].tolist() == ref_toks.tolist()
+
+
+def test_argument_errors():
+    m, e, c = open_model("micro.en")
+    with pytest.raises(capi.WspError) as ex:
+        c.encode(2)            # context was created for batch 1
+    assert ex.value.status == -7
+    with pytest.raises(capi.WspError):
+        c.decode([[m.n_vocab + 5]], 0, 1, 0)
+    with pytest.raises(capi.WspError):
+        c.decode([[1]], m.n_text_ctx, 1, 0)
+    with pytest.raises(capi.WspError):
+        c.get_tensor("no-such-tensor")
+
+
+def test_launch_counter_counts_kernels():
+    L = capi.lib()
+    m, e, c = open_model("micro.en")
+    before = L.wsp_launch_count()
+    c.run_chunks([synth.synth_pcm(0)], m.prompt_init(), 4)
+    assert L.wsp_launch_count() - before > 100

@@ -1,0 +1,127 @@
+"""Pins the numpy restatement (oracle/whisper_np.py) against the reference's own CPU implementation: live against
+oracle/_ref when it has been built here, and always against the committed fixtures tests/golden/*.npz (generated from
+oracle/_ref by tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import whisper_np as wn
+from whisper_b200 import synth
+
+from tests.golden.make_golden import CASES, LOGIT_STEP, MEL_STEP, N_STEPS, ROW_STEP  # noqa: E402
+
+# tolerances, in the units of each tensor (all activations are O(1)); measured gaps are 3-10x smaller
+TOL_MEL = 5e-4
+TOL_ENC = 6e-3
+TOL_KV = 4e-3
+TOL_LOGIT = 2e-2
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.fixture(scope="module")
+def np_runs(golden_dir):
+    """numpy restatement outputs for every golden case (computed once)."""
+    runs = {}
+    for name, (model, chunk, n, off) in CASES.items():
+        m = wn.NpModel(synth.model_path(model))
+        pcm = synth.synth_pcm(chunk, n)
+        mel = wn.log_mel(pcm, m.filters)
+        tr = {}
+        out, ck, cv = wn.encode(m, mel, off, tr)
+        runs[name] = dict(m=m, mel=mel, tr=tr, out=out, ck=ck, cv=cv)
+    return runs
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_mel_restatement_vs_golden(name, golden_dir, np_runs):
+    g = load(golden_dir, name)
+    mel = np_runs[name]["mel"]
+    assert tuple(g["mel_shape"]) == mel.shape
+    assert np.abs(mel[:, ::MEL_STEP] - g["mel"]).max() < TOL_MEL
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_encoder_restatement_vs_golden(name, golden_dir, np_runs):
+    g = load(golden_dir, name)
+    r = np_runs[name]
+    assert np.abs(r["tr"]["enc.temp1"][::ROW_STEP * 2] - g["enc_temp1"]).max() < TOL_ENC
+    for il in (0, 1):
+        assert np.abs(r["tr"]["enc.layer[ %d ].in" % il][::ROW_STEP] - g["enc_layer%d_in" % il]).max() < TOL_ENC
+    assert np.abs(r["tr"]["enc.layers"][::ROW_STEP] - g["enc_layers"]).max() < TOL_ENC
+    assert np.abs(r["out"][::ROW_STEP] - g["encode_out"]).max() < TOL_ENC
+    assert np.abs(r["ck"][:, ::ROW_STEP] - g["cross_k"].astype(np.float32)).max() < TOL_KV
+    assert np.abs(r["cv"][:, ::ROW_STEP] - g["cross_v"].astype(np.float32)).max() < TOL_KV
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("threads", [1, 4])
+def test_decoder_restatement_vs_golden(name, threads, golden_dir, np_runs):
+    """Teacher-forced on the reference's tokens: logits within TOL_LOGIT; greedy choice identical wherever the reference's own
+    top-2 gap exceeds the tolerance.  The thread count matters: the reference accumulates V^T*P in f16 per thread."""
+    g = load(golden_dir, name)
+    r = np_runs[name]
+    m = r["m"]
+    dec = wn.NpDecoder(m, r["ck"], r["cv"], pv_threads=threads)
+    prompt = g["prompt"].tolist()
+    lg, pr = dec.decode(prompt, 0)
+    idx = np.arange(0, m.n_vocab, LOGIT_STEP)
+    assert np.abs(lg[:, idx] - g["t%d_prompt_logits" % threads]).max() < TOL_LOGIT
+    first = wn.sample_best(m, pr[-1], force_timestamp=True, is_initial=True)
+    toks = g["t%d_tokens" % threads]
+    assert first["id"] == toks[0] and first["tid"] == g["t%d_tids" % threads][0]
+    n_past = len(prompt)
+    for i in range(1, N_STEPS):
+        lg, pr = dec.decode([int(toks[i - 1])], n_past)
+        n_past += 1
+        assert np.abs(lg[0, idx] - g["t%d_step_logits" % threads][i - 1]).max() < TOL_LOGIT
+        s = wn.sample_best(m, pr[0])
+        srt = np.sort(lg[0])
+        if srt[-1] - srt[-2] > 2 * TOL_LOGIT:
+            assert s["id"] == toks[i], "step %d" % i
+
+
+def test_thread_count_changes_reference_logits(golden_dir):
+    """Documents SURVEY.md §0.8: the reference's decoder output depends on its thread count (f16 accumulators)."""
+    g = load(golden_dir, "micro_en_30s")
+    assert np.abs(g["t1_prompt_logits"] - g["t4_prompt_logits"]).max() > 0.05
+
+
+def test_live_reference_matches_golden(ref_available, golden_dir):
+    """When oracle/_ref is built here, re-derive a few fixture entries from it: guards against stale fixtures."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    from oracle.ref import RefOracle
+    model, chunk, n, off = CASES["micro_en_30s"]
+    g = load(golden_dir, "micro_en_30s")
+    o = RefOracle(synth.model_path(model), threads=4)
+    mel = o.pcm_to_mel(synth.synth_pcm(chunk, n))
+    assert np.array_equal(mel[:, ::MEL_STEP], g["mel"])
+    o.encode(off)
+    lg, _ = o.decode(g["prompt"].tolist(), 0)
+    assert np.array_equal(lg[:, ::LOGIT_STEP].astype(np.float32), g["t4_prompt_logits"])
+
+
+def test_sampler_rules():
+    """whisper_sample_best rules (whisper.cpp:1875-1964) on hand-made distributions."""
+    m = wn.NpModel(synth.model_path("micro.en"))
+    n, beg = m.n_vocab, m.token_beg
+    p = np.full(n, 1e-9)
+    p[100] = 0.5
+    p[beg + 5] = 0.3
+    s = wn.sample_best(m, p)
+    assert s["id"] == 100 and s["tid"] == beg + 5 and abs(s["ptsum"] - (0.3 + 1e-9 * (n - beg - 1))) < 1e-6
+    # timestamps win when their total mass exceeds the best text token
+    p[beg + 6] = 0.25
+    assert wn.sample_best(m, p)["id"] == beg + 5
+    # forced timestamp, initial: nothing later than beg+100
+    p[beg + 300] = 0.9
+    assert wn.sample_best(m, p, force_timestamp=True, is_initial=True)["id"] == beg + 5
+    assert wn.sample_best(m, p, force_timestamp=True, is_initial=False)["id"] == beg + 300
+    # sot / solm / not are skipped among the first three candidates
+    q = np.full(n, 1e-9)
+    q[m.token_sot], q[m.token_not], q[7] = 0.4, 0.3, 0.2
+    assert wn.sample_best(m, q)["id"] == 7

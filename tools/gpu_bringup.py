@@ -266,11 +266,21 @@ def stage_perf(model_name="medium", batch=8, n_decode=100):
     print("  tokens[0][:16]", toks[0][:16].tolist(), flush=True)
 
 
+def stage_profile(model_name="medium", batch=8, n_decode=3):
+    """short run for ncu: one mel + encode + n_decode steps, no graph"""
+    from whisper_b200 import synth
+    path, m, e, c = _open(model_name, batch=batch)
+    c.set_graph(os.environ.get("WSP_GRAPH", "0") == "1")
+    pcms = [synth.synth_pcm(i) for i in range(batch)]
+    toks, st = c.run_chunks(pcms, m.prompt_init(), n_decode)
+    print("  profile run stages", st.tolist(), flush=True)
+
+
 STAGES = {
     "gemm": stage_gemm, "ln": stage_ln, "skinny": stage_skinny, "attn": stage_attn, "mel": stage_mel,
     "encoder": stage_encoder, "decoder": stage_decoder, "batch": stage_batch,
     "encoder_tiny": stage_encoder_tiny, "decoder_tiny": stage_decoder_tiny,
-    "gemm_perf": stage_gemm_perf, "perf": stage_perf,
+    "gemm_perf": stage_gemm_perf, "perf": stage_perf, "profile": stage_profile,
 }
 
 if __name__ == "__main__":

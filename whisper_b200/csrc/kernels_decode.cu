@@ -63,13 +63,39 @@ namespace kern
 		const int col0 = blockIdx.y * SK_COLS;
 		const int ncols = min( SK_COLS, a.nCols - col0 );
 
+		// ---- weight stream: the first batch of 16-byte loads is issued before anything else, so HBM latency overlaps the
+		//      activation staging below (weights do not depend on the previous kernel's output) ----
+		const int g = lane >> 2, t = lane & 3;
+		const int rA = min( row0 + g, a.nOut - 1 );
+		const int rB = min( row0 + g + 8, a.nOut - 1 );
+		const uint4* wA = reinterpret_cast<const uint4*>( a.W + (size_t)rA * K + 8 * t );
+		const uint4* wB = reinterpret_cast<const uint4*>( a.W + (size_t)rB * K + 8 * t );
+		const int steps = K / 32;
+		constexpr int U = 8;
+		uint4 va[ U ], vb[ U ];
+#pragma unroll
+		for( int u = 0; u < U; u++ )
+		{
+			const int st = warp + u * SK_WARPS;
+			if( st < steps )
+			{
+				va[ u ] = ldg_stream( wA + st * 4 );   // 32 halves = 4 uint4 per step
+				vb[ u ] = ldg_stream( wB + st * 4 );
+			}
+		}
+
 		// ---- stage activations as f16 (LayerNorm fused when gamma is given) ----
 		for( int c = warp; c < SK_COLS; c += SK_WARPS )
 		{
 			__half* dst = sx + (size_t)c * rowStride;
 			if( c >= ncols )
 			{
-				for( int k = lane; k < K; k += 32 ) dst[ k ] = __float2half_rn( 0.0f );
+				// unused columns of a tile that is computed must be finite; the second n-tile is skipped entirely when ncols <= 8
+				if( c < 8 || ncols > 8 )
+				{
+					uint4* z4 = reinterpret_cast<uint4*>( dst );
+					for( int k = lane; k < K / 8; k += 32 ) z4[ k ] = make_uint4( 0, 0, 0, 0 );
+				}
 				continue;
 			}
 			if( a.xF32 )
@@ -77,15 +103,46 @@ namespace kern
 				const float* src = a.xF32 + (size_t)( col0 + c ) * a.xStride;
 				if( a.gamma )
 				{
-					// oracle: ggml_norm (ggml.c:4098-4156) + gamma/beta, then f16 conversion at the mul_mat (ggml.c:4592-4603)
+					// oracle: ggml_norm (ggml.c:4098-4156) + gamma/beta, then f16 conversion at the mul_mat (ggml.c:4592-4603).
+					// The row (K = d <= 1280, multiple of 128) is loaded once into registers, all loads in flight together.
+					constexpr int MAXV = 10;
+					const int n4 = K >> 7;
+					const float4* s4 = reinterpret_cast<const float4*>( src );
+					float4 v[ MAXV ];
 					float s = 0.0f;
-					for( int k = lane; k < K; k += 32 ) s += src[ k ];
+#pragma unroll
+					for( int q4 = 0; q4 < MAXV; q4++ )
+						if( q4 < n4 )
+						{
+							v[ q4 ] = s4[ q4 * 32 + lane ];
+							s += v[ q4 ].x + v[ q4 ].y + v[ q4 ].z + v[ q4 ].w;
+						}
 					const float mean = warpSumD( s ) / (float)K;
 					float sq = 0.0f;
-					for( int k = lane; k < K; k += 32 ) { const float v = src[ k ] - mean; sq += v * v; }
+#pragma unroll
+					for( int q4 = 0; q4 < MAXV; q4++ )
+						if( q4 < n4 )
+						{
+							v[ q4 ].x -= mean; v[ q4 ].y -= mean; v[ q4 ].z -= mean; v[ q4 ].w -= mean;
+							sq += v[ q4 ].x * v[ q4 ].x + v[ q4 ].y * v[ q4 ].y + v[ q4 ].z * v[ q4 ].z + v[ q4 ].w * v[ q4 ].w;
+						}
 					const float rstd = 1.0f / sqrtf( warpSumD( sq ) / (float)K + 1e-5f );
-					for( int k = lane; k < K; k += 32 )
-						dst[ k ] = __float2half_rn( ( src[ k ] - mean ) * rstd * a.gamma[ k ] + a.beta[ k ] );
+					const float4* g4 = reinterpret_cast<const float4*>( a.gamma );
+					const float4* b4 = reinterpret_cast<const float4*>( a.beta );
+					uint2* d2 = reinterpret_cast<uint2*>( dst );
+#pragma unroll
+					for( int q4 = 0; q4 < MAXV; q4++ )
+						if( q4 < n4 )
+						{
+							const float4 g = g4[ q4 * 32 + lane ];
+							const float4 bb = b4[ q4 * 32 + lane ];
+							__half2 h0 = __floats2half2_rn( v[ q4 ].x * rstd * g.x + bb.x, v[ q4 ].y * rstd * g.y + bb.y );
+							__half2 h1 = __floats2half2_rn( v[ q4 ].z * rstd * g.z + bb.z, v[ q4 ].w * rstd * g.w + bb.w );
+							uint2 u;
+							u.x = *reinterpret_cast<uint32_t*>( &h0 );
+							u.y = *reinterpret_cast<uint32_t*>( &h1 );
+							d2[ q4 * 32 + lane ] = u;
+						}
 				}
 				else
 					for( int k = lane; k < K; k += 32 ) dst[ k ] = __float2half_rn( src[ k ] );
@@ -100,29 +157,12 @@ namespace kern
 		__syncthreads();
 
 		// ---- main loop: 32 k per step, steps interleaved across the 8 warps (8 warps x 64 B = 512 contiguous bytes per row) ----
-		const int g = lane >> 2, t = lane & 3;
-		const int rA = min( row0 + g, a.nOut - 1 );
-		const int rB = min( row0 + g + 8, a.nOut - 1 );
-		const uint4* wA = reinterpret_cast<const uint4*>( a.W + (size_t)rA * K + 8 * t );
-		const uint4* wB = reinterpret_cast<const uint4*>( a.W + (size_t)rB * K + 8 * t );
 		const __half* xb0 = sx + (size_t)g * rowStride + 8 * t;         // n-tile 0: column g
 		const __half* xb1 = sx + (size_t)( g + 8 ) * rowStride + 8 * t; // n-tile 1: column g+8
 		float acc0[ 4 ] = { 0, 0, 0, 0 }, acc1[ 4 ] = { 0, 0, 0, 0 };
-		const int steps = K / 32;
-		constexpr int U = 4;
-		for( int s0 = warp; s0 < steps; s0 += SK_WARPS * U )
+		const bool twoTiles = ncols > 8;
+		for( int s0 = warp; s0 < steps; )
 		{
-			uint4 va[ U ], vb[ U ];
-#pragma unroll
-			for( int u = 0; u < U; u++ )
-			{
-				const int st = s0 + u * SK_WARPS;
-				if( st < steps )
-				{
-					va[ u ] = ldg_stream( wA + st * 4 );   // 32 halves = 4 uint4 per step
-					vb[ u ] = ldg_stream( wB + st * 4 );
-				}
-			}
 #pragma unroll
 			for( int u = 0; u < U; u++ )
 			{
@@ -130,13 +170,30 @@ namespace kern
 				if( st < steps )
 				{
 					const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 32 );
-					const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 32 );
 					const uint32_t a1[ 4 ] = { va[ u ].x, vb[ u ].x, va[ u ].y, vb[ u ].y };
 					const uint32_t a2[ 4 ] = { va[ u ].z, vb[ u ].z, va[ u ].w, vb[ u ].w };
 					mma16816( acc0, a1, x0.x, x0.y );
 					mma16816( acc0, a2, x0.z, x0.w );
-					mma16816( acc1, a1, x1.x, x1.y );
-					mma16816( acc1, a2, x1.z, x1.w );
+					if( twoTiles )
+					{
+						const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 32 );
+						mma16816( acc1, a1, x1.x, x1.y );
+						mma16816( acc1, a2, x1.z, x1.w );
+					}
+				}
+			}
+			s0 += SK_WARPS * U;
+			if( s0 < steps )
+			{
+#pragma unroll
+				for( int u = 0; u < U; u++ )
+				{
+					const int st = s0 + u * SK_WARPS;
+					if( st < steps )
+					{
+						va[ u ] = ldg_stream( wA + st * 4 );
+						vb[ u ] = ldg_stream( wB + st * 4 );
+					}
 				}
 			}
 		}
@@ -199,8 +256,11 @@ namespace kern
 
 	static size_t skinnySmem( int K ) { return (size_t)SK_COLS * ( K + SK_PAD ) * sizeof( __half ) + (size_t)SK_WARPS * SK_ROWS * SK_COLS * sizeof( float ); }
 	static size_t g_skinnySmemSet = 0;
+	static cudaError_t crossPrepare( int T );
 	cudaError_t prepare( int maxK )
 	{
+		cudaError_t ce = crossPrepare( 1500 );
+		if( ce != cudaSuccess ) return ce;
 		const size_t smem = skinnySmem( maxK );
 		if( smem > g_skinnySmemSet )
 		{
@@ -213,6 +273,7 @@ namespace kern
 	cudaError_t skinnyGemm( const SkinnyArgs& a, cudaStream_t s )
 	{
 		if( a.K % 32 != 0 ) return cudaErrorInvalidValue;
+		if( a.gamma && ( a.K % 128 != 0 || a.K > 1280 ) ) return cudaErrorInvalidValue;   // fused LayerNorm keeps the row in registers
 		const size_t smem = skinnySmem( a.K );
 		if( smem > g_skinnySmemSet )
 		{
@@ -371,14 +432,23 @@ namespace kern
 	// every access below is a 16-byte load, 8 lanes per 128-byte row, fully coalesced.
 	constexpr int CA_THREADS = 256;
 	constexpr int CA_MAXT = 1536;
+	constexpr int CA_UNROLL = 12;
+
+	__device__ __forceinline__ void cp_async16( void* smemDst, const void* gmemSrc )
+	{
+		asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( ptx::smem_u32( smemDst ) ), "l"( gmemSrc ) : "memory" );
+	}
+	__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
+	__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;" ::: "memory" ); }
 
 	__global__ void __launch_bounds__( CA_THREADS )
 		cross_attn_decode_kernel( const float* __restrict__ q, const __half* __restrict__ kMem, const __half* __restrict__ vMem, __half* __restrict__ out,
 			int N, int H, int d, int T, int refThreads )
 	{
+		extern __shared__ __align__( 16 ) uint8_t ca_smem[];   // the whole V tile of this (chunk, head): T x 128 bytes
 		__shared__ float sp[ CA_MAXT ];
 		__shared__ float sred[ CA_THREADS / 32 ];
-		__shared__ float so[ CA_THREADS / 32 ][ 4 ][ 64 ];   // per warp, per row-group partial outputs (8 KB)
+		__shared__ float so[ CA_THREADS / 32 ][ 4 ][ 64 ];   // per warp, per row-group partial outputs (8 KB) | [refThreads][64]
 		const int bh = blockIdx.x;
 		const int b = bh / H, h = bh - b * H;
 		const int i = blockIdx.y;
@@ -386,36 +456,52 @@ namespace kern
 		const int col = b * N + i;
 		const int sub = lane & 7;        // which 16-byte chunk of the 128-byte row
 		const int rgrp = lane >> 3;      // row within a group of 4
+		const uint4* K4 = reinterpret_cast<const uint4*>( kMem + (size_t)bh * T * 64 );
+		const uint4* V4 = reinterpret_cast<const uint4*>( vMem + (size_t)bh * T * 64 );
+
+		// V streams into shared memory (cp.async, no registers) behind the whole K phase
+		{
+			uint4* sv = reinterpret_cast<uint4*>( ca_smem );
+			for( int idx = tid; idx < T * 8; idx += CA_THREADS ) cp_async16( sv + idx, V4 + idx );
+			cp_async_commit();
+		}
+
 		float qf[ 8 ];
 #pragma unroll
 		for( int e = 0; e < 8; e++ )
 			qf[ e ] = __half2float( __float2half_rn( q[ (size_t)col * d + h * 64 + sub * 8 + e ] ) );
-		const uint4* K4 = reinterpret_cast<const uint4*>( kMem + (size_t)bh * T * 64 );
-		const uint4* V4 = reinterpret_cast<const uint4*>( vMem + (size_t)bh * T * 64 );
 
+		// scores: a warp covers 4 key rows per load instruction (512 contiguous bytes), CA_UNROLL loads in flight per lane
 		float lmax = -INFINITY;
-		for( int j0 = warp * 4; j0 < T; j0 += ( CA_THREADS / 32 ) * 4 )
+		for( int jb = warp * 4 + rgrp; jb < T; jb += ( CA_THREADS / 32 ) * 4 * CA_UNROLL )
 		{
-			const int j = j0 + rgrp;
-			float s = 0.0f;
-			if( j < T )
+			uint4 u[ CA_UNROLL ];
+#pragma unroll
+			for( int k = 0; k < CA_UNROLL; k++ )
 			{
-				const uint4 u = K4[ (size_t)j * 8 + sub ];
-				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+				const int j = jb + k * ( CA_THREADS / 32 ) * 4;
+				u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+			}
+#pragma unroll
+			for( int k = 0; k < CA_UNROLL; k++ )
+			{
+				const int j = jb + k * ( CA_THREADS / 32 ) * 4;
+				const __half2* h2 = reinterpret_cast<const __half2*>( &u[ k ] );
+				float s = 0.0f;
 #pragma unroll
 				for( int e = 0; e < 4; e++ )
 				{
 					const float2 f = __half22float2( h2[ e ] );
 					s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
 				}
-			}
-			s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-			s += __shfl_xor_sync( 0xffffffffu, s, 2 );
-			s += __shfl_xor_sync( 0xffffffffu, s, 4 );
-			if( j < T )
-			{
-				if( sub == 0 ) sp[ j ] = s;
-				lmax = fmaxf( lmax, s );
+				s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+				s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+				s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+				if( j < T )
+				{
+					if( sub == 0 ) sp[ j ] = s;
+					lmax = fmaxf( lmax, s );
+				}
 			}
 		}
 		lmax = warpMaxD( lmax );
@@ -438,19 +524,20 @@ namespace kern
 		for( int w = 0; w < CA_THREADS / 32; w++ ) tot += sred[ w ];
 		const float inv = 1.0f / tot;
 		for( int j = tid; j < T; j += CA_THREADS ) sp[ j ] *= inv;   // normalised P (ggml.c:5085-5090)
+		cp_async_wait_all();
 		__syncthreads();
 
+		const __half* sv = reinterpret_cast<const __half*>( ca_smem );
 		if( refThreads > 0 )
 		{
-			// reference arithmetic (see pvChainF16): one f16 chain per (reference thread, output dim)
+			// reference arithmetic (see pvChainF16): one f16 chain per (reference thread, output dim), V read from shared memory
 			float* sof = &so[ 0 ][ 0 ][ 0 ];   // reused as [refThreads][64]
-			const __half* vb = vMem + (size_t)bh * T * 64;
 			const int dc = ( T + refThreads - 1 ) / refThreads;
 			for( int idx = tid; idx < refThreads * 64; idx += CA_THREADS )
 			{
 				const int part = idx >> 6, e = idx & 63;
 				const int j0 = min( part * dc, T ), j1 = min( ( part + 1 ) * dc, T );
-				sof[ idx ] = pvChainF16( sp, vb + e, 64, j0, j1 );
+				sof[ idx ] = pvChainF16( sp, sv + e, 64, j0, j1 );
 			}
 			__syncthreads();
 			if( tid < 64 )
@@ -462,22 +549,20 @@ namespace kern
 			return;
 		}
 
+		// exact mode: f32 accumulation
 		float o[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-		for( int j0 = warp * 4; j0 < T; j0 += ( CA_THREADS / 32 ) * 4 )
+		const uint4* sv4 = reinterpret_cast<const uint4*>( ca_smem );
+		for( int j = warp * 4 + rgrp; j < T; j += ( CA_THREADS / 32 ) * 4 )
 		{
-			const int j = j0 + rgrp;
-			if( j < T )
-			{
-				const float p = sp[ j ];
-				const uint4 u = V4[ (size_t)j * 8 + sub ];
-				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+			const float p = sp[ j ];
+			const uint4 u = sv4[ (size_t)j * 8 + sub ];
+			const __half2* h2 = reinterpret_cast<const __half2*>( &u );
 #pragma unroll
-				for( int e = 0; e < 4; e++ )
-				{
-					const float2 f = __half22float2( h2[ e ] );
-					o[ e * 2 ] += p * f.x;
-					o[ e * 2 + 1 ] += p * f.y;
-				}
+			for( int e = 0; e < 4; e++ )
+			{
+				const float2 f = __half22float2( h2[ e ] );
+				o[ e * 2 ] += p * f.x;
+				o[ e * 2 + 1 ] += p * f.y;
 			}
 		}
 #pragma unroll
@@ -492,11 +577,25 @@ namespace kern
 			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc );
 		}
 	}
+	static size_t g_crossSmemSet = 0;
+	static cudaError_t crossPrepare( int T )
+	{
+		const size_t smem = (size_t)T * 128;
+		if( smem > g_crossSmemSet )
+		{
+			cudaError_t e = cudaFuncSetAttribute( cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+			if( e != cudaSuccess ) return e;
+			g_crossSmemSet = smem;
+		}
+		return cudaSuccess;
+	}
 	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, int refThreads, cudaStream_t s )
 	{
 		if( T > CA_MAXT || refThreads < 0 || refThreads > PV_MAX_THREADS ) return cudaErrorInvalidValue;
+		cudaError_t e = crossPrepare( T );
+		if( e != cudaSuccess ) return e;
 		dim3 grid( B * H, N );
-		cross_attn_decode_kernel<<<grid, CA_THREADS, 0, s>>>( q, kMem, vMem, out, N, H, d, T, refThreads );
+		cross_attn_decode_kernel<<<grid, CA_THREADS, (size_t)T * 128, s>>>( q, kMem, vMem, out, N, H, d, T, refThreads );
 		return cudaGetLastError();
 	}
 
