@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds per wall-second of the Whisper hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # this engine
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's own CPU path on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # N > 1, one rank per GPU
+
+One "step" = one pass of the hot path over one batch of synthetic input per GPU: `batch` independent 30 s chunks of 16 kHz
+PCM -> log-mel -> encoder -> cross-KV -> prompt + n_decode greedy decoder steps (timestamp rules, tokens fed back on the device).
+Workload = BASELINE.json configs[2]: ggml-medium shapes (synthetic weights, seed 1234), batch 8 per GPU, beam 1, 100 tokens.
+
+  value : whole-job audio-s/s with the PCM already resident in HBM (wsp_upload_pcm + wsp_run_chunks_resident) — the log-mel
+          front end, encoder and decoder all run inside the timed region; device time from CUDA events on the launching stream.
+  e2e   : the same through the public C-ABI call with HOST buffers (wsp_run_chunks): pinned PCM -> H2D every step, tokens D2H.
+  roofline: the dominant kernel (skinny_gemm_kernel: the decoder's weight-streaming GEMMs) against the measured HBM peak; its
+          per-launch duration is measured live by an instrumented decoder pass (CUDA event pair around every launch).
+  cpu_baseline: oracle/_ref (the reference's unmodified ggml.c + whisper.cpp) on this box's host cores, bounded sample.
+
+Multi-GPU: chunks are independent, so ranks shard the batch with no data-path collective ("weak" scaling: batch per GPU fixed).
+The only collective is the NCCL broadcast of the ggml file image at load (rank 0 reads the file once).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio-sec/s (RTF) medium 30s chunks @1/2/4/8 B200 vs reference CPU path"
+UNIT = "audio-s/s"
+CHUNK_SECONDS = 30.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="medium")
+    ap.add_argument("--batch", type=int, default=8, help="chunks per GPU per step")
+    ap.add_argument("--n-decode", type=int, default=100, help="greedy tokens per chunk (BASELINE.md §2)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: CPU threads (0 = min(cores, 16))")
+    ap.add_argument("--ref-tokens", type=int, default=12, help="reference arm: decoder tokens actually run per sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "ggml-%s shapes (synthetic weights seed 1234), batch=%d independent 30 s chunks per GPU, greedy beam=1, n_decode=%d" % (a.model, a.batch, a.n_decode)
+
+
+def decoder_weight_bytes(m):
+    d, L = m.n_text_state, m.n_text_layer
+    return L * 14 * d * d * 2 + m.n_vocab * d * 2   # read once per step regardless of batch
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_sample(model_name, threads, n_tokens, n_decode):
+    """One bounded sample of the workload on the host: one chunk — log-mel + encoder + prompt + (n_tokens-1) decoder steps with the
+    reference's own code; the decode time is scaled to n_decode tokens.  Returns (audio_s_per_s, detail dict)."""
+    from whisper_b200 import synth
+    from oracle import ref
+    path = synth.model_path(model_name)
+    if ref.available():
+        o = _REF_CACHE.get("o")
+        if o is None:
+            o = ref.RefOracle(path, threads=threads)
+            _REF_CACHE["o"] = o
+        prompt = [o.special["sot"]] + ([o.special["sot"] + 1, o.special["transcribe"]] if o.n_vocab == 51865 else [])
+        wall, toks, st = o.bench_chunk(synth.synth_pcm(0), prompt, n_tokens, threads=threads)
+        kind = "reference"
+    else:
+        # oracle port (numpy restatement), only when the reference library did not travel
+        from oracle import whisper_np as wn
+        m = _REF_CACHE.get("m") or wn.NpModel(path)
+        _REF_CACHE["m"] = m
+        pcm = synth.synth_pcm(0)
+        t0 = time.time(); mel = wn.log_mel(pcm, m.filters)
+        t1 = time.time(); out, ck, cv = wn.encode(m, mel)
+        t2 = time.time()
+        dec = wn.NpDecoder(m, ck, cv, pv_threads=4)
+        prompt = [m.token_sot] + ([m.token_sot + 1, 50359] if m.n_vocab == 51865 else [])
+        cur, n_past = prompt, 0
+        for _ in range(n_tokens):
+            lg, pr = dec.decode(cur, n_past)
+            n_past += len(cur)
+            cur = [wn.sample_best(m, pr[-1])["id"]]
+        t3 = time.time()
+        st = [(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3]
+        kind = "port"
+    per_tok = st[2] / n_tokens
+    total_s = (st[0] + st[1] + per_tok * n_decode) / 1e3
+    return CHUNK_SECONDS / total_s, dict(kind=kind, mel_ms=st[0], encode_ms=st[1], decode_ms_per_token=per_tok, sampled_tokens=n_tokens)
+
+
+_REF_CACHE = {}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from whisper_b200 import synth
+    synth.model_path(a.model)
+    cores = os.cpu_count() or 1
+    threads = a.ref_threads or min(cores, 16)
+    budget_s = 200.0
+    t_begin = time.time()
+    vals, det = [], None
+    for _ in range(min(a.warmup, 1)):
+        v, det = reference_sample(a.model, threads, a.ref_tokens, a.n_decode)
+    est = time.time() - t_begin
+    steps_done = 0
+    t0 = time.time()
+    while steps_done < a.steps:
+        v, det = reference_sample(a.model, threads, a.ref_tokens, a.n_decode)
+        vals.append(v)
+        steps_done += 1
+        one = (time.time() - t0) / steps_done
+        if time.time() - t_begin + one > budget_s:
+            break
+    value = float(np.mean(vals))
+    sample = ("1 chunk/step: log-mel + full encoder + prompt + %d decoder tokens with the reference's whisper_pcm_to_mel/encode/decode/sample_best; "
+              "decode time scaled to n_decode=%d; %d of %d requested steps fit the %.0f s budget" % (a.ref_tokens - 1, a.n_decode, steps_done, a.steps, budget_s))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps_done, "warmup": min(a.warmup, 1),
+        "ms_per_step": 1e3 * CHUNK_SECONDS / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 weights x f16-rounded activations, f32 accumulate (ggml CPU)",
+        "data": "synthetic", "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (n/a on CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": det["kind"], "sample": sample,
+                         "mel_ms": det["mel_ms"], "encode_ms": det["encode_ms"], "decode_ms_per_token": det["decode_ms_per_token"], "host_cores": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from whisper_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = capi.lib()
+    if L.wsp_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — whisper_b200 has no CPU fallback")
+
+    # ---- load: rank 0 reads the ggml file once; peers get the host meta blob + the file image over NCCL (NVLink) ----
+    t_load = time.time()
+    if world == 1:
+        model = capi.Model(synth.model_path(a.model))
+        engine = capi.Engine(model, local)
+        bcast_ms = 0.0
+    else:
+        from whisper_b200 import dist as wdist
+        model, engine, bcast_ms = wdist.load_broadcast(a.model, rank, local, world)
+    load_s = time.time() - t_load
+    ctx = capi.Context(engine, a.batch)
+    prompt = model.prompt_init()
+    B, K, W = a.batch, a.steps, a.warmup
+
+    # ---- inputs: distinct synthetic chunks per rank, pinned host memory for the e2e leg ----
+    pcms = [synth.synth_pcm(rank * B + i) for i in range(B)]
+    n_samp = pcms[0].size
+    pinned = []
+    for p in pcms:
+        ptr = L.wsp_host_alloc(p.nbytes)
+        if not ptr:
+            raise SystemExit("wsp_host_alloc failed")
+        C.memmove(ptr, p.ctypes.data, p.nbytes)
+        pinned.append(ptr)
+    ptrs = (C.POINTER(C.c_float) * B)(*[C.cast(p, C.POINTER(C.c_float)) for p in pinned])
+    ns = np.full(B, n_samp, np.int32)
+    for i, p in enumerate(pcms):
+        ctx.upload_pcm(i, p)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx_sync()
+
+    def ctx_sync():
+        capi.check(L.wsp_synchronize(ctx.h))
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (both paths) ----
+    toks = None
+    for _ in range(max(W, 3)):
+        toks, _ = ctx.run_chunks_ptrs(ptrs, ns, B, prompt, a.n_decode)
+    ctx.run_chunks_resident(B, prompt, a.n_decode)
+
+    # ---- e2e leg: host PCM in, tokens out, through the public C-ABI call ----
+    barrier()
+    t0 = time.time()
+    ctx.timer_start()
+    for _ in range(K):
+        toks, _ = ctx.run_chunks_ptrs(ptrs, ns, B, prompt, a.n_decode)
+    e2e_ms_dev = ctx.timer_stop()
+    barrier()
+    e2e_wall = time.time() - t0
+    e2e_ms = max_over_ranks(max(e2e_ms_dev, 0.0))
+    e2e_wall = max_over_ranks(e2e_wall)
+
+    # ---- value leg: PCM resident in HBM; clocks sampled during this region ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = L.wsp_launch_count()
+    stage = np.zeros(3)
+    barrier()
+    ctx.timer_start()
+    for _ in range(K):
+        toks_r, st = ctx.run_chunks_resident(B, prompt, a.n_decode)
+        stage += st
+    val_ms_dev = ctx.timer_stop()
+    barrier()
+    launches = int(L.wsp_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    val_ms = max_over_ranks(val_ms_dev)
+    same_tokens = bool((toks_r == toks).all())
+
+    # ---- roofline of the dominant kernel: instrumented decoder pass (event pair around every launch) ----
+    n_prof = 6
+    ms_kind, n_kind = ctx.profile_decode(B, n_prof)
+    wbytes = decoder_weight_bytes(model)
+    sk_launches_per_step = n_kind[0] / n_prof
+    sk_bytes_per_launch = wbytes / sk_launches_per_step
+    sk_ms_per_launch = ms_kind[0] / max(1, n_kind[0])
+    achieved = sk_bytes_per_launch / (sk_ms_per_launch * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+    roofline = {
+        "kernel": "kern::skinny_gemm_kernel (decoder weight-streaming GEMM, 6 per layer + logits)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "bytes_per_launch": sk_bytes_per_launch, "ms_per_launch": sk_ms_per_launch, "launches_per_decoder_step": sk_launches_per_step,
+        "decoder_step_ms_by_kind": {"skinny_gemm": ms_kind[0] / n_prof, "cross_attention": ms_kind[1] / n_prof, "self_attention": ms_kind[2] / n_prof, "other": ms_kind[3] / n_prof},
+        "how": "wsp_profile_decode: %d un-graphed decoder steps, cudaEvent pair around every launch on the launching stream" % n_prof,
+    }
+
+    total_audio = CHUNK_SECONDS * B * world * K
+    value = total_audio / (val_ms * 1e-3)
+    e2e_value = total_audio / (e2e_ms * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1:
+        cores = os.cpu_count() or 1
+        threads = a.ref_threads or min(cores, 16)
+        try:
+            v, det = reference_sample(a.model, threads, a.ref_tokens, a.n_decode)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": det["kind"], "host_cores": cores,
+                   "sample": "1 chunk: log-mel + full encoder + prompt + %d decoder tokens, decode scaled to n_decode=%d" % (a.ref_tokens - 1, a.n_decode),
+                   "mel_ms": det["mel_ms"], "encode_ms": det["encode_ms"], "decode_ms_per_token": det["decode_ms_per_token"]}
+        except Exception as ex:   # the bench line must still be printed
+            cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": val_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (f16 weights x f16-rounded activations, f32 accumulate; KV f16)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": "replicas x%d (independent chunks, no step-loop collective)" % world,
+                       "chunks_per_step": B * world, "l2": "inputs larger than L2: every step streams 0.81 GB of decoder weights per token x %d tokens + 0.71 GB encoder weights" % a.n_decode,
+                       "reference_threads_arithmetic": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * n_samp * 4 + B * len(prompt) * 4), "d2h_bytes_per_step": int(B * model.n_text_ctx * 4),
+                    "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "stage_ms_per_step": {"mel": stage[0] / K, "encode": stage[1] / K, "decode": stage[2] / K},
+            "load": {"seconds": load_s, "nccl_broadcast_ms": bcast_ms, "weight_bytes": engine.weight_bytes()},
+            "tokens_equal_e2e_vs_resident": same_tokens,
+        }
+        print(json.dumps(line), flush=True)
+    for p in pinned:
+        L.wsp_host_free(p)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

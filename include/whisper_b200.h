@@ -128,8 +128,17 @@ wsp_status wsp_get_probs( wsp_context* c, float* dst, size_t cap_floats );
  * without host round trips.  tokens_out[b*n_decode + i].  stage_ms (nullable): { h2d+mel, encode, decode } from CUDA events. */
 wsp_status wsp_run_chunks( wsp_context* c, const float* const* pcm, const int32_t* n_samples, int32_t batch,
 	const int32_t* prompt, int32_t n_prompt, int32_t n_decode, int32_t* tokens_out, float* stage_ms );
-/* same with the mel already resident (wsp_pcm_to_mel / wsp_set_mel called before): the device-resident `value` leg of bench.py */
+/* keep a chunk's PCM resident in HBM (slot-owned copy) ... */
+wsp_status wsp_upload_pcm( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples );
+/* ... and run the same path from it: mel + encode + decode with no host->device input copy inside (bench.py's `value` leg) */
 wsp_status wsp_run_chunks_resident( wsp_context* c, int32_t batch, const int32_t* prompt, int32_t n_prompt, int32_t n_decode, int32_t* tokens_out, float* stage_ms );
+
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on) */
+wsp_status wsp_timer_start( wsp_context* c );
+wsp_status wsp_timer_stop( wsp_context* c, float* ms );
+/* instrumented decoder pass for roofline accounting: n_steps more single-token steps, launched kernel by kernel with an event pair
+ * around every launch.  kinds: 0 skinny GEMM, 1 cross-attention, 2 self-attention, 3 other (embedding, sampler) */
+wsp_status wsp_profile_decode( wsp_context* c, int32_t batch, int32_t n_steps, float ms_by_kind[ 4 ], int32_t launches_by_kind[ 4 ] );
 
 /* test hook: named intermediates as f32.  Names: "mel", "enc.conv1" ([3000][d] after GELU), "enc.x0" ([1500][d] input of layer 0),
  * "enc.layers" (residual stream after the last layer), "encode-out" (ln_post, f16-rounded), "cross_k", "cross_v" ([L][T][d] of slot 0). */

@@ -33,7 +33,7 @@ EXPORTS = [
     "wsp_engine_create", "wsp_engine_create_from_image", "wsp_engine_destroy", "wsp_engine_weight_bytes",
     "wsp_context_create", "wsp_context_destroy", "wsp_synchronize",
     "wsp_pcm_to_mel", "wsp_set_mel", "wsp_mel_len", "wsp_get_mel", "wsp_encode", "wsp_decode", "wsp_get_logits", "wsp_get_probs",
-    "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_set_reference_threads",
+    "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_set_reference_threads",
     "wsp_host_alloc", "wsp_host_free", "wsp_timings",
     "wsp_test_gemm", "wsp_test_attention", "wsp_test_skinny", "wsp_test_layernorm",
 ]
@@ -93,6 +93,10 @@ def lib():
     sig("wsp_get_probs", i32, [vp, fp, sz])
     sig("wsp_run_chunks", i32, [vp, C.POINTER(fp), ip, i32, ip, i32, i32, ip, fp])
     sig("wsp_run_chunks_resident", i32, [vp, i32, ip, i32, i32, ip, fp])
+    sig("wsp_upload_pcm", i32, [vp, i32, fp, i32])
+    sig("wsp_timer_start", i32, [vp])
+    sig("wsp_timer_stop", i32, [vp, fp])
+    sig("wsp_profile_decode", i32, [vp, i32, i32, fp, ip])
     sig("wsp_get_tensor", i32, [vp, C.c_char_p, i32, fp, sz, C.POINTER(sz)])
     sig("wsp_debug_set_encoder_layers", i32, [vp, i32])
     sig("wsp_debug_set_graph", i32, [vp, i32])
@@ -291,6 +295,25 @@ class Context:
         st = np.zeros(3, np.float32)
         check(self.L.wsp_run_chunks_resident(self.h, batch, _i(pr), pr.size, n_decode, _i(toks), _f(st)))
         return toks, st
+
+    def upload_pcm(self, slot: int, pcm: np.ndarray):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        check(self.L.wsp_upload_pcm(self.h, slot, _f(pcm), pcm.size))
+
+    def timer_start(self):
+        check(self.L.wsp_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(self.L.wsp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_decode(self, batch: int, n_steps: int):
+        """-> (ms_by_kind[4], launches_by_kind[4]) for kinds (skinny GEMM, cross-attn, self-attn, other)."""
+        ms = np.zeros(4, np.float32)
+        n = np.zeros(4, np.int32)
+        check(self.L.wsp_profile_decode(self.h, batch, n_steps, _f(ms), _i(n)))
+        return ms, n
 
     def get_tensor(self, name: str, slot: int = 0) -> np.ndarray:
         n = C.c_size_t()

@@ -237,6 +237,32 @@ wsp_status wsp_run_chunks_resident( wsp_context* c, int32_t batch, const int32_t
 	return guarded( [ & ]() -> wsp_status { return ctxRunChunks( *c->c, nullptr, nullptr, batch, prompt, n_prompt, n_decode, tokens_out, stage_ms, true ); } );
 }
 
+wsp_status wsp_upload_pcm( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	return guarded( [ & ]() -> wsp_status { return ctxUploadPcm( *c->c, slot, pcm, n_samples ); } );
+}
+wsp_status wsp_profile_decode( wsp_context* c, int32_t batch, int32_t n_steps, float ms_by_kind[ 4 ], int32_t launches_by_kind[ 4 ] )
+{
+	if( !c || !ms_by_kind || !launches_by_kind ) return fail( WSP_E_POINTER, "context/out" );
+	return guarded( [ & ]() -> wsp_status { return ctxProfileDecode( *c->c, batch, n_steps, ms_by_kind, launches_by_kind ); } );
+}
+wsp_status wsp_timer_start( wsp_context* c )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	WSP_CUDA( cudaSetDevice( c->c->e->device ) );
+	WSP_CUDA( cudaEventRecord( c->c->timerEv[ 0 ], c->c->stream ) );
+	return WSP_OK;
+}
+wsp_status wsp_timer_stop( wsp_context* c, float* ms )
+{
+	if( !c || !ms ) return fail( WSP_E_POINTER, "context/ms" );
+	WSP_CUDA( cudaEventRecord( c->c->timerEv[ 1 ], c->c->stream ) );
+	WSP_CUDA( cudaEventSynchronize( c->c->timerEv[ 1 ] ) );
+	WSP_CUDA( cudaEventElapsedTime( ms, c->c->timerEv[ 0 ], c->c->timerEv[ 1 ] ) );
+	return WSP_OK;
+}
+
 __global__ void half_to_float_kernel( const __half* src, float* dst, size_t n )
 {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -30,7 +30,9 @@ namespace wsp
 	{
 		if( e ) cudaSetDevice( e->device );
 		if( stepGraph ) cudaGraphExecDestroy( stepGraph );
-		for( auto& s : slots ) if( s.mel ) cudaFree( s.mel );
+		for( auto& s : slots ) { if( s.mel ) cudaFree( s.mel ); if( s.pcm ) cudaFree( s.pcm ); }
+		for( auto& v : prof.pool ) cudaEventDestroy( v );
+		for( auto& v : timerEv ) if( v ) cudaEventDestroy( v );
 		void* bufs[] = { melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
 			tokensDev, dNPast, sampled, history };
 		for( void* b : bufs ) if( b ) cudaFree( b );
@@ -52,6 +54,7 @@ namespace wsp
 		c.Tp = ( ( T + 127 ) / 128 ) * 128;
 		WSP_CUDA( cudaStreamCreateWithFlags( &c.stream, cudaStreamNonBlocking ) );
 		for( auto& v : c.ev ) WSP_CUDA( cudaEventCreate( &v ) );
+		for( auto& v : c.timerEv ) WSP_CUDA( cudaEventCreate( &v ) );
 		c.slots.resize( maxBatch );
 		const size_t B = (size_t)maxBatch;
 		WSP_CHECK( devAlloc( c.melMax, B ) );
@@ -284,6 +287,33 @@ namespace wsp
 	// ===============================================================================================================
 	// decoder
 	// ===============================================================================================================
+	namespace
+	{
+		struct ProfScope
+		{
+			Context& c;
+			bool active;
+			ProfScope( Context& ctx, int kind ) : c( ctx ), active( ctx.prof.on )
+			{
+				if( !active ) return;
+				KernelProfile& p = c.prof;
+				if( p.used + 2 > p.pool.size() )
+				{
+					for( int i = 0; i < 2; i++ ) { cudaEvent_t e; cudaEventCreate( &e ); p.pool.push_back( e ); }
+				}
+				p.kinds.push_back( kind );
+				cudaEventRecord( p.pool[ p.used ], c.stream );
+			}
+			~ProfScope()
+			{
+				if( !active ) return;
+				cudaEventRecord( c.prof.pool[ c.prof.used + 1 ], c.stream );
+				c.prof.used += 2;
+			}
+		};
+	}
+#define WSP_KERNEL( kind, expr ) do { ProfScope _ps( c, kind ); WSP_CUDA( expr ); } while( 0 )
+
 	// Enqueue one decoder pass for `batch` chunks x N tokens.  Reads tokens from c.tokensDev, n_past / sampling flags from device
 	// scalars (so the N = 1 instance can be captured once as a CUDA graph and replayed for every step).
 	static int decodeEnqueue( Context& c, int N, int batch, bool allLogits, bool sample, int* launchesOut )
@@ -295,7 +325,7 @@ namespace wsp
 		const int cols = batch * N;
 		const float qkScale = (float)pow( 64.0, -0.25 );   // whisper.cpp:1588, 1595, 1700
 		int n = 0;
-		WSP_CUDA( kern::embedTokens( e.tokEmb, e.decPos, c.tokensDev, c.dNPast, c.xd, batch, N, d, s ) ); n++;
+		WSP_KERNEL( KK_OTHER, kern::embedTokens( e.tokEmb, e.decPos, c.tokensDev, c.dNPast, c.xd, batch, N, d, s ) ); n++;
 		for( int il = 0; il < hp.n_text_layer; il++ )
 		{
 			const DecLayerW& W = e.dec[ il ];
@@ -307,32 +337,32 @@ namespace wsp
 			a.W = W.wqkv; a.nOut = 3 * d; a.K = d; a.xF32 = c.xd; a.xStride = d; a.gamma = W.ln1.g; a.beta = W.ln1.b; a.nCols = cols;
 			a.epi = kern::SK_QKV; a.bias = W.bqkv; a.scale = qkScale; a.outF32 = c.qd; a.ld = d; a.kCache = kc; a.vCache = vc;
 			a.d = d; a.N = N; a.nTextCtx = nCtx; a.dNPast = c.dNPast;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
-			WSP_CUDA( kern::selfAttnDecode( c.qd, kc, vc, c.attnD, batch, N, H, d, nCtx, c.dNPast, c.refThreads, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SELF, kern::selfAttnDecode( c.qd, kc, vc, c.attnD, batch, N, H, d, nCtx, c.dNPast, c.refThreads, s ) );
 			a = kern::SkinnyArgs();
 			a.W = W.wo; a.nOut = d; a.K = d; a.xF16 = c.attnD; a.xStride = d; a.nCols = cols;
 			a.epi = kern::SK_BIAS_RESID; a.bias = W.bo; a.outF32 = c.xd; a.ld = d;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
 			// cross attention (a15)
 			a = kern::SkinnyArgs();
 			a.W = W.wcq; a.nOut = d; a.K = d; a.xF32 = c.xd; a.xStride = d; a.gamma = W.lnc.g; a.beta = W.lnc.b; a.nCols = cols;
 			a.epi = kern::SK_Q_SCALE; a.bias = W.bcq; a.scale = qkScale; a.outF32 = c.qd; a.ld = d;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
 			const size_t crossOff = (size_t)il * c.maxB * T * d;
-			WSP_CUDA( kern::crossAttnDecode( c.qd, c.crossK + crossOff, c.crossV + crossOff, c.attnD, batch, N, H, d, T, c.refThreads, s ) );
+			WSP_KERNEL( KK_CROSS, kern::crossAttnDecode( c.qd, c.crossK + crossOff, c.crossV + crossOff, c.attnD, batch, N, H, d, T, c.refThreads, s ) );
 			a = kern::SkinnyArgs();
 			a.W = W.wco; a.nOut = d; a.K = d; a.xF16 = c.attnD; a.xStride = d; a.nCols = cols;
 			a.epi = kern::SK_BIAS_RESID; a.bias = W.bco; a.outF32 = c.xd; a.ld = d;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
 			// MLP (a16)
 			a = kern::SkinnyArgs();
 			a.W = W.w1; a.nOut = 4 * d; a.K = d; a.xF32 = c.xd; a.xStride = d; a.gamma = W.ln3.g; a.beta = W.ln3.b; a.nCols = cols;
 			a.epi = kern::SK_GELU_F16; a.bias = W.b1; a.outF16 = c.hD; a.ld = 4 * d;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
 			a = kern::SkinnyArgs();
 			a.W = W.w2; a.nOut = d; a.K = 4 * d; a.xF16 = c.hD; a.xStride = 4 * d; a.nCols = cols;
 			a.epi = kern::SK_BIAS_RESID; a.bias = W.b2; a.outF32 = c.xd; a.ld = d;
-			WSP_CUDA( kern::skinnyGemm( a, s ) );
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) );
 			n += 8;
 		}
 		// final LN + logits = tok_emb^T x (a17): only the last token of each chunk unless all logits were requested
@@ -342,7 +372,7 @@ namespace wsp
 			if( allLogits ) { a.xF32 = c.xd; a.xStride = d; a.nCols = cols; }
 			else { a.xF32 = c.xd + (size_t)( N - 1 ) * d; a.xStride = (int64_t)N * d; a.nCols = batch; }
 			a.epi = kern::SK_LOGITS; a.outF32 = c.logits; a.ld = hp.n_vocab;
-			WSP_CUDA( kern::skinnyGemm( a, s ) ); n++;
+			WSP_KERNEL( KK_SKINNY, kern::skinnyGemm( a, s ) ); n++;
 		}
 		if( sample && !allLogits )
 		{
@@ -351,7 +381,7 @@ namespace wsp
 			sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
 			sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
 			sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;
-			WSP_CUDA( kern::sampleGreedy( sa, s ) ); n += 2;
+			WSP_KERNEL( KK_OTHER, kern::sampleGreedy( sa, s ) ); n += 2;
 		}
 		if( launchesOut ) *launchesOut = n;
 		return WSP_OK;
@@ -361,7 +391,7 @@ namespace wsp
 	static int decodeSubmit( Context& c, int N, int batch, bool allLogits, bool sample )
 	{
 		int n = 0;
-		if( N == 1 && !allLogits && sample && c.useGraph )
+		if( N == 1 && !allLogits && sample && c.useGraph && !c.prof.on )
 		{
 			if( !c.stepGraph || c.stepGraphBatch != batch )
 			{
@@ -429,6 +459,49 @@ namespace wsp
 		return WSP_OK;
 	}
 
+	int ctxUploadPcm( Context& c, int slot, const float* pcmHost, int nSamples )
+	{
+		if( slot < 0 || slot >= c.maxB ) return fail( WSP_E_BOUNDS, "chunk slot out of range" );
+		if( !pcmHost || nSamples < 0 ) return fail( WSP_E_INVALIDARG, "pcm" );
+		WSP_CUDA( cudaSetDevice( c.e->device ) );
+		MelSlot& s = c.slots[ slot ];
+		if( nSamples > s.pcmCap )
+		{
+			if( s.pcm ) { WSP_CUDA( cudaStreamSynchronize( c.stream ) ); cudaFree( s.pcm ); s.pcm = nullptr; }
+			WSP_CHECK( devAlloc( s.pcm, (size_t)( nSamples > 0 ? nSamples : 1 ) ) );
+			s.pcmCap = nSamples;
+		}
+		s.pcmSamples = nSamples;
+		WSP_CUDA( cudaMemcpyAsync( s.pcm, pcmHost, (size_t)nSamples * 4, cudaMemcpyHostToDevice, c.stream ) );
+		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
+		return WSP_OK;
+	}
+
+	// Instrumented decoder pass: nSteps single-token steps launched kernel by kernel with a CUDA event pair around every launch
+	// (on the launching stream).  Continues from the context's current decoder state; used by bench.py for the roofline figure.
+	int ctxProfileDecode( Context& c, int batch, int nSteps, float* msByKind, int* launchesByKind )
+	{
+		if( batch < 1 || batch > c.maxB || nSteps < 1 ) return fail( WSP_E_INVALIDARG, "batch / steps" );
+		WSP_CUDA( cudaSetDevice( c.e->device ) );
+		c.prof.on = true;
+		c.prof.used = 0;
+		c.prof.kinds.clear();
+		int rc = WSP_OK;
+		for( int i = 0; i < nSteps && rc >= 0; i++ ) rc = decodeSubmit( c, 1, batch, false, true );
+		c.prof.on = false;
+		if( rc < 0 ) return rc;
+		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
+		for( int k = 0; k < KK_COUNT; k++ ) { msByKind[ k ] = 0; launchesByKind[ k ] = 0; }
+		for( size_t i = 0; i < c.prof.kinds.size(); i++ )
+		{
+			float ms = 0;
+			cudaEventElapsedTime( &ms, c.prof.pool[ 2 * i ], c.prof.pool[ 2 * i + 1 ] );
+			msByKind[ c.prof.kinds[ i ] ] += ms;
+			launchesByKind[ c.prof.kinds[ i ] ]++;
+		}
+		return WSP_OK;
+	}
+
 	// ===============================================================================================================
 	// the measured path: mel + encode + n_decode greedy steps, tokens fed back on the device
 	// ===============================================================================================================
@@ -443,7 +516,17 @@ namespace wsp
 		WSP_CUDA( cudaSetDevice( c.e->device ) );
 		cudaStream_t s = c.stream;
 		WSP_CUDA( cudaEventRecord( c.ev[ 0 ], s ) );
-		if( !resident )
+		if( resident )
+		{
+			// inputs already in HBM (wsp_upload_pcm): the log-mel front end still runs inside the timed region
+			for( int b = 0; b < batch; b++ )
+			{
+				const MelSlot& ms = c.slots[ b ];
+				if( !ms.pcm ) return fail( WSP_E_INVALIDARG, "no resident PCM in slot " + std::to_string( b ) + " (call wsp_upload_pcm)" );
+				WSP_CHECK( melFromDevicePcm( c, b, ms.pcm, ms.pcmSamples ) );
+			}
+		}
+		else
 		{
 			size_t total = 0;
 			for( int b = 0; b < batch; b++ ) { if( nSamples[ b ] < 0 ) return fail( WSP_E_INVALIDARG, "n_samples" ); total += (size_t)nSamples[ b ]; }

@@ -88,6 +88,19 @@ namespace wsp
 		float* mel = nullptr;   // [80][nLen]
 		int cap = 0;            // frames allocated
 		int nLen = 0;
+		float* pcm = nullptr;   // optional device-resident PCM (wsp_upload_pcm), for the HBM-resident bench leg
+		int pcmCap = 0;
+		int pcmSamples = 0;
+	};
+
+	// per-kernel-kind device time of the decoder, collected by an instrumented (un-graphed) pass: wsp_profile_decode
+	enum KernelKind { KK_SKINNY = 0, KK_CROSS = 1, KK_SELF = 2, KK_OTHER = 3, KK_COUNT = 4 };
+	struct KernelProfile
+	{
+		bool on = false;
+		std::vector<cudaEvent_t> pool;
+		std::vector<int> kinds;     // kind of interval i = [pool[2i], pool[2i+1]]
+		size_t used = 0;
 	};
 
 	struct Context
@@ -146,6 +159,9 @@ namespace wsp
 		int stepGraphLaunches = 0;
 		bool useGraph = true;
 
+		KernelProfile prof;
+		cudaEvent_t timerEv[ 2 ] = { nullptr, nullptr };
+
 		// timing
 		cudaEvent_t ev[ 4 ] = { nullptr, nullptr, nullptr, nullptr };
 		float ms[ 4 ] = { 0, 0, 0, 0 };
@@ -159,5 +175,7 @@ namespace wsp
 	int ctxSetMel( Context& c, int slot, const float* melHost, int nLen );
 	int ctxEncode( Context& c, const int32_t* offsets, int batch );
 	int ctxDecode( Context& c, const int32_t* tokensHost, int nTokens, int nPast, int batch, uint32_t flags, wsp_token_data* sampledHost );
+	int ctxUploadPcm( Context& c, int slot, const float* pcmHost, int nSamples );
+	int ctxProfileDecode( Context& c, int batch, int nSteps, float* msByKind, int* launchesByKind );
 	int ctxRunChunks( Context& c, const float* const* pcm, const int32_t* nSamples, int batch, const int32_t* prompt, int nPrompt, int nDecode, int32_t* tokensOut, float* stageMs, bool resident );
 }
