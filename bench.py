@@ -74,6 +74,16 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {k: _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, np.generic):
+        return o.item()
+    return o
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -191,7 +201,7 @@ def run_reference(a):
                          "mel_ms": det["mel_ms"], "encode_ms": det["encode_ms"], "decode_ms_per_token": det["decode_ms_per_token"], "host_cores": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(_jsonable(line)), flush=True)
     return 0
 
 
@@ -345,7 +355,7 @@ def run_ours(a):
             "load": {"seconds": load_s, "nccl_broadcast_ms": bcast_ms, "weight_bytes": engine.weight_bytes()},
             "tokens_equal_e2e_vs_resident": same_tokens,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_jsonable(line)), flush=True)
     for p in pinned:
         L.wsp_host_free(p)
     if world > 1:
