@@ -49,6 +49,7 @@ def lib():
         L.ora_trace_size.restype = C.c_int64; L.ora_trace_size.argtypes = [ci]
         L.ora_trace_data.argtypes = [ci, fp]
         L.ora_full.argtypes = [vp, fp, ci, ci, ci, C.c_char_p, ci, ci]
+        L.ora_full_ex.argtypes = [vp, fp, ci, ci, ci, C.c_char_p, ci, ci, ci, ci]
         L.ora_full_n_segments.argtypes = [vp]
         L.ora_full_segment_t0.restype = C.c_int64; L.ora_full_segment_t0.argtypes = [vp, ci]
         L.ora_full_segment_t1.restype = C.c_int64; L.ora_full_segment_t1.argtypes = [vp, ci]

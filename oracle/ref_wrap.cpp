@@ -193,6 +193,23 @@ int ora_full( whisper_context* c, const float* pcm, int n, int threads, int flag
 	p.audio_ctx = audio_ctx;
 	return whisper_full( c, p, pcm, n );
 }
+int ora_full_ex( whisper_context* c, const float* pcm, int n, int threads, int flags, const char* language, int max_tokens, int audio_ctx, int offset_ms, int duration_ms )
+{
+	whisper_full_params p = whisper_full_default_params( WHISPER_SAMPLING_GREEDY );
+	p.n_threads = threads;
+	p.translate = ( flags & 1 ) != 0;
+	p.no_context = ( flags & 2 ) != 0;
+	p.single_segment = ( flags & 4 ) != 0;
+	p.print_special = ( flags & 8 ) != 0;
+	p.print_progress = false;
+	p.print_realtime = false;
+	p.language = language;
+	p.max_tokens = max_tokens;
+	p.audio_ctx = audio_ctx;
+	p.offset_ms = offset_ms;
+	p.duration_ms = duration_ms;
+	return whisper_full( c, p, pcm, n );
+}
 int ora_full_n_segments( whisper_context* c ) { return whisper_full_n_segments( c ); }
 int64_t ora_full_segment_t0( whisper_context* c, int i ) { return whisper_full_get_segment_t0( c, i ); }
 int64_t ora_full_segment_t1( whisper_context* c, int i ) { return whisper_full_get_segment_t1( c, i ); }

@@ -90,7 +90,52 @@ CASES = {
     "micro_en_offset": ("micro.en", 2, 640000, 1000),  # 40 s clip, window starting at frame 1000 (ragged tail)
 }
 
+# whisper_full() runs (the transcription driver, whisper.cpp:2765-3125) on a timestamp-happy synthetic model
+FULL_MODEL = "micro.en-ts"
+FULL_SECONDS = 75
+FULL_RUNS = {
+    # name: (eFullParamsFlags, max_tokens, offset_ms, duration_ms)      flags: 2 NoContext, 4 SingleSegment, 8 PrintSpecial
+    "plain": (0, 0, 0, 0),
+    "special": (8, 0, 0, 0),
+    "special_nocontext_max40": (8 | 2, 40, 0, 0),
+    "single_segment_max16": (4, 16, 0, 0),
+    "special_offset_duration": (8 | 2, 30, 10000, 40000),
+}
+
+
+def full_pcm():
+    n = 16000 * FULL_SECONDS
+    return np.concatenate([synth.synth_pcm(10 + i) for i in range((n + 479999) // 480000)])[:n]
+
+
+def make_full():
+    path = synth.model_path(FULL_MODEL)
+    pcm = full_pcm()
+    out = {}
+    for name, (flags, max_tokens, off, dur) in FULL_RUNS.items():
+        o = RefOracle(path, threads=4, log_level=0)
+        L = o.L
+        import ctypes as C
+        # ora_full has no offset/duration arguments: emulate them by slicing is NOT equivalent, so extend through the params struct
+        rc = L.ora_full_ex(o.ctx, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size, 4, flags, b"en", max_tokens, 0, off, dur)
+        assert rc == 0
+        segs = []
+        for i in range(L.ora_full_n_segments(o.ctx)):
+            toks = [L.ora_full_token_id(o.ctx, i, j) for j in range(L.ora_full_n_tokens(o.ctx, i))]
+            segs.append((L.ora_full_segment_t0(o.ctx, i), L.ora_full_segment_t1(o.ctx, i), toks, L.ora_full_segment_text(o.ctx, i)))
+        out[name + "_t"] = np.array([[s[0], s[1]] for s in segs], np.int64).reshape(-1, 2)
+        out[name + "_ntok"] = np.array([len(s[2]) for s in segs], np.int32)
+        out[name + "_tokens"] = np.array([t for s in segs for t in s[2]], np.int32)
+        out[name + "_text"] = np.array([s[3].decode(errors="replace") for s in segs])
+        print("  full/%s: %d segments, %d tokens" % (name, len(segs), out[name + "_tokens"].size))
+    return out
+
+
 if __name__ == "__main__":
+    data = make_full()
+    p = os.path.join(HERE, "full_micro_en_ts.npz")
+    np.savez_compressed(p, **data)
+    print("full_micro_en_ts", "%.0f KB" % (os.path.getsize(p) / 1024))
     for name, (model, chunk, n, off) in CASES.items():
         data = make(model, chunk, n, off)
         p = os.path.join(HERE, name + ".npz")

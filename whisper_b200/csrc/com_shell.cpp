@@ -1,0 +1,954 @@
+// COM-style shell over the C ABI: iModel / iContext / iTranscribeResult / iAudioBuffer, the exported factory functions, and the
+// transcription driver.
+//
+// The shell mirrors the reference's own wrapper around its CPU back-end (Whisper/whisperCom.cpp:67-212: class Context implements
+// iContext + iModel over whisper_context) and the driver follows the oracle's whisper_full() (Whisper/source/whisper.cpp:2765-3125)
+// step for step — windowing by the last timestamp token, prompt carry-over, the retry / skip-one-second rule, segment splitting —
+// with whisper_encode -> wsp_encode and whisper_decode + whisper_sample_* -> wsp_decode (sampling happens on the GPU).
+// The D3D back-end's driver (Whisper/Whisper/ContextImpl.cpp:452-794) differs slightly (it always skips 1 s on failure); the oracle wins.
+#include "../../include/whisper_b200.h"
+#include "../../include/whisper_b200_com.h"
+#include <atomic>
+#include <map>
+
+#include <memory>
+#include <mutex>
+#include <regex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+namespace
+{
+	using namespace Whisper;
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// logger (Whisper/API/loggerApi.h, Whisper/Utils/Logger.cpp)
+	std::mutex g_logMutex;
+	sLoggerSetup g_logger = { nullptr, nullptr, eLogLevel::Warning, eLoggerFlags::UseStandardError };
+
+	void logMessage( eLogLevel lvl, const char* fmt, ... )
+	{
+		sLoggerSetup ls;
+		{
+			std::lock_guard<std::mutex> lk( g_logMutex );
+			ls = g_logger;
+		}
+		if( (uint8_t)lvl > (uint8_t)ls.level ) return;
+		char buf[ 1024 ];
+		va_list ap;
+		va_start( ap, fmt );
+		vsnprintf( buf, sizeof( buf ), fmt, ap );
+		va_end( ap );
+		if( ls.sink ) ls.sink( ls.context, lvl, buf );
+		if( !ls.sink || ( (uint8_t)ls.flags & (uint8_t)eLoggerFlags::UseStandardError ) ) fprintf( stderr, "%s\n", buf );
+	}
+
+	HRESULT hrFromStatus( wsp_status s )
+	{
+		switch( s )
+		{
+		case WSP_OK: return S_OK;
+		case WSP_S_FALSE: return S_FALSE;
+		case WSP_E_INVALIDARG: return E_INVALIDARG;
+		case WSP_E_POINTER: return E_POINTER;
+		case WSP_E_OUTOFMEMORY: return E_OUTOFMEMORY;
+		case WSP_E_BOUNDS: return E_BOUNDS;
+		case WSP_E_NOTIMPL: return E_NOTIMPL;
+		default: return E_FAIL;
+		}
+	}
+	HRESULT check( wsp_status s, const char* what )
+	{
+		if( s >= 0 ) return hrFromStatus( s );
+		logMessage( eLogLevel::Error, "%s failed: %s", what, wsp_last_error() );
+		return hrFromStatus( s );
+	}
+#define HR( expr )                              \
+	do {                                        \
+		const HRESULT _hr = ( expr );           \
+		if( FAILED( _hr ) ) return _hr;         \
+	} while( 0 )
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// ref-counted object base (ComLightLib/server/ObjectRoot.hpp equivalent)
+	template<class I>
+	class Object : public I
+	{
+		std::atomic<uint32_t> refs{ 1 };
+
+	protected:
+		virtual ~Object() = default;
+		virtual bool queryExtra( REFIID, void** ) { return false; }
+
+	public:
+		HRESULT WSPCALL QueryInterface( REFIID riid, void** pp ) override
+		{
+			if( !pp ) return E_POINTER;
+			if( riid == I::iid() || riid == ComLight::IUnknown::iid() )
+			{
+				*pp = static_cast<I*>( this );
+				AddRef();
+				return S_OK;
+			}
+			if( queryExtra( riid, pp ) ) return S_OK;
+			*pp = nullptr;
+			return E_NOINTERFACE;
+		}
+		uint32_t WSPCALL AddRef() override { return ++refs; }
+		uint32_t WSPCALL Release() override
+		{
+			const uint32_t r = --refs;
+			if( r == 0 ) delete this;
+			return r;
+		}
+	};
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// languages (table order = token order after <|startoftranscript|>; codes/names as in OpenAI Whisper, cf. whisper.cpp:33-133)
+	const char* const kLanguages =
+		"en:english zh:chinese de:german es:spanish ru:russian ko:korean fr:french ja:japanese pt:portuguese tr:turkish pl:polish ca:catalan nl:dutch "
+		"ar:arabic sv:swedish it:italian id:indonesian hi:hindi fi:finnish vi:vietnamese iw:hebrew uk:ukrainian el:greek ms:malay cs:czech ro:romanian "
+		"da:danish hu:hungarian ta:tamil no:norwegian th:thai ur:urdu hr:croatian bg:bulgarian lt:lithuanian la:latin mi:maori ml:malayalam cy:welsh "
+		"sk:slovak te:telugu fa:persian lv:latvian bn:bengali sr:serbian az:azerbaijani sl:slovenian kn:kannada et:estonian mk:macedonian br:breton "
+		"eu:basque is:icelandic hy:armenian ne:nepali mn:mongolian bs:bosnian kk:kazakh sq:albanian sw:swahili gl:galician mr:marathi pa:punjabi "
+		"si:sinhala km:khmer sn:shona yo:yoruba so:somali af:afrikaans oc:occitan ka:georgian be:belarusian tg:tajik sd:sindhi gu:gujarati am:amharic "
+		"yi:yiddish lo:lao uz:uzbek fo:faroese ht:haitian_creole ps:pashto tk:turkmen nn:nynorsk mt:maltese sa:sanskrit lb:luxembourgish my:myanmar "
+		"bo:tibetan tl:tagalog mg:malagasy as:assamese tt:tatar haw:hawaiian ln:lingala ha:hausa ba:bashkir jw:javanese su:sundanese";
+
+	struct LanguageTable
+	{
+		std::vector<std::string> codes, names;
+		std::vector<sLanguageEntry> entries;
+		LanguageTable()
+		{
+			std::string all( kLanguages );
+			size_t pos = 0;
+			while( pos < all.size() )
+			{
+				size_t sp = all.find( ' ', pos );
+				if( sp == std::string::npos ) sp = all.size();
+				const std::string item = all.substr( pos, sp - pos );
+				const size_t colon = item.find( ':' );
+				codes.push_back( item.substr( 0, colon ) );
+				std::string nm = item.substr( colon + 1 );
+				for( char& c : nm ) if( c == '_' ) c = ' ';
+				names.push_back( nm );
+				pos = sp + 1;
+			}
+			for( size_t i = 0; i < codes.size(); i++ )
+				entries.push_back( sLanguageEntry{ makeLanguageKey( codes[ i ].c_str() ), (int)i, names[ i ].c_str() } );
+		}
+		int idFromKey( uint32_t key ) const
+		{
+			for( const auto& e : entries ) if( e.key == key ) return e.id;
+			return -1;
+		}
+	};
+	const LanguageTable& languages()
+	{
+		static const LanguageTable t;
+		return t;
+	}
+
+	std::string utf8FromWide( const wchar_t* w )
+	{
+		std::string out;
+		if( !w ) return out;
+		for( ; *w; w++ )
+		{
+			uint32_t c = (uint32_t)*w;
+			if( sizeof( wchar_t ) == 2 && c >= 0xD800 && c <= 0xDBFF && w[ 1 ] )
+			{
+				c = 0x10000 + ( ( c - 0xD800 ) << 10 ) + ( (uint32_t)w[ 1 ] - 0xDC00 );
+				w++;
+			}
+			if( c < 0x80 ) out.push_back( (char)c );
+			else if( c < 0x800 ) { out.push_back( (char)( 0xC0 | ( c >> 6 ) ) ); out.push_back( (char)( 0x80 | ( c & 0x3F ) ) ); }
+			else if( c < 0x10000 ) { out.push_back( (char)( 0xE0 | ( c >> 12 ) ) ); out.push_back( (char)( 0x80 | ( ( c >> 6 ) & 0x3F ) ) ); out.push_back( (char)( 0x80 | ( c & 0x3F ) ) ); }
+			else { out.push_back( (char)( 0xF0 | ( c >> 18 ) ) ); out.push_back( (char)( 0x80 | ( ( c >> 12 ) & 0x3F ) ) ); out.push_back( (char)( 0x80 | ( ( c >> 6 ) & 0x3F ) ) ); out.push_back( (char)( 0x80 | ( c & 0x3F ) ) ); }
+		}
+		return out;
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
+	struct SharedEngine
+	{
+		wsp_model* model = nullptr;
+		wsp_engine* engine = nullptr;
+		int32_t hp[ 11 ] = {};
+		int32_t special[ 8 ] = {};
+		~SharedEngine()
+		{
+			if( engine ) wsp_engine_destroy( engine );
+			if( model ) wsp_model_close( model );
+		}
+		int nVocab() const { return hp[ 0 ]; }
+		int nTextCtx() const { return hp[ 5 ]; }
+		int tokEot() const { return special[ 0 ]; }
+		int tokSot() const { return special[ 1 ]; }
+		int tokPrev() const { return special[ 2 ]; }
+		int tokBeg() const { return special[ 5 ]; }
+	};
+
+	class AudioBufferObj : public Object<iAudioBuffer>
+	{
+		std::vector<float> pcm;
+
+	public:
+		AudioBufferObj( const float* p, uint32_t n ) : pcm( p, p + n ) {}
+		uint32_t WSPCALL countSamples() const override { return (uint32_t)pcm.size(); }
+		const float* WSPCALL getPcmMono() const override { return pcm.data(); }
+		const float* WSPCALL getPcmStereo() const override { return nullptr; }
+		HRESULT WSPCALL getTime( int64_t& rdi ) const override { rdi = 0; return S_OK; }
+	};
+
+	struct ResultData
+	{
+		struct Seg { int64_t t0, t1; std::string text; std::vector<wsp_token_data> tokens; };
+		std::vector<Seg> segs;
+	};
+
+	class ResultObj : public Object<iTranscribeResult>
+	{
+	public:
+		std::vector<std::string> texts;
+		std::vector<sSegment> segments;
+		std::vector<sToken> tokens;
+		std::shared_ptr<SharedEngine> eng;   // token text pointers live in the model
+
+		void build( const ResultData& rd, const std::shared_ptr<SharedEngine>& e, bool makeTokens )
+		{
+			// Whisper/source.compat/convertThings.cpp:160-213 (makeNewResults): 10 ms units -> 100 ns ticks, Special = id >= eot
+			eng = e;
+			texts.clear(); segments.clear(); tokens.clear();
+			texts.reserve( rd.segs.size() );
+			for( const auto& s : rd.segs ) texts.push_back( s.text );
+			for( size_t i = 0; i < rd.segs.size(); i++ )
+			{
+				const auto& s = rd.segs[ i ];
+				sSegment seg;
+				seg.text = texts[ i ].c_str();
+				seg.time.begin.ticks = (uint64_t)( s.t0 * 100000 );
+				seg.time.end.ticks = (uint64_t)( s.t1 * 100000 );
+				seg.firstToken = (uint32_t)tokens.size();
+				seg.countTokens = 0;
+				if( makeTokens )
+				{
+					seg.countTokens = (uint32_t)s.tokens.size();
+					for( const auto& t : s.tokens )
+					{
+						sToken tk;
+						tk.text = wsp_model_token_text( e->model, t.id );
+						tk.time.begin.ticks = 0; tk.time.end.ticks = 0;
+						tk.probability = t.p; tk.probabilityTimestamp = t.pt; tk.ptsum = t.ptsum; tk.vlen = 0;
+						tk.id = t.id;
+						tk.flags = t.id >= e->tokEot() ? eTokenFlags::Special : eTokenFlags::None;
+						tokens.push_back( tk );
+					}
+				}
+				segments.push_back( seg );
+			}
+		}
+		HRESULT WSPCALL getSize( sTranscribeLength& rdi ) const override
+		{
+			rdi.countSegments = (uint32_t)segments.size();
+			rdi.countTokens = (uint32_t)tokens.size();
+			return S_OK;
+		}
+		const sSegment* WSPCALL getSegments() const override { return segments.empty() ? nullptr : segments.data(); }
+		const sToken* WSPCALL getTokens() const override { return tokens.empty() ? nullptr : tokens.data(); }
+	};
+
+	class ModelObj;
+
+	class ContextObj : public Object<iContext>
+	{
+		ModelObj* owner;                       // holds a reference (ContextImpl.h:16)
+		std::shared_ptr<SharedEngine> eng;
+		wsp_context* ctx = nullptr;
+		std::vector<int32_t> promptPast;       // text context carried across windows and calls (whisper_context::prompt_past)
+		ResultData results;
+		mutable ResultObj* staticResult = nullptr;
+
+		~ContextObj() override;
+
+		HRESULT decode( const std::vector<int32_t>& tokens, int nPast, bool first, wsp_token_data& out )
+		{
+			const uint32_t flags = first ? ( WSP_DECODE_FORCE_TIMESTAMP | WSP_DECODE_INITIAL ) : 0u;
+			return check( wsp_decode( ctx, tokens.data(), (int32_t)tokens.size(), nPast, 1, flags, &out ), "wsp_decode" );
+		}
+		HRESULT detectLanguage( int& langId );
+
+	public:
+		ContextObj( ModelObj* m, const std::shared_ptr<SharedEngine>& e );
+		HRESULT init() { return check( wsp_context_create( eng->engine, 1, &ctx ), "wsp_context_create" ); }
+
+		HRESULT WSPCALL runFull( const sFullParams& params, const iAudioBuffer* buffer ) override;
+		HRESULT WSPCALL runStreamed( const sFullParams&, const sProgressSink&, const iAudioReader* ) override
+		{
+			logMessage( eLogLevel::Error, "whisper_b200: runStreamed is not implemented (same as the Reference back-end, whisperCom.cpp:139-143)" );
+			return E_NOTIMPL;
+		}
+		HRESULT WSPCALL runCapture( const sFullParams&, const sCaptureCallbacks&, const iAudioCapture* ) override
+		{
+			logMessage( eLogLevel::Error, "whisper_b200: runCapture is not implemented (same as the Reference back-end, whisperCom.cpp:144-148)" );
+			return E_NOTIMPL;
+		}
+		HRESULT WSPCALL getResults( eResultFlags flags, iTranscribeResult** pp ) const override
+		{
+			if( !pp ) return E_POINTER;
+			const bool makeTokens = 0 != ( (uint32_t)flags & (uint32_t)eResultFlags::Tokens );
+			if( (uint32_t)flags & (uint32_t)eResultFlags::NewObject )
+			{
+				ResultObj* r = new ResultObj();
+				r->build( results, eng, makeTokens );
+				*pp = r;
+				return S_OK;
+			}
+			// context-owned object whose content is replaced by the next call (TranscribeStructs.h:110-114)
+			if( !staticResult ) staticResult = new ResultObj();
+			staticResult->build( results, eng, makeTokens );
+			staticResult->AddRef();
+			*pp = staticResult;
+			return S_OK;
+		}
+		HRESULT WSPCALL detectSpeaker( const sTimeInterval&, eSpeakerChannel& result ) const override
+		{
+			result = eSpeakerChannel::NoStereoData;
+			return E_NOTIMPL;
+		}
+		HRESULT WSPCALL getModel( iModel** pp ) override;
+		HRESULT WSPCALL fullDefaultParams( eSamplingStrategy strategy, sFullParams* rdi ) override
+		{
+			if( !rdi ) return E_POINTER;
+			// whisper_full_default_params (whisper.cpp:2596-2710) through makeNewParams (convertThings.cpp:7-60)
+			memset( rdi, 0, sizeof( *rdi ) );
+			rdi->strategy = strategy;
+			rdi->cpuThreads = 4;
+			rdi->n_max_text_ctx = 16384;
+			rdi->flags = (eFullParamsFlags)( (uint32_t)eFullParamsFlags::PrintProgress | (uint32_t)eFullParamsFlags::PrintTimestamps );
+			rdi->language = makeLanguageKey( "en" );
+			rdi->thold_pt = 0.01f;
+			rdi->thold_ptsum = 0.01f;
+			if( strategy == eSamplingStrategy::BeamSearch ) { rdi->greedy.n_past = -1; rdi->beam_search.beam_width = 10; rdi->beam_search.n_best = 5; }
+			else { rdi->beam_search.n_past = -1; rdi->beam_search.beam_width = -1; rdi->beam_search.n_best = -1; }
+			return S_OK;
+		}
+		HRESULT WSPCALL timingsPrint() override
+		{
+			float ms[ 4 ]; int32_t calls[ 4 ];
+			HR( check( wsp_timings( ctx, ms, calls, 0 ), "wsp_timings" ) );
+			logMessage( eLogLevel::Info, "whisper_b200 timings (device):      mel = %8.2f ms / %d calls", ms[ 0 ], calls[ 0 ] );
+			logMessage( eLogLevel::Info, "whisper_b200 timings (device):   encode = %8.2f ms / %d calls", ms[ 1 ], calls[ 1 ] );
+			logMessage( eLogLevel::Info, "whisper_b200 timings (device):   decode = %8.2f ms / %d calls (sampling included)", ms[ 2 ], calls[ 2 ] );
+			return S_OK;
+		}
+		HRESULT WSPCALL timingsReset() override
+		{
+			float ms[ 4 ]; int32_t calls[ 4 ];
+			return check( wsp_timings( ctx, ms, calls, 1 ), "wsp_timings" );
+		}
+		// not part of the COM surface: used by the flat test helpers below
+		const ResultData& data() const { return results; }
+		void clearPromptPast() { promptPast.clear(); }
+	};
+
+	class ModelObj : public Object<iModel>
+	{
+		std::shared_ptr<SharedEngine> eng;
+		~ModelObj() override = default;
+
+	public:
+		explicit ModelObj( const std::shared_ptr<SharedEngine>& e ) : eng( e ) {}
+		HRESULT WSPCALL createContext( iContext** pp ) override
+		{
+			if( !pp ) return E_POINTER;
+			ContextObj* c = new ContextObj( this, eng );
+			const HRESULT hr = c->init();
+			if( FAILED( hr ) ) { c->Release(); return hr; }
+			*pp = c;
+			return S_OK;
+		}
+		HRESULT WSPCALL tokenize( const char* text, pfnDecodedTokens pfn, void* pv ) override
+		{
+			// whisper.cpp:2192-2245: GPT-2 style pre-split, then greedy longest match against the vocabulary
+			if( !text || !pfn ) return E_POINTER;
+			std::vector<int> out;
+			try
+			{
+				static const std::regex re( R"('s|'t|'re|'ve|'m|'ll|'d| ?[[:alpha:]]+| ?[[:digit:]]+| ?[^\s[:alpha:][:digit:]]+|\s+(?!\S)|\s+)" );
+				std::string str( text );
+				std::vector<std::string> words;
+				for( std::sregex_iterator it( str.begin(), str.end(), re ), end; it != end; ++it ) words.push_back( it->str() );
+				const int nv = eng->nVocab();
+				// reverse map built on first use
+				static std::mutex mtx;
+				std::lock_guard<std::mutex> lk( mtx );
+				if( vocabMap.empty() )
+					for( int i = 0; i < nv; i++ )
+					{
+						const char* t = wsp_model_token_text( eng->model, i );
+						if( t ) vocabMap[ t ] = i;   // later duplicates win, like std::map assignment in the loader (whisper.cpp:569)
+					}
+				for( const auto& word : words )
+				{
+					const int n = (int)word.size();
+					int i = 0;
+					while( i < n )
+					{
+						int j = n;
+						while( j > i )
+						{
+							auto f = vocabMap.find( word.substr( i, j - i ) );
+							if( f != vocabMap.end() ) { out.push_back( f->second ); i = j; break; }
+							--j;
+						}
+						if( i == n ) break;
+						if( j == i )
+						{
+							logMessage( eLogLevel::Warning, "tokenize: unknown token '%c'", word[ i ] );
+							++i;
+						}
+					}
+				}
+			}
+			catch( const std::exception& ) { return E_FAIL; }
+			if( !out.empty() ) pfn( out.data(), (int)out.size(), pv );
+			return S_OK;
+		}
+		HRESULT WSPCALL isMultilingual() override { return wsp_model_is_multilingual( eng->model ) ? S_OK : S_FALSE; }
+		HRESULT WSPCALL getSpecialTokens( SpecialTokens& rdi ) override
+		{
+			const int32_t* s = eng->special;
+			rdi = SpecialTokens{ s[ 0 ], s[ 1 ], s[ 2 ], s[ 3 ], s[ 4 ], s[ 5 ], s[ 6 ], s[ 7 ] };
+			return S_OK;
+		}
+		const char* WSPCALL stringFromToken( whisper_token token ) override { return wsp_model_token_text( eng->model, token ); }
+		HRESULT WSPCALL clone( iModel** rdi ) override
+		{
+			// the reference needs a second D3D device sharing the weight buffers (ModelImpl.cpp:40-60); here the engine is immutable and
+			// every context has its own stream and state, so a clone is simply another handle on the same weights
+			if( !rdi ) return E_POINTER;
+			*rdi = new ModelObj( eng );
+			return S_OK;
+		}
+
+	private:
+		std::map<std::string, int> vocabMap;
+	};
+
+	ContextObj::ContextObj( ModelObj* m, const std::shared_ptr<SharedEngine>& e ) : owner( m ), eng( e ) { owner->AddRef(); }
+	ContextObj::~ContextObj()
+	{
+		if( staticResult ) staticResult->Release();
+		if( ctx ) wsp_context_destroy( ctx );
+		owner->Release();
+	}
+	HRESULT WSPCALL ContextObj::getModel( iModel** pp )
+	{
+		if( !pp ) return E_POINTER;
+		owner->AddRef();
+		*pp = owner;
+		return S_OK;
+	}
+
+	// whisper_lang_auto_detect (whisper.cpp:2428-2495): encode at offset 0, decode [sot], most probable language token
+	HRESULT ContextObj::detectLanguage( int& langId )
+	{
+		const int32_t off = 0;
+		HR( check( wsp_encode( ctx, &off, 1 ), "wsp_encode" ) );
+		const int32_t sot = eng->tokSot();
+		HR( check( wsp_decode( ctx, &sot, 1, 0, 1, WSP_DECODE_ALL_LOGITS, nullptr ), "wsp_decode" ) );
+		std::vector<float> probs( (size_t)eng->nVocab() );
+		HR( check( wsp_get_probs( ctx, probs.data(), probs.size() ), "wsp_get_probs" ) );
+		const int n = (int)languages().codes.size();
+		int best = 0;
+		for( int i = 1; i < n; i++ )
+			if( sot + 1 + i < eng->nVocab() && probs[ sot + 1 + i ] > probs[ sot + 1 + best ] ) best = i;
+		langId = best;
+		return S_OK;
+	}
+
+	HRESULT WSPCALL ContextObj::runFull( const sFullParams& params, const iAudioBuffer* buffer )
+	{
+		if( !buffer ) return E_POINTER;
+		if( params.flag( eFullParamsFlags::SpeedupAudio ) )
+		{
+			logMessage( eLogLevel::Error, "whisper_b200: SpeedupAudio (phase vocoder) is not implemented" );
+			return E_NOTIMPL;
+		}
+		const int nAudioCtx = eng->hp[ 1 ];
+		if( params.audio_ctx != 0 && params.audio_ctx != nAudioCtx )
+		{
+			logMessage( eLogLevel::Error, "whisper_b200: audio_ctx override is not supported" );
+			return E_NOTIMPL;
+		}
+		if( params.flag( eFullParamsFlags::TokenTimestamps ) )
+			logMessage( eLogLevel::Warning, "whisper_b200: token-level timestamps are not computed (segment timestamps are)" );
+		// the reference's decoder arithmetic depends on its thread count; follow the caller's cpuThreads
+		const int threads = params.cpuThreads < 1 ? 1 : ( params.cpuThreads > 16 ? 16 : params.cpuThreads );
+		HR( check( wsp_set_reference_threads( ctx, threads ), "wsp_set_reference_threads" ) );
+
+		results.segs.clear();                                                                     // whisper.cpp:2771-2773
+		const float* pcm = buffer->getPcmMono();
+		const int nSamples = (int)buffer->countSamples();
+		if( !pcm && nSamples > 0 ) return E_POINTER;
+		HR( check( wsp_pcm_to_mel( ctx, 0, pcm, nSamples ), "wsp_pcm_to_mel" ) );                 // :2782
+		const int nLen = wsp_mel_len( ctx, 0 );
+
+		const int tokEot = eng->tokEot(), tokSot = eng->tokSot(), tokPrev = eng->tokPrev(), tokBeg = eng->tokBeg();
+		const int nTextCtx = eng->nTextCtx();
+		const bool multilingual = wsp_model_is_multilingual( eng->model ) != 0;
+
+		int langId = languages().idFromKey( params.language );
+		if( params.language == 0 || params.language == makeLanguageKey( "auto" ) )              // :2789-2801
+		{
+			if( nLen < 1 ) return S_OK;
+			HR( detectLanguage( langId ) );
+			logMessage( eLogLevel::Info, "whisper_b200: auto-detected language: %s", languages().codes[ langId ].c_str() );
+		}
+		if( langId < 0 )
+		{
+			logMessage( eLogLevel::Error, "whisper_b200: unknown language key 0x%x", params.language );
+			return E_INVALIDARG;
+		}
+
+		const int seekStart = params.offset_ms / 10;                                               // :2810-2818
+		const int seekEnd = seekStart + ( params.duration_ms == 0 ? nLen : params.duration_ms / 10 );
+		if( seekEnd < 100 + seekStart ) return S_OK;
+
+		if( params.flag( eFullParamsFlags::NoContext ) ) promptPast.clear();                      // :2821-2824
+		if( params.prompt_tokens && params.prompt_n_tokens > 0 )                                   // :2827-2833
+		{
+			promptPast.insert( promptPast.begin(), params.prompt_tokens, params.prompt_tokens + params.prompt_n_tokens );
+		}
+
+		std::vector<int32_t> promptInit = { tokSot };                                              // :2839-2848
+		if( multilingual )
+		{
+			promptInit.push_back( tokSot + 1 + langId );
+			promptInit.push_back( params.flag( eFullParamsFlags::Translate ) ? eng->special[ 6 ] : eng->special[ 7 ] );
+		}
+
+		int progressPrev = 0;
+		std::vector<wsp_token_data> tokensCur;
+		std::vector<int32_t> prompt;
+		const bool singleSegment = params.flag( eFullParamsFlags::SingleSegment );
+		const bool printSpecial = params.flag( eFullParamsFlags::PrintSpecial );
+
+		int seek = seekStart;
+		while( true )                                                                              // :2861
+		{
+			const int progressCur = ( 100 * ( seek - seekStart ) ) / ( seekEnd - seekStart );
+			while( progressCur >= progressPrev + 5 )
+			{
+				progressPrev += 5;
+				if( params.flag( eFullParamsFlags::PrintProgress ) ) logMessage( eLogLevel::Info, "runFull: progress = %3d%%", progressPrev );
+			}
+			if( seek + 100 >= seekEnd ) break;                                                    // :2871
+			if( seek > seekStart && seek + 500 >= seekEnd ) promptPast.clear();                    // :2877
+			if( params.encoder_begin_callback )                                                    // :2881-2886 (HRESULT flavour: sFullParams.h:18-19)
+			{
+				const HRESULT hr = params.encoder_begin_callback( this, params.encoder_begin_callback_user_data );
+				if( FAILED( hr ) ) return hr;
+				if( hr != S_OK ) break;
+			}
+			const int32_t seek32 = seek;
+			HR( check( wsp_encode( ctx, &seek32, 1 ), "wsp_encode" ) );                            // :2889
+
+			int nPast = 0;
+			prompt.clear();
+			if( !promptPast.empty() )                                                              // :2898-2906
+			{
+				int nTake = params.n_max_text_ctx < nTextCtx / 2 ? params.n_max_text_ctx : nTextCtx / 2;
+				if( nTake > (int)promptPast.size() ) nTake = (int)promptPast.size();
+				prompt.push_back( tokPrev );
+				prompt.insert( prompt.end(), promptPast.end() - nTake, promptPast.end() );
+				promptPast.assign( prompt.begin() + 1, prompt.end() );
+			}
+			prompt.insert( prompt.end(), promptInit.begin(), promptInit.end() );
+
+			int seekDelta = 100 * 30;                                                              // WHISPER_CHUNK_SIZE = 30
+			int resultLen = 0;
+			tokensCur.clear();
+			bool failed = false, hasTs = false;
+
+			const int nMax = nTextCtx / 2 - 4;                                                     // :2926
+			for( int i = 0; i < nMax; i++ )
+			{
+				wsp_token_data token;
+				HR( decode( prompt, nPast, i == 0, token ) );                                      // :2927-2943 decode + sample
+				nPast += (int)prompt.size();
+				prompt.clear();
+				if( token.id > tokBeg )                                                            // :2946-2957
+				{
+					const int seekDeltaNew = 2 * ( token.id - tokBeg );
+					if( hasTs && seekDelta > seekDeltaNew && resultLen < i ) break;
+					seekDelta = seekDeltaNew;
+					resultLen = i + 1;
+					hasTs = true;
+				}
+				prompt.push_back( token.id );
+				tokensCur.push_back( token );
+				if( token.id == tokEot || ( params.max_tokens > 0 && i >= params.max_tokens ) || ( hasTs && seek + seekDelta + 100 >= seekEnd ) )   // :2969-2988
+				{
+					if( resultLen == 0 )
+					{
+						if( seek + seekDelta + 100 >= seekEnd ) resultLen = i + 1;
+						else { failed = true; break; }
+					}
+					if( singleSegment ) { resultLen = i + 1; seekDelta = 100 * 30; }
+					break;
+				}
+				if( i == nMax - 1 && ( resultLen == 0 || seekDelta < 100 * 30 / 2 ) ) { failed = true; break; }   // :3000-3003
+			}
+
+			if( failed )                                                                           // :3006-3016
+			{
+				if( !promptPast.empty() ) promptPast.clear();
+				else
+				{
+					logMessage( eLogLevel::Warning, "runFull: failed to generate timestamp token - skipping one second" );
+					seek += 100;
+				}
+				continue;
+			}
+
+			tokensCur.resize( (size_t)resultLen );                                                 // :3019
+			for( const auto& r : tokensCur ) promptPast.push_back( r.id );
+
+			auto emit = [ & ]( int64_t t0, int64_t t1, const std::string& text, int i0, int i1 ) -> HRESULT {
+				ResultData::Seg s;
+				s.t0 = t0; s.t1 = t1; s.text = text;
+				s.tokens.assign( tokensCur.begin() + i0, tokensCur.begin() + i1 );
+				results.segs.push_back( std::move( s ) );
+				if( params.new_segment_callback )
+				{
+					const HRESULT hr = params.new_segment_callback( this, 1, params.new_segment_callback_user_data );
+					if( FAILED( hr ) ) return hr;
+				}
+				return S_OK;
+			};
+
+			if( !tokensCur.empty() )                                                               // :3026-3119
+			{
+				int i0 = 0;
+				int64_t t0 = seek + 2 * ( (int64_t)tokensCur.front().tid - tokBeg );
+				std::string text;
+				for( int i = 0; i < (int)tokensCur.size(); i++ )
+				{
+					const int id = tokensCur[ i ].id;
+					if( printSpecial || id < tokEot )
+					{
+						const char* t = wsp_model_token_text( eng->model, id );
+						if( t ) text += t;
+					}
+					if( id > tokBeg && !singleSegment )
+					{
+						const int64_t t1 = seek + 2 * ( (int64_t)tokensCur[ i ].tid - tokBeg );
+						if( !text.empty() ) HR( emit( t0, t1, text, i0, i + 1 ) );
+						text.clear();
+						while( i < (int)tokensCur.size() && tokensCur[ i ].id > tokBeg ) i++;
+						i--;
+						t0 = t1;
+						i0 = i + 1;
+					}
+				}
+				if( !text.empty() ) HR( emit( t0, (int64_t)seek + seekDelta, text, i0, (int)tokensCur.size() ) );
+			}
+			seek += seekDelta;                                                                     // :3121
+		}
+		return S_OK;
+	}
+
+	const std::vector<std::string>& deviceNames()
+	{
+		static std::vector<std::string> names;
+		if( names.empty() )
+		{
+			const int n = wsp_device_count();
+			for( int i = 0; i < n; i++ )
+			{
+				char buf[ 256 ] = {};
+				if( wsp_device_name( i, buf, sizeof( buf ) ) == WSP_OK ) names.push_back( buf );
+			}
+		}
+		return names;
+	}
+}
+
+
+
+// ===================================================================================================================
+// exported functions (Whisper/whisper.def:1-8)
+// ===================================================================================================================
+namespace Whisper
+{
+	HRESULT WSPCALL setupLogger( const sLoggerSetup& setup )
+	{
+		std::lock_guard<std::mutex> lk( g_logMutex );
+		g_logger = setup;
+		return S_OK;
+	}
+
+	HRESULT WSPCALL loadModel( const wchar_t* path, const sModelSetup& setup, const sLoadModelCallbacks* callbacks, iModel** pp )
+	{
+		if( !path || !pp ) return E_POINTER;
+		*pp = nullptr;
+		if( setup.impl != eModelImplementation::GPU && setup.impl != eModelImplementation::B200 )
+		{
+			// the published reference DLL answers the same for its compiled-out back-ends (modelFactory.cpp:15-19, stdafx.h:30-34)
+			logMessage( eLogLevel::Error, "whisper_b200: model implementation %u is not available in this build", (unsigned)setup.impl );
+			return E_NOTIMPL;
+		}
+		int device = 0;
+		if( setup.adapter && *setup.adapter )
+		{
+			// adapter = the name listGPUs reported, or a plain device index
+			const std::string want = utf8FromWide( setup.adapter );
+			const auto& names = deviceNames();
+			bool found = false;
+			for( size_t i = 0; i < names.size(); i++ ) if( names[ i ] == want ) { device = (int)i; found = true; }
+			if( !found )
+			{
+				char* end = nullptr;
+				const long v = strtol( want.c_str(), &end, 10 );
+				if( end && *end == 0 && v >= 0 ) device = (int)v;
+				else
+				{
+					logMessage( eLogLevel::Error, "whisper_b200: no such GPU: %s", want.c_str() );
+					return E_INVALIDARG;
+				}
+			}
+		}
+		auto eng = std::make_shared<SharedEngine>();
+		const std::string p8 = utf8FromWide( path );
+		HR( check( wsp_model_open( p8.c_str(), &eng->model ), "wsp_model_open" ) );
+		wsp_model_hparams( eng->model, eng->hp );
+		wsp_model_special_tokens( eng->model, eng->special );
+		if( callbacks && callbacks->cancel )
+		{
+			const HRESULT hr = callbacks->cancel( callbacks->pv );
+			if( FAILED( hr ) ) return hr;
+			if( hr != S_OK ) return E_ABORT;
+		}
+		if( callbacks && callbacks->progress ) callbacks->progress( 0.1, callbacks->pv );
+		HR( check( wsp_engine_create( eng->model, device, &eng->engine ), "wsp_engine_create" ) );
+		if( callbacks && callbacks->progress ) callbacks->progress( 1.0, callbacks->pv );
+		logMessage( eLogLevel::Debug, "whisper_b200: loaded %s, %.1f MB of weights on device %d", p8.c_str(), wsp_engine_weight_bytes( eng->engine ) / 1e6, device );
+		*pp = new ModelObj( eng );
+		return S_OK;
+	}
+
+	uint32_t WSPCALL findLanguageKeyA( const char* lang )
+	{
+		if( !lang ) return UINT32_MAX;
+		std::string s( lang );
+		for( char& c : s ) c = (char)tolower( (unsigned char)c );
+		const auto& t = languages();
+		for( size_t i = 0; i < t.codes.size(); i++ )
+			if( t.codes[ i ] == s || t.names[ i ] == s ) return t.entries[ i ].key;
+		return UINT32_MAX;
+	}
+	uint32_t WSPCALL findLanguageKeyW( const wchar_t* lang )
+	{
+		if( !lang ) return UINT32_MAX;
+		return findLanguageKeyA( utf8FromWide( lang ).c_str() );
+	}
+	HRESULT WSPCALL getSupportedLanguages( sLanguageList& rdi )
+	{
+		const auto& t = languages();
+		rdi.length = (uint32_t)t.entries.size();
+		rdi.pointer = t.entries.data();
+		return S_OK;
+	}
+	HRESULT WSPCALL listGPUs( pfnListAdapters pfn, void* pv )
+	{
+		if( !pfn ) return E_POINTER;
+		for( const auto& n : deviceNames() )
+		{
+			std::wstring w( n.begin(), n.end() );
+			pfn( w.c_str(), pv );
+		}
+		return S_OK;
+	}
+	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp )
+	{
+		if( pp ) *pp = nullptr;
+		return E_NOTIMPL;
+	}
+	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp )
+	{
+		if( !pp || ( !pcmMono && countSamples ) ) return E_POINTER;
+		*pp = new AudioBufferObj( pcmMono, countSamples );
+		return S_OK;
+	}
+}
+
+// ===================================================================================================================
+// flat C helpers over the COM surface, for tests/ (ctypes cannot call C++ vtables): every call goes loadModel -> createContext ->
+// fullDefaultParams -> runFull -> getResults exactly as Examples/main/main.cpp:210-318 does.
+// ===================================================================================================================
+namespace
+{
+	struct Session
+	{
+		iModel* model = nullptr;
+		iContext* context = nullptr;
+		iTranscribeResult* result = nullptr;
+		std::vector<int> segCallbackCounts;
+	};
+	HRESULT segCallback( iContext*, uint32_t nNew, void* pv ) noexcept
+	{
+		static_cast<Session*>( pv )->segCallbackCounts.push_back( (int)nNew );
+		return S_OK;
+	}
+}
+
+extern "C" {
+
+int32_t wspc_open( const char* modelPathUtf8, int32_t device, void** out )
+{
+	if( !modelPathUtf8 || !out ) return E_POINTER;
+	std::wstring w;
+	for( const char* p = modelPathUtf8; *p; p++ ) w.push_back( (wchar_t)(unsigned char)*p );   // test paths are ASCII
+	std::wstring adapter = std::to_wstring( device );
+	sModelSetup setup;
+	setup.impl = eModelImplementation::B200;
+	setup.adapter = adapter.c_str();
+	Session* s = new Session();
+	HRESULT hr = loadModel( w.c_str(), setup, nullptr, &s->model );
+	if( SUCCEEDED( hr ) ) hr = s->model->createContext( &s->context );
+	if( FAILED( hr ) )
+	{
+		if( s->model ) s->model->Release();
+		delete s;
+		return hr;
+	}
+	*out = s;
+	return S_OK;
+}
+void wspc_close( void* h )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return;
+	if( s->result ) s->result->Release();
+	if( s->context ) s->context->Release();
+	if( s->model ) s->model->Release();
+	delete s;
+}
+// flags = eFullParamsFlags bits; language = code such as "en" or "auto"
+int32_t wspc_run_full( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t maxTokens, int32_t cpuThreads,
+	int32_t offsetMs, int32_t durationMs, const int32_t* promptTokens, int32_t nPromptTokens )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return E_POINTER;
+	sFullParams p;
+	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
+	if( FAILED( hr ) ) return hr;
+	p.flags = (eFullParamsFlags)flags;
+	p.language = ( language && strcmp( language, "auto" ) != 0 ) ? findLanguageKeyA( language ) : makeLanguageKey( "auto" );
+	p.max_tokens = maxTokens;
+	p.cpuThreads = cpuThreads;
+	p.offset_ms = offsetMs;
+	p.duration_ms = durationMs;
+	p.prompt_tokens = promptTokens;
+	p.prompt_n_tokens = nPromptTokens;
+	p.new_segment_callback = &segCallback;
+	p.new_segment_callback_user_data = s;
+	s->segCallbackCounts.clear();
+	iAudioBuffer* buf = nullptr;
+	hr = createAudioBuffer( pcm, (uint32_t)nSamples, &buf );
+	if( FAILED( hr ) ) return hr;
+	hr = s->context->runFull( p, buf );
+	buf->Release();
+	if( FAILED( hr ) ) return hr;
+	if( s->result ) { s->result->Release(); s->result = nullptr; }
+	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
+	return FAILED( hr2 ) ? hr2 : hr;
+}
+int32_t wspc_n_segments( void* h )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s || !s->result ) return 0;
+	sTranscribeLength len;
+	s->result->getSize( len );
+	return (int32_t)len.countSegments;
+}
+int32_t wspc_n_segment_callbacks( void* h ) { Session* s = static_cast<Session*>( h ); return s ? (int32_t)s->segCallbackCounts.size() : 0; }
+int64_t wspc_segment_t0( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.begin.ticks / 100000 ); }
+int64_t wspc_segment_t1( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.end.ticks / 100000 ); }
+const char* wspc_segment_text( void* h, int32_t i ) { return static_cast<Session*>( h )->result->getSegments()[ i ].text; }
+int32_t wspc_segment_n_tokens( void* h, int32_t i ) { return (int32_t) static_cast<Session*>( h )->result->getSegments()[ i ].countTokens; }
+int32_t wspc_token_id( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return s->result->getTokens()[ seg.firstToken + j ].id;
+}
+float wspc_token_p( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return s->result->getTokens()[ seg.firstToken + j ].probability;
+}
+int32_t wspc_token_flags( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return (int32_t)s->result->getTokens()[ seg.firstToken + j ].flags;
+}
+// iModel surface
+int32_t wspc_tokenize( void* h, const char* text, int32_t* dst, int32_t cap )
+{
+	Session* s = static_cast<Session*>( h );
+	struct Sink { int32_t* dst; int32_t cap; int32_t n; } sink{ dst, cap, 0 };
+	auto cb = []( const int* tokens, int n, void* pv ) {
+		Sink* k = static_cast<Sink*>( pv );
+		for( int i = 0; i < n && k->n < k->cap; i++ ) k->dst[ k->n++ ] = tokens[ i ];
+	};
+	const HRESULT hr = s->model->tokenize( text, cb, &sink );
+	return FAILED( hr ) ? hr : sink.n;
+}
+const char* wspc_string_from_token( void* h, int32_t id ) { return static_cast<Session*>( h )->model->stringFromToken( id ); }
+int32_t wspc_is_multilingual( void* h ) { return static_cast<Session*>( h )->model->isMultilingual() == S_OK ? 1 : 0; }
+int32_t wspc_special_tokens( void* h, int32_t* out8 )
+{
+	SpecialTokens st;
+	const HRESULT hr = static_cast<Session*>( h )->model->getSpecialTokens( st );
+	memcpy( out8, &st, sizeof( st ) );
+	return hr;
+}
+int32_t wspc_query_interfaces( void* h )
+{
+	// IUnknown plumbing: QueryInterface round trips and reference counts behave like COM
+	Session* s = static_cast<Session*>( h );
+	void* p = nullptr;
+	if( s->model->QueryInterface( iModel::iid(), &p ) != S_OK || p != s->model ) return 1;
+	s->model->Release();
+	if( s->model->QueryInterface( ComLight::IUnknown::iid(), &p ) != S_OK ) return 2;
+	s->model->Release();
+	if( s->model->QueryInterface( iContext::iid(), &p ) != E_NOINTERFACE || p != nullptr ) return 3;
+	iModel* m2 = nullptr;
+	if( s->context->getModel( &m2 ) != S_OK || m2 != s->model ) return 4;
+	m2->Release();
+	iModel* clone = nullptr;
+	if( s->model->clone( &clone ) != S_OK || !clone ) return 5;
+	clone->Release();
+	sProgressSink sink{ nullptr, nullptr };
+	sFullParams fp;
+	s->context->fullDefaultParams( eSamplingStrategy::Greedy, &fp );
+	if( s->context->runStreamed( fp, sink, nullptr ) != E_NOTIMPL ) return 6;
+	return 0;
+}
+uint32_t wspc_find_language_key( const char* lang ) { return findLanguageKeyA( lang ); }
+int32_t wspc_language_count( void )
+{
+	sLanguageList l;
+	getSupportedLanguages( l );
+	return (int32_t)l.length;
+}
+
+} // extern "C"

@@ -7,6 +7,25 @@
 
 namespace kern
 {
+	// Launch with the programmatic-stream-serialization attribute (PDL).  Kernels launched this way call pdl_launch_dependents() first
+	// thing and pdl_wait() before touching anything a predecessor wrote.  WSP_PDL=0 in the environment disables the attribute.
+	bool pdlEnabled();
+	template<class... KArgs, class... Args>
+	inline cudaError_t launchPdl( void ( *kernel )( KArgs... ), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args )
+	{
+		cudaLaunchConfig_t cfg{};
+		cfg.gridDim = grid;
+		cfg.blockDim = block;
+		cfg.dynamicSmemBytes = smem;
+		cfg.stream = s;
+		cudaLaunchAttribute at[ 1 ];
+		at[ 0 ].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[ 0 ].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at;
+		cfg.numAttrs = pdlEnabled() ? 1 : 0;
+		return cudaLaunchKernelEx( &cfg, kernel, static_cast<KArgs>( args )... );
+	}
+
 	// ---- log-mel (a1: whisper.cpp:2060-2181) -------------------------------------------------------------------
 	struct MelTables
 	{

@@ -62,6 +62,7 @@ namespace kern
 		const int row0 = blockIdx.x * SK_ROWS;
 		const int col0 = blockIdx.y * SK_COLS;
 		const int ncols = min( SK_COLS, a.nCols - col0 );
+		ptx::pdl_launch_dependents();
 
 		// ---- weight stream: the first batch of 16-byte loads is issued before anything else, so HBM latency overlaps the
 		//      activation staging below (weights do not depend on the previous kernel's output) ----
@@ -83,6 +84,9 @@ namespace kern
 				vb[ u ] = ldg_stream( wB + st * 4 );
 			}
 		}
+
+		// everything below reads what the previous kernel wrote
+		ptx::pdl_wait();
 
 		// ---- stage activations as f16 (LayerNorm fused when gamma is given) ----
 		for( int c = warp; c < SK_COLS; c += SK_WARPS )
@@ -281,8 +285,7 @@ namespace kern
 			if( e != cudaSuccess ) return e;
 		}
 		dim3 grid( ( a.nOut + SK_ROWS - 1 ) / SK_ROWS, ( a.nCols + SK_COLS - 1 ) / SK_COLS );
-		skinny_gemm_kernel<<<grid, SK_WARPS * 32, smem, s>>>( a );
-		return cudaGetLastError();
+		return launchPdl( skinny_gemm_kernel, grid, dim3( SK_WARPS * 32 ), smem, s, a );
 	}
 
 	// ---------------------------------------------------------------------------------------------------------------
@@ -334,6 +337,8 @@ namespace kern
 		__shared__ float sp[ SA_MAXKV ];
 		__shared__ float sred[ SA_THREADS / 32 ];
 		__shared__ float so[ PV_MAX_THREADS ][ 64 ];
+		ptx::pdl_launch_dependents();
+		ptx::pdl_wait();
 		const int bh = blockIdx.x;
 		const int b = bh / H, h = bh - b * H;
 		const int i = blockIdx.y;
@@ -421,8 +426,7 @@ namespace kern
 	{
 		if( nTextCtx > SA_MAXKV || refThreads < 0 || refThreads > PV_MAX_THREADS ) return cudaErrorInvalidValue;
 		dim3 grid( B * H, N );
-		self_attn_decode_kernel<<<grid, SA_THREADS, 0, s>>>( q, kCache, vCache, out, N, H, d, nTextCtx, dNPast, refThreads );
-		return cudaGetLastError();
+		return launchPdl( self_attn_decode_kernel, grid, dim3( SA_THREADS ), 0, s, q, kCache, vCache, out, N, H, d, nTextCtx, dNPast, refThreads );
 	}
 
 	// ---------------------------------------------------------------------------------------------------------------
@@ -459,13 +463,25 @@ namespace kern
 		const uint4* K4 = reinterpret_cast<const uint4*>( kMem + (size_t)bh * T * 64 );
 		const uint4* V4 = reinterpret_cast<const uint4*>( vMem + (size_t)bh * T * 64 );
 
-		// V streams into shared memory (cp.async, no registers) behind the whole K phase
+		ptx::pdl_launch_dependents();
+		// V streams into shared memory (cp.async, no registers) behind the whole K phase.  Neither V nor K depends on the previous
+		// kernel (the cross-KV memories were written by the encoder), so both prefetches are issued before the dependency wait.
 		{
 			uint4* sv = reinterpret_cast<uint4*>( ca_smem );
 			for( int idx = tid; idx < T * 8; idx += CA_THREADS ) cp_async16( sv + idx, V4 + idx );
 			cp_async_commit();
 		}
+		constexpr int JSTEP = ( CA_THREADS / 32 ) * 4;
+		int jb = warp * 4 + rgrp;
+		uint4 u[ CA_UNROLL ];
+#pragma unroll
+		for( int k = 0; k < CA_UNROLL; k++ )
+		{
+			const int j = jb + k * JSTEP;
+			u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+		}
 
+		ptx::pdl_wait();
 		float qf[ 8 ];
 #pragma unroll
 		for( int e = 0; e < 8; e++ )
@@ -473,19 +489,12 @@ namespace kern
 
 		// scores: a warp covers 4 key rows per load instruction (512 contiguous bytes), CA_UNROLL loads in flight per lane
 		float lmax = -INFINITY;
-		for( int jb = warp * 4 + rgrp; jb < T; jb += ( CA_THREADS / 32 ) * 4 * CA_UNROLL )
+		while( jb < T )
 		{
-			uint4 u[ CA_UNROLL ];
 #pragma unroll
 			for( int k = 0; k < CA_UNROLL; k++ )
 			{
-				const int j = jb + k * ( CA_THREADS / 32 ) * 4;
-				u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
-			}
-#pragma unroll
-			for( int k = 0; k < CA_UNROLL; k++ )
-			{
-				const int j = jb + k * ( CA_THREADS / 32 ) * 4;
+				const int j = jb + k * JSTEP;
 				const __half2* h2 = reinterpret_cast<const __half2*>( &u[ k ] );
 				float s = 0.0f;
 #pragma unroll
@@ -501,6 +510,16 @@ namespace kern
 				{
 					if( sub == 0 ) sp[ j ] = s;
 					lmax = fmaxf( lmax, s );
+				}
+			}
+			jb += JSTEP * CA_UNROLL;
+			if( jb < T )
+			{
+#pragma unroll
+				for( int k = 0; k < CA_UNROLL; k++ )
+				{
+					const int j = jb + k * JSTEP;
+					u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
 				}
 			}
 		}
@@ -595,8 +614,7 @@ namespace kern
 		cudaError_t e = crossPrepare( T );
 		if( e != cudaSuccess ) return e;
 		dim3 grid( B * H, N );
-		cross_attn_decode_kernel<<<grid, CA_THREADS, (size_t)T * 128, s>>>( q, kMem, vMem, out, N, H, d, T, refThreads );
-		return cudaGetLastError();
+		return launchPdl( cross_attn_decode_kernel, grid, dim3( CA_THREADS ), (size_t)T * 128, s, q, kMem, vMem, out, N, H, d, T, refThreads );
 	}
 
 	// ---------------------------------------------------------------------------------------------------------------
@@ -662,6 +680,8 @@ namespace kern
 		__shared__ float sf[ SM_THREADS / 32 ];
 		__shared__ double sd[ SM_THREADS / 32 ];
 		__shared__ Top1 st[ SM_THREADS / 32 ];
+		ptx::pdl_launch_dependents();
+		ptx::pdl_wait();
 		const int b = blockIdx.x;
 		const int tid = threadIdx.x;
 		const int nv = a.nVocab;
@@ -770,6 +790,8 @@ namespace kern
 
 	__global__ void advance_kernel( int* dNPast, int N, int* dForceTs, int* dStep )
 	{
+		ptx::pdl_launch_dependents();
+		ptx::pdl_wait();
 		if( dNPast ) *dNPast += N;
 		if( dForceTs ) { dForceTs[ 0 ] = 0; dForceTs[ 1 ] = 0; }
 		if( dStep ) *dStep += 1;
@@ -777,9 +799,9 @@ namespace kern
 
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s )
 	{
-		sample_kernel<<<a.B, SM_THREADS, 0, s>>>( a );
+		cudaError_t e = launchPdl( sample_kernel, dim3( a.B ), dim3( SM_THREADS ), 0, s, a );
+		if( e != cudaSuccess ) return e;
 		// step-global state is advanced by a separate 1-thread kernel so that no CTA of the sampler races with it
-		advance_kernel<<<1, 1, 0, s>>>( a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );
-		return cudaGetLastError();
+		return launchPdl( advance_kernel, dim3( 1 ), dim3( 1 ), 0, s, a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );
 	}
 }

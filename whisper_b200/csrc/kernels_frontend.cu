@@ -1,9 +1,17 @@
 // Front-end + normalisation kernels (HBM/latency-bound, no tensor cores): log-mel spectrogram, window gather, LayerNorm, embedding.
 #include "kernels.cuh"
+#include "ptx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace kern
 {
+	bool pdlEnabled()
+	{
+		static const bool on = []() { const char* e = getenv( "WSP_PDL" ); return !( e && e[ 0 ] == '0' ); }();
+		return on;
+	}
+
 	// float <-> order-preserving int, for atomicMax on floats of any sign
 	__device__ __forceinline__ int orderedFromFloat( float f )
 	{
@@ -211,6 +219,8 @@ namespace kern
 	__global__ void embed_kernel( const __half* __restrict__ te, const float* __restrict__ pe, const int* __restrict__ tokens, const int* __restrict__ dNPast,
 		float* __restrict__ x, int N, int d )
 	{
+		ptx::pdl_launch_dependents();
+		ptx::pdl_wait();
 		const int col = blockIdx.x;   // b*N + i
 		const int i = col % N;
 		const int tok = tokens[ col ];
@@ -223,8 +233,7 @@ namespace kern
 	}
 	cudaError_t embedTokens( const __half* te, const float* pe, const int* tokens, const int* dNPast, float* x, int B, int N, int d, cudaStream_t s )
 	{
-		embed_kernel<<<B * N, 128, 0, s>>>( te, pe, tokens, dNPast, x, N, d );
-		return cudaGetLastError();
+		return launchPdl( embed_kernel, dim3( B * N ), dim3( 128 ), 0, s, te, pe, tokens, dNPast, x, N, d );
 	}
 
 	__global__ void set_ints_kernel( int* dst, int a, int b ) { dst[ 0 ] = a; dst[ 1 ] = b; }

@@ -141,6 +141,11 @@ namespace ptx
 		return ( 1u << 4 ) | ( (uint32_t)( N >> 3 ) << 17 ) | ( (uint32_t)( M >> 4 ) << 24 );
 	}
 
+	// Programmatic dependent launch: let the next kernel of the stream start its prologue (weight / KV prefetch) while this one runs,
+	// and block until every kernel this one depends on has completed and flushed its writes.
+	__device__ __forceinline__ void pdl_launch_dependents() { asm volatile( "griddepcontrol.launch_dependents;" ::: "memory" ); }
+	__device__ __forceinline__ void pdl_wait() { asm volatile( "griddepcontrol.wait;" ::: "memory" ); }
+
 	__device__ __forceinline__ float gelu_f16_semantics( float x )
 	{
 		// Oracle: y = f32( T[f16(x)] ), T[i] = f16( gelu_f32( f32(i) ) )  (ggml.c:999-1021, table init :1372-1383).

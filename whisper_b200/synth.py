@@ -123,7 +123,7 @@ def _mel_filters(n_mel=80, n_fft=201, seed=7):
     return f
 
 
-def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0) -> HParams:
+def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0, ts_boost: float = 1.0, eot_boost: float = 1.0) -> HParams:
     """Write a synthetic ggml model file.  Matrices ~ N(0, 1/fan_in) stored f16; LN gamma = 1 + N(0, 0.01);
     biases N(0, 0.01); positional embeddings N(0, 0.01); the token embedding is scaled by
     `emb_scale` so that greedy decisions are not near-ties on random weights (SURVEY.md §7 "Parity definition")."""
@@ -150,6 +150,13 @@ def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0)
                 data = rng.standard_normal(n, dtype=np.float32) * np.float32(1.0 / np.sqrt(fan_in))
             elif kind == "emb":
                 data = rng.standard_normal(n, dtype=np.float32) * np.float32(emb_scale / np.sqrt(ne[0]))
+                if ts_boost != 1.0 or eot_boost != 1.0:
+                    # "-ts" variants: larger timestamp / end-of-text rows, so that greedy decoding on random weights emits timestamps
+                    # and EOT and the transcription driver's windowing / segment logic gets exercised
+                    rows = data.reshape(ne[1], ne[0])
+                    sh = 1 if hp.n_vocab == 51865 else 0
+                    rows[50363 + sh:] *= np.float32(ts_boost)
+                    rows[50256 + sh] *= np.float32(eot_boost)
             elif kind == "gamma":
                 data = 1.0 + rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
             elif kind == "pos":
@@ -171,7 +178,10 @@ def model_path(name: str, seed: int = 1234, cache_dir: str | None = None) -> str
     os.makedirs(cache_dir, exist_ok=True)
     p = os.path.join(cache_dir, "ggml-%s-synth%d.bin" % (name, seed))
     if not os.path.exists(p):
-        write_model(p, name, seed)
+        if name.endswith("-ts"):
+            write_model(p, name[:-3], seed, ts_boost=1.3, eot_boost=2.2)
+        else:
+            write_model(p, name, seed)
     return p
 
 
