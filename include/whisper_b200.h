@@ -151,6 +151,8 @@ wsp_status wsp_debug_set_encoder_layers( wsp_context* c, int32_t n );
 wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n );
 /* debug: 0 = launch the N = 1 decoder step kernel by kernel instead of replaying the captured CUDA graph */
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on );
+/* debug: 0 = run the single-token decoder step as one kernel per op instead of the persistent decoder-step kernel */
+wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on );
 /* pinned host memory for callers that want asynchronous H2D copies of PCM (bench.py's e2e leg) */
 void* wsp_host_alloc( size_t bytes );
 void wsp_host_free( void* p );

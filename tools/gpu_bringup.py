@@ -225,6 +225,10 @@ def stage_decoder(model_name="micro.en"):
     c.set_graph(False)
     toks2, st2 = c.run_chunks([pcm], prompt, 16)
     print("  run_chunks (no graph):", "same" if (toks2 == toks).all() else toks2[0].tolist(), st2.tolist(), flush=True)
+    c.set_mega(False)
+    toks3, st3 = c.run_chunks([pcm], prompt, 16)
+    print("  run_chunks (no mega, no graph):", "same" if (toks3 == toks).all() else toks3[0].tolist(), st3.tolist(), flush=True)
+    c.set_mega(True); c.set_graph(True)
     ref_s, ref_toks, ref_st = o.bench_chunk(pcm, prompt, 16, threads=th)
     print("  oracle tokens    :", ref_toks.tolist(), flush=True)
 

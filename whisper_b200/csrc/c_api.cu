@@ -339,6 +339,13 @@ wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n )
 	c->c->refThreads = n;
 	return WSP_OK;
 }
+wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	if( ( on != 0 ) != c->c->useMega && c->c->stepGraph ) { cudaGraphExecDestroy( c->c->stepGraph ); c->c->stepGraph = nullptr; }
+	c->c->useMega = on != 0;
+	return WSP_OK;
+}
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on )
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );

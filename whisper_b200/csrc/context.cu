@@ -4,6 +4,7 @@
 #include "engine.h"
 #include <math.h>
 #include <memory>
+#include <stdlib.h>
 
 namespace wsp
 {
@@ -33,7 +34,7 @@ namespace wsp
 		for( auto& s : slots ) { if( s.mel ) cudaFree( s.mel ); if( s.pcm ) cudaFree( s.pcm ); }
 		for( auto& v : prof.pool ) cudaEventDestroy( v );
 		for( auto& v : timerEv ) if( v ) cudaEventDestroy( v );
-		void* bufs[] = { melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
+		void* bufs[] = { megaLayers, megaBarrier, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
 			tokensDev, dNPast, sampled, history };
 		for( void* b : bufs ) if( b ) cudaFree( b );
 		for( auto& v : ev ) if( v ) cudaEventDestroy( v );
@@ -113,7 +114,29 @@ namespace wsp
 		ok &= gemm::makeMap2D( &c.mapK, c.k, 64, B * H * T, 128, 128 );
 		ok &= gemm::makeMap2D( &c.mapVt, c.vt, c.Tp, B * H * 64, (uint64_t)c.Tp * 2, 64 );
 		if( !ok ) return fail( WSP_E_CUDA, "cuTensorMapEncodeTiled failed (driver too old for TMA?)" );
+		// per-layer pointer table for the persistent decoder-step kernel
+		{
+			std::vector<kern::MegaLayer> ml( (size_t)L );
+			for( int i = 0; i < L; i++ )
+			{
+				const DecLayerW& W = e->dec[ i ];
+				kern::MegaLayer& m = ml[ i ];
+				m.ln1g = W.ln1.g; m.ln1b = W.ln1.b; m.lncg = W.lnc.g; m.lncb = W.lnc.b; m.ln3g = W.ln3.g; m.ln3b = W.ln3.b;
+				m.wqkv = W.wqkv; m.wo = W.wo; m.wcq = W.wcq; m.wco = W.wco; m.w1 = W.w1; m.w2 = W.w2;
+				m.bqkv = W.bqkv; m.bo = W.bo; m.bcq = W.bcq; m.bco = W.bco; m.b1 = W.b1; m.b2 = W.b2;
+				m.kCache = c.selfK + (size_t)i * B * hp.n_text_ctx * d;
+				m.vCache = c.selfV + (size_t)i * B * hp.n_text_ctx * d;
+				m.crossK = c.crossK + (size_t)i * B * T * d;
+				m.crossV = c.crossV + (size_t)i * B * T * d;
+			}
+			WSP_CHECK( devAlloc( c.megaLayers, (size_t)L ) );
+			WSP_CUDA( cudaMemcpy( c.megaLayers, ml.data(), ml.size() * sizeof( kern::MegaLayer ), cudaMemcpyHostToDevice ) );
+			WSP_CHECK( devAlloc( c.megaBarrier, 4, true ) );
+			const char* env = getenv( "WSP_MEGA" );
+			c.useMega = !( env && env[ 0 ] == '0' );
+		}
 		WSP_CUDA( kern::prepare( 4 * d ) );
+		WSP_CUDA( kern::megaPrepare( d ) );
 		WSP_CUDA( cudaDeviceSynchronize() );
 		*out = cp.release();
 		return WSP_OK;
@@ -160,11 +183,12 @@ namespace wsp
 
 	int ctxPcmToMel( Context& c, int slot, const float* pcmHost, int nSamples )
 	{
-		if( !pcmHost || nSamples < 0 ) return fail( WSP_E_INVALIDARG, "pcm" );
+		if( ( !pcmHost && nSamples != 0 ) || nSamples < 0 ) return fail( WSP_E_INVALIDARG, "pcm" );
 		WSP_CUDA( cudaSetDevice( c.e->device ) );
 		WSP_CHECK( ensurePcm( c, (size_t)( nSamples > 0 ? nSamples : 1 ) ) );
 		WSP_CUDA( cudaEventRecord( c.ev[ 0 ], c.stream ) );
-		WSP_CUDA( cudaMemcpyAsync( c.pcmDev, pcmHost, (size_t)nSamples * 4, cudaMemcpyHostToDevice, c.stream ) );
+		if( nSamples > 0 )
+			WSP_CUDA( cudaMemcpyAsync( c.pcmDev, pcmHost, (size_t)nSamples * 4, cudaMemcpyHostToDevice, c.stream ) );
 		WSP_CHECK( melFromDevicePcm( c, slot, c.pcmDev, nSamples ) );
 		WSP_CUDA( cudaEventRecord( c.ev[ 1 ], c.stream ) );
 		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
@@ -325,6 +349,28 @@ namespace wsp
 		const int cols = batch * N;
 		const float qkScale = (float)pow( 64.0, -0.25 );   // whisper.cpp:1588, 1595, 1700
 		int n = 0;
+		if( N == 1 && !allLogits && c.useMega && kern::megaSupported( d, batch, T ) )
+		{
+			// steady state: one persistent kernel for embedding + all layers + logits (decode_mega.cu), then the sampler
+			kern::MegaArgs ma;
+			ma.layers = c.megaLayers; ma.L = hp.n_text_layer; ma.B = batch; ma.H = H; ma.nTextCtx = nCtx; ma.T = T; ma.nVocab = hp.n_vocab;
+			ma.refThreads = c.refThreads;
+			ma.tokEmb = e.tokEmb; ma.decPos = e.decPos; ma.lnfg = e.decLn.g; ma.lnfb = e.decLn.b;
+			ma.tokens = c.tokensDev; ma.dNPast = c.dNPast;
+			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier;
+			WSP_KERNEL( KK_SKINNY, kern::decodeStepMega( ma, d, e.numSMs, s ) ); n++;
+			if( sample )
+			{
+				kern::SampleArgs sa;
+				sa.logits = c.logits; sa.probs = c.probs; sa.B = batch; sa.nVocab = hp.n_vocab;
+				sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
+				sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
+				sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;
+				WSP_KERNEL( KK_OTHER, kern::sampleGreedy( sa, s ) ); n += 2;
+			}
+			if( launchesOut ) *launchesOut = n;
+			return WSP_OK;
+		}
 		WSP_KERNEL( KK_OTHER, kern::embedTokens( e.tokEmb, e.decPos, c.tokensDev, c.dNPast, c.xd, batch, N, d, s ) ); n++;
 		for( int il = 0; il < hp.n_text_layer; il++ )
 		{
@@ -462,7 +508,7 @@ namespace wsp
 	int ctxUploadPcm( Context& c, int slot, const float* pcmHost, int nSamples )
 	{
 		if( slot < 0 || slot >= c.maxB ) return fail( WSP_E_BOUNDS, "chunk slot out of range" );
-		if( !pcmHost || nSamples < 0 ) return fail( WSP_E_INVALIDARG, "pcm" );
+		if( ( !pcmHost && nSamples != 0 ) || nSamples < 0 ) return fail( WSP_E_INVALIDARG, "pcm" );
 		WSP_CUDA( cudaSetDevice( c.e->device ) );
 		MelSlot& s = c.slots[ slot ];
 		if( nSamples > s.pcmCap )

@@ -1,0 +1,767 @@
+// Persistent decoder-step kernel: one launch runs a whole single-token decoder step (embedding, every layer, final LayerNorm and
+// logits) for up to 16 chunks, with grid-wide barriers between the data-dependent phases instead of ~190 kernel launches.
+//
+// Why: at batch 8 the step is a chain of ~190 tiny weight-streaming ops (SURVEY.md §7 "Decode latency").  Launched as separate
+// kernels each one costs 5-12 us of launch / drain / first-byte latency while it moves only 2-8 MB, i.e. < 10 % of HBM rate.
+// Here one CTA per SM stays resident; every phase is split into small units (8 weight rows, or one (chunk, head)) distributed
+// round-robin over the 148 CTAs; each CTA issues the HBM loads of its NEXT phase (weights / cross-KV, which do not depend on the
+// previous phase) BEFORE it waits at the grid barrier, so memory latency overlaps the barrier and the predecessor's tail.
+//
+// Arithmetic is identical to the kernel-per-op path (kernels_decode.cu): f16 x f16 -> f32 through mma.sync.m16n8k16 with the
+// k-permuted fragments, LayerNorm / bias / scale / residual / GELU fused, reference-exact f16 V^T*P chains (pvChainF16).
+#include "decode_mega.cuh"
+#include "ptx.cuh"
+#include <math.h>
+
+namespace kern
+{
+	namespace
+	{
+		constexpr int MG_THREADS = 256;
+		constexpr int MG_WARPS = 8;
+		constexpr int MG_PAD = 32;         // halves of padding per activation row (conflict-free LDS.128)
+		constexpr int MG_ROWS = 8;         // weight rows per unit
+		constexpr int MG_MAXUPB = 4;       // units per register batch
+		constexpr int MG_SMEM_A = 192000;  // activations [16][K+32] f16  |  V tile [1500][64] f16
+		constexpr int MG_SMEM_RED = MG_MAXUPB * MG_WARPS * MG_ROWS * 16 * 4;   // 16 KB: cross-warp partials | attention partial outputs
+		constexpr int MG_SMEM_SP = 1536 * 4;
+		constexpr int MG_SMEM_MISC = 256;
+
+		__device__ __forceinline__ float warpSumM( float v )
+		{
+			for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+			return v;
+		}
+		__device__ __forceinline__ float warpMaxM( float v )
+		{
+			for( int o = 16; o > 0; o >>= 1 ) v = fmaxf( v, __shfl_xor_sync( 0xffffffffu, v, o ) );
+			return v;
+		}
+		__device__ __forceinline__ void mmaM( float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1 )
+		{
+			// rows 8..15 of the A tile are unused (registers a1, a3 = 0): a unit is 8 weight rows
+			const uint32_t z = 0;
+			asm volatile(
+				"mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+				: "+f"( c[ 0 ] ), "+f"( c[ 1 ] ), "+f"( c[ 2 ] ), "+f"( c[ 3 ] )
+				: "r"( a0 ), "r"( z ), "r"( a2 ), "r"( z ), "r"( b0 ), "r"( b1 ) );
+		}
+		__device__ __forceinline__ uint4 ldgStream( const uint4* p )
+		{
+			uint4 r;
+			asm volatile( "ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( r.x ), "=r"( r.y ), "=r"( r.z ), "=r"( r.w ) : "l"( p ) );
+			return r;
+		}
+		// data written by other CTAs earlier in this launch: read at L2 (never through a possibly stale L1 line)
+		__device__ __forceinline__ float4 ldcg4( const float* p ) { return __ldcg( reinterpret_cast<const float4*>( p ) ); }
+		__device__ __forceinline__ uint4 ldcgU4( const void* p ) { return __ldcg( reinterpret_cast<const uint4*>( p ) ); }
+
+		__device__ __forceinline__ void cpAsync16( void* smemDst, const void* gmemSrc )
+		{
+			asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( ptx::smem_u32( smemDst ) ), "l"( gmemSrc ) : "memory" );
+		}
+		__device__ __forceinline__ void cpAsyncCommit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
+		__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile( "cp.async.wait_group 0;" ::: "memory" ); }
+
+		__device__ __forceinline__ float expTab( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
+
+		// see kernels_decode.cu: the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893)
+		__device__ __forceinline__ float pvChain( const float* __restrict__ sp, const __half* __restrict__ v, size_t vStride, int j0, int j1 )
+		{
+			float y = 0.0f;
+			int j = j0;
+			for( ; j + 4 <= j1; j += 4 )
+			{
+				const float x0 = __half2float( v[ (size_t)j * vStride ] );
+				const float x1 = __half2float( v[ (size_t)( j + 1 ) * vStride ] );
+				const float x2 = __half2float( v[ (size_t)( j + 2 ) * vStride ] );
+				const float x3 = __half2float( v[ (size_t)( j + 3 ) * vStride ] );
+				y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
+				y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
+				y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
+				y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
+			}
+			for( ; j < j1; j++ )
+				y = __half2float( __float2half_rn( __fmaf_rn( __half2float( v[ (size_t)j * vStride ] ), sp[ j ], y ) ) );
+			return y;
+		}
+
+		struct Smem
+		{
+			uint8_t* a;      // MG_SMEM_A
+			float* red;      // MG_SMEM_RED
+			float* sp;       // MG_SMEM_SP
+			float* misc;     // 64 floats
+		};
+
+		struct Grid
+		{
+			unsigned* counter;
+			unsigned target;
+			__device__ __forceinline__ void sync()
+			{
+				target += gridDim.x;
+				__syncthreads();
+				if( threadIdx.x == 0 )
+				{
+					__threadfence();
+					atomicAdd( counter, 1u );
+					unsigned spins = 0;
+					while( true )
+					{
+						unsigned v;
+						asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( v ) : "l"( counter ) : "memory" );
+						if( v >= target ) break;
+						if( ++spins > ( 1u << 25 ) ) __trap();   // a protocol bug must not hang the GPU
+					}
+					__threadfence();
+				}
+				__syncthreads();
+			}
+		};
+
+		// -----------------------------------------------------------------------------------------------------------
+		// weight-streaming GEMV phase:  out[col][n] = sum_k W[n][k] * act[col][k],  n in [0, nOut), col in [0, B)
+		enum { EP_QKV = 0, EP_RESID = 1, EP_QSCALE = 2, EP_GELU = 3, EP_LOGITS = 4 };
+		struct GemvOp
+		{
+			const __half* W;
+			int nOut;
+			const float* xF32;      // LayerNorm input rows (stride = xStride)  — or —
+			const __half* xF16;     // ready f16 rows
+			int xStride;
+			const float* gamma;
+			const float* beta;
+			int epi;
+			const float* bias;
+			float scale;
+			float* outF32;
+			__half* outF16;
+			int ld;
+			__half* kCache;
+			__half* vCache;
+			int d, nTextCtx, nPast;
+		};
+
+		template<int K>
+		struct GemvShape
+		{
+			static constexpr int STEPS = K / 32;
+			static constexpr int SPW = ( STEPS + MG_WARPS - 1 ) / MG_WARPS;        // 32-wide k steps per warp per unit
+			static constexpr int SUB = SPW < 16 ? SPW : 16;                         // steps per register batch
+			static constexpr int NSUB = ( SPW + SUB - 1 ) / SUB;
+			static constexpr int UPB = SPW <= 16 ? ( 16 / SPW < MG_MAXUPB ? 16 / SPW : MG_MAXUPB ) : 1;   // units per batch
+		};
+
+		// registers holding one batch of weights
+		template<int K>
+		struct WBatch
+		{
+			uint4 w[ GemvShape<K>::UPB * GemvShape<K>::SUB ];
+		};
+
+		template<int K>
+		__device__ __forceinline__ void loadBatch( WBatch<K>& wb, const GemvOp& op, int firstUnitIdx, int nMine, int sub, int warp, int lane )
+		{
+			using S = GemvShape<K>;
+			const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+			for( int u = 0; u < S::UPB; u++ )
+			{
+				const int ui = firstUnitIdx + u;
+				const int unit = blockIdx.x + ui * gridDim.x;
+				const int row = min( unit * MG_ROWS + g, op.nOut - 1 );
+				const uint4* wr = reinterpret_cast<const uint4*>( op.W + (size_t)row * K + 8 * t );
+#pragma unroll
+				for( int s = 0; s < S::SUB; s++ )
+				{
+					const int st = warp + MG_WARPS * ( sub * S::SUB + s );
+					if( ui < nMine && st < S::STEPS )
+						wb.w[ u * S::SUB + s ] = ldgStream( wr + st * 4 );
+				}
+			}
+		}
+
+		template<int K>
+		__device__ __forceinline__ int myUnits( const GemvOp& op )
+		{
+			const int units = ( op.nOut + MG_ROWS - 1 ) / MG_ROWS;
+			return units > (int)blockIdx.x ? ( units - (int)blockIdx.x + (int)gridDim.x - 1 ) / (int)gridDim.x : 0;
+		}
+
+		// stage the B activation rows as f16 into smem: LayerNorm fused (K == D <= 1280, multiple of 128: one warp per column, the
+		// row is held in registers)
+		template<int K>
+		__device__ __forceinline__ void stageLN( const GemvOp& op, int B, __half* sx, int warp, int lane )
+		{
+			constexpr int RS = K + MG_PAD;
+			constexpr int N4 = K / 128;
+			const int ncolTiles = B > 8 ? 16 : 8;
+			for( int c = warp; c < ncolTiles; c += MG_WARPS )
+			{
+				__half* dst = sx + (size_t)c * RS;
+				if( c >= B )
+				{
+					uint4* z4 = reinterpret_cast<uint4*>( dst );
+					for( int k = lane; k < K / 8; k += 32 ) z4[ k ] = make_uint4( 0, 0, 0, 0 );
+					continue;
+				}
+				const float* src = op.xF32 + (size_t)c * op.xStride;
+				float4 v[ N4 ];
+				float s = 0.0f;
+#pragma unroll
+				for( int i = 0; i < N4; i++ )
+				{
+					v[ i ] = ldcg4( src + ( i * 32 + lane ) * 4 );
+					s += v[ i ].x + v[ i ].y + v[ i ].z + v[ i ].w;
+				}
+				const float mean = warpSumM( s ) / (float)K;
+				float sq = 0.0f;
+#pragma unroll
+				for( int i = 0; i < N4; i++ )
+				{
+					v[ i ].x -= mean; v[ i ].y -= mean; v[ i ].z -= mean; v[ i ].w -= mean;
+					sq += v[ i ].x * v[ i ].x + v[ i ].y * v[ i ].y + v[ i ].z * v[ i ].z + v[ i ].w * v[ i ].w;
+				}
+				const float rstd = 1.0f / sqrtf( warpSumM( sq ) / (float)K + 1e-5f );
+				const float4* g4 = reinterpret_cast<const float4*>( op.gamma );
+				const float4* b4 = reinterpret_cast<const float4*>( op.beta );
+				uint2* d2 = reinterpret_cast<uint2*>( dst );
+#pragma unroll
+				for( int i = 0; i < N4; i++ )
+				{
+					const float4 gg = g4[ i * 32 + lane ];
+					const float4 bb = b4[ i * 32 + lane ];
+					__half2 h0 = __floats2half2_rn( v[ i ].x * rstd * gg.x + bb.x, v[ i ].y * rstd * gg.y + bb.y );
+					__half2 h1 = __floats2half2_rn( v[ i ].z * rstd * gg.z + bb.z, v[ i ].w * rstd * gg.w + bb.w );
+					uint2 u;
+					u.x = *reinterpret_cast<uint32_t*>( &h0 );
+					u.y = *reinterpret_cast<uint32_t*>( &h1 );
+					d2[ i * 32 + lane ] = u;
+				}
+			}
+		}
+		// ... or ready f16 rows (attention output, GELU output)
+		template<int K>
+		__device__ __forceinline__ void stageF16( const GemvOp& op, int B, __half* sx, int tid )
+		{
+			constexpr int RS = K + MG_PAD;
+			constexpr int V8 = K / 8;   // uint4 per row
+			const int ncolTiles = B > 8 ? 16 : 8;
+			for( int i = tid; i < ncolTiles * V8; i += MG_THREADS )
+			{
+				const int c = i / V8, k = i - c * V8;
+				uint4 val = make_uint4( 0, 0, 0, 0 );
+				if( c < B ) val = ldcgU4( op.xF16 + (size_t)c * op.xStride + k * 8 );
+				*reinterpret_cast<uint4*>( sx + (size_t)c * RS + k * 8 ) = val;
+			}
+		}
+
+		__device__ __forceinline__ void gemvEpilogue( const GemvOp& op, int col, int n, float v )
+		{
+			switch( op.epi )
+			{
+			case EP_QKV:
+			{
+				const int which = n / op.d;
+				const int nn = n - which * op.d;
+				if( which == 0 ) op.outF32[ (size_t)col * op.ld + nn ] = ( v + op.bias[ n ] ) * op.scale;
+				else
+				{
+					const size_t off = ( (size_t)col * op.nTextCtx + op.nPast ) * op.d + nn;
+					if( which == 1 ) op.kCache[ off ] = __float2half_rn( v * op.scale );
+					else op.vCache[ off ] = __float2half_rn( v + op.bias[ n ] );
+				}
+				break;
+			}
+			case EP_RESID:
+			{
+				float* p = op.outF32 + (size_t)col * op.ld + n;
+				*p = v + op.bias[ n ] + __ldcg( p );
+				break;
+			}
+			case EP_QSCALE:
+				op.outF32[ (size_t)col * op.ld + n ] = ( v + op.bias[ n ] ) * op.scale;
+				break;
+			case EP_GELU:
+				op.outF16[ (size_t)col * op.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( v + op.bias[ n ] ) );
+				break;
+			default:
+				op.outF32[ (size_t)col * op.ld + n ] = v;
+				break;
+			}
+		}
+
+		// compute all units of this CTA; `wb` already holds the first batch (loaded before the barrier)
+		template<int K>
+		__device__ __forceinline__ void gemvCompute( const GemvOp& op, int B, WBatch<K>& wb, const Smem& sm, int warp, int lane, int tid )
+		{
+			using S = GemvShape<K>;
+			constexpr int RS = K + MG_PAD;
+			const __half* sx = reinterpret_cast<const __half*>( sm.a );
+			const int g = lane >> 2, t = lane & 3;
+			const __half* xb0 = sx + (size_t)g * RS + 8 * t;
+			const __half* xb1 = sx + (size_t)( g + 8 ) * RS + 8 * t;
+			const bool twoTiles = B > 8;
+			const int nMine = myUnits<K>( op );
+			const int ncols = twoTiles ? 16 : 8;
+			for( int u0 = 0; u0 < nMine; u0 += S::UPB )
+			{
+				float acc0[ S::UPB ][ 4 ], acc1[ S::UPB ][ 4 ];
+#pragma unroll
+				for( int u = 0; u < S::UPB; u++ )
+#pragma unroll
+					for( int i = 0; i < 4; i++ ) { acc0[ u ][ i ] = 0.0f; acc1[ u ][ i ] = 0.0f; }
+#pragma unroll
+				for( int sub = 0; sub < S::NSUB; sub++ )
+				{
+					if( u0 != 0 || sub != 0 ) loadBatch<K>( wb, op, u0, nMine, sub, warp, lane );
+#pragma unroll
+					for( int u = 0; u < S::UPB; u++ )
+#pragma unroll
+						for( int s = 0; s < S::SUB; s++ )
+						{
+							const int st = warp + MG_WARPS * ( sub * S::SUB + s );
+							if( u0 + u < nMine && st < S::STEPS )
+							{
+								const uint4 w = wb.w[ u * S::SUB + s ];
+								const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 32 );
+								mmaM( acc0[ u ], w.x, w.y, x0.x, x0.y );
+								mmaM( acc0[ u ], w.z, w.w, x0.z, x0.w );
+								if( twoTiles )
+								{
+									const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 32 );
+									mmaM( acc1[ u ], w.x, w.y, x1.x, x1.y );
+									mmaM( acc1[ u ], w.z, w.w, x1.z, x1.w );
+								}
+							}
+						}
+				}
+				// cross-warp reduction: red[u][warp][row g][col]
+#pragma unroll
+				for( int u = 0; u < S::UPB; u++ )
+				{
+					float* my = sm.red + ( ( u * MG_WARPS + warp ) * MG_ROWS + g ) * 16;
+					my[ 2 * t ] = acc0[ u ][ 0 ];
+					my[ 2 * t + 1 ] = acc0[ u ][ 1 ];
+					if( twoTiles ) { my[ 8 + 2 * t ] = acc1[ u ][ 0 ]; my[ 8 + 2 * t + 1 ] = acc1[ u ][ 1 ]; }
+				}
+				__syncthreads();
+				for( int idx = tid; idx < S::UPB * ncols * MG_ROWS; idx += MG_THREADS )
+				{
+					const int u = idx / ( ncols * MG_ROWS );
+					const int rem = idx - u * ncols * MG_ROWS;
+					const int c = rem / MG_ROWS, r = rem - c * MG_ROWS;
+					const int unit = blockIdx.x + ( u0 + u ) * gridDim.x;
+					const int n = unit * MG_ROWS + r;
+					if( u0 + u < nMine && c < B && n < op.nOut )
+					{
+						float v = 0.0f;
+#pragma unroll
+						for( int w = 0; w < MG_WARPS; w++ ) v += sm.red[ ( ( u * MG_WARPS + w ) * MG_ROWS + r ) * 16 + c ];
+						gemvEpilogue( op, c, n, v );
+					}
+				}
+				__syncthreads();
+			}
+		}
+
+		// -----------------------------------------------------------------------------------------------------------
+		// self attention over the self-KV cache (N = 1): units = (chunk, head)
+		__device__ void selfAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, int nPast, const Smem& sm, int warp, int lane, int tid )
+		{
+			const int H = a.H;
+			const int nkv = min( nPast + 1, a.nTextCtx );
+			float* sq = sm.misc;
+			float* sred = sm.misc + 64;
+			float* so = sm.red;
+			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
+			{
+				const int b = unit / H, h = unit - b * H;
+				if( tid < 64 ) sq[ tid ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + tid ) ) );
+				__syncthreads();
+				const __half* kb = L.kCache + (size_t)b * a.nTextCtx * d + h * 64;
+				const __half* vb = L.vCache + (size_t)b * a.nTextCtx * d + h * 64;
+				float lmax = -INFINITY;
+				for( int j = tid; j < nkv; j += MG_THREADS )
+				{
+					const uint4* kr = reinterpret_cast<const uint4*>( kb + (size_t)j * d );
+					float s = 0.0f;
+#pragma unroll
+					for( int c = 0; c < 8; c++ )
+					{
+						const uint4 u = __ldcg( kr + c );
+						const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+#pragma unroll
+						for( int e = 0; e < 4; e++ )
+						{
+							const float2 f = __half22float2( h2[ e ] );
+							s += f.x * sq[ c * 8 + e * 2 ] + f.y * sq[ c * 8 + e * 2 + 1 ];
+						}
+					}
+					sm.sp[ j ] = s;
+					lmax = fmaxf( lmax, s );
+				}
+				lmax = warpMaxM( lmax );
+				if( lane == 0 ) sred[ warp ] = lmax;
+				__syncthreads();
+				float mx = sred[ 0 ];
+				for( int w = 1; w < MG_WARPS; w++ ) mx = fmaxf( mx, sred[ w ] );
+				__syncthreads();
+				float lsum = 0.0f;
+				for( int j = tid; j < nkv; j += MG_THREADS )
+				{
+					const float e = expTab( sm.sp[ j ] - mx );
+					sm.sp[ j ] = e;
+					lsum += e;
+				}
+				lsum = warpSumM( lsum );
+				if( lane == 0 ) sred[ warp ] = lsum;
+				__syncthreads();
+				float tot = 0.0f;
+				for( int w = 0; w < MG_WARPS; w++ ) tot += sred[ w ];
+				const float inv = 1.0f / tot;
+				for( int j = tid; j < nkv; j += MG_THREADS ) sm.sp[ j ] *= inv;
+				__syncthreads();
+				const int parts = a.refThreads > 0 ? a.refThreads : 4;
+				const int dc = ( nkv + parts - 1 ) / parts;
+				for( int idx = tid; idx < parts * 64; idx += MG_THREADS )
+				{
+					const int part = idx >> 6, e = idx & 63;
+					const int j0 = min( part * dc, nkv ), j1 = min( ( part + 1 ) * dc, nkv );
+					float y;
+					if( a.refThreads > 0 ) y = pvChain( sm.sp, vb + e, (size_t)d, j0, j1 );
+					else
+					{
+						y = 0.0f;
+						for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
+					}
+					so[ idx ] = y;
+				}
+				__syncthreads();
+				if( tid < 64 )
+				{
+					float acc = so[ tid ];
+					for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
+					a.attn[ (size_t)b * d + h * 64 + tid ] = __float2half_rn( acc );
+				}
+				__syncthreads();
+			}
+		}
+
+		// -----------------------------------------------------------------------------------------------------------
+		// cross attention over the encoder's f16 K/V memories: units = (chunk, head).  The V tile and the first batch of K rows are
+		// requested BEFORE the grid barrier (they do not depend on this step), q is read after it.
+		constexpr int CA_U = 12;
+		struct CrossPrefetch
+		{
+			uint4 u[ CA_U ];
+			int unit;
+		};
+		__device__ __forceinline__ void crossPrefetch( const MegaArgs& a, const MegaLayer& L, CrossPrefetch& pf, const Smem& sm, int unit, int warp, int lane, int tid )
+		{
+			pf.unit = unit;
+			if( unit >= a.B * a.H ) return;
+			const int T = a.T;
+			const int b = unit / a.H, h = unit - b * a.H;
+			const size_t base = ( (size_t)b * a.H + h ) * T * 64;
+			const uint4* V4 = reinterpret_cast<const uint4*>( L.crossV + base );
+			const uint4* K4 = reinterpret_cast<const uint4*>( L.crossK + base );
+			uint4* sv = reinterpret_cast<uint4*>( sm.a );
+			for( int idx = tid; idx < T * 8; idx += MG_THREADS ) cpAsync16( sv + idx, V4 + idx );
+			cpAsyncCommit();
+			const int sub = lane & 7, rgrp = lane >> 3;
+			const int jb = warp * 4 + rgrp;
+#pragma unroll
+			for( int k = 0; k < CA_U; k++ )
+			{
+				const int j = jb + k * MG_WARPS * 4;
+				pf.u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+			}
+		}
+		__device__ void crossAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, CrossPrefetch& pf, const Smem& sm, int warp, int lane, int tid )
+		{
+			const int T = a.T, H = a.H;
+			float* sred = sm.misc + 64;
+			float* so = sm.red;
+			const int sub = lane & 7, rgrp = lane >> 3;
+			constexpr int JSTEP = MG_WARPS * 4;
+			bool first = true;
+			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
+			{
+				if( !first ) { crossPrefetch( a, L, pf, sm, unit, warp, lane, tid ); }
+				first = false;
+				const int b = unit / H, h = unit - b * H;
+				const size_t base = ( (size_t)b * H + h ) * T * 64;
+				const uint4* K4 = reinterpret_cast<const uint4*>( L.crossK + base );
+				float qf[ 8 ];
+#pragma unroll
+				for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + sub * 8 + e ) ) );
+				float lmax = -INFINITY;
+				int jb = warp * 4 + rgrp;
+				while( jb < T )
+				{
+#pragma unroll
+					for( int k = 0; k < CA_U; k++ )
+					{
+						const int j = jb + k * JSTEP;
+						const __half2* h2 = reinterpret_cast<const __half2*>( &pf.u[ k ] );
+						float s = 0.0f;
+#pragma unroll
+						for( int e = 0; e < 4; e++ )
+						{
+							const float2 f = __half22float2( h2[ e ] );
+							s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
+						}
+						s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+						s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+						s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+						if( j < T )
+						{
+							if( sub == 0 ) sm.sp[ j ] = s;
+							lmax = fmaxf( lmax, s );
+						}
+					}
+					jb += JSTEP * CA_U;
+					if( jb < T )
+					{
+#pragma unroll
+						for( int k = 0; k < CA_U; k++ )
+						{
+							const int j = jb + k * JSTEP;
+							pf.u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+						}
+					}
+				}
+				lmax = warpMaxM( lmax );
+				if( lane == 0 ) sred[ warp ] = lmax;
+				__syncthreads();
+				float mx = sred[ 0 ];
+				for( int w = 1; w < MG_WARPS; w++ ) mx = fmaxf( mx, sred[ w ] );
+				__syncthreads();
+				float lsum = 0.0f;
+				for( int j = tid; j < T; j += MG_THREADS )
+				{
+					const float e = expTab( sm.sp[ j ] - mx );
+					sm.sp[ j ] = e;
+					lsum += e;
+				}
+				lsum = warpSumM( lsum );
+				if( lane == 0 ) sred[ warp ] = lsum;
+				__syncthreads();
+				float tot = 0.0f;
+				for( int w = 0; w < MG_WARPS; w++ ) tot += sred[ w ];
+				const float inv = 1.0f / tot;
+				for( int j = tid; j < T; j += MG_THREADS ) sm.sp[ j ] *= inv;
+				cpAsyncWaitAll();
+				__syncthreads();
+				const __half* sv = reinterpret_cast<const __half*>( sm.a );
+				const int parts = a.refThreads > 0 ? a.refThreads : 4;
+				const int dc = ( T + parts - 1 ) / parts;
+				for( int idx = tid; idx < parts * 64; idx += MG_THREADS )
+				{
+					const int part = idx >> 6, e = idx & 63;
+					const int j0 = min( part * dc, T ), j1 = min( ( part + 1 ) * dc, T );
+					float y;
+					if( a.refThreads > 0 ) y = pvChain( sm.sp, sv + e, 64, j0, j1 );
+					else
+					{
+						y = 0.0f;
+						for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( sv[ (size_t)j * 64 + e ] );
+					}
+					so[ idx ] = y;
+				}
+				__syncthreads();
+				if( tid < 64 )
+				{
+					float acc = so[ tid ];
+					for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
+					a.attn[ (size_t)b * d + h * 64 + tid ] = __float2half_rn( acc );
+				}
+				__syncthreads();
+			}
+		}
+
+		// -----------------------------------------------------------------------------------------------------------
+		template<int D>
+		__global__ void __launch_bounds__( MG_THREADS, 1 )
+			decode_step_kernel( MegaArgs a )
+		{
+			extern __shared__ __align__( 16 ) uint8_t mg_smem[];
+			Smem sm;
+			sm.a = mg_smem;
+			sm.red = reinterpret_cast<float*>( mg_smem + MG_SMEM_A );
+			sm.sp = reinterpret_cast<float*>( mg_smem + MG_SMEM_A + MG_SMEM_RED );
+			sm.misc = reinterpret_cast<float*>( mg_smem + MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP );
+			const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+			const int B = a.B;
+			const int nPast = *a.dNPast;              // read once: the sampler's advance kernel updates it after this launch
+			const float qkScale = 0.35355339059327379f;   // 64^-1/4 (whisper.cpp:1588, 1595, 1700)
+			Grid grid{ a.barrier, 0u };
+			__half* sx = reinterpret_cast<__half*>( sm.a );
+
+			GemvOp op{};
+			op.d = D; op.nTextCtx = a.nTextCtx; op.nPast = nPast;
+
+			// ---- layer 0 QKV weights are requested first; then the embedding (a13) is written by the first B CTAs ----
+			WBatch<D> wbD;
+			WBatch<4 * D> wb4D;
+			{
+				const MegaLayer& L0 = a.layers[ 0 ];
+				op.W = L0.wqkv; op.nOut = 3 * D;
+				loadBatch<D>( wbD, op, 0, myUnits<D>( op ), 0, warp, lane );
+			}
+			for( int b = blockIdx.x; b < B; b += gridDim.x )
+			{
+				const int tok = a.tokens[ b ];
+				const __half* src = a.tokEmb + (size_t)tok * D;
+				const float* pe = a.decPos + (size_t)nPast * D;
+				for( int e = tid; e < D; e += MG_THREADS ) a.x[ (size_t)b * D + e ] = __half2float( src[ e ] ) + pe[ e ];
+			}
+			grid.sync();
+
+			for( int il = 0; il < a.L; il++ )
+			{
+				const MegaLayer& L = a.layers[ il ];
+				// ---- P1: LN1 + (Q | K | V), K/V appended to the cache (a14) ----
+				op.W = L.wqkv; op.nOut = 3 * D; op.xF32 = a.x; op.xF16 = nullptr; op.xStride = D; op.gamma = L.ln1g; op.beta = L.ln1b;
+				op.epi = EP_QKV; op.bias = L.bqkv; op.scale = qkScale; op.outF32 = a.q; op.ld = D; op.kCache = L.kCache; op.vCache = L.vCache;
+				stageLN<D>( op, B, sx, warp, lane );
+				__syncthreads();
+				gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
+				// prefetch out-proj weights, then wait for Q/K/V of every CTA
+				GemvOp opO = op;
+				opO.W = L.wo; opO.nOut = D; opO.xF32 = nullptr; opO.xF16 = a.attn; opO.xStride = D; opO.gamma = nullptr; opO.beta = nullptr;
+				opO.epi = EP_RESID; opO.bias = L.bo; opO.outF32 = a.x; opO.ld = D;
+				loadBatch<D>( wbD, opO, 0, myUnits<D>( opO ), 0, warp, lane );
+				grid.sync();
+				// ---- P2: self attention ----
+				selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid );
+				grid.sync();
+				// ---- P3: out projection + residual ----
+				stageF16<D>( opO, B, sx, tid );
+				__syncthreads();
+				gemvCompute<D>( opO, B, wbD, sm, warp, lane, tid );
+				GemvOp opQ = op;
+				opQ.W = L.wcq; opQ.nOut = D; opQ.xF32 = a.x; opQ.xF16 = nullptr; opQ.xStride = D; opQ.gamma = L.lncg; opQ.beta = L.lncb;
+				opQ.epi = EP_QSCALE; opQ.bias = L.bcq; opQ.scale = qkScale; opQ.outF32 = a.q; opQ.ld = D;
+				loadBatch<D>( wbD, opQ, 0, myUnits<D>( opQ ), 0, warp, lane );
+				grid.sync();
+				// ---- P4: cross-attention query (a15) ----
+				stageLN<D>( opQ, B, sx, warp, lane );
+				__syncthreads();
+				gemvCompute<D>( opQ, B, wbD, sm, warp, lane, tid );
+				__syncthreads();
+				CrossPrefetch pf;
+				crossPrefetch( a, L, pf, sm, blockIdx.x, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
+				grid.sync();
+				// ---- P5: cross attention ----
+				crossAttnPhase( a, L, D, pf, sm, warp, lane, tid );
+				GemvOp opC = op;
+				opC.W = L.wco; opC.nOut = D; opC.xF32 = nullptr; opC.xF16 = a.attn; opC.xStride = D; opC.gamma = nullptr; opC.beta = nullptr;
+				opC.epi = EP_RESID; opC.bias = L.bco; opC.outF32 = a.x; opC.ld = D;
+				loadBatch<D>( wbD, opC, 0, myUnits<D>( opC ), 0, warp, lane );
+				grid.sync();
+				// ---- P6: cross out projection + residual ----
+				stageF16<D>( opC, B, sx, tid );
+				__syncthreads();
+				gemvCompute<D>( opC, B, wbD, sm, warp, lane, tid );
+				GemvOp op1 = op;
+				op1.W = L.w1; op1.nOut = 4 * D; op1.xF32 = a.x; op1.xF16 = nullptr; op1.xStride = D; op1.gamma = L.ln3g; op1.beta = L.ln3b;
+				op1.epi = EP_GELU; op1.bias = L.b1; op1.outF16 = a.h; op1.ld = 4 * D;
+				loadBatch<D>( wbD, op1, 0, myUnits<D>( op1 ), 0, warp, lane );
+				grid.sync();
+				// ---- P7: LN3 + fc1 + GELU (a16) ----
+				stageLN<D>( op1, B, sx, warp, lane );
+				__syncthreads();
+				gemvCompute<D>( op1, B, wbD, sm, warp, lane, tid );
+				GemvOp op2 = op;
+				op2.W = L.w2; op2.nOut = D; op2.xF32 = nullptr; op2.xF16 = a.h; op2.xStride = 4 * D; op2.gamma = nullptr; op2.beta = nullptr;
+				op2.epi = EP_RESID; op2.bias = L.b2; op2.outF32 = a.x; op2.ld = D;
+				loadBatch<4 * D>( wb4D, op2, 0, myUnits<4 * D>( op2 ), 0, warp, lane );
+				grid.sync();
+				// ---- P8: fc2 + residual ----
+				stageF16<4 * D>( op2, B, sx, tid );
+				__syncthreads();
+				gemvCompute<4 * D>( op2, B, wb4D, sm, warp, lane, tid );
+				// next: QKV of the following layer, or the logits
+				if( il + 1 < a.L )
+				{
+					const MegaLayer& Ln = a.layers[ il + 1 ];
+					op.W = Ln.wqkv; op.nOut = 3 * D;
+				}
+				else
+				{
+					op.W = a.tokEmb; op.nOut = a.nVocab;
+				}
+				loadBatch<D>( wbD, op, 0, myUnits<D>( op ), 0, warp, lane );
+				grid.sync();
+			}
+			// ---- final LayerNorm + logits = tok_emb^T x (a17) ----
+			op.W = a.tokEmb; op.nOut = a.nVocab; op.xF32 = a.x; op.xF16 = nullptr; op.xStride = D; op.gamma = a.lnfg; op.beta = a.lnfb;
+			op.epi = EP_LOGITS; op.outF32 = a.logits; op.ld = a.nVocab;
+			stageLN<D>( op, B, sx, warp, lane );
+			__syncthreads();
+			gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
+		}
+
+		constexpr int SMEM = MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP + MG_SMEM_MISC * 4;
+		template<int D>
+		cudaError_t prepareD()
+		{
+			static_assert( 16 * ( 4 * D + MG_PAD ) * 2 <= MG_SMEM_A, "activation rows must fit region A" );
+			static bool attr = false;
+			if( !attr )
+			{
+				cudaError_t e = cudaFuncSetAttribute( decode_step_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
+				if( e != cudaSuccess ) return e;
+				attr = true;
+			}
+			return cudaSuccess;
+		}
+		template<int D>
+		cudaError_t launchD( const MegaArgs& a, int numSMs, cudaStream_t s )
+		{
+			cudaError_t e = prepareD<D>();
+			if( e != cudaSuccess ) return e;
+			e = cudaMemsetAsync( a.barrier, 0, sizeof( unsigned ), s );
+			if( e != cudaSuccess ) return e;
+			decode_step_kernel<D><<<numSMs, MG_THREADS, SMEM, s>>>( a );
+			return cudaGetLastError();
+		}
+	}
+
+	bool megaSupported( int d, int B, int T )
+	{
+		if( B < 1 || B > 16 || T * 128 > MG_SMEM_A ) return false;
+		return d == 128 || d == 384 || d == 512 || d == 768 || d == 1024 || d == 1280;
+	}
+
+	cudaError_t megaPrepare( int d )
+	{
+		switch( d )
+		{
+		case 128: return prepareD<128>();
+		case 384: return prepareD<384>();
+		case 512: return prepareD<512>();
+		case 768: return prepareD<768>();
+		case 1024: return prepareD<1024>();
+		case 1280: return prepareD<1280>();
+		default: return cudaSuccess;
+		}
+	}
+
+	cudaError_t decodeStepMega( const MegaArgs& a, int d, int numSMs, cudaStream_t s )
+	{
+		switch( d )
+		{
+		case 128: return launchD<128>( a, numSMs, s );
+		case 384: return launchD<384>( a, numSMs, s );
+		case 512: return launchD<512>( a, numSMs, s );
+		case 768: return launchD<768>( a, numSMs, s );
+		case 1024: return launchD<1024>( a, numSMs, s );
+		case 1280: return launchD<1280>( a, numSMs, s );
+		default: return cudaErrorInvalidValue;
+		}
+	}
+}

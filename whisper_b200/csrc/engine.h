@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/whisper_b200.h"
 #include "attn_enc.cuh"
+#include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "model.h"
@@ -152,6 +153,11 @@ namespace wsp
 		std::vector<CUtensorMap> mapWqkv, mapWo, mapW1, mapW2;
 		CUtensorMap mapQ, mapK, mapVt;
 		int bnD = 128, bn3D = 128, bn4D = 128, bnCross = 128;
+
+		// persistent decoder-step kernel (decode_mega.cu): per-layer pointer table on the device, grid-barrier counter
+		kern::MegaLayer* megaLayers = nullptr;
+		unsigned* megaBarrier = nullptr;
+		bool useMega = true;
 
 		// decode CUDA graph (N = 1 steady state)
 		cudaGraphExec_t stepGraph = nullptr;
