@@ -153,6 +153,8 @@ wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n );
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on );
 /* debug: 0 = run the single-token decoder step as one kernel per op instead of the persistent decoder-step kernel */
 wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on );
+/* debug: %globaltimer marks (ns) of CTA 0 around every grid barrier of the last persistent decoder step (needs WSP_MEGA_TIMING=1) */
+wsp_status wsp_debug_mega_timing( wsp_context* c, uint64_t* dst, int32_t cap );
 /* pinned host memory for callers that want asynchronous H2D copies of PCM (bench.py's e2e leg) */
 void* wsp_host_alloc( size_t bytes );
 void wsp_host_free( void* p );

@@ -280,11 +280,46 @@ def stage_profile(model_name="medium", batch=8, n_decode=3):
     print("  profile run stages", st.tolist(), flush=True)
 
 
+def stage_megatiming(model_name="medium", batch=8):
+    """per-phase time of the persistent decoder step (CTA 0's view): run with WSP_MEGA_TIMING=1"""
+    import ctypes as C
+    from whisper_b200 import capi, synth
+    os.environ["WSP_MEGA_TIMING"] = "1"
+    path, m, e, c = _open(model_name, batch=batch)
+    pcms = [synth.synth_pcm(i) for i in range(batch)]
+    c.run_chunks(pcms, m.prompt_init(), 40)
+    buf = (C.c_uint64 * 4096)()
+    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4096))
+    raw = np.array(buf[:], dtype=np.int64).reshape(-1, 2)
+    raw = raw[raw[:, 1] > 0]
+    ids, t = raw[:, 0], raw[:, 1]
+    print("  marks", len(ids), "total us", (t[-1] - t[0]) / 1000.0, flush=True)
+    # generic: average interval from each mark id-class to the next mark
+    names = {1001: "P1 staged", 1002: "P1 computed", 1003: "P3 staged", 1004: "P3 computed", 1007: "P7 staged", 1008: "P7 computed"}
+    L = m.n_text_layer
+    acc = {}
+    for k in range(len(ids) - 1):
+        i = int(ids[k])
+        if i >= 1000:
+            key = names[i]
+        else:
+            # barrier marks: phaseId 0 = start, 1 = before embed barrier, 2 = after ...; per layer 16 marks
+            j = i - 2
+            if j < 0 or j >= L * 16:
+                key = "misc %d" % i
+            else:
+                p = (j % 16)
+                key = "P%d %s" % (p // 2 + 1, "after-barrier" if p % 2 == 0 else "before-barrier->after")
+        acc.setdefault(key, []).append((t[k + 1] - t[k]) / 1000.0)
+    for key in sorted(acc):
+        print("  %-34s -> next mark: %.2f us (n=%d)" % (key, np.mean(acc[key]), len(acc[key])), flush=True)
+
+
 STAGES = {
     "gemm": stage_gemm, "ln": stage_ln, "skinny": stage_skinny, "attn": stage_attn, "mel": stage_mel,
     "encoder": stage_encoder, "decoder": stage_decoder, "batch": stage_batch,
     "encoder_tiny": stage_encoder_tiny, "decoder_tiny": stage_decoder_tiny,
-    "gemm_perf": stage_gemm_perf, "perf": stage_perf, "profile": stage_profile,
+    "gemm_perf": stage_gemm_perf, "perf": stage_perf, "profile": stage_profile, "megatiming": stage_megatiming,
 }
 
 if __name__ == "__main__":

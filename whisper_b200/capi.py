@@ -33,7 +33,7 @@ EXPORTS = [
     "wsp_engine_create", "wsp_engine_create_from_image", "wsp_engine_destroy", "wsp_engine_weight_bytes",
     "wsp_context_create", "wsp_context_destroy", "wsp_synchronize",
     "wsp_pcm_to_mel", "wsp_set_mel", "wsp_mel_len", "wsp_get_mel", "wsp_encode", "wsp_decode", "wsp_get_logits", "wsp_get_probs",
-    "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_debug_set_mega", "wsp_set_reference_threads",
+    "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_debug_set_mega", "wsp_debug_mega_timing", "wsp_set_reference_threads",
     "wsp_host_alloc", "wsp_host_free", "wsp_timings",
     "wsp_test_gemm", "wsp_test_attention", "wsp_test_skinny", "wsp_test_layernorm",
 ]
@@ -102,6 +102,7 @@ def lib():
     sig("wsp_debug_set_graph", i32, [vp, i32])
     sig("wsp_set_reference_threads", i32, [vp, i32])
     sig("wsp_debug_set_mega", i32, [vp, i32])
+    sig("wsp_debug_mega_timing", i32, [vp, C.POINTER(C.c_uint64), i32])
     sig("wsp_host_alloc", vp, [sz])
     sig("wsp_host_free", None, [vp])
     sig("wsp_timings", i32, [vp, fp, ip, i32])

@@ -339,6 +339,13 @@ wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n )
 	c->c->refThreads = n;
 	return WSP_OK;
 }
+wsp_status wsp_debug_mega_timing( wsp_context* c, uint64_t* dst, int32_t cap )
+{
+	if( !c || !dst ) return fail( WSP_E_POINTER, "context/dst" );
+	WSP_CUDA( cudaStreamSynchronize( c->c->stream ) );
+	WSP_CUDA( cudaMemcpy( dst, c->c->megaTiming, sizeof( uint64_t ) * (size_t)( cap < 4096 ? cap : 4096 ), cudaMemcpyDeviceToHost ) );
+	return WSP_OK;
+}
 wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on )
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );

@@ -34,7 +34,7 @@ namespace wsp
 		for( auto& s : slots ) { if( s.mel ) cudaFree( s.mel ); if( s.pcm ) cudaFree( s.pcm ); }
 		for( auto& v : prof.pool ) cudaEventDestroy( v );
 		for( auto& v : timerEv ) if( v ) cudaEventDestroy( v );
-		void* bufs[] = { megaLayers, megaBarrier, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
+		void* bufs[] = { megaLayers, megaBarrier, megaTiming, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
 			tokensDev, dNPast, sampled, history };
 		for( void* b : bufs ) if( b ) cudaFree( b );
 		for( auto& v : ev ) if( v ) cudaEventDestroy( v );
@@ -132,6 +132,7 @@ namespace wsp
 			WSP_CHECK( devAlloc( c.megaLayers, (size_t)L ) );
 			WSP_CUDA( cudaMemcpy( c.megaLayers, ml.data(), ml.size() * sizeof( kern::MegaLayer ), cudaMemcpyHostToDevice ) );
 			WSP_CHECK( devAlloc( c.megaBarrier, 4, true ) );
+			WSP_CHECK( devAlloc( c.megaTiming, 4096, true ) );
 			const char* env = getenv( "WSP_MEGA" );
 			c.useMega = !( env && env[ 0 ] == '0' );
 		}
@@ -357,7 +358,7 @@ namespace wsp
 			ma.refThreads = c.refThreads;
 			ma.tokEmb = e.tokEmb; ma.decPos = e.decPos; ma.lnfg = e.decLn.g; ma.lnfb = e.decLn.b;
 			ma.tokens = c.tokensDev; ma.dNPast = c.dNPast;
-			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier;
+			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier; ma.timing = getenv( "WSP_MEGA_TIMING" ) ? c.megaTiming : nullptr;
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepMega( ma, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

@@ -26,6 +26,8 @@ namespace kern
 		constexpr int MG_SMEM_RED = MG_MAXUPB * MG_WARPS * MG_ROWS * 16 * 4;   // 16 KB: cross-warp partials | attention partial outputs
 		constexpr int MG_SMEM_SP = 1536 * 4;
 		constexpr int MG_SMEM_MISC = 256;
+		constexpr int MG_SMEM_PARAM = 2 * 1280 * 4 + 8 * MG_ROWS * 4;   // LayerNorm gamma | beta of the next phase + biases of this CTA's units
+		constexpr int MG_MAXBIASUNITS = 8;
 
 		__device__ __forceinline__ float warpSumM( float v )
 		{
@@ -92,6 +94,9 @@ namespace kern
 			float* red;      // MG_SMEM_RED
 			float* sp;       // MG_SMEM_SP
 			float* misc;     // 64 floats
+			float* gamma;    // [D] staged by cp.async before the barrier
+			float* beta;     // [D]
+			float* bias;     // [MG_MAXBIASUNITS][8]
 		};
 
 		struct Grid
@@ -182,6 +187,36 @@ namespace kern
 			}
 		}
 
+		__device__ __forceinline__ void prefetchL2( const void* p ) { asm volatile( "prefetch.global.L2 [%0];" ::"l"( p ) ); }
+
+		// LayerNorm gamma/beta and the bias entries of this CTA's units of the NEXT phase -> shared memory, requested before the
+		// barrier: per-layer parameters are cold in L2 (every step streams ~2 GB through it), and a DRAM miss on them would sit in the
+		// middle of the post-barrier critical path (measured: 4.5 us per LayerNorm phase without this)
+		__device__ __forceinline__ void prefetchParams( const GemvOp& op, int K, const Smem& sm, int tid )
+		{
+			if( op.gamma )
+			{
+				const int n16 = K / 4;   // 16-byte chunks per vector
+				for( int i = tid; i < 2 * n16; i += MG_THREADS )
+				{
+					if( i < n16 ) cpAsync16( sm.gamma + i * 4, op.gamma + i * 4 );
+					else cpAsync16( sm.beta + ( i - n16 ) * 4, op.beta + ( i - n16 ) * 4 );
+				}
+			}
+			if( op.bias )
+			{
+				const int units = ( op.nOut + MG_ROWS - 1 ) / MG_ROWS;
+				if( tid < MG_MAXBIASUNITS * 2 )
+				{
+					const int ui = tid >> 1, half = tid & 1;
+					const int unit = blockIdx.x + ui * gridDim.x;
+					if( unit < units && unit * MG_ROWS + half * 4 + 4 <= op.nOut )
+						cpAsync16( sm.bias + ui * MG_ROWS + half * 4, op.bias + unit * MG_ROWS + half * 4 );
+				}
+			}
+			cpAsyncCommit();
+		}
+
 		template<int K>
 		__device__ __forceinline__ int myUnits( const GemvOp& op )
 		{
@@ -192,7 +227,7 @@ namespace kern
 		// stage the B activation rows as f16 into smem: LayerNorm fused (K == D <= 1280, multiple of 128: one warp per column, the
 		// row is held in registers)
 		template<int K>
-		__device__ __forceinline__ void stageLN( const GemvOp& op, int B, __half* sx, int warp, int lane )
+		__device__ __forceinline__ void stageLN( const GemvOp& op, int B, __half* sx, const Smem& sm, int warp, int lane )
 		{
 			constexpr int RS = K + MG_PAD;
 			constexpr int N4 = K / 128;
@@ -224,8 +259,8 @@ namespace kern
 					sq += v[ i ].x * v[ i ].x + v[ i ].y * v[ i ].y + v[ i ].z * v[ i ].z + v[ i ].w * v[ i ].w;
 				}
 				const float rstd = 1.0f / sqrtf( warpSumM( sq ) / (float)K + 1e-5f );
-				const float4* g4 = reinterpret_cast<const float4*>( op.gamma );
-				const float4* b4 = reinterpret_cast<const float4*>( op.beta );
+				const float4* g4 = reinterpret_cast<const float4*>( sm.gamma );
+				const float4* b4 = reinterpret_cast<const float4*>( sm.beta );
 				uint2* d2 = reinterpret_cast<uint2*>( dst );
 #pragma unroll
 				for( int i = 0; i < N4; i++ )
@@ -257,7 +292,7 @@ namespace kern
 			}
 		}
 
-		__device__ __forceinline__ void gemvEpilogue( const GemvOp& op, int col, int n, float v )
+		__device__ __forceinline__ void gemvEpilogue( const GemvOp& op, int col, int n, float v, float biasN )
 		{
 			switch( op.epi )
 			{
@@ -265,26 +300,26 @@ namespace kern
 			{
 				const int which = n / op.d;
 				const int nn = n - which * op.d;
-				if( which == 0 ) op.outF32[ (size_t)col * op.ld + nn ] = ( v + op.bias[ n ] ) * op.scale;
+				if( which == 0 ) op.outF32[ (size_t)col * op.ld + nn ] = ( v + biasN ) * op.scale;
 				else
 				{
 					const size_t off = ( (size_t)col * op.nTextCtx + op.nPast ) * op.d + nn;
 					if( which == 1 ) op.kCache[ off ] = __float2half_rn( v * op.scale );
-					else op.vCache[ off ] = __float2half_rn( v + op.bias[ n ] );
+					else op.vCache[ off ] = __float2half_rn( v + biasN );
 				}
 				break;
 			}
 			case EP_RESID:
 			{
 				float* p = op.outF32 + (size_t)col * op.ld + n;
-				*p = v + op.bias[ n ] + __ldcg( p );
+				*p = v + biasN + __ldcg( p );
 				break;
 			}
 			case EP_QSCALE:
-				op.outF32[ (size_t)col * op.ld + n ] = ( v + op.bias[ n ] ) * op.scale;
+				op.outF32[ (size_t)col * op.ld + n ] = ( v + biasN ) * op.scale;
 				break;
 			case EP_GELU:
-				op.outF16[ (size_t)col * op.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( v + op.bias[ n ] ) );
+				op.outF16[ (size_t)col * op.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( v + biasN ) );
 				break;
 			default:
 				op.outF32[ (size_t)col * op.ld + n ] = v;
@@ -359,7 +394,9 @@ namespace kern
 						float v = 0.0f;
 #pragma unroll
 						for( int w = 0; w < MG_WARPS; w++ ) v += sm.red[ ( ( u * MG_WARPS + w ) * MG_ROWS + r ) * 16 + c ];
-						gemvEpilogue( op, c, n, v );
+						float biasN = 0.0f;
+						if( op.bias ) biasN = ( u0 + u < MG_MAXBIASUNITS ) ? sm.bias[ ( u0 + u ) * MG_ROWS + r ] : op.bias[ n ];
+						gemvEpilogue( op, c, n, v, biasN );
 					}
 				}
 				__syncthreads();
@@ -367,7 +404,28 @@ namespace kern
 		}
 
 		// -----------------------------------------------------------------------------------------------------------
-		// self attention over the self-KV cache (N = 1): units = (chunk, head)
+		// self attention over the self-KV cache (N = 1): units = (chunk, head).  The rows of earlier tokens are final, so they are
+		// copied to shared memory by cp.async BEFORE the barrier that publishes this step's new row; after it only 2 x 128 bytes remain.
+		constexpr int SA_KSTRIDE = 144;   // bytes per K row in smem (128 + 16: conflict-free 16-byte reads of one row per thread)
+		constexpr int SA_MAXKV = 448;
+		__device__ __forceinline__ void selfLoadRows( const MegaArgs& a, const MegaLayer& L, int d, const Smem& sm, int unit, int j0, int j1, int tid )
+		{
+			if( unit >= a.B * a.H ) return;
+			const int b = unit / a.H, h = unit - b * a.H;
+			const __half* kb = L.kCache + (size_t)b * a.nTextCtx * d + h * 64;
+			const __half* vb = L.vCache + (size_t)b * a.nTextCtx * d + h * 64;
+			uint8_t* sK = sm.a;
+			uint8_t* sV = sm.a + SA_MAXKV * SA_KSTRIDE;
+			const int n = ( j1 - j0 ) * 8;   // 16-byte chunks per matrix
+			for( int i = tid; i < 2 * n; i += MG_THREADS )
+			{
+				const bool isV = i >= n;
+				const int k = isV ? i - n : i;
+				const int j = j0 + ( k >> 3 ), c = k & 7;
+				if( isV ) cpAsync16( sV + j * 128 + c * 16, vb + (size_t)j * d + c * 8 );
+				else cpAsync16( sK + j * SA_KSTRIDE + c * 16, kb + (size_t)j * d + c * 8 );
+			}
+		}
 		__device__ void selfAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, int nPast, const Smem& sm, int warp, int lane, int tid )
 		{
 			const int H = a.H;
@@ -375,22 +433,28 @@ namespace kern
 			float* sq = sm.misc;
 			float* sred = sm.misc + 64;
 			float* so = sm.red;
+			const uint8_t* sK = sm.a;
+			const __half* sV = reinterpret_cast<const __half*>( sm.a + SA_MAXKV * SA_KSTRIDE );
+			bool first = true;
 			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
 			{
 				const int b = unit / H, h = unit - b * H;
+				// rows [0, nkv-1) of the first unit were requested before the barrier; the new row (and everything for further units) now
+				selfLoadRows( a, L, d, sm, unit, first ? nkv - 1 : 0, nkv, tid );
+				cpAsyncCommit();
+				first = false;
 				if( tid < 64 ) sq[ tid ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + tid ) ) );
+				cpAsyncWaitAll();
 				__syncthreads();
-				const __half* kb = L.kCache + (size_t)b * a.nTextCtx * d + h * 64;
-				const __half* vb = L.vCache + (size_t)b * a.nTextCtx * d + h * 64;
 				float lmax = -INFINITY;
 				for( int j = tid; j < nkv; j += MG_THREADS )
 				{
-					const uint4* kr = reinterpret_cast<const uint4*>( kb + (size_t)j * d );
+					const uint4* kr = reinterpret_cast<const uint4*>( sK + j * SA_KSTRIDE );
 					float s = 0.0f;
 #pragma unroll
 					for( int c = 0; c < 8; c++ )
 					{
-						const uint4 u = __ldcg( kr + c );
+						const uint4 u = kr[ c ];
 						const __half2* h2 = reinterpret_cast<const __half2*>( &u );
 #pragma unroll
 						for( int e = 0; e < 4; e++ )
@@ -430,11 +494,11 @@ namespace kern
 					const int part = idx >> 6, e = idx & 63;
 					const int j0 = min( part * dc, nkv ), j1 = min( ( part + 1 ) * dc, nkv );
 					float y;
-					if( a.refThreads > 0 ) y = pvChain( sm.sp, vb + e, (size_t)d, j0, j1 );
+					if( a.refThreads > 0 ) y = pvChain( sm.sp, sV + e, 64, j0, j1 );
 					else
 					{
 						y = 0.0f;
-						for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
+						for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( sV[ (size_t)j * 64 + e ] );
 					}
 					so[ idx ] = y;
 				}
@@ -593,24 +657,65 @@ namespace kern
 			sm.red = reinterpret_cast<float*>( mg_smem + MG_SMEM_A );
 			sm.sp = reinterpret_cast<float*>( mg_smem + MG_SMEM_A + MG_SMEM_RED );
 			sm.misc = reinterpret_cast<float*>( mg_smem + MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP );
+			sm.gamma = reinterpret_cast<float*>( mg_smem + MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP + MG_SMEM_MISC * 4 );
+			sm.beta = sm.gamma + 1280;
+			sm.bias = sm.beta + 1280;
 			const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 			const int B = a.B;
 			const int nPast = *a.dNPast;              // read once: the sampler's advance kernel updates it after this launch
+			const int nkvOld = min( nPast, a.nTextCtx - 1 );
 			const float qkScale = 0.35355339059327379f;   // 64^-1/4 (whisper.cpp:1588, 1595, 1700)
 			Grid grid{ a.barrier, 0u };
+			int markIdx = 0;
+			auto markId = [ & ]( int id ) {
+				if( a.timing && blockIdx.x == 0 && tid == 0 && markIdx < 2040 )
+				{
+					unsigned long long t;
+					asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
+					a.timing[ 2 * markIdx ] = (unsigned long long)id;
+					a.timing[ 2 * markIdx + 1 ] = t;
+				}
+				markIdx++;
+			};
+			int phaseId = 0;
+			auto mark = [ & ]() { markId( phaseId++ ); };   // even ids: before a barrier, odd: after it
+			mark();
 			__half* sx = reinterpret_cast<__half*>( sm.a );
 
-			GemvOp op{};
-			op.d = D; op.nTextCtx = a.nTextCtx; op.nPast = nPast;
-
-			// ---- layer 0 QKV weights are requested first; then the embedding (a13) is written by the first B CTAs ----
 			WBatch<D> wbD;
 			WBatch<4 * D> wb4D;
-			{
-				const MegaLayer& L0 = a.layers[ 0 ];
-				op.W = L0.wqkv; op.nOut = 3 * D;
-				loadBatch<D>( wbD, op, 0, myUnits<D>( op ), 0, warp, lane );
-			}
+			GemvOp base{};
+			base.d = D; base.nTextCtx = a.nTextCtx; base.nPast = nPast; base.scale = 1.0f;
+
+			auto opQKV = [ & ]( const MegaLayer& L ) {
+				GemvOp o = base;
+				o.W = L.wqkv; o.nOut = 3 * D; o.xF32 = a.x; o.xStride = D; o.gamma = L.ln1g; o.beta = L.ln1b;
+				o.epi = EP_QKV; o.bias = L.bqkv; o.scale = qkScale; o.outF32 = a.q; o.ld = D; o.kCache = L.kCache; o.vCache = L.vCache;
+				return o;
+			};
+			// everything a phase needs that does not depend on the previous phase is requested before the barrier
+			auto prepD = [ & ]( const GemvOp& o ) {
+				loadBatch<D>( wbD, o, 0, myUnits<D>( o ), 0, warp, lane );
+				prefetchParams( o, D, sm, tid );
+			};
+			// after the barrier: parameters have landed
+			auto landed = [ & ]() { cpAsyncWaitAll(); __syncthreads(); };
+
+			// a layer's cross-attention K/V tile of "my" (chunk, head) starts moving HBM -> L2 several phases ahead of its use (those
+			// phases are latency-bound and leave the DRAM pipe idle); issued right before a barrier wait, off the critical path
+			auto crossL2 = [ & ]( const MegaLayer& L ) {
+				if( (int)blockIdx.x < B * a.H )
+				{
+					const size_t cb = (size_t)blockIdx.x * a.T * 64;
+					const uint8_t* kp = reinterpret_cast<const uint8_t*>( L.crossK + cb );
+					const uint8_t* vp = reinterpret_cast<const uint8_t*>( L.crossV + cb );
+					for( int i = tid; i < a.T; i += MG_THREADS ) { prefetchL2( kp + (size_t)i * 128 ); prefetchL2( vp + (size_t)i * 128 ); }
+				}
+			};
+
+			// ---- embedding (a13) by the first B CTAs; layer 0's QKV weights and LayerNorm parameters are already in flight ----
+			GemvOp op = opQKV( a.layers[ 0 ] );
+			prepD( op );
 			for( int b = blockIdx.x; b < B; b += gridDim.x )
 			{
 				const int tok = a.tokens[ b ];
@@ -618,94 +723,115 @@ namespace kern
 				const float* pe = a.decPos + (size_t)nPast * D;
 				for( int e = tid; e < D; e += MG_THREADS ) a.x[ (size_t)b * D + e ] = __half2float( src[ e ] ) + pe[ e ];
 			}
-			grid.sync();
+			crossL2( a.layers[ 0 ] );
+			mark(); grid.sync(); mark();
 
 			for( int il = 0; il < a.L; il++ )
 			{
 				const MegaLayer& L = a.layers[ il ];
 				// ---- P1: LN1 + (Q | K | V), K/V appended to the cache (a14) ----
-				op.W = L.wqkv; op.nOut = 3 * D; op.xF32 = a.x; op.xF16 = nullptr; op.xStride = D; op.gamma = L.ln1g; op.beta = L.ln1b;
-				op.epi = EP_QKV; op.bias = L.bqkv; op.scale = qkScale; op.outF32 = a.q; op.ld = D; op.kCache = L.kCache; op.vCache = L.vCache;
-				stageLN<D>( op, B, sx, warp, lane );
+				landed();
+				stageLN<D>( op, B, sx, sm, warp, lane );
 				__syncthreads();
+				markId( 1001 );
 				gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
-				// prefetch out-proj weights, then wait for Q/K/V of every CTA
-				GemvOp opO = op;
-				opO.W = L.wo; opO.nOut = D; opO.xF32 = nullptr; opO.xF16 = a.attn; opO.xStride = D; opO.gamma = nullptr; opO.beta = nullptr;
-				opO.epi = EP_RESID; opO.bias = L.bo; opO.outF32 = a.x; opO.ld = D;
-				loadBatch<D>( wbD, opO, 0, myUnits<D>( opO ), 0, warp, lane );
-				grid.sync();
+				markId( 1002 );
+				GemvOp opO = base;
+				opO.W = L.wo; opO.nOut = D; opO.xF16 = a.attn; opO.xStride = D; opO.epi = EP_RESID; opO.bias = L.bo; opO.outF32 = a.x; opO.ld = D;
+				prepD( opO );
+				// earlier tokens' K/V rows of my (chunk, head) -> smem (region A is free: P1's activations are consumed)
+				selfLoadRows( a, L, D, sm, blockIdx.x, 0, nkvOld, tid );
+				cpAsyncCommit();
+				mark(); grid.sync(); mark();
 				// ---- P2: self attention ----
 				selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid );
-				grid.sync();
+				mark(); grid.sync(); mark();
 				// ---- P3: out projection + residual ----
+				landed();
 				stageF16<D>( opO, B, sx, tid );
 				__syncthreads();
+				markId( 1003 );
 				gemvCompute<D>( opO, B, wbD, sm, warp, lane, tid );
-				GemvOp opQ = op;
-				opQ.W = L.wcq; opQ.nOut = D; opQ.xF32 = a.x; opQ.xF16 = nullptr; opQ.xStride = D; opQ.gamma = L.lncg; opQ.beta = L.lncb;
+				markId( 1004 );
+				GemvOp opQ = base;
+				opQ.W = L.wcq; opQ.nOut = D; opQ.xF32 = a.x; opQ.xStride = D; opQ.gamma = L.lncg; opQ.beta = L.lncb;
 				opQ.epi = EP_QSCALE; opQ.bias = L.bcq; opQ.scale = qkScale; opQ.outF32 = a.q; opQ.ld = D;
-				loadBatch<D>( wbD, opQ, 0, myUnits<D>( opQ ), 0, warp, lane );
-				grid.sync();
+				prepD( opQ );
+				mark(); grid.sync(); mark();
 				// ---- P4: cross-attention query (a15) ----
-				stageLN<D>( opQ, B, sx, warp, lane );
+				landed();
+				stageLN<D>( opQ, B, sx, sm, warp, lane );
 				__syncthreads();
 				gemvCompute<D>( opQ, B, wbD, sm, warp, lane, tid );
 				__syncthreads();
 				CrossPrefetch pf;
 				crossPrefetch( a, L, pf, sm, blockIdx.x, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
-				grid.sync();
+				mark(); grid.sync(); mark();
 				// ---- P5: cross attention ----
 				crossAttnPhase( a, L, D, pf, sm, warp, lane, tid );
-				GemvOp opC = op;
-				opC.W = L.wco; opC.nOut = D; opC.xF32 = nullptr; opC.xF16 = a.attn; opC.xStride = D; opC.gamma = nullptr; opC.beta = nullptr;
-				opC.epi = EP_RESID; opC.bias = L.bco; opC.outF32 = a.x; opC.ld = D;
-				loadBatch<D>( wbD, opC, 0, myUnits<D>( opC ), 0, warp, lane );
-				grid.sync();
+				GemvOp opC = base;
+				opC.W = L.wco; opC.nOut = D; opC.xF16 = a.attn; opC.xStride = D; opC.epi = EP_RESID; opC.bias = L.bco; opC.outF32 = a.x; opC.ld = D;
+				prepD( opC );
+				mark(); grid.sync(); mark();
 				// ---- P6: cross out projection + residual ----
+				landed();
 				stageF16<D>( opC, B, sx, tid );
 				__syncthreads();
 				gemvCompute<D>( opC, B, wbD, sm, warp, lane, tid );
-				GemvOp op1 = op;
-				op1.W = L.w1; op1.nOut = 4 * D; op1.xF32 = a.x; op1.xF16 = nullptr; op1.xStride = D; op1.gamma = L.ln3g; op1.beta = L.ln3b;
+				GemvOp op1 = base;
+				op1.W = L.w1; op1.nOut = 4 * D; op1.xF32 = a.x; op1.xStride = D; op1.gamma = L.ln3g; op1.beta = L.ln3b;
 				op1.epi = EP_GELU; op1.bias = L.b1; op1.outF16 = a.h; op1.ld = 4 * D;
-				loadBatch<D>( wbD, op1, 0, myUnits<D>( op1 ), 0, warp, lane );
-				grid.sync();
+				prepD( op1 );
+				mark(); grid.sync(); mark();
 				// ---- P7: LN3 + fc1 + GELU (a16) ----
-				stageLN<D>( op1, B, sx, warp, lane );
+				landed();
+				if( il + 1 == a.L )
+				{
+					// last layer: start pulling this CTA's rows of the unembedding matrix into L2 (106 MB over all CTAs)
+					const int units = ( a.nVocab + MG_ROWS - 1 ) / MG_ROWS;
+					for( int u = blockIdx.x; u < units; u += gridDim.x )
+					{
+						const uint8_t* wp = reinterpret_cast<const uint8_t*>( a.tokEmb + (size_t)u * MG_ROWS * D );
+						const int rows = min( MG_ROWS, a.nVocab - u * MG_ROWS );
+						for( int i = tid; i < rows * D * 2 / 128; i += MG_THREADS ) prefetchL2( wp + (size_t)i * 128 );
+					}
+				}
+				stageLN<D>( op1, B, sx, sm, warp, lane );
 				__syncthreads();
+				markId( 1007 );
 				gemvCompute<D>( op1, B, wbD, sm, warp, lane, tid );
-				GemvOp op2 = op;
-				op2.W = L.w2; op2.nOut = D; op2.xF32 = nullptr; op2.xF16 = a.h; op2.xStride = 4 * D; op2.gamma = nullptr; op2.beta = nullptr;
-				op2.epi = EP_RESID; op2.bias = L.b2; op2.outF32 = a.x; op2.ld = D;
+				markId( 1008 );
+				GemvOp op2 = base;
+				op2.W = L.w2; op2.nOut = D; op2.xF16 = a.h; op2.xStride = 4 * D; op2.epi = EP_RESID; op2.bias = L.b2; op2.outF32 = a.x; op2.ld = D;
 				loadBatch<4 * D>( wb4D, op2, 0, myUnits<4 * D>( op2 ), 0, warp, lane );
-				grid.sync();
+				prefetchParams( op2, 4 * D, sm, tid );
+				mark(); grid.sync(); mark();
 				// ---- P8: fc2 + residual ----
+				landed();
 				stageF16<4 * D>( op2, B, sx, tid );
 				__syncthreads();
 				gemvCompute<4 * D>( op2, B, wb4D, sm, warp, lane, tid );
-				// next: QKV of the following layer, or the logits
-				if( il + 1 < a.L )
-				{
-					const MegaLayer& Ln = a.layers[ il + 1 ];
-					op.W = Ln.wqkv; op.nOut = 3 * D;
-				}
+				// next: QKV of the following layer, or the final LayerNorm + logits
+				if( il + 1 < a.L ) op = opQKV( a.layers[ il + 1 ] );
 				else
 				{
-					op.W = a.tokEmb; op.nOut = a.nVocab;
+					op = base;
+					op.W = a.tokEmb; op.nOut = a.nVocab; op.xF32 = a.x; op.xStride = D; op.gamma = a.lnfg; op.beta = a.lnfb;
+					op.epi = EP_LOGITS; op.outF32 = a.logits; op.ld = a.nVocab;
 				}
-				loadBatch<D>( wbD, op, 0, myUnits<D>( op ), 0, warp, lane );
-				grid.sync();
+				prepD( op );
+				if( il + 1 < a.L ) crossL2( a.layers[ il + 1 ] );
+				mark(); grid.sync(); mark();
 			}
 			// ---- final LayerNorm + logits = tok_emb^T x (a17) ----
-			op.W = a.tokEmb; op.nOut = a.nVocab; op.xF32 = a.x; op.xF16 = nullptr; op.xStride = D; op.gamma = a.lnfg; op.beta = a.lnfb;
-			op.epi = EP_LOGITS; op.outF32 = a.logits; op.ld = a.nVocab;
-			stageLN<D>( op, B, sx, warp, lane );
+			landed();
+			stageLN<D>( op, B, sx, sm, warp, lane );
 			__syncthreads();
 			gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
+			mark();
 		}
 
-		constexpr int SMEM = MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP + MG_SMEM_MISC * 4;
+		constexpr int SMEM = MG_SMEM_A + MG_SMEM_RED + MG_SMEM_SP + MG_SMEM_MISC * 4 + MG_SMEM_PARAM;
 		template<int D>
 		cudaError_t prepareD()
 		{

@@ -30,6 +30,7 @@ namespace kern
 		__half* h = nullptr;                // [B][4d]
 		float* logits = nullptr;            // [B][nVocab]
 		unsigned* barrier = nullptr;        // grid barrier counter (zeroed by the launcher)
+		unsigned long long* timing = nullptr;   // optional: %globaltimer marks of CTA 0 around every barrier (debug)
 	};
 	bool megaSupported( int d, int B, int T );
 	cudaError_t megaPrepare( int d );   // function attributes, outside any stream capture

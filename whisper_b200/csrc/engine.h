@@ -157,6 +157,7 @@ namespace wsp
 		// persistent decoder-step kernel (decode_mega.cu): per-layer pointer table on the device, grid-barrier counter
 		kern::MegaLayer* megaLayers = nullptr;
 		unsigned* megaBarrier = nullptr;
+		unsigned long long* megaTiming = nullptr;   // [4096] debug marks
 		bool useMega = true;
 
 		// decode CUDA graph (N = 1 steady state)
