@@ -196,4 +196,4 @@ def test_launch_counter_counts_kernels():
     m, e, c = open_model("micro.en")
     before = L.wsp_launch_count()
     c.run_chunks([synth.synth_pcm(0)], m.prompt_init(), 4)
-    assert L.wsp_launch_count() - before > 100
+    assert L.wsp_launch_count() - before > 40   # encoder ~45 launches + 4 token steps (persistent decoder kernel + sampler)

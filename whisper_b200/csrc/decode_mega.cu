@@ -99,27 +99,36 @@ namespace kern
 			float* bias;     // [MG_MAXBIASUNITS][8]
 		};
 
+		// Grid-wide barrier for the resident CTAs.  Arrival is one release-atomic on a counter; the last arriver publishes the epoch
+		// in a separate 128-byte line that everybody else polls with acquire loads, so the pollers do not queue behind the atomics.
 		struct Grid
 		{
-			unsigned* counter;
+			unsigned* counter;   // [0] arrivals, [32] epoch flag (separate line); both zeroed by the launcher
 			unsigned target;
+			unsigned epoch;
 			__device__ __forceinline__ void sync()
 			{
 				target += gridDim.x;
+				epoch += 1;
 				__syncthreads();
 				if( threadIdx.x == 0 )
 				{
-					__threadfence();
-					atomicAdd( counter, 1u );
-					unsigned spins = 0;
-					while( true )
+					unsigned old;
+					asm volatile( "atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"( old ) : "l"( counter ) : "memory" );
+					unsigned* flag = counter + 32;
+					if( old == target - 1 )
+						asm volatile( "st.release.gpu.global.u32 [%0], %1;" ::"l"( flag ), "r"( epoch ) : "memory" );
+					else
 					{
-						unsigned v;
-						asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( v ) : "l"( counter ) : "memory" );
-						if( v >= target ) break;
-						if( ++spins > ( 1u << 25 ) ) __trap();   // a protocol bug must not hang the GPU
+						unsigned spins = 0;
+						while( true )
+						{
+							unsigned v;
+							asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( v ) : "l"( flag ) : "memory" );
+							if( v >= epoch ) break;
+							if( ++spins > ( 1u << 25 ) ) __trap();   // a protocol bug must not hang the GPU
+						}
 					}
-					__threadfence();
 				}
 				__syncthreads();
 			}
@@ -665,7 +674,7 @@ namespace kern
 			const int nPast = *a.dNPast;              // read once: the sampler's advance kernel updates it after this launch
 			const int nkvOld = min( nPast, a.nTextCtx - 1 );
 			const float qkScale = 0.35355339059327379f;   // 64^-1/4 (whisper.cpp:1588, 1595, 1700)
-			Grid grid{ a.barrier, 0u };
+			Grid grid{ a.barrier, 0u, 0u };
 			int markIdx = 0;
 			auto markId = [ & ]( int id ) {
 				if( a.timing && blockIdx.x == 0 && tid == 0 && markIdx < 2040 )
@@ -850,7 +859,7 @@ namespace kern
 		{
 			cudaError_t e = prepareD<D>();
 			if( e != cudaSuccess ) return e;
-			e = cudaMemsetAsync( a.barrier, 0, sizeof( unsigned ), s );
+			e = cudaMemsetAsync( a.barrier, 0, 64 * sizeof( unsigned ), s );
 			if( e != cudaSuccess ) return e;
 			decode_step_kernel<D><<<numSMs, MG_THREADS, SMEM, s>>>( a );
 			return cudaGetLastError();
