@@ -165,6 +165,133 @@ namespace gemm
 	}
 
 	// ---------------------------------------------------------------------------------------------------------------
+	// Coalesced epilogues.  tcgen05.ld hands every thread one ROW of the accumulator tile, so a direct store makes each warp
+	// instruction touch 32 different rows (16 bytes each): half of every 32-byte sector is wasted and a 128-byte line needs 8
+	// separate instructions (measured: the out-projection GEMM ran at 17 % tensor-pipe utilisation, epilogue-bound).  The
+	// accumulator chunk (32 rows x 32 columns) is therefore transposed through a padded per-warp shared-memory tile so that a
+	// thread owns one COLUMN: every load / store instruction of the warp then covers 32 consecutive elements of one output row.
+	template<int MODE>
+	__device__ __forceinline__ void epilogueT( const EpiParams& ep, int mBase, int n, const float* w )
+	{
+		if( n >= ep.N ) return;
+		if constexpr( MODE == EPI_F32 )
+		{
+			const float b = ep.bias ? ep.bias[ n ] : 0.0f;
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				const int m = mBase + rr;
+				if( m < ep.M ) ep.out_f32[ (size_t)m * ep.ld + n ] = w[ rr ] + b;
+			}
+		}
+		else if constexpr( MODE == EPI_CONV1 )
+		{
+			const float b = ep.bias[ n ];
+			int cb = mBase / ep.rows_per_chunk;
+			int t = mBase - cb * ep.rows_per_chunk;
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				if( cb < ep.nchunks && t < ep.valid_per_chunk )
+					ep.out_a[ (size_t)( mBase + rr + 1 ) * ep.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( w[ rr ] + b ) );
+				if( ++t == ep.rows_per_chunk ) { t = 0; cb++; }
+			}
+		}
+		else if constexpr( MODE == EPI_CONV2 )
+		{
+			const float b = ep.bias[ n ];
+			const int cb0 = mBase / ep.rows_per_chunk;
+			const int j0 = mBase - cb0 * ep.rows_per_chunk;
+			// positional rows first (loads must not be serialised behind the stores: pos and out_f32 are both float*)
+			float pe[ 32 ];
+			{
+				int j = j0;
+#pragma unroll
+				for( int rr = 0; rr < 32; rr++ )
+				{
+					pe[ rr ] = j < ep.valid_per_chunk ? ep.pos[ (size_t)j * ep.d + n ] : 0.0f;
+					if( ++j == ep.rows_per_chunk ) j = 0;
+				}
+			}
+			int cb = cb0, j = j0;
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				if( cb < ep.nchunks && j < ep.valid_per_chunk )
+					ep.out_f32[ ( (size_t)cb * ep.T + j ) * ep.ld + n ] = ptx::gelu_f16_semantics( w[ rr ] + b ) + pe[ rr ];
+				if( ++j == ep.rows_per_chunk ) { j = 0; cb++; }
+			}
+		}
+		else if constexpr( MODE == EPI_QKV )
+		{
+			// Q and K only (the V^T part keeps the row-per-thread layout, which is the coalesced one for a transposed store)
+			const int which = n / ep.d;
+			const int nn = n - which * ep.d;
+			const int h = nn >> 6, e = nn & 63;
+			const float b = ep.bias[ n ];
+			__half* base = which == 0 ? ep.out_a : ep.out_b;
+			int cb = mBase / ep.T;
+			int t = mBase - cb * ep.T;
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				if( mBase + rr < ep.M )
+					base[ ( ( (size_t)cb * ep.H + h ) * ep.T + t ) * 64 + e ] = __float2half_rn( w[ rr ] + b );
+				if( ++t == ep.T ) { t = 0; cb++; }
+			}
+		}
+		else if constexpr( MODE == EPI_BIAS_RESID )
+		{
+			const float b = ep.bias[ n ];
+			// resid may alias out_f32 (in-place residual add): read all 32 rows first so the loads are not serialised behind the stores
+			float rs[ 32 ];
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				const int m = mBase + rr;
+				rs[ rr ] = m < ep.M ? ep.resid[ (size_t)m * ep.ld + n ] : 0.0f;
+			}
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				const int m = mBase + rr;
+				if( m < ep.M ) ep.out_f32[ (size_t)m * ep.ld + n ] = w[ rr ] + b + rs[ rr ];
+			}
+		}
+		else if constexpr( MODE == EPI_BIAS_GELU_F16 )
+		{
+			const float b = ep.bias[ n ];
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				const int m = mBase + rr;
+				if( m < ep.M ) ep.out_a[ (size_t)m * ep.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( w[ rr ] + b ) );
+			}
+		}
+		else if constexpr( MODE == EPI_CROSSKV )
+		{
+			const int d2 = 2 * ep.d;
+			const int l = n / d2;
+			const int r = n - l * d2;
+			const bool isV = r >= ep.d;
+			const int nn = isV ? r - ep.d : r;
+			const int h = nn >> 6, e = nn & 63;
+			const float b = isV ? ep.bias[ n ] : 0.0f;
+			const float sc = isV ? 1.0f : ep.scale;
+			__half* base = isV ? ep.out_b : ep.out_a;
+			int cb = mBase / ep.T;
+			int t = mBase - cb * ep.T;
+#pragma unroll
+			for( int rr = 0; rr < 32; rr++ )
+			{
+				if( mBase + rr < ep.M )
+					base[ ( ( ( (size_t)l * ep.nchunks + cb ) * ep.H + h ) * ep.T + t ) * 64 + e ] = __float2half_rn( w[ rr ] * sc + b );
+				if( ++t == ep.T ) { t = 0; cb++; }
+			}
+		}
+	}
+
+	// ---------------------------------------------------------------------------------------------------------------
 	template<int BN, int STAGES>
 	struct SmemLayout
 	{
@@ -172,7 +299,7 @@ namespace gemm
 		static constexpr int B_BYTES = BN * BK * 2;
 		static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 		static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-		static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
+		static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack (the transpose tiles are static smem)
 	};
 
 	template<int BN, int STAGES, int MODE, int AMODE>
@@ -182,6 +309,7 @@ namespace gemm
 	{
 		using SL = SmemLayout<BN, STAGES>;
 		extern __shared__ uint8_t smem_raw[];
+		__shared__ float xposeTiles[ 4 ][ 32 * 33 ];   // one padded 32x32 transpose tile per epilogue warp (static: compiled to LDS/STS)
 		uint8_t* smem = reinterpret_cast<uint8_t*>( ( reinterpret_cast<uintptr_t>( smem_raw ) + 1023 ) & ~(uintptr_t)1023 );
 		uint64_t* bar_full = reinterpret_cast<uint64_t*>( smem + SL::BAR_OFFSET );
 		uint64_t* bar_empty = bar_full + STAGES;
@@ -318,17 +446,39 @@ namespace gemm
 				ptx::tc_fence_after();
 				const int m = m0 + q * 32 + lane;
 				const uint32_t taddr = tmem_base + ( (uint32_t)( q * 32 ) << 16 ) + (uint32_t)( as * BN );
+				float* xpose = xposeTiles[ warp - 2 ];
 #pragma unroll 1
 				for( int c = 0; c < BN / 32; c++ )
 				{
 					uint32_t r[ 32 ];
 					ptx::tmem_ld_32x32( taddr + (uint32_t)( c * 32 ), r );
 					ptx::tmem_ld_wait();
-					float v[ 32 ];
+					const int nc = n0 + c * 32;
+					// f32 outputs go through the transpose (measured: out-projection 99 -> 79 us); f16 outputs keep the row-per-thread
+					// layout with 16-byte stores — 2-byte scalar stores, even though contiguous across the warp, were measured 2x slower
+					// (fc1 144 -> 269 us), and the V^T band of the QKV GEMM is stored transposed, for which row-per-thread is the coalesced layout
+					constexpr bool rowLayout = ( MODE == EPI_QKV ) || ( MODE == EPI_CONV1 ) || ( MODE == EPI_BIAS_GELU_F16 ) || ( MODE == EPI_CROSSKV );
+					if( rowLayout )
+					{
+						float v[ 32 ];
 #pragma unroll
-					for( int i = 0; i < 32; i++ )
-						v[ i ] = __uint_as_float( r[ i ] );
-					epilogue<MODE>( ep, m, n0 + c * 32, v );
+						for( int i = 0; i < 32; i++ )
+							v[ i ] = __uint_as_float( r[ i ] );
+						epilogue<MODE>( ep, m, nc, v );
+					}
+					else
+					{
+#pragma unroll
+						for( int i = 0; i < 32; i++ )
+							xpose[ lane * 33 + i ] = __uint_as_float( r[ i ] );
+						__syncwarp();
+						float w[ 32 ];
+#pragma unroll
+						for( int rr = 0; rr < 32; rr++ )
+							w[ rr ] = xpose[ rr * 33 + lane ];
+						__syncwarp();
+						epilogueT<MODE>( ep, m0 + q * 32, nc + lane, w );
+					}
 				}
 				ptx::tc_fence_before();
 				__syncwarp();
