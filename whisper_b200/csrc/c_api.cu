@@ -343,7 +343,7 @@ wsp_status wsp_debug_mega_timing( wsp_context* c, uint64_t* dst, int32_t cap )
 {
 	if( !c || !dst ) return fail( WSP_E_POINTER, "context/dst" );
 	WSP_CUDA( cudaStreamSynchronize( c->c->stream ) );
-	WSP_CUDA( cudaMemcpy( dst, c->c->megaTiming, sizeof( uint64_t ) * (size_t)( cap < 4096 ? cap : 4096 ), cudaMemcpyDeviceToHost ) );
+	WSP_CUDA( cudaMemcpy( dst, c->c->megaTiming, sizeof( uint64_t ) * (size_t)( cap < 4608 ? cap : 4608 ), cudaMemcpyDeviceToHost ) );
 	return WSP_OK;
 }
 wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on )

@@ -132,7 +132,7 @@ namespace wsp
 			WSP_CHECK( devAlloc( c.megaLayers, (size_t)L ) );
 			WSP_CUDA( cudaMemcpy( c.megaLayers, ml.data(), ml.size() * sizeof( kern::MegaLayer ), cudaMemcpyHostToDevice ) );
 			WSP_CHECK( devAlloc( c.megaBarrier, 64, true ) );
-			WSP_CHECK( devAlloc( c.megaTiming, 4096, true ) );
+			WSP_CHECK( devAlloc( c.megaTiming, 4608, true ) );
 			const char* env = getenv( "WSP_MEGA" );
 			c.useMega = !( env && env[ 0 ] == '0' );
 		}
