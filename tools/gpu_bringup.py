@@ -288,11 +288,9 @@ def stage_megatiming(model_name="medium", batch=8):
     path, m, e, c = _open(model_name, batch=batch)
     pcms = [synth.synth_pcm(i) for i in range(batch)]
     c.run_chunks(pcms, m.prompt_init(), 40)
-    buf = (C.c_uint64 * 4608)()
-    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4608))
-    ct = np.array(buf[4000:4005], dtype=np.int64)
-    print("  cross-attn (last layer, CTA 0): scores %.2f us | softmax %.2f | V seg0 wait %.2f | chains %.2f" % tuple((np.diff(ct) / 1000.0).tolist()), flush=True)
-    raw = np.array(buf[:4000], dtype=np.int64).reshape(-1, 2)
+    buf = (C.c_uint64 * 4096)()
+    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4096))
+    raw = np.array(buf[:], dtype=np.int64).reshape(-1, 2)
     raw = raw[raw[:, 1] > 0]
     ids, t = raw[:, 0], raw[:, 1]
     print("  marks", len(ids), "total us", (t[-1] - t[0]) / 1000.0, flush=True)

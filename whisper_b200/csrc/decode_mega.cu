@@ -523,14 +523,12 @@ namespace kern
 		}
 
 		// -----------------------------------------------------------------------------------------------------------
-		// cross attention over the encoder's f16 K/V memories: units = (chunk, head).
-		//   before the barrier : the K tile (T x 128 B) is requested into shared memory by cp.async (it does not depend on this step)
-		//   after the barrier  : scores from shared memory; the tile space is then reused for V, requested in 4 row-interleaved groups
-		//                        (segment g of every reference-thread part first) while the softmax runs; the f16 V^T*P chains start on
-		//                        segment 0 as soon as it has landed and consume the later segments as they arrive.
-		// (measured before this restructure: K phase from global 8.5 us, chain 5.2 us per layer)
+		// cross attention over the encoder's f16 K/V memories: units = (chunk, head).  The V tile and the first batch of K rows are
+		// requested BEFORE the grid barrier (they do not depend on this step), q is read after it.
+		constexpr int CA_U = 12;
 		struct CrossPrefetch
 		{
+			uint4 u[ CA_U ];
 			int unit;
 		};
 		__device__ __forceinline__ void crossPrefetch( const MegaArgs& a, const MegaLayer& L, CrossPrefetch& pf, const Smem& sm, int unit, int warp, int lane, int tid )
@@ -538,11 +536,21 @@ namespace kern
 			pf.unit = unit;
 			if( unit >= a.B * a.H ) return;
 			const int T = a.T;
-			const size_t base = (size_t)unit * T * 64;
+			const int b = unit / a.H, h = unit - b * a.H;
+			const size_t base = ( (size_t)b * a.H + h ) * T * 64;
+			const uint4* V4 = reinterpret_cast<const uint4*>( L.crossV + base );
 			const uint4* K4 = reinterpret_cast<const uint4*>( L.crossK + base );
-			uint4* sk = reinterpret_cast<uint4*>( sm.a );
-			for( int idx = tid; idx < T * 8; idx += MG_THREADS ) cpAsync16( sk + idx, K4 + idx );
+			uint4* sv = reinterpret_cast<uint4*>( sm.a );
+			for( int idx = tid; idx < T * 8; idx += MG_THREADS ) cpAsync16( sv + idx, V4 + idx );
 			cpAsyncCommit();
+			const int sub = lane & 7, rgrp = lane >> 3;
+			const int jb = warp * 4 + rgrp;
+#pragma unroll
+			for( int k = 0; k < CA_U; k++ )
+			{
+				const int j = jb + k * MG_WARPS * 4;
+				pf.u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+			}
 		}
 		__device__ void crossAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, CrossPrefetch& pf, const Smem& sm, int warp, int lane, int tid )
 		{
@@ -551,72 +559,56 @@ namespace kern
 			float* so = sm.red;
 			const int sub = lane & 7, rgrp = lane >> 3;
 			constexpr int JSTEP = MG_WARPS * 4;
-			constexpr int NSEG = 4;
 			bool first = true;
-			auto tmark = [ & ]( int k ) {
-				if( a.timing && blockIdx.x == 0 && tid == 0 )
-				{
-					unsigned long long t;
-					asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
-					a.timing[ 4000 + k ] = t;
-				}
-			};
-			tmark( 0 );
 			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
 			{
 				if( !first ) { crossPrefetch( a, L, pf, sm, unit, warp, lane, tid ); }
 				first = false;
 				const int b = unit / H, h = unit - b * H;
-				const size_t base = (size_t)unit * T * 64;
+				const size_t base = ( (size_t)b * H + h ) * T * 64;
+				const uint4* K4 = reinterpret_cast<const uint4*>( L.crossK + base );
 				float qf[ 8 ];
 #pragma unroll
 				for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + sub * 8 + e ) ) );
-				cpAsyncWaitAll();
-				__syncthreads();
-				// scores: 8 lanes per key row (16 bytes each), 4 rows per warp instruction -> conflict-free 512-byte shared-memory reads
-				const uint4* sk = reinterpret_cast<const uint4*>( sm.a );
 				float lmax = -INFINITY;
-				for( int j = warp * 4 + rgrp; j < T; j += JSTEP )
+				int jb = warp * 4 + rgrp;
+				while( jb < T )
 				{
-					const uint4 u = sk[ (size_t)j * 8 + sub ];
-					const __half2* h2 = reinterpret_cast<const __half2*>( &u );
-					float s = 0.0f;
 #pragma unroll
-					for( int e = 0; e < 4; e++ )
+					for( int k = 0; k < CA_U; k++ )
 					{
-						const float2 f = __half22float2( h2[ e ] );
-						s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
+						const int j = jb + k * JSTEP;
+						const __half2* h2 = reinterpret_cast<const __half2*>( &pf.u[ k ] );
+						float s = 0.0f;
+#pragma unroll
+						for( int e = 0; e < 4; e++ )
+						{
+							const float2 f = __half22float2( h2[ e ] );
+							s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
+						}
+						s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+						s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+						s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+						if( j < T )
+						{
+							if( sub == 0 ) sm.sp[ j ] = s;
+							lmax = fmaxf( lmax, s );
+						}
 					}
-					s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-					s += __shfl_xor_sync( 0xffffffffu, s, 2 );
-					s += __shfl_xor_sync( 0xffffffffu, s, 4 );
-					if( sub == 0 ) sm.sp[ j ] = s;
-					lmax = fmaxf( lmax, s );
+					jb += JSTEP * CA_U;
+					if( jb < T )
+					{
+#pragma unroll
+						for( int k = 0; k < CA_U; k++ )
+						{
+							const int j = jb + k * JSTEP;
+							pf.u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
+						}
+					}
 				}
 				lmax = warpMaxM( lmax );
 				if( lane == 0 ) sred[ warp ] = lmax;
-				__syncthreads();   // every score is written and the K tile is no longer needed
-				tmark( 1 );
-				// V into the same space, segment-major: group g = rows [part*dc + g*seg, part*dc + (g+1)*seg) of every part
-				const int parts = a.refThreads > 0 ? a.refThreads : 4;
-				const int dc = ( T + parts - 1 ) / parts;
-				const int seg = ( dc + NSEG - 1 ) / NSEG;
-				{
-					const uint4* V4 = reinterpret_cast<const uint4*>( L.crossV + base );
-					uint4* sv4 = reinterpret_cast<uint4*>( sm.a );
-					for( int g = 0; g < NSEG; g++ )
-					{
-						for( int idx = tid; idx < parts * seg * 8; idx += MG_THREADS )
-						{
-							const int part = idx / ( seg * 8 );
-							const int rem = idx - part * seg * 8;
-							const int jr = g * seg + ( rem >> 3 );
-							const int j = part * dc + jr;
-							if( jr < dc && j < T ) cpAsync16( sv4 + (size_t)j * 8 + ( rem & 7 ), V4 + (size_t)j * 8 + ( rem & 7 ) );
-						}
-						cpAsyncCommit();
-					}
-				}
+				__syncthreads();
 				float mx = sred[ 0 ];
 				for( int w = 1; w < MG_WARPS; w++ ) mx = fmaxf( mx, sred[ w ] );
 				__syncthreads();
@@ -634,64 +626,25 @@ namespace kern
 				for( int w = 0; w < MG_WARPS; w++ ) tot += sred[ w ];
 				const float inv = 1.0f / tot;
 				for( int j = tid; j < T; j += MG_THREADS ) sm.sp[ j ] *= inv;
-				tmark( 2 );
+				cpAsyncWaitAll();
+				__syncthreads();
 				const __half* sv = reinterpret_cast<const __half*>( sm.a );
-				// chains: thread -> (part, e), carried across the segments as they land
-				float ych[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };   // up to 4 (part, e) pairs per thread when parts*64 > 256
-#pragma unroll
-				for( int g = 0; g < NSEG; g++ )
+				const int parts = a.refThreads > 0 ? a.refThreads : 4;
+				const int dc = ( T + parts - 1 ) / parts;
+				for( int idx = tid; idx < parts * 64; idx += MG_THREADS )
 				{
-					if( g == 0 ) asm volatile( "cp.async.wait_group 3;" ::: "memory" );
-					else if( g == 1 ) asm volatile( "cp.async.wait_group 2;" ::: "memory" );
-					else if( g == 2 ) asm volatile( "cp.async.wait_group 1;" ::: "memory" );
-					else asm volatile( "cp.async.wait_group 0;" ::: "memory" );
-					__syncthreads();
-					if( g == 0 ) tmark( 3 );
-#pragma unroll
-					for( int k = 0; k < 4; k++ )
+					const int part = idx >> 6, e = idx & 63;
+					const int j0 = min( part * dc, T ), j1 = min( ( part + 1 ) * dc, T );
+					float y;
+					if( a.refThreads > 0 ) y = pvChain( sm.sp, sv + e, 64, j0, j1 );
+					else
 					{
-						const int idx = tid + k * MG_THREADS;
-						if( idx < parts * 64 )
-						{
-							const int part = idx >> 6, e = idx & 63;
-							const int jEnd = min( ( part + 1 ) * dc, T );
-							const int j0 = min( part * dc + g * seg, jEnd ), j1 = min( part * dc + ( g + 1 ) * seg, jEnd );
-							if( a.refThreads > 0 )
-							{
-								float y = ych[ k ];
-								int j = j0;
-								for( ; j + 4 <= j1; j += 4 )
-								{
-									const float x0 = __half2float( sv[ (size_t)j * 64 + e ] );
-									const float x1 = __half2float( sv[ (size_t)( j + 1 ) * 64 + e ] );
-									const float x2 = __half2float( sv[ (size_t)( j + 2 ) * 64 + e ] );
-									const float x3 = __half2float( sv[ (size_t)( j + 3 ) * 64 + e ] );
-									y = __half2float( __float2half_rn( __fmaf_rn( x0, sm.sp[ j ], y ) ) );
-									y = __half2float( __float2half_rn( __fmaf_rn( x1, sm.sp[ j + 1 ], y ) ) );
-									y = __half2float( __float2half_rn( __fmaf_rn( x2, sm.sp[ j + 2 ], y ) ) );
-									y = __half2float( __float2half_rn( __fmaf_rn( x3, sm.sp[ j + 3 ], y ) ) );
-								}
-								for( ; j < j1; j++ )
-									y = __half2float( __float2half_rn( __fmaf_rn( __half2float( sv[ (size_t)j * 64 + e ] ), sm.sp[ j ], y ) ) );
-								ych[ k ] = y;
-							}
-							else
-							{
-								float y = ych[ k ];
-								for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( sv[ (size_t)j * 64 + e ] );
-								ych[ k ] = y;
-							}
-						}
+						y = 0.0f;
+						for( int j = j0; j < j1; j++ ) y += sm.sp[ j ] * __half2float( sv[ (size_t)j * 64 + e ] );
 					}
-				}
-#pragma unroll
-				for( int k = 0; k < 4; k++ )
-				{
-					const int idx = tid + k * MG_THREADS;
-					if( idx < parts * 64 ) so[ idx ] = ych[ k ];
+					so[ idx ] = y;
 				}
 				__syncthreads();
-				tmark( 4 );
 				if( tid < 64 )
 				{
 					float acc = so[ tid ];
