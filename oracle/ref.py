@@ -40,6 +40,7 @@ def lib():
         L.ora_get_probs.argtypes = [vp, fp]
         L.ora_sample_best.argtypes = [vp, ip, fp]
         L.ora_sample_timestamp.argtypes = [vp, ci, ip, fp]
+        L.ora_tokenize.restype = ci; L.ora_tokenize.argtypes = [vp, C.c_char_p, ip, ci]
         L.ora_cross_kv_elements.restype = C.c_int64; L.ora_cross_kv_elements.argtypes = [vp]
         L.ora_get_cross_kv.argtypes = [vp, fp, fp]
         L.ora_self_kv_elements.restype = C.c_int64; L.ora_self_kv_elements.argtypes = [vp]
@@ -130,6 +131,11 @@ class RefOracle:
         self.L.ora_get_logits(self.ctx, _f(logits))
         self.L.ora_get_probs(self.ctx, _f(probs))
         return logits.reshape(t.size, self.n_vocab), probs.reshape(t.size, self.n_vocab)
+
+    def tokenize(self, text: bytes, cap: int = 256):
+        out = np.zeros(cap, np.int32)
+        n = self.L.ora_tokenize(self.ctx, text, _i(out), cap)
+        return None if n < 0 else out[:n].tolist()
 
     def sample(self, initial: bool = False, force_timestamp: bool = False):
         ids = np.zeros(2, np.int32)

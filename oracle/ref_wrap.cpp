@@ -148,6 +148,8 @@ static void packToken( const whisper_token_data& t, int32_t* ids2, float* f3 )
 	ids2[ 0 ] = t.id; ids2[ 1 ] = t.tid; f3[ 0 ] = t.p; f3[ 1 ] = t.pt; f3[ 2 ] = t.ptsum;
 }
 void ora_sample_best( whisper_context* c, int32_t* ids2, float* f3 ) { packToken( whisper_sample_best( c ), ids2, f3 ); }
+// GPT-2 pre-split + greedy longest match (whisper.cpp:2192-2245, 2378-2391); returns the token count or -1
+int ora_tokenize( whisper_context* c, const char* text, int32_t* tokens, int cap ) { return whisper_tokenize( c, text, tokens, cap ); }
 void ora_sample_timestamp( whisper_context* c, int is_initial, int32_t* ids2, float* f3 ) { packToken( whisper_sample_timestamp( c, is_initial != 0 ), ids2, f3 ); }
 
 // f16 cross-attention memories written by whisper_encode (whisper.cpp:1479-1485), as f32: [n_text_layer][n_ctx][n_state]

@@ -131,7 +131,20 @@ def make_full():
     return out
 
 
+TOKENIZER_TEXTS = [b" hello hellox 12345!", b" hello world's , worlds 345 12", b" t12 t345", b""]
+
+
+def make_tokenizer():
+    """Prints the TOKENIZER_GOLDEN table of tests/test_gpu_com.py: whisper_tokenize of the reference on the "-words" vocabulary."""
+    o = RefOracle(synth.model_path("micro.en-words"))
+    for t in TOKENIZER_TEXTS:
+        print("    %r: %r," % (t, o.tokenize(t)))
+
+
 if __name__ == "__main__":
+    if "--tokenizer" in sys.argv:
+        make_tokenizer()
+        sys.exit(0)
     data = make_full()
     p = os.path.join(HERE, "full_micro_en_ts.npz")
     np.savez_compressed(p, **data)

@@ -295,7 +295,10 @@ def stage_megatiming(model_name="medium", batch=8):
     ids, t = raw[:, 0], raw[:, 1]
     print("  marks", len(ids), "total us", (t[-1] - t[0]) / 1000.0, flush=True)
     # generic: average interval from each mark id-class to the next mark
-    names = {1001: "P1 staged", 1002: "P1 computed", 1003: "P3 staged", 1004: "P3 computed", 1007: "P7 staged", 1008: "P7 computed"}
+    names = {}
+    for ph in range(8):   # GEMV phases mark 1001 + 2*ph when the activations are staged, 1002 + 2*ph when computed (ph = 0-based phase)
+        names[1001 + 2 * ph] = "P%d staged" % (ph + 1)
+        names[1002 + 2 * ph] = "P%d computed" % (ph + 1)
     L = m.n_text_layer
     acc = {}
     for k in range(len(ids) - 1):

@@ -408,7 +408,11 @@ namespace
 						if( i == n ) break;
 						if( j == i )
 						{
-							logMessage( eLogLevel::Warning, "tokenize: unknown token '%c'", word[ i ] );
+							// Reached both when nothing matched and right after a match that did not end the word (i was just set to j):
+							// the reference then emits the next character on its own (whisper.cpp:2232-2241).  Kept, quirk included.
+							auto f1 = vocabMap.find( word.substr( i, 1 ) );
+							if( f1 != vocabMap.end() ) out.push_back( f1->second );
+							else logMessage( eLogLevel::Warning, "tokenize: unknown token '%c'", word[ i ] );
 							++i;
 						}
 					}

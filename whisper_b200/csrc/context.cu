@@ -359,6 +359,10 @@ namespace wsp
 			ma.tokEmb = e.tokEmb; ma.decPos = e.decPos; ma.lnfg = e.decLn.g; ma.lnfb = e.decLn.b;
 			ma.tokens = c.tokensDev; ma.dNPast = c.dNPast;
 			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier; ma.timing = getenv( "WSP_MEGA_TIMING" ) ? c.megaTiming : nullptr;
+			{
+				const char* mf = getenv( "WSP_MEGA_FLAGS" );
+				ma.flags = mf ? atoi( mf ) : 0;
+			}
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepMega( ma, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

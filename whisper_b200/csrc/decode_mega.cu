@@ -138,7 +138,6 @@ namespace kern
 				}
 				__syncthreads();
 			}
-			__device__ __forceinline__ void sync() { arrive(); wait(); }
 		};
 
 		// -----------------------------------------------------------------------------------------------------------
@@ -175,11 +174,13 @@ namespace kern
 		};
 
 		// registers holding one batch of weights
-		template<int K>
-		struct WBatch
+		// (one type for every K, so that the d-wide phases and fc2 share the same 16 x 128-bit registers in the phase loop)
+		struct WRegs
 		{
-			uint4 w[ GemvShape<K>::UPB * GemvShape<K>::SUB ];
+			uint4 w[ 16 ];
 		};
+		template<int K>
+		using WBatch = WRegs;
 
 		template<int K>
 		__device__ __forceinline__ void loadBatch( WBatch<K>& wb, const GemvOp& op, int firstUnitIdx, int nMine, int sub, int warp, int lane )
@@ -698,27 +699,61 @@ namespace kern
 			mark();
 			__half* sx = reinterpret_cast<__half*>( sm.a );
 
-			WBatch<D> wbD;
-			WBatch<4 * D> wb4D;
+			static_assert( GemvShape<D>::UPB * GemvShape<D>::SUB <= 16 && GemvShape<4 * D>::UPB * GemvShape<4 * D>::SUB <= 16, "register batch" );
+			WRegs wb;
 			GemvOp base{};
 			base.d = D; base.nTextCtx = a.nTextCtx; base.nPast = nPast; base.scale = 1.0f;
 
-			auto opQKV = [ & ]( const MegaLayer& L ) {
+			// The phases of a layer.  The step is ONE loop over (layer, phase) with a single call site per code path: the straight-line
+			// version instantiated the GEMV code seven times (12.4 K SASS instructions = 199 KB, 16 % of all stall samples were
+			// instruction-fetch misses); this form keeps the kernel within reach of the instruction cache.
+			enum { PH_QKV = 0, PH_SELF = 1, PH_O = 2, PH_CQ = 3, PH_CROSS = 4, PH_CO = 5, PH_FC1 = 6, PH_FC2 = 7, PH_COUNT = 8 };
+			// operands of GEMV phase `ph` of layer `il`; il == L is the final LayerNorm + logits (a17)
+			auto makeOp = [ & ]( int il, int ph ) {
 				GemvOp o = base;
-				o.W = L.wqkv; o.nOut = 3 * D; o.xF32 = a.x; o.xStride = D; o.gamma = L.ln1g; o.beta = L.ln1b;
-				o.epi = EP_QKV; o.bias = L.bqkv; o.scale = qkScale; o.outF32 = a.q; o.ld = D; o.kCache = L.kCache; o.vCache = L.vCache;
+				if( il >= a.L )
+				{
+					o.W = a.tokEmb; o.nOut = a.nVocab; o.xF32 = a.x; o.xStride = D; o.gamma = a.lnfg; o.beta = a.lnfb;
+					o.epi = EP_LOGITS; o.outF32 = a.logits; o.ld = a.nVocab;
+					return o;
+				}
+				const MegaLayer& L = a.layers[ il ];
+				switch( ph )
+				{
+				case PH_QKV:   // LN1 + (Q | K | V), K/V appended to the cache (a14)
+					o.W = L.wqkv; o.nOut = 3 * D; o.xF32 = a.x; o.xStride = D; o.gamma = L.ln1g; o.beta = L.ln1b;
+					o.epi = EP_QKV; o.bias = L.bqkv; o.scale = qkScale; o.outF32 = a.q; o.ld = D; o.kCache = L.kCache; o.vCache = L.vCache;
+					break;
+				case PH_O:     // self-attention out projection + residual
+					o.W = L.wo; o.nOut = D; o.xF16 = a.attn; o.xStride = D; o.epi = EP_RESID; o.bias = L.bo; o.outF32 = a.x; o.ld = D;
+					break;
+				case PH_CQ:    // cross-attention query (a15)
+					o.W = L.wcq; o.nOut = D; o.xF32 = a.x; o.xStride = D; o.gamma = L.lncg; o.beta = L.lncb;
+					o.epi = EP_QSCALE; o.bias = L.bcq; o.scale = qkScale; o.outF32 = a.q; o.ld = D;
+					break;
+				case PH_CO:    // cross-attention out projection + residual
+					o.W = L.wco; o.nOut = D; o.xF16 = a.attn; o.xStride = D; o.epi = EP_RESID; o.bias = L.bco; o.outF32 = a.x; o.ld = D;
+					break;
+				case PH_FC1:   // LN3 + fc1 + GELU (a16)
+					o.W = L.w1; o.nOut = 4 * D; o.xF32 = a.x; o.xStride = D; o.gamma = L.ln3g; o.beta = L.ln3b;
+					o.epi = EP_GELU; o.bias = L.b1; o.outF16 = a.h; o.ld = 4 * D;
+					break;
+				default:       // PH_FC2: fc2 + residual
+					o.W = L.w2; o.nOut = D; o.xF16 = a.h; o.xStride = 4 * D; o.epi = EP_RESID; o.bias = L.b2; o.outF32 = a.x; o.ld = D;
+					break;
+				}
 				return o;
 			};
-			// everything a phase needs that does not depend on the previous phase is requested before the barrier
+			// everything a phase needs that does not depend on the previous phase is requested before the barrier wait
 			auto prepD = [ & ]( const GemvOp& o ) {
-				loadBatch<D>( wbD, o, 0, myUnits<D>( o ), 0, warp, lane );
+				loadBatch<D>( wb, o, 0, myUnits<D>( o ), 0, warp, lane );
 				prefetchParams( o, D, sm, tid );
 			};
 			// after the barrier: parameters have landed
 			auto landed = [ & ]() { cpAsyncWaitAll(); __syncthreads(); };
 
 			// a layer's cross-attention K/V tile of "my" (chunk, head) starts moving HBM -> L2 several phases ahead of its use (those
-			// phases are latency-bound and leave the DRAM pipe idle); issued right before a barrier wait, off the critical path
+			// phases are latency-bound and leave the DRAM pipe idle); issued while waiting at a barrier, off the critical path
 			auto crossL2 = [ & ]( const MegaLayer& L ) {
 				if( (int)blockIdx.x < B * a.H )
 				{
@@ -730,7 +765,7 @@ namespace kern
 			};
 
 			// ---- embedding (a13) by the first B CTAs; layer 0's QKV weights and LayerNorm parameters are already in flight ----
-			GemvOp op = opQKV( a.layers[ 0 ] );
+			GemvOp op = makeOp( 0, PH_QKV );
 			prepD( op );
 			for( int b = blockIdx.x; b < B; b += gridDim.x )
 			{
@@ -743,114 +778,84 @@ namespace kern
 			crossL2( a.layers[ 0 ] );
 			mark(); grid.wait(); mark();
 
-			for( int il = 0; il < a.L; il++ )
+			CrossPrefetch pf;
+			pf.unit = 0;
+#pragma unroll 1
+			for( int il = 0; il <= a.L; il++ )
 			{
-				const MegaLayer& L = a.layers[ il ];
-				// ---- P1: LN1 + (Q | K | V), K/V appended to the cache (a14) ----
-				landed();
-				stageLN<D>( op, B, sx, sm, warp, lane );
-				__syncthreads();
-				markId( 1001 );
-				gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
-				markId( 1002 );
-				grid.arrive();
-				GemvOp opO = base;
-				opO.W = L.wo; opO.nOut = D; opO.xF16 = a.attn; opO.xStride = D; opO.epi = EP_RESID; opO.bias = L.bo; opO.outF32 = a.x; opO.ld = D;
-				prepD( opO );
-				// earlier tokens' K/V rows of my (chunk, head) -> smem (region A is free: P1's activations are consumed)
-				selfLoadRows( a, L, D, sm, blockIdx.x, 0, nkvOld, tid );
-				cpAsyncCommit();
-				mark(); grid.wait(); mark();
-				// ---- P2: self attention ----
-				selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid );
-				mark(); grid.sync(); mark();
-				// ---- P3: out projection + residual ----
-				landed();
-				stageF16<D>( opO, B, sx, tid );
-				__syncthreads();
-				markId( 1003 );
-				gemvCompute<D>( opO, B, wbD, sm, warp, lane, tid );
-				markId( 1004 );
-				grid.arrive();
-				GemvOp opQ = base;
-				opQ.W = L.wcq; opQ.nOut = D; opQ.xF32 = a.x; opQ.xStride = D; opQ.gamma = L.lncg; opQ.beta = L.lncb;
-				opQ.epi = EP_QSCALE; opQ.bias = L.bcq; opQ.scale = qkScale; opQ.outF32 = a.q; opQ.ld = D;
-				prepD( opQ );
-				mark(); grid.wait(); mark();
-				// ---- P4: cross-attention query (a15) ----
-				landed();
-				stageLN<D>( opQ, B, sx, sm, warp, lane );
-				__syncthreads();
-				gemvCompute<D>( opQ, B, wbD, sm, warp, lane, tid );
-				grid.arrive();   // (its block barrier also frees region A for the V tile)
-				CrossPrefetch pf;
-				crossPrefetch( a, L, pf, sm, blockIdx.x, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
-				mark(); grid.wait(); mark();
-				// ---- P5: cross attention ----
-				crossAttnPhase( a, L, D, pf, sm, warp, lane, tid );
-				grid.arrive();
-				GemvOp opC = base;
-				opC.W = L.wco; opC.nOut = D; opC.xF16 = a.attn; opC.xStride = D; opC.epi = EP_RESID; opC.bias = L.bco; opC.outF32 = a.x; opC.ld = D;
-				prepD( opC );
-				mark(); grid.wait(); mark();
-				// ---- P6: cross out projection + residual ----
-				landed();
-				stageF16<D>( opC, B, sx, tid );
-				__syncthreads();
-				gemvCompute<D>( opC, B, wbD, sm, warp, lane, tid );
-				grid.arrive();
-				GemvOp op1 = base;
-				op1.W = L.w1; op1.nOut = 4 * D; op1.xF32 = a.x; op1.xStride = D; op1.gamma = L.ln3g; op1.beta = L.ln3b;
-				op1.epi = EP_GELU; op1.bias = L.b1; op1.outF16 = a.h; op1.ld = 4 * D;
-				prepD( op1 );
-				mark(); grid.wait(); mark();
-				// ---- P7: LN3 + fc1 + GELU (a16) ----
-				landed();
-				if( il + 1 == a.L )
+				const MegaLayer& L = a.layers[ il < a.L ? il : a.L - 1 ];
+#pragma unroll 1
+				for( int ph = 0; ph < PH_COUNT; ph++ )
 				{
-					// last layer: start pulling this CTA's rows of the unembedding matrix into L2 (106 MB over all CTAs)
-					const int units = ( a.nVocab + MG_ROWS - 1 ) / MG_ROWS;
-					for( int u = blockIdx.x; u < units; u += gridDim.x )
+					// ---------------- the phase's work ----------------
+					if( ph == PH_SELF ) selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid );
+					else if( ph == PH_CROSS ) crossAttnPhase( a, L, D, pf, sm, warp, lane, tid );
+					else if( ph == PH_FC2 )
 					{
-						const uint8_t* wp = reinterpret_cast<const uint8_t*>( a.tokEmb + (size_t)u * MG_ROWS * D );
-						const int rows = min( MG_ROWS, a.nVocab - u * MG_ROWS );
-						for( int i = tid; i < rows * D * 2 / 128; i += MG_THREADS ) prefetchL2( wp + (size_t)i * 128 );
+						landed();
+						stageF16<4 * D>( op, B, sx, tid );
+						__syncthreads();
+						markId( 1001 + 2 * PH_FC2 );
+						gemvCompute<4 * D>( op, B, wb, sm, warp, lane, tid );
+						markId( 1002 + 2 * PH_FC2 );
 					}
+					else
+					{
+						landed();
+						if( ph == PH_FC1 && il + 1 == a.L )
+						{
+							// last layer: start pulling this CTA's rows of the unembedding matrix into L2 (106 MB over all CTAs)
+							const int units = ( a.nVocab + MG_ROWS - 1 ) / MG_ROWS;
+							for( int u = blockIdx.x; u < units; u += gridDim.x )
+							{
+								const uint8_t* wp = reinterpret_cast<const uint8_t*>( a.tokEmb + (size_t)u * MG_ROWS * D );
+								const int rows = min( MG_ROWS, a.nVocab - u * MG_ROWS );
+								for( int i = tid; i < rows * D * 2 / 128; i += MG_THREADS ) prefetchL2( wp + (size_t)i * 128 );
+							}
+						}
+						if( op.xF32 ) stageLN<D>( op, B, sx, sm, warp, lane );
+						else stageF16<D>( op, B, sx, tid );
+						__syncthreads();
+						markId( 1001 + 2 * ph );
+						gemvCompute<D>( op, B, wb, sm, warp, lane, tid );
+						markId( 1002 + 2 * ph );
+					}
+					if( il == a.L ) break;   // the logits were the last thing to do
+					grid.arrive();
+					// ---------------- requests for what follows, issued while the other CTAs arrive ----------------
+					int nextPh = -1, nextIl = il;
+					switch( ph )
+					{
+					case PH_QKV: nextPh = PH_O; break;          // (self attention does not use the weight registers)
+					case PH_O: nextPh = PH_CQ; break;
+					case PH_CROSS: nextPh = PH_CO; break;
+					case PH_CO: nextPh = PH_FC1; break;
+					case PH_FC2: nextPh = PH_QKV; nextIl = il + 1; break;
+					default: break;
+					}
+					if( nextPh >= 0 )
+					{
+						op = makeOp( nextIl, nextPh );
+						prepD( op );
+					}
+					if( ph == PH_QKV )
+					{
+						// earlier tokens' K/V rows of my (chunk, head) -> smem (region A is free: the activations are consumed)
+						selfLoadRows( a, L, D, sm, blockIdx.x, 0, nkvOld, tid );
+						cpAsyncCommit();
+					}
+					else if( ph == PH_CQ )
+						crossPrefetch( a, L, pf, sm, blockIdx.x, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
+					else if( ph == PH_FC1 )
+					{
+						op = makeOp( il, PH_FC2 );
+						loadBatch<4 * D>( wb, op, 0, myUnits<4 * D>( op ), 0, warp, lane );
+						prefetchParams( op, 4 * D, sm, tid );
+					}
+					else if( ph == PH_FC2 && il + 1 < a.L ) crossL2( a.layers[ il + 1 ] );
+					mark(); grid.wait(); mark();
 				}
-				stageLN<D>( op1, B, sx, sm, warp, lane );
-				__syncthreads();
-				markId( 1007 );
-				gemvCompute<D>( op1, B, wbD, sm, warp, lane, tid );
-				markId( 1008 );
-				grid.arrive();
-				GemvOp op2 = base;
-				op2.W = L.w2; op2.nOut = D; op2.xF16 = a.h; op2.xStride = 4 * D; op2.epi = EP_RESID; op2.bias = L.b2; op2.outF32 = a.x; op2.ld = D;
-				loadBatch<4 * D>( wb4D, op2, 0, myUnits<4 * D>( op2 ), 0, warp, lane );
-				prefetchParams( op2, 4 * D, sm, tid );
-				mark(); grid.wait(); mark();
-				// ---- P8: fc2 + residual ----
-				landed();
-				stageF16<4 * D>( op2, B, sx, tid );
-				__syncthreads();
-				gemvCompute<4 * D>( op2, B, wb4D, sm, warp, lane, tid );
-				grid.arrive();
-				// next: QKV of the following layer, or the final LayerNorm + logits
-				if( il + 1 < a.L ) op = opQKV( a.layers[ il + 1 ] );
-				else
-				{
-					op = base;
-					op.W = a.tokEmb; op.nOut = a.nVocab; op.xF32 = a.x; op.xStride = D; op.gamma = a.lnfg; op.beta = a.lnfb;
-					op.epi = EP_LOGITS; op.outF32 = a.logits; op.ld = a.nVocab;
-				}
-				prepD( op );
-				if( il + 1 < a.L ) crossL2( a.layers[ il + 1 ] );
-				mark(); grid.wait(); mark();
 			}
-			// ---- final LayerNorm + logits = tok_emb^T x (a17) ----
-			landed();
-			stageLN<D>( op, B, sx, sm, warp, lane );
-			__syncthreads();
-			gemvCompute<D>( op, B, wbD, sm, warp, lane, tid );
 			mark();
 		}
 

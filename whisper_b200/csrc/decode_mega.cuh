@@ -31,6 +31,7 @@ namespace kern
 		float* logits = nullptr;            // [B][nVocab]
 		unsigned* barrier = nullptr;        // grid barrier counter (zeroed by the launcher)
 		unsigned long long* timing = nullptr;   // optional: %globaltimer marks of CTA 0 around every barrier (debug)
+		int flags = 0;                      // experiment switches (env WSP_MEGA_FLAGS) for same-box A/B runs; 0 = the shipped configuration
 	};
 	bool megaSupported( int d, int B, int T );
 	cudaError_t megaPrepare( int d );   // function attributes, outside any stream capture

@@ -107,6 +107,7 @@ namespace kern
 		int* history = nullptr;         // optional [B][histCap] token log, written at column *dStep
 		int histCap = 0;
 		int* dStep = nullptr;
+		int rowInSmem = 0;              // set by sampleGreedy: the row fits the 227 KB shared memory
 	};
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s );
 

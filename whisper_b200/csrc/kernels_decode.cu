@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace kern
 {
@@ -686,17 +687,25 @@ namespace kern
 		const int tid = threadIdx.x;
 		const int nv = a.nVocab;
 		const float* lg = a.logits + (size_t)b * nv;
-		float* pr = a.probs + (size_t)b * nv;
+		float* gpr = a.probs + (size_t)b * nv;
+		// the row lives in shared memory when it fits (207 KB for 51865 tokens): seven passes over L2 cost 65 us, over smem ~15 us
+		extern __shared__ float sampleRow[];
+		float* pr = a.rowInSmem ? sampleRow : gpr;
 		const bool forceTs = a.dForceTs && a.dForceTs[ 0 ] != 0;
 		const bool isInitial = a.dForceTs && a.dForceTs[ 1 ] != 0;
 
 		float mx = -INFINITY;
-		for( int i = tid; i < nv; i += SM_THREADS ) mx = fmaxf( mx, lg[ i ] );
+		for( int i = tid; i < nv; i += SM_THREADS )
+		{
+			const float v = __ldcg( lg + i );
+			pr[ i ] = v;
+			mx = fmaxf( mx, v );
+		}
 		mx = blockMaxF( mx, sf );
 		double dsum = 0.0;
 		for( int i = tid; i < nv; i += SM_THREADS )
 		{
-			const float e = expF16Table( lg[ i ] - mx );
+			const float e = expF16Table( pr[ i ] - mx );
 			pr[ i ] = e;
 			dsum += (double)e;
 		}
@@ -712,6 +721,7 @@ namespace kern
 		{
 			const float p = pr[ i ] * inv;
 			pr[ i ] = p;
+			if( a.rowInSmem ) gpr[ i ] = p;
 			if( i < beg ) maxTx = fmaxf( maxTx, p );
 			else if( i < tsEnd )
 			{
@@ -799,7 +809,18 @@ namespace kern
 
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s )
 	{
-		cudaError_t e = launchPdl( sample_kernel, dim3( a.B ), dim3( SM_THREADS ), 0, s, a );
+		SampleArgs sa = a;
+		const size_t rowBytes = (size_t)a.nVocab * sizeof( float );
+		static const bool forceGlobal = getenv( "WSP_SAMPLER_GLOBAL" ) != nullptr;   // A/B switch for measurements
+		sa.rowInSmem = ( rowBytes <= 220 * 1024 && !forceGlobal ) ? 1 : 0;
+		static size_t smemSet = 0;
+		if( sa.rowInSmem && rowBytes > smemSet )
+		{
+			cudaError_t ea = cudaFuncSetAttribute( sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowBytes );
+			if( ea != cudaSuccess ) return ea;
+			smemSet = rowBytes;
+		}
+		cudaError_t e = launchPdl( sample_kernel, dim3( a.B ), dim3( SM_THREADS ), sa.rowInSmem ? rowBytes : 0, s, sa );
 		if( e != cudaSuccess ) return e;
 		// step-global state is advanced by a separate 1-thread kernel so that no CTA of the sampler races with it
 		return launchPdl( advance_kernel, dim3( 1 ), dim3( 1 ), 0, s, a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );

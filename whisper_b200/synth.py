@@ -123,7 +123,22 @@ def _mel_filters(n_mel=80, n_fft=201, seed=7):
     return f
 
 
-def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0, ts_boost: float = 1.0, eot_boost: float = 1.0) -> HParams:
+def tokenizer_test_words(i: int) -> bytes:
+    """Vocabulary of the "-words" model variants: letters, digits, space and a few multi-character entries, so that the GPT-2
+    pre-split + greedy longest match of the reference tokenizer (whisper.cpp:2192-2245) has something to match."""
+    special = {100: b" hello", 101: b"hel", 102: b"lo", 103: b" 12", 104: b"345", 105: b" wor", 106: b"ld", 107: b"'s", 108: b" ,", 109: b" world"}
+    if i < 26:
+        return bytes([97 + i])
+    if i < 36:
+        return bytes([48 + i - 26])
+    if i == 36:
+        return b" "
+    if i in special:
+        return special[i]
+    return (" t%d" % i).encode() if i != 50256 else b""
+
+
+def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0, ts_boost: float = 1.0, eot_boost: float = 1.0, words=None) -> HParams:
     """Write a synthetic ggml model file.  Matrices ~ N(0, 1/fan_in) stored f16; LN gamma = 1 + N(0, 0.01);
     biases N(0, 0.01); positional embeddings N(0, 0.01); the token embedding is scaled by
     `emb_scale` so that greedy decisions are not near-ties on random weights (SURVEY.md §7 "Parity definition")."""
@@ -140,7 +155,7 @@ def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0,
         f.write(struct.pack("<i", n_words))
         chunks = []
         for i in range(n_words):
-            w = (" t%d" % i).encode() if i != 50256 else b""
+            w = words(i) if words else ((" t%d" % i).encode() if i != 50256 else b"")
             chunks.append(struct.pack("<I", len(w)) + w)
         f.write(b"".join(chunks))
         for name, ne, is_f16, kind in tensor_list(hp):
@@ -180,6 +195,8 @@ def model_path(name: str, seed: int = 1234, cache_dir: str | None = None) -> str
     if not os.path.exists(p):
         if name.endswith("-ts"):
             write_model(p, name[:-3], seed, ts_boost=1.3, eot_boost=2.2)
+        elif name.endswith("-words"):
+            write_model(p, name[:-6], seed, words=tokenizer_test_words)
         else:
             write_model(p, name, seed)
     return p
