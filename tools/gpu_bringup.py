@@ -37,6 +37,27 @@ def stage_gemm():
         err_stats("gemm %dx%dx%d bn%d" % (M, N, K, bn), D, ref)
 
 
+def stage_gemm_stress():
+    """Repeat the large GEMM shapes and report WHERE any mismatch is (race hunting)."""
+    from whisper_b200 import capi
+    for (M, N, K, bn) in [(12000, 1280, 1280, 256), (12000, 1024, 1024, 256), (12000, 4096, 1024, 256), (12000, 1024, 4096, 256)]:
+        rng = np.random.default_rng(M * 7 + N)
+        A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+        B = (rng.standard_normal((N, K)) * 0.5).astype(np.float16)
+        ref = A.astype(np.float32) @ B.astype(np.float32).T
+        bad = 0
+        for it in range(40):
+            D, _ = capi.test_gemm(A, B, bn=bn, iters=(3 if it % 2 else 0))
+            err = np.abs(D - ref)
+            if err.max() > 1e-3:
+                bad += 1
+                rows, cols = np.nonzero(err > 1e-3)
+                print("  iter %d: %d bad elements, max err %.3e; rows %d..%d (tiles %s) cols %d..%d (tiles %s); sample D=%.4f ref=%.4f" % (
+                    it, rows.size, err.max(), rows.min(), rows.max(), sorted(set((rows // 128).tolist()))[:8], cols.min(), cols.max(),
+                    sorted(set((cols // bn).tolist()))[:8], D[rows[0], cols[0]], ref[rows[0], cols[0]]), flush=True)
+        print("  gemm %dx%dx%d bn%d: %d / 40 runs with mismatches" % (M, N, K, bn, bad), flush=True)
+
+
 def stage_gemm_perf():
     from whisper_b200 import capi
     rng = np.random.default_rng(1)
@@ -322,7 +343,7 @@ STAGES = {
     "gemm": stage_gemm, "ln": stage_ln, "skinny": stage_skinny, "attn": stage_attn, "mel": stage_mel,
     "encoder": stage_encoder, "decoder": stage_decoder, "batch": stage_batch,
     "encoder_tiny": stage_encoder_tiny, "decoder_tiny": stage_decoder_tiny,
-    "gemm_perf": stage_gemm_perf, "perf": stage_perf, "profile": stage_profile, "megatiming": stage_megatiming,
+    "gemm_perf": stage_gemm_perf, "gemm_stress": stage_gemm_stress, "perf": stage_perf, "profile": stage_profile, "megatiming": stage_megatiming,
 }
 
 if __name__ == "__main__":

@@ -716,13 +716,20 @@ namespace kern
 		const int tsEnd = isInitial ? min( beg + 101, nv ) : nv;   // initial timestamp <= 1 s (whisper.cpp:1902-1911)
 		float maxTx = -1.0f;
 		double sumTs = 0.0;
+		// The reference ranks the top 4 and skips sot / solm / not at most 3 times (whisper.cpp:1945-1953); those are the only three
+		// banned ids, so the pick is simply the arg-max over every other eligible token.  Eligibility depends on the timestamp test
+		// below, hence two candidates from the same pass: the best text token and the best timestamp token.
 		Top1 bestTs = { -INFINITY, 0x7fffffff };
+		Top1 bestTx = { -INFINITY, 0x7fffffff };
 		for( int i = tid; i < nv; i += SM_THREADS )
 		{
 			const float p = pr[ i ] * inv;
-			pr[ i ] = p;
-			if( a.rowInSmem ) gpr[ i ] = p;
-			if( i < beg ) maxTx = fmaxf( maxTx, p );
+			if( a.rowInSmem ) gpr[ i ] = p; else pr[ i ] = p;
+			if( i < beg )
+			{
+				maxTx = fmaxf( maxTx, p );
+				if( i != a.tokenSot && i != a.tokenSolm && i != a.tokenNot ) bestTx = better( bestTx, Top1{ p, i } );
+			}
 			else if( i < tsEnd )
 			{
 				sumTs += (double)p;
@@ -732,36 +739,17 @@ namespace kern
 		maxTx = blockMaxF( maxTx, sf );
 		sumTs = blockSumD( sumTs, sd );
 		bestTs = blockArgmax( bestTs, st );
+		bestTx = blockArgmax( bestTx, st );
 		const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
-
-		// top-4 of the (masked) distribution by repeated argmax
-		int topI[ 4 ];
-		float topV[ 4 ];
-		for( int k = 0; k < 4; k++ )
-		{
-			Top1 best = { -INFINITY, 0x7fffffff };
-			for( int i = tid; i < nv; i += SM_THREADS )
-			{
-				bool skip = false;
-				for( int kk = 0; kk < k; kk++ ) skip |= ( topI[ kk ] == i );
-				if( skip ) continue;
-				float p = pr[ i ];
-				if( maskText && i < beg ) p = -INFINITY;
-				if( isInitial && i >= beg + 101 ) p = -INFINITY;
-				best = better( best, Top1{ p, i } );
-			}
-			best = blockArgmax( best, st );
-			topI[ k ] = best.i;
-			topV[ k ] = best.v;
-		}
 		if( tid == 0 )
 		{
-			int res = 0;
-			while( ( topI[ res ] == a.tokenSot || topI[ res ] == a.tokenSolm || topI[ res ] == a.tokenNot ) && res < 3 ) res++;
+			Top1 pick = bestTs;
+			if( !maskText ) pick = better( bestTx, bestTs );
+			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0 };
 			TokenData td;
-			td.id = topI[ res ];
+			td.id = pick.i;
 			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
-			td.p = topV[ res ];
+			td.p = pick.v;
 			td.pt = (float)( (double)bestTs.v / ( sumTs + 1e-10 ) );
 			td.ptsum = (float)sumTs;
 			a.out[ b ] = td;

@@ -68,6 +68,14 @@ namespace ptx
 			::"r"( smem_u32( dst ) ), "l"( map ), "r"( smem_u32( bar ) ), "r"( c0 ), "r"( c1 )
 			: "memory" );
 	}
+	// 1-D bulk copy global -> shared by the TMA engine (no tensor map): one instruction moves up to the whole tile, completion is
+	// counted in bytes on the mbarrier.  Addresses and size must be multiples of 16.
+	__device__ __forceinline__ void bulk_load_1d( void* dst, const void* src, uint32_t bytes, uint64_t* bar )
+	{
+		asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"( smem_u32( dst ) ), "l"( src ),
+			"r"( bytes ), "r"( smem_u32( bar ) )
+			: "memory" );
+	}
 	__device__ __forceinline__ void prefetch_tensormap( const CUtensorMap* map )
 	{
 		asm volatile( "prefetch.tensormap [%0];" ::"l"( map ) : "memory" );
