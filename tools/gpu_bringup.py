@@ -309,9 +309,19 @@ def stage_megatiming(model_name="medium", batch=8):
     path, m, e, c = _open(model_name, batch=batch)
     pcms = [synth.synth_pcm(i) for i in range(batch)]
     c.run_chunks(pcms, m.prompt_init(), 40)
-    buf = (C.c_uint64 * 4096)()
-    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4096))
-    raw = np.array(buf[:], dtype=np.int64).reshape(-1, 2)
+    buf = (C.c_uint64 * 4608)()
+    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4608))
+    sub = np.array(buf[4000:4064], dtype=np.int64).reshape(8, 8)
+    print("  sub-marks of the last layer, CTA 0 thread 0 (us): entry->MMA done | ->reduced | ->epilogue | ->end | ->arrived(atomic back) | ->prefetch issued | ->flag seen")
+    for ph in range(8):
+        r = sub[ph]
+        if r[0] == 0 or r[5] == 0:
+            if r[5] and r[7]:
+                print("    P%d: arrive->prefetch issued %.2f | ->flag seen %.2f" % (ph + 1, (r[6] - r[5]) / 1e3, (r[7] - r[6]) / 1e3))
+            continue
+        d = np.diff(r) / 1e3
+        print("    P%d: %.2f | %.2f | %.2f | %.2f | %.2f | %.2f | %.2f" % ((ph + 1,) + tuple(d.tolist())), flush=True)
+    raw = np.array(buf[:4000], dtype=np.int64).reshape(-1, 2)
     raw = raw[raw[:, 1] > 0]
     ids, t = raw[:, 0], raw[:, 1]
     print("  marks", len(ids), "total us", (t[-1] - t[0]) / 1000.0, flush=True)

@@ -88,6 +88,17 @@ namespace kern
 			return y;
 		}
 
+		// debug: CTA 0 / thread 0 writes %globaltimer into a fixed slot (last layer wins); tm == nullptr in normal runs
+		__device__ __forceinline__ void subMark( unsigned long long* tm, int k )
+		{
+			if( tm && threadIdx.x == 0 )
+			{
+				unsigned long long t;
+				asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
+				tm[ k ] = t;
+			}
+		}
+
 		struct Smem
 		{
 			uint8_t* a;      // MG_SMEM_A
@@ -103,13 +114,15 @@ namespace kern
 		// in a separate 128-byte line that everybody else polls with acquire loads, so the pollers do not queue behind the atomics.
 		struct Grid
 		{
-			unsigned* counter;   // [0] arrivals, [32] epoch flag (separate line); both zeroed by the launcher
+			unsigned* counter;   // [0] arrivals, [32] epoch flag (separate line); zeroed by the launcher
 			unsigned target;
 			unsigned epoch;
+			// (measured alternative: per-CTA epoch slots polled by warp 0 of every CTA, no atomics — arrive got cheaper, 0.5-1.2 us
+			// instead of 0.8-2.1, but observing 148 slots cost more than it saved: decode 167 vs 160 ms)
 			// Split barrier: arrive() right after a phase's last global store, wait() after the next phase's prefetches have been
 			// issued.  (A release-atomic drains the issuing warp's outstanding loads first, so arriving AFTER the prefetch issue put
 			// an HBM round trip on every barrier's critical path: 2.3 -> 0.85 us per barrier, 1862 -> 1638 us per step.)
-			__device__ __forceinline__ void arrive()
+			__device__ __forceinline__ void arrive( unsigned long long* tm = nullptr )
 			{
 				target += gridDim.x;
 				epoch += 1;
@@ -120,6 +133,12 @@ namespace kern
 					asm volatile( "atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"( old ) : "l"( counter ) : "memory" );
 					if( old == target - 1 )
 						asm volatile( "st.release.gpu.global.u32 [%0], %1;" ::"l"( counter + 32 ), "r"( epoch ) : "memory" );
+					if( tm )
+					{
+						unsigned long long t;
+						asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
+						tm[ 5 ] = t;
+					}
 				}
 			}
 			__device__ __forceinline__ void wait()
@@ -346,8 +365,9 @@ namespace kern
 
 		// compute all units of this CTA; `wb` already holds the first batch (loaded before the barrier)
 		template<int K>
-		__device__ __forceinline__ void gemvCompute( const GemvOp& op, int B, WBatch<K>& wb, const Smem& sm, int warp, int lane, int tid )
+		__device__ __forceinline__ void gemvCompute( const GemvOp& op, int B, WBatch<K>& wb, const Smem& sm, int warp, int lane, int tid, unsigned long long* tm = nullptr )
 		{
+			subMark( tm, 0 );
 			using S = GemvShape<K>;
 			constexpr int RS = K + MG_PAD;
 			const __half* sx = reinterpret_cast<const __half*>( sm.a );
@@ -389,6 +409,7 @@ namespace kern
 							}
 						}
 				}
+				subMark( tm, 1 );   // MMA loop done (the weight registers had to have landed)
 				// cross-warp reduction: red[u][warp][row g][col]
 #pragma unroll
 				for( int u = 0; u < S::UPB; u++ )
@@ -399,6 +420,7 @@ namespace kern
 					if( twoTiles ) { my[ 8 + 2 * t ] = acc1[ u ][ 0 ]; my[ 8 + 2 * t + 1 ] = acc1[ u ][ 1 ]; }
 				}
 				__syncthreads();
+				subMark( tm, 2 );
 				for( int idx = tid; idx < S::UPB * ncols * MG_ROWS; idx += MG_THREADS )
 				{
 					const int u = idx / ( ncols * MG_ROWS );
@@ -416,8 +438,10 @@ namespace kern
 						gemvEpilogue( op, c, n, v, biasN );
 					}
 				}
+				subMark( tm, 3 );
 				__syncthreads();
 			}
+			subMark( tm, 4 );
 		}
 
 		// -----------------------------------------------------------------------------------------------------------
@@ -745,6 +769,7 @@ namespace kern
 				return o;
 			};
 			// everything a phase needs that does not depend on the previous phase is requested before the barrier wait
+			// (measured alternative: prefetching these rows into L2 only and loading the registers after the barrier is exactly as fast)
 			auto prepD = [ & ]( const GemvOp& o ) {
 				loadBatch<D>( wb, o, 0, myUnits<D>( o ), 0, warp, lane );
 				prefetchParams( o, D, sm, tid );
@@ -778,6 +803,7 @@ namespace kern
 			crossL2( a.layers[ 0 ] );
 			mark(); grid.wait(); mark();
 
+			unsigned long long* tmBase = ( a.timing && blockIdx.x == 0 ) ? a.timing + 4000 : nullptr;
 			CrossPrefetch pf;
 			pf.unit = 0;
 #pragma unroll 1
@@ -796,7 +822,7 @@ namespace kern
 						stageF16<4 * D>( op, B, sx, tid );
 						__syncthreads();
 						markId( 1001 + 2 * PH_FC2 );
-						gemvCompute<4 * D>( op, B, wb, sm, warp, lane, tid );
+						gemvCompute<4 * D>( op, B, wb, sm, warp, lane, tid, tmBase ? tmBase + ph * 8 : nullptr );
 						markId( 1002 + 2 * PH_FC2 );
 					}
 					else
@@ -817,11 +843,11 @@ namespace kern
 						else stageF16<D>( op, B, sx, tid );
 						__syncthreads();
 						markId( 1001 + 2 * ph );
-						gemvCompute<D>( op, B, wb, sm, warp, lane, tid );
+						gemvCompute<D>( op, B, wb, sm, warp, lane, tid, tmBase ? tmBase + ph * 8 : nullptr );
 						markId( 1002 + 2 * ph );
 					}
 					if( il == a.L ) break;   // the logits were the last thing to do
-					grid.arrive();
+					grid.arrive( tmBase ? tmBase + ph * 8 : nullptr );
 					// ---------------- requests for what follows, issued while the other CTAs arrive ----------------
 					int nextPh = -1, nextIl = il;
 					switch( ph )
@@ -853,7 +879,9 @@ namespace kern
 						prefetchParams( op, 4 * D, sm, tid );
 					}
 					else if( ph == PH_FC2 && il + 1 < a.L ) crossL2( a.layers[ il + 1 ] );
+					subMark( tmBase ? tmBase + ph * 8 : nullptr, 6 );
 					mark(); grid.wait(); mark();
+					subMark( tmBase ? tmBase + ph * 8 : nullptr, 7 );
 				}
 			}
 			mark();
