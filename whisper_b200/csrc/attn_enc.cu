@@ -25,6 +25,21 @@ namespace attn
 	constexpr int SMEM_BYTES = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + 128 + 1024;
 	constexpr uint32_t TMEM_COLS = 256;           // S: [0,128)  O tile: [128,192)
 
+	// 2^x on the MUFU pipe without exp2f's range-reduction wrapper (x <= 0 here; results below 2^-126 may flush to zero, far below
+	// the f16 P that is kept).  The wrapper cost ~12 extra instructions per score: the kernel was instruction-issue bound (54 %).
+	__device__ __forceinline__ float ex2Approx( float x )
+	{
+		float y;
+		asm( "ex2.approx.ftz.f32 %0, %1;" : "=f"( y ) : "f"( x ) );
+		return y;
+	}
+	__device__ __forceinline__ float max3( float a, float b, float c )
+	{
+		float y;
+		asm( "max.f32 %0, %1, %2, %3;" : "=f"( y ) : "f"( a ), "f"( b ), "f"( c ) );
+		return y;
+	}
+
 	__global__ void __launch_bounds__( 128, 2 )
 		attn_enc_kernel( const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapVt, EncParams p )
 	{
@@ -122,7 +137,8 @@ namespace attn
 			const int kv_base = j * TK;
 			const int nvalid = p.T - kv_base;   // columns >= nvalid are padding / the next head's rows
 
-			// pass 1: row maximum
+			// pass 1: row maximum (full tiles take the predicate-free path; only the last tile of a head has padding columns)
+			const bool fullTile = nvalid >= TK;
 			float mx = m_run;
 #pragma unroll 1
 			for( int ch = 0; ch < TK / 32; ch++ )
@@ -130,15 +146,25 @@ namespace attn
 				uint32_t rg[ 32 ];
 				ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), rg );
 				ptx::tmem_ld_wait();
-#pragma unroll
-				for( int i = 0; i < 32; i++ )
+				if( fullTile )
 				{
-					const float s = __uint_as_float( rg[ i ] );
-					if( ch * 32 + i < nvalid ) mx = fmaxf( mx, s );
+#pragma unroll
+					for( int i = 0; i < 32; i += 2 )
+						mx = max3( mx, __uint_as_float( rg[ i ] ), __uint_as_float( rg[ i + 1 ] ) );
+				}
+				else
+				{
+#pragma unroll
+					for( int i = 0; i < 32; i++ )
+					{
+						const float s = __uint_as_float( rg[ i ] );
+						if( ch * 32 + i < nvalid ) mx = fmaxf( mx, s );
+					}
 				}
 			}
-			const float alpha = exp2f( ( m_run - mx ) * c );   // m_run = -inf on the first tile -> 0
+			const float alpha = m_run == -INFINITY ? 0.0f : ex2Approx( ( m_run - mx ) * c );   // first tile: nothing to rescale
 			m_run = mx;
+			const float nmc = -mx * c;
 
 			// pass 2: probabilities -> f16 -> swizzled smem (A operand of P*V)
 			float lsum = 0.0f;
@@ -149,13 +175,25 @@ namespace attn
 				ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), rg );
 				ptx::tmem_ld_wait();
 				float pv[ 32 ];
-#pragma unroll
-				for( int i = 0; i < 32; i++ )
+				if( fullTile )
 				{
-					const float s = __uint_as_float( rg[ i ] );
-					const float e = ( ch * 32 + i < nvalid ) ? exp2f( ( s - mx ) * c ) : 0.0f;
-					pv[ i ] = e;
-					lsum += e;
+#pragma unroll
+					for( int i = 0; i < 32; i++ )
+					{
+						const float e = ex2Approx( fmaf( __uint_as_float( rg[ i ] ), c, nmc ) );
+						pv[ i ] = e;
+						lsum += e;
+					}
+				}
+				else
+				{
+#pragma unroll
+					for( int i = 0; i < 32; i++ )
+					{
+						const float e = ( ch * 32 + i < nvalid ) ? ex2Approx( fmaf( __uint_as_float( rg[ i ] ), c, nmc ) ) : 0.0f;
+						pv[ i ] = e;
+						lsum += e;
+					}
 				}
 				uint8_t* sub = sP + ( ch >> 1 ) * ( SP_BYTES / 2 ) + r * 128;
 #pragma unroll

@@ -170,8 +170,17 @@ namespace gemm
 	// separate instructions (measured: the out-projection GEMM ran at 17 % tensor-pipe utilisation, epilogue-bound).  The
 	// accumulator chunk (32 rows x 32 columns) is therefore transposed through a padded per-warp shared-memory tile so that a
 	// thread owns one COLUMN: every load / store instruction of the warp then covers 32 consecutive elements of one output row.
+	__device__ __forceinline__ void loadResid( const EpiParams& ep, int mBase, int n, float* rs )
+	{
+#pragma unroll
+		for( int rr = 0; rr < 32; rr++ )
+		{
+			const int m = mBase + rr;
+			rs[ rr ] = ( m < ep.M && n < ep.N ) ? ep.resid[ (size_t)m * ep.ld + n ] : 0.0f;
+		}
+	}
 	template<int MODE>
-	__device__ __forceinline__ void epilogueT( const EpiParams& ep, int mBase, int n, const float* w )
+	__device__ __forceinline__ void epilogueT( const EpiParams& ep, int mBase, int n, const float* w, const float* rs = nullptr )
 	{
 		if( n >= ep.N ) return;
 		if constexpr( MODE == EPI_F32 )
@@ -242,15 +251,9 @@ namespace gemm
 		}
 		else if constexpr( MODE == EPI_BIAS_RESID )
 		{
+			// rs = the residual column, fetched by the caller one 32-column chunk ahead (loadResid): the 32 loads of a chunk are a
+			// full L2 round trip, and with only 4 epilogue warps that latency - not bandwidth - set the epilogue time (16 us per tile)
 			const float b = ep.bias[ n ];
-			// resid may alias out_f32 (in-place residual add): read all 32 rows first so the loads are not serialised behind the stores
-			float rs[ 32 ];
-#pragma unroll
-			for( int rr = 0; rr < 32; rr++ )
-			{
-				const int m = mBase + rr;
-				rs[ rr ] = m < ep.M ? ep.resid[ (size_t)m * ep.ld + n ] : 0.0f;
-			}
 #pragma unroll
 			for( int rr = 0; rr < 32; rr++ )
 			{
@@ -442,6 +445,9 @@ namespace gemm
 			{
 				const int m0 = ( tile / num_n ) * BM;
 				const int n0 = ( tile % num_n ) * BN;
+				// the residual of the first column chunk does not depend on the accumulator: request it before waiting for the MMAs
+				float rsNext[ 32 ];
+				if constexpr( MODE == EPI_BIAS_RESID ) loadResid( ep, m0 + q * 32, n0 + lane, rsNext );
 				ptx::mbar_wait( &bar_tfull[ as ], aphase );
 				ptx::tc_fence_after();
 				const int m = m0 + q * 32 + lane;
@@ -477,7 +483,16 @@ namespace gemm
 						for( int rr = 0; rr < 32; rr++ )
 							w[ rr ] = xpose[ rr * 33 + lane ];
 						__syncwarp();
-						epilogueT<MODE>( ep, m0 + q * 32, nc + lane, w );
+						if constexpr( MODE == EPI_BIAS_RESID )
+						{
+							float rs[ 32 ];
+#pragma unroll
+							for( int rr = 0; rr < 32; rr++ ) rs[ rr ] = rsNext[ rr ];
+							if( c + 1 < BN / 32 ) loadResid( ep, m0 + q * 32, nc + 32 + lane, rsNext );   // next chunk's residual while this one is stored
+							epilogueT<MODE>( ep, m0 + q * 32, nc + lane, w, rs );
+						}
+						else
+							epilogueT<MODE>( ep, m0 + q * 32, nc + lane, w );
 					}
 				}
 				ptx::tc_fence_before();
