@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="chunks per GPU per step")
     ap.add_argument("--n-decode", type=int, default=100, help="greedy tokens per chunk (BASELINE.md §2)")
     ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: CPU threads (0 = min(cores, 16))")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference CPU leg (model sweeps; the default run keeps it)")
     ap.add_argument("--ref-tokens", type=int, default=12, help="reference arm: decoder tokens actually run per sample")
     return ap.parse_args()
 
@@ -327,8 +328,18 @@ def run_ours(a):
         kernel = "kern::skinny_gemm_kernel (decoder weight-streaming GEMM, 6 per layer + logits)"
         detail = {"launches_per_decoder_step": per_step}
     achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
+    # measured DRAM traffic of that kernel (ncu --set full, one capture per kernel change): profiles/ncu_traffic.json
+    traffic = None
+    if per_step <= 1.5:
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get("decode_step_kernel<%d>|B=%d|L=%d|T=%d" % (model.n_text_state, B, model.n_text_layer, model.n_audio_ctx))
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {
-        "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch,
         "decoder_step_ms_by_kind": {"decoder_kernel": ms_kind[0] / n_prof, "cross_attention": ms_kind[1] / n_prof, "self_attention": ms_kind[2] / n_prof, "sampler": ms_kind[3] / n_prof},
         "how": "wsp_profile_decode: %d un-graphed decoder steps, cudaEvent pair around every launch on the launching stream" % n_prof,
@@ -340,7 +351,7 @@ def run_ours(a):
     e2e_value = total_audio / (e2e_ms * 1e-3)
 
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = a.ref_threads or min(cores, 16)
         try:
