@@ -9,6 +9,7 @@ tensors are stored as deterministic sub-samples to keep the fixtures small.
 
     python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
 """
+import ctypes as C
 import os
 import sys
 
@@ -131,6 +132,31 @@ def make_full():
     return out
 
 
+# Real model shapes (BASELINE.json configs): greedy tokens of the bench loop (timestamp-first sampling, then whisper_sample_best) at
+# 4 reference threads, plus a subsample of the last step's logits.  Small files; the reference needs seconds (tiny) to a minute (medium).
+REAL_SHAPES = {"tiny.en": [0, 5], "base.en": [0, 5], "medium": [0, 5]}
+REAL_STEPS = 24
+
+
+def make_real_shapes():
+    out = {}
+    for model, chunks in REAL_SHAPES.items():
+        o = RefOracle(synth.model_path(model), threads=4)
+        prompt = np.array([o.special["sot"]] + ([o.special["sot"] + 1, o.special["transcribe"]] if o.n_vocab == 51865 else []), np.int32)
+        for ch in chunks:
+            pcm = synth.synth_pcm(ch)
+            secs, toks, st = o.bench_chunk(pcm, prompt, REAL_STEPS, threads=8)
+            logits = np.empty(o.L.ora_logits_size(o.ctx), np.float32)
+            o.L.ora_get_logits(o.ctx, logits.ctypes.data_as(C.POINTER(C.c_float)))
+            key = "%s_c%d" % (model.replace(".", "_"), ch)
+            out[key + "_tokens"] = toks.astype(np.int32)
+            out[key + "_prompt"] = prompt
+            out[key + "_last_logits_sub"] = logits[::LOGIT_STEP].astype(np.float32)
+            print("  real/%s chunk %d: %.1f s, tokens %s..." % (model, ch, secs, toks[:6].tolist()), flush=True)
+        del o
+    return out
+
+
 TOKENIZER_TEXTS = [b" hello hellox 12345!", b" hello world's , worlds 345 12", b" t12 t345", b""]
 
 
@@ -144,6 +170,12 @@ def make_tokenizer():
 if __name__ == "__main__":
     if "--tokenizer" in sys.argv:
         make_tokenizer()
+        sys.exit(0)
+    if "--real-shapes" in sys.argv:
+        data = make_real_shapes()
+        p = os.path.join(HERE, "real_shapes.npz")
+        np.savez_compressed(p, **data)
+        print("real_shapes", "%.0f KB" % (os.path.getsize(p) / 1024))
         sys.exit(0)
     data = make_full()
     p = os.path.join(HERE, "full_micro_en_ts.npz")

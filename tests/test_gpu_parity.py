@@ -178,6 +178,32 @@ def test_live_reference_when_prebuilt():
     assert toks[0].tolist() == ref_toks.tolist()
 
 
+@pytest.mark.parametrize("model", ["tiny.en", "base.en", "medium"])
+def test_real_model_shapes_match_reference_fixture(model):
+    """BASELINE.json's model shapes (synthetic weights): the bench loop's greedy tokens and the last step's logits against the
+    reference's (tests/golden/real_shapes.npz, made by `make_golden.py --real-shapes`); both chunks run as ONE batch here."""
+    from tests.golden.make_golden import REAL_SHAPES, REAL_STEPS
+    g = golden("real_shapes")
+    chunks = REAL_SHAPES[model]
+    m = capi.Model(synth.model_path(model))
+    e = capi.Engine(m, 0)
+    c = capi.Context(e, len(chunks))
+    try:
+        key = model.replace(".", "_")
+        prompt = g["%s_c%d_prompt" % (key, chunks[0])].tolist()
+        assert prompt == m.prompt_init()
+        toks, _ = c.run_chunks([synth.synth_pcm(ch) for ch in chunks], prompt, REAL_STEPS)
+        logits = c.logits(len(chunks))
+        for i, ch in enumerate(chunks):
+            assert toks[i].tolist() == g["%s_c%d_tokens" % (key, ch)].tolist(), (model, ch)
+            ref = g["%s_c%d_last_logits_sub" % (key, ch)]
+            assert np.abs(logits[i][::LOGIT_STEP] - ref).max() < TOL_LOGIT, (model, ch)
+    finally:
+        c.close()
+        e.close()
+        m.close()
+
+
 def test_argument_errors():
     m, e, c = open_model("micro.en")
     with pytest.raises(capi.WspError) as ex:
