@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "liboracle_ref.so")
+# WSP_ORACLE_LIB selects another build of the same sources (e.g. the scalar, non-AVX build `make scalar` produces, used to measure
+# the reference's own build-to-build spread; see tests/golden/make_golden.py --spread)
+LIB_PATH = os.environ.get("WSP_ORACLE_LIB") or os.path.join(_HERE, "_ref", "liboracle_ref.so")
 
 
 def available() -> bool:

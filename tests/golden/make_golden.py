@@ -145,7 +145,7 @@ def make_real_shapes():
         prompt = np.array([o.special["sot"]] + ([o.special["sot"] + 1, o.special["transcribe"]] if o.n_vocab == 51865 else []), np.int32)
         for ch in chunks:
             pcm = synth.synth_pcm(ch)
-            secs, toks, st = o.bench_chunk(pcm, prompt, REAL_STEPS, threads=8)
+            secs, toks, st = o.bench_chunk(pcm, prompt, REAL_STEPS, threads=4)   # = the arithmetic the fixtures are compared under
             logits = np.empty(o.L.ora_logits_size(o.ctx), np.float32)
             o.L.ora_get_logits(o.ctx, logits.ctypes.data_as(C.POINTER(C.c_float)))
             key = "%s_c%d" % (model.replace(".", "_"), ch)

@@ -37,6 +37,8 @@ namespace kern
 		__shared__ float sx[ MEL_FFT ];
 		__shared__ double sc[ MEL_FFT ];
 		__shared__ double ss[ MEL_FFT ];
+		__shared__ double sA[ 2 ][ MEL_FFT / 4 ];   // [k parity][n]: cosine-side combinations
+		__shared__ double sB[ 2 ][ MEL_FFT / 4 ];   //                 sine-side combinations
 		__shared__ float sp[ MEL_BINS + 7 ];
 		__shared__ float smax[ 8 ];
 		const int frame = blockIdx.x;
@@ -50,17 +52,46 @@ namespace kern
 			ss[ n ] = tb.sinT[ n ];
 		}
 		__syncthreads();
+		// Real 400-point DFT in a quarter of the multiply-adds.  With w = exp(-2 pi i k / 400):
+		//   X[k] = sum_{n<200} y[n] w^n,  y[n] = x[n] + (-1)^k x[n+200]           (w^200 = (-1)^k)
+		//        = y[0] + y[100] (-i)^k + sum_{n=1..99} ( y[n] w^n + (-1)^k y[200-n] conj(w^n) )
+		//   Re = y[0] + Re(y[100] (-i)^k) + sum cos(t_n) A[n],   A[n] = y[n] + (-1)^k y[200-n]
+		//   Im =        Im(y[100] (-i)^k) - sum sin(t_n) B[n],   B[n] = y[n] - (-1)^k y[200-n]
+		// (f64 accumulation as before; only the summation order differs from the plain 400-term sum)
+		constexpr int Q = MEL_FFT / 4;   // 100
+		if( tid < 2 * Q )
+		{
+			const int par = tid / Q, n = tid - par * Q;
+			const double sg = par ? -1.0 : 1.0;
+			const double yn = (double)sx[ n ] + sg * (double)sx[ n + 2 * Q ];
+			const double ym = n == 0 ? 0.0 : (double)sx[ 2 * Q - n ] + sg * (double)sx[ 4 * Q - n ];   // y[200-n]
+			sA[ par ][ n ] = yn + sg * ym;
+			sB[ par ][ n ] = yn - sg * ym;
+		}
+		__syncthreads();
 		if( tid < MEL_BINS )
 		{
 			const int k = tid;
-			double re = 0.0, im = 0.0;
-			int idx = 0;
-#pragma unroll 4
-			for( int n = 0; n < MEL_FFT; n++ )
+			const int par = k & 1;
+			const double sg = par ? -1.0 : 1.0;
+			const double y0 = (double)sx[ 0 ] + sg * (double)sx[ 2 * Q ];
+			const double y100 = (double)sx[ Q ] + sg * (double)sx[ 3 * Q ];
+			double re = y0, im = 0.0;
+			switch( k & 3 )   // y[100] * (-i)^k
 			{
-				const double x = (double)sx[ n ];
-				re += x * sc[ idx ];
-				im -= x * ss[ idx ];
+			case 0: re += y100; break;
+			case 1: im -= y100; break;
+			case 2: re -= y100; break;
+			default: im += y100; break;
+			}
+			const double* A = sA[ par ];
+			const double* Bv = sB[ par ];
+			int idx = k;
+#pragma unroll 4
+			for( int n = 1; n < Q; n++ )
+			{
+				re += A[ n ] * sc[ idx ];
+				im -= Bv[ n ] * ss[ idx ];
 				idx += k;
 				if( idx >= MEL_FFT ) idx -= MEL_FFT;
 			}
