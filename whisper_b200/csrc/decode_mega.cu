@@ -387,7 +387,7 @@ namespace kern
 #pragma unroll
 				for( int sub = 0; sub < S::NSUB; sub++ )
 				{
-					if( u0 != 0 || sub != 0 ) loadBatch<K>( wb, op, u0, nMine, sub, warp, lane );
+					if( sub != 0 ) loadBatch<K>( wb, op, u0, nMine, sub, warp, lane );   // (sub 0 of every batch is already in flight)
 #pragma unroll
 					for( int u = 0; u < S::UPB; u++ )
 #pragma unroll
@@ -410,6 +410,9 @@ namespace kern
 						}
 				}
 				subMark( tm, 1 );   // MMA loop done (the weight registers had to have landed)
+				// the weight registers are dead now: request the next batch before the reduction / epilogue of this one (the logits
+				// phase walks 11 batches per CTA; this hides one reduction + epilogue behind every HBM round trip)
+				if( u0 + S::UPB < nMine ) loadBatch<K>( wb, op, u0 + S::UPB, nMine, 0, warp, lane );
 				// cross-warp reduction: red[u][warp][row g][col]
 #pragma unroll
 				for( int u = 0; u < S::UPB; u++ )

@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <math.h>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace kern
@@ -758,6 +759,123 @@ namespace kern
 		}
 	}
 
+	// The same sampler with one vocabulary row spread over a cluster of SC_CL CTAs: every CTA keeps its slice of the row in shared
+	// memory, the three row-wide reductions go through distributed shared memory (each CTA publishes its partial, cluster barrier,
+	// everybody combines the SC_CL partials in rank order).  8 rows on 8 SMs left 140 SMs idle for 37 us per token step.
+	constexpr int SC_CL = 4;
+	struct ClusterPart
+	{
+		float mx, maxTx;
+		double dsum, sumTs;
+		Top1 bestTs, bestTx;
+	};
+	__global__ void __launch_bounds__( SM_THREADS )
+		sample_cluster_kernel( SampleArgs a )
+	{
+		namespace cg = cooperative_groups;
+		cg::cluster_group cluster = cg::this_cluster();
+		const unsigned rank = cluster.block_rank();
+		__shared__ ClusterPart part;
+		__shared__ float sf[ SM_THREADS / 32 ];
+		__shared__ double sd[ SM_THREADS / 32 ];
+		__shared__ Top1 st[ SM_THREADS / 32 ];
+		extern __shared__ float sampleRow[];
+		const int b = blockIdx.y;
+		const int tid = threadIdx.x;
+		const int nv = a.nVocab;
+		const int per = ( nv + SC_CL - 1 ) / SC_CL;
+		const int i0 = min( (int)rank * per, nv ), i1 = min( i0 + per, nv );
+		const int n = i1 - i0;
+		const float* lg = a.logits + (size_t)b * nv + i0;
+		float* gpr = a.probs + (size_t)b * nv + i0;
+		float* pr = sampleRow;
+		const bool forceTs = a.dForceTs && a.dForceTs[ 0 ] != 0;
+		const bool isInitial = a.dForceTs && a.dForceTs[ 1 ] != 0;
+
+		float mx = -INFINITY;
+		for( int i = tid; i < n; i += SM_THREADS )
+		{
+			const float v = __ldcg( lg + i );
+			pr[ i ] = v;
+			mx = fmaxf( mx, v );
+		}
+		mx = blockMaxF( mx, sf );
+		if( tid == 0 ) part.mx = mx;
+		cluster.sync();
+		for( unsigned r = 0; r < SC_CL; r++ ) mx = fmaxf( mx, cluster.map_shared_rank( &part, r )->mx );
+
+		double dsum = 0.0;
+		for( int i = tid; i < n; i += SM_THREADS )
+		{
+			const float e = expF16Table( pr[ i ] - mx );
+			pr[ i ] = e;
+			dsum += (double)e;
+		}
+		dsum = blockSumD( dsum, sd );
+		if( tid == 0 ) part.dsum = dsum;
+		cluster.sync();
+		double total = 0.0;   // the terms are f16 values: this double sum is exact, so the split does not change it
+		for( unsigned r = 0; r < SC_CL; r++ ) total += cluster.map_shared_rank( &part, r )->dsum;
+		const float inv = (float)( 1.0 / total );
+
+		const int beg = a.tokenBeg;
+		const int tsEnd = isInitial ? min( beg + 101, nv ) : nv;
+		float maxTx = -1.0f;
+		double sumTs = 0.0;
+		Top1 bestTs = { -INFINITY, 0x7fffffff };
+		Top1 bestTx = { -INFINITY, 0x7fffffff };
+		for( int i = tid; i < n; i += SM_THREADS )
+		{
+			const float p = pr[ i ] * inv;
+			gpr[ i ] = p;
+			const int gi = i0 + i;
+			if( gi < beg )
+			{
+				maxTx = fmaxf( maxTx, p );
+				if( gi != a.tokenSot && gi != a.tokenSolm && gi != a.tokenNot ) bestTx = better( bestTx, Top1{ p, gi } );
+			}
+			else if( gi < tsEnd )
+			{
+				sumTs += (double)p;
+				bestTs = better( bestTs, Top1{ p, gi } );
+			}
+		}
+		maxTx = blockMaxF( maxTx, sf );
+		sumTs = blockSumD( sumTs, sd );
+		bestTs = blockArgmax( bestTs, st );
+		bestTx = blockArgmax( bestTx, st );
+		if( tid == 0 )
+		{
+			part.maxTx = maxTx; part.sumTs = sumTs; part.bestTs = bestTs; part.bestTx = bestTx;
+		}
+		cluster.sync();
+		if( rank == 0 && tid == 0 )
+		{
+			for( unsigned r = 1; r < SC_CL; r++ )
+			{
+				const ClusterPart* q = cluster.map_shared_rank( &part, r );
+				maxTx = fmaxf( maxTx, q->maxTx );
+				sumTs += q->sumTs;
+				bestTs = better( bestTs, q->bestTs );
+				bestTx = better( bestTx, q->bestTx );
+			}
+			const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
+			Top1 pick = bestTs;
+			if( !maskText ) pick = better( bestTx, bestTs );
+			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0 };
+			TokenData td;
+			td.id = pick.i;
+			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
+			td.p = pick.v;
+			td.pt = (float)( (double)bestTs.v / ( sumTs + 1e-10 ) );
+			td.ptsum = (float)sumTs;
+			a.out[ b ] = td;
+			if( a.nextTokens ) a.nextTokens[ b ] = td.id;
+			if( a.history && a.dStep && *a.dStep < a.histCap ) a.history[ (size_t)b * a.histCap + *a.dStep ] = td.id;
+		}
+		cluster.sync();   // nobody leaves while a peer may still read its partials
+	}
+
 	__global__ void __launch_bounds__( SM_THREADS )
 		softmax_rows_kernel( const float* __restrict__ logits, float* __restrict__ probs, int n )
 	{
@@ -798,6 +916,31 @@ namespace kern
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s )
 	{
 		SampleArgs sa = a;
+		static const bool noCluster = getenv( "WSP_SAMPLER_CLUSTER" ) && getenv( "WSP_SAMPLER_CLUSTER" )[ 0 ] == '0';   // A/B switch
+		if( !noCluster && a.nVocab >= 4096 )
+		{
+			const size_t sliceBytes = (size_t)( ( a.nVocab + SC_CL - 1 ) / SC_CL ) * sizeof( float );
+			static size_t sliceSet = 0;
+			if( sliceBytes > sliceSet )
+			{
+				cudaError_t ea = cudaFuncSetAttribute( sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliceBytes );
+				if( ea != cudaSuccess ) return ea;
+				sliceSet = sliceBytes;
+			}
+			cudaLaunchConfig_t cfg{};
+			cfg.gridDim = dim3( SC_CL, a.B );
+			cfg.blockDim = dim3( SM_THREADS );
+			cfg.dynamicSmemBytes = sliceBytes;
+			cfg.stream = s;
+			cudaLaunchAttribute at[ 1 ];
+			at[ 0 ].id = cudaLaunchAttributeClusterDimension;
+			at[ 0 ].val.clusterDim.x = SC_CL; at[ 0 ].val.clusterDim.y = 1; at[ 0 ].val.clusterDim.z = 1;
+			cfg.attrs = at;
+			cfg.numAttrs = 1;
+			cudaError_t e = cudaLaunchKernelEx( &cfg, sample_cluster_kernel, sa );
+			if( e != cudaSuccess ) return e;
+			return launchPdl( advance_kernel, dim3( 1 ), dim3( 1 ), 0, s, a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );
+		}
 		const size_t rowBytes = (size_t)a.nVocab * sizeof( float );
 		static const bool forceGlobal = getenv( "WSP_SAMPLER_GLOBAL" ) != nullptr;   // A/B switch for measurements
 		sa.rowInSmem = ( rowBytes <= 220 * 1024 && !forceGlobal ) ? 1 : 0;
