@@ -762,13 +762,13 @@ namespace kern
 	// The same sampler with one vocabulary row spread over a cluster of SC_CL CTAs: every CTA keeps its slice of the row in shared
 	// memory, the three row-wide reductions go through distributed shared memory (each CTA publishes its partial, cluster barrier,
 	// everybody combines the SC_CL partials in rank order).  8 rows on 8 SMs left 140 SMs idle for 37 us per token step.
-	constexpr int SC_CL = 4;
 	struct ClusterPart
 	{
 		float mx, maxTx;
 		double dsum, sumTs;
 		Top1 bestTs, bestTx;
 	};
+	template<int SC_CL>
 	__global__ void __launch_bounds__( SM_THREADS )
 		sample_cluster_kernel( SampleArgs a )
 	{
@@ -916,28 +916,32 @@ namespace kern
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s )
 	{
 		SampleArgs sa = a;
-		static const bool noCluster = getenv( "WSP_SAMPLER_CLUSTER" ) && getenv( "WSP_SAMPLER_CLUSTER" )[ 0 ] == '0';   // A/B switch
-		if( !noCluster && a.nVocab >= 4096 )
+		// cluster size: 4 by default (measured 157.0 -> 155.4 ms per 100 tokens against the single-CTA kernel); WSP_SAMPLER_CLUSTER=0|4|8 for A/B runs
+		static const int clusterSize = []() { const char* e = getenv( "WSP_SAMPLER_CLUSTER" ); return e ? atoi( e ) : 4; }();
+		if( ( clusterSize == 4 || clusterSize == 8 ) && a.nVocab >= 4096 )
 		{
-			const size_t sliceBytes = (size_t)( ( a.nVocab + SC_CL - 1 ) / SC_CL ) * sizeof( float );
+			const int cl = clusterSize;
+			const size_t sliceBytes = (size_t)( ( a.nVocab + cl - 1 ) / cl ) * sizeof( float );
 			static size_t sliceSet = 0;
 			if( sliceBytes > sliceSet )
 			{
-				cudaError_t ea = cudaFuncSetAttribute( sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliceBytes );
+				cudaError_t ea = cudaFuncSetAttribute( sample_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)( (size_t)( ( a.nVocab + 3 ) / 4 ) * sizeof( float ) ) );
+				if( ea != cudaSuccess ) return ea;
+				ea = cudaFuncSetAttribute( sample_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)( (size_t)( ( a.nVocab + 7 ) / 8 ) * sizeof( float ) ) );
 				if( ea != cudaSuccess ) return ea;
 				sliceSet = sliceBytes;
 			}
 			cudaLaunchConfig_t cfg{};
-			cfg.gridDim = dim3( SC_CL, a.B );
+			cfg.gridDim = dim3( cl, a.B );
 			cfg.blockDim = dim3( SM_THREADS );
 			cfg.dynamicSmemBytes = sliceBytes;
 			cfg.stream = s;
 			cudaLaunchAttribute at[ 1 ];
 			at[ 0 ].id = cudaLaunchAttributeClusterDimension;
-			at[ 0 ].val.clusterDim.x = SC_CL; at[ 0 ].val.clusterDim.y = 1; at[ 0 ].val.clusterDim.z = 1;
+			at[ 0 ].val.clusterDim.x = cl; at[ 0 ].val.clusterDim.y = 1; at[ 0 ].val.clusterDim.z = 1;
 			cfg.attrs = at;
 			cfg.numAttrs = 1;
-			cudaError_t e = cudaLaunchKernelEx( &cfg, sample_cluster_kernel, sa );
+			cudaError_t e = cl == 4 ? cudaLaunchKernelEx( &cfg, sample_cluster_kernel<4>, sa ) : cudaLaunchKernelEx( &cfg, sample_cluster_kernel<8>, sa );
 			if( e != cudaSuccess ) return e;
 			return launchPdl( advance_kernel, dim3( 1 ), dim3( 1 ), 0, s, a.dNPast, a.N, const_cast<int*>( a.dForceTs ), a.dStep );
 		}
