@@ -12,9 +12,6 @@
 #include "decode_mega.cuh"
 #include "ptx.cuh"
 #include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <cooperative_groups.h>
 
 namespace kern
 {
@@ -28,7 +25,7 @@ namespace kern
 		constexpr int MG_SMEM_A = 192000;  // activations [16][K+32] f16  |  V tile [1500][64] f16
 		constexpr int MG_SMEM_RED = MG_MAXUPB * MG_WARPS * MG_ROWS * 16 * 4;   // 16 KB: cross-warp partials | attention partial outputs
 		constexpr int MG_SMEM_SP = 1536 * 4;
-		constexpr int MG_SMEM_MISC = 768;        // floats: [0,64) q | [64,128) reductions | [256,448) QKV exchange | [512,576) cross-q exchange
+		constexpr int MG_SMEM_MISC = 256;
 		constexpr int MG_SMEM_PARAM = 2 * 1280 * 4 + 8 * MG_ROWS * 4;   // LayerNorm gamma | beta of the next phase + biases of this CTA's units
 		constexpr int MG_MAXBIASUNITS = 8;
 
@@ -183,10 +180,6 @@ namespace kern
 			__half* kCache;
 			__half* vCache;
 			int d, nTextCtx, nPast;
-			// this CTA's units of 8 weight rows: u0, u0 + ustride, ... (ucount of them).  Default = round-robin over the grid; the
-			// cluster-fused phases map "my rows of head h" instead
-			int u0, ustride, ucount;
-			float* xch;             // fused phases: the epilogue also leaves its results in shared memory [which][row][col] for the cluster
 		};
 
 		template<int K>
@@ -217,7 +210,7 @@ namespace kern
 			for( int u = 0; u < S::UPB; u++ )
 			{
 				const int ui = firstUnitIdx + u;
-				const int unit = op.u0 + ui * op.ustride;
+				const int unit = blockIdx.x + ui * gridDim.x;
 				const int row = min( unit * MG_ROWS + g, op.nOut - 1 );
 				const uint4* wr = reinterpret_cast<const uint4*>( op.W + (size_t)row * K + 8 * t );
 #pragma unroll
@@ -252,8 +245,8 @@ namespace kern
 				if( tid < MG_MAXBIASUNITS * 2 )
 				{
 					const int ui = tid >> 1, half = tid & 1;
-					const int unit = op.u0 + ui * op.ustride;
-					if( ui < op.ucount && unit < units && unit * MG_ROWS + half * 4 + 4 <= op.nOut )
+					const int unit = blockIdx.x + ui * gridDim.x;
+					if( unit < units && unit * MG_ROWS + half * 4 + 4 <= op.nOut )
 						cpAsync16( sm.bias + ui * MG_ROWS + half * 4, op.bias + unit * MG_ROWS + half * 4 );
 				}
 			}
@@ -263,7 +256,8 @@ namespace kern
 		template<int K>
 		__device__ __forceinline__ int myUnits( const GemvOp& op )
 		{
-			return op.ucount;
+			const int units = ( op.nOut + MG_ROWS - 1 ) / MG_ROWS;
+			return units > (int)blockIdx.x ? ( units - (int)blockIdx.x + (int)gridDim.x - 1 ) / (int)gridDim.x : 0;
 		}
 
 		// stage the B activation rows as f16 into smem: LayerNorm fused (K == D <= 1280, multiple of 128: one warp per column, the
@@ -334,7 +328,7 @@ namespace kern
 			}
 		}
 
-		__device__ __forceinline__ void gemvEpilogue( const GemvOp& op, int col, int n, float v, float biasN, int r )
+		__device__ __forceinline__ void gemvEpilogue( const GemvOp& op, int col, int n, float v, float biasN )
 		{
 			switch( op.epi )
 			{
@@ -342,16 +336,13 @@ namespace kern
 			{
 				const int which = n / op.d;
 				const int nn = n - which * op.d;
-				float res;
-				if( which == 0 ) { res = ( v + biasN ) * op.scale; op.outF32[ (size_t)col * op.ld + nn ] = res; }
+				if( which == 0 ) op.outF32[ (size_t)col * op.ld + nn ] = ( v + biasN ) * op.scale;
 				else
 				{
 					const size_t off = ( (size_t)col * op.nTextCtx + op.nPast ) * op.d + nn;
-					const __half hv = which == 1 ? __float2half_rn( v * op.scale ) : __float2half_rn( v + biasN );
-					if( which == 1 ) op.kCache[ off ] = hv; else op.vCache[ off ] = hv;
-					res = __half2float( hv );
+					if( which == 1 ) op.kCache[ off ] = __float2half_rn( v * op.scale );
+					else op.vCache[ off ] = __float2half_rn( v + biasN );
 				}
-				if( op.xch ) op.xch[ ( which * MG_ROWS + r ) * 8 + col ] = res;
 				break;
 			}
 			case EP_RESID:
@@ -361,12 +352,8 @@ namespace kern
 				break;
 			}
 			case EP_QSCALE:
-			{
-				const float res = ( v + biasN ) * op.scale;
-				op.outF32[ (size_t)col * op.ld + n ] = res;
-				if( op.xch ) op.xch[ r * 8 + col ] = res;
+				op.outF32[ (size_t)col * op.ld + n ] = ( v + biasN ) * op.scale;
 				break;
-			}
 			case EP_GELU:
 				op.outF16[ (size_t)col * op.ld + n ] = __float2half_rn( ptx::gelu_f16_semantics( v + biasN ) );
 				break;
@@ -442,7 +429,7 @@ namespace kern
 					const int u = idx / ( ncols * MG_ROWS );
 					const int rem = idx - u * ncols * MG_ROWS;
 					const int c = rem / MG_ROWS, r = rem - c * MG_ROWS;
-					const int unit = op.u0 + ( u0 + u ) * op.ustride;
+					const int unit = blockIdx.x + ( u0 + u ) * gridDim.x;
 					const int n = unit * MG_ROWS + r;
 					if( u0 + u < nMine && c < B && n < op.nOut )
 					{
@@ -451,7 +438,7 @@ namespace kern
 						for( int w = 0; w < MG_WARPS; w++ ) v += sm.red[ ( ( u * MG_WARPS + w ) * MG_ROWS + r ) * 16 + c ];
 						float biasN = 0.0f;
 						if( op.bias ) biasN = ( u0 + u < MG_MAXBIASUNITS ) ? sm.bias[ ( u0 + u ) * MG_ROWS + r ] : op.bias[ n ];
-						gemvEpilogue( op, c, n, v, biasN, r );
+						gemvEpilogue( op, c, n, v, biasN );
 					}
 				}
 				subMark( tm, 3 );
@@ -465,16 +452,14 @@ namespace kern
 		// copied to shared memory by cp.async BEFORE the barrier that publishes this step's new row; after it only 2 x 128 bytes remain.
 		constexpr int SA_KSTRIDE = 144;   // bytes per K row in smem (128 + 16: conflict-free 16-byte reads of one row per thread)
 		constexpr int SA_MAXKV = 448;
-		constexpr int SA_BASE = 24576;    // the K/V rows sit behind the d-wide activation rows (8 x (1280 + 32) f16), so that the fused
-		                                  // QKV + self-attention phase can have both in region A
 		__device__ __forceinline__ void selfLoadRows( const MegaArgs& a, const MegaLayer& L, int d, const Smem& sm, int unit, int j0, int j1, int tid )
 		{
 			if( unit >= a.B * a.H ) return;
 			const int b = unit / a.H, h = unit - b * a.H;
 			const __half* kb = L.kCache + (size_t)b * a.nTextCtx * d + h * 64;
 			const __half* vb = L.vCache + (size_t)b * a.nTextCtx * d + h * 64;
-			uint8_t* sK = sm.a + SA_BASE;
-			uint8_t* sV = sm.a + SA_BASE + SA_MAXKV * SA_KSTRIDE;
+			uint8_t* sK = sm.a;
+			uint8_t* sV = sm.a + SA_MAXKV * SA_KSTRIDE;
 			const int n = ( j1 - j0 ) * 8;   // 16-byte chunks per matrix
 			for( int i = tid; i < 2 * n; i += MG_THREADS )
 			{
@@ -485,31 +470,26 @@ namespace kern
 				else cpAsync16( sK + j * SA_KSTRIDE + c * 16, kb + (size_t)j * d + c * 8 );
 			}
 		}
-		// gathered = true: q and the new K/V row are already in shared memory (collected from the cluster), one unit only
-		__device__ void selfAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, int nPast, const Smem& sm, int warp, int lane, int tid,
-			int unitFirst, int unitStride, bool gathered )
+		__device__ void selfAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, int nPast, const Smem& sm, int warp, int lane, int tid )
 		{
 			const int H = a.H;
 			const int nkv = min( nPast + 1, a.nTextCtx );
 			float* sq = sm.misc;
 			float* sred = sm.misc + 64;
 			float* so = sm.red;
-			const uint8_t* sK = sm.a + SA_BASE;
-			const __half* sV = reinterpret_cast<const __half*>( sm.a + SA_BASE + SA_MAXKV * SA_KSTRIDE );
+			const uint8_t* sK = sm.a;
+			const __half* sV = reinterpret_cast<const __half*>( sm.a + SA_MAXKV * SA_KSTRIDE );
 			bool first = true;
-			for( int unit = unitFirst; unit < a.B * H; unit += unitStride )
+			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
 			{
 				const int b = unit / H, h = unit - b * H;
-				if( !gathered )
-				{
-					// rows [0, nkv-1) of the first unit were requested before the barrier; the new row (and everything for further units) now
-					selfLoadRows( a, L, d, sm, unit, first ? nkv - 1 : 0, nkv, tid );
-					cpAsyncCommit();
-					if( tid < 64 ) sq[ tid ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + tid ) ) );
-					cpAsyncWaitAll();
-					__syncthreads();
-				}
+				// rows [0, nkv-1) of the first unit were requested before the barrier; the new row (and everything for further units) now
+				selfLoadRows( a, L, d, sm, unit, first ? nkv - 1 : 0, nkv, tid );
+				cpAsyncCommit();
 				first = false;
+				if( tid < 64 ) sq[ tid ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + tid ) ) );
+				cpAsyncWaitAll();
+				__syncthreads();
 				float lmax = -INFINITY;
 				for( int j = tid; j < nkv; j += MG_THREADS )
 				{
@@ -607,9 +587,7 @@ namespace kern
 				pf.u[ k ] = j < T ? K4[ (size_t)j * 8 + sub ] : make_uint4( 0, 0, 0, 0 );
 			}
 		}
-		// gq != nullptr: the (f32) query of the single unit is in shared memory (collected from the cluster)
-		__device__ void crossAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, CrossPrefetch& pf, const Smem& sm, int warp, int lane, int tid,
-			int unitFirst, int unitStride, const float* gq )
+		__device__ void crossAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, CrossPrefetch& pf, const Smem& sm, int warp, int lane, int tid )
 		{
 			const int T = a.T, H = a.H;
 			float* sred = sm.misc + 64;
@@ -617,7 +595,7 @@ namespace kern
 			const int sub = lane & 7, rgrp = lane >> 3;
 			constexpr int JSTEP = MG_WARPS * 4;
 			bool first = true;
-			for( int unit = unitFirst; unit < a.B * H; unit += unitStride )
+			for( int unit = blockIdx.x; unit < a.B * H; unit += gridDim.x )
 			{
 				if( !first ) { crossPrefetch( a, L, pf, sm, unit, warp, lane, tid ); }
 				first = false;
@@ -626,7 +604,7 @@ namespace kern
 				const uint4* K4 = reinterpret_cast<const uint4*>( L.crossK + base );
 				float qf[ 8 ];
 #pragma unroll
-				for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( __float2half_rn( gq ? gq[ sub * 8 + e ] : __ldcg( a.q + (size_t)b * d + h * 64 + sub * 8 + e ) ) );
+				for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( __float2half_rn( __ldcg( a.q + (size_t)b * d + h * 64 + sub * 8 + e ) ) );
 				float lmax = -INFINITY;
 				int jb = warp * 4 + rgrp;
 				while( jb < T )
@@ -757,36 +735,13 @@ namespace kern
 			// version instantiated the GEMV code seven times (12.4 K SASS instructions = 199 KB, 16 % of all stall samples were
 			// instruction-fetch misses); this form keeps the kernel within reach of the instruction cache.
 			enum { PH_QKV = 0, PH_SELF = 1, PH_O = 2, PH_CQ = 3, PH_CROSS = 4, PH_CO = 5, PH_FC1 = 6, PH_FC2 = 7, PH_COUNT = 8 };
-			// Cluster-fused mode (a.fused, launched as clusters of 8 CTAs, B <= 8, H <= number of clusters): cluster c owns head c.
-			// Its CTA r computes rows 8r..8r+7 of that head's q (| k | v) for all chunks, the results are exchanged through
-			// distributed shared memory, and CTA r then runs the attention of (chunk r, head c) right away - no grid barrier between
-			// the projection and the attention (P1+P2 and P4+P5 become one phase each: 6 instead of 8 grid barriers per layer).
-			namespace cg = cooperative_groups;
-			cg::cluster_group cluster = cg::this_cluster();
-			const bool fused = a.fused != 0;
-			const int crank = fused ? (int)cluster.block_rank() : 0;
-			const int cid = fused ? (int)blockIdx.x / 8 : 0;
-			const bool headMine = fused && cid < a.H;
-			const int noUnit = B * a.H;
-			// my (chunk, head) attention unit: round-robin over the grid, or (chunk = rank, head = cluster) when fused
-			const int attnUnit = fused ? ( ( headMine && crank < B ) ? crank * a.H + cid : noUnit ) : (int)blockIdx.x;
-			const int attnStride = fused ? noUnit : (int)gridDim.x;
-			float* xchQKV = sm.misc + 256;   // [3][8][8]
-			float* xchCQ = sm.misc + 512;    // [8][8]
-			float* gq = sm.misc + 640;       // gathered cross-attention query [64]
 			// operands of GEMV phase `ph` of layer `il`; il == L is the final LayerNorm + logits (a17)
-			auto roundRobin = [ & ]( GemvOp& o ) {
-				const int units = ( o.nOut + MG_ROWS - 1 ) / MG_ROWS;
-				o.u0 = (int)blockIdx.x; o.ustride = (int)gridDim.x;
-				o.ucount = units > o.u0 ? ( units - o.u0 + o.ustride - 1 ) / o.ustride : 0;
-			};
 			auto makeOp = [ & ]( int il, int ph ) {
 				GemvOp o = base;
 				if( il >= a.L )
 				{
 					o.W = a.tokEmb; o.nOut = a.nVocab; o.xF32 = a.x; o.xStride = D; o.gamma = a.lnfg; o.beta = a.lnfb;
 					o.epi = EP_LOGITS; o.outF32 = a.logits; o.ld = a.nVocab;
-					roundRobin( o );
 					return o;
 				}
 				const MegaLayer& L = a.layers[ il ];
@@ -814,14 +769,6 @@ namespace kern
 					o.W = L.w2; o.nOut = D; o.xF16 = a.h; o.xStride = 4 * D; o.epi = EP_RESID; o.bias = L.b2; o.outF32 = a.x; o.ld = D;
 					break;
 				}
-				roundRobin( o );
-				if( fused && ( ph == PH_QKV || ph == PH_CQ ) )
-				{
-					// rows 8r..8r+7 of head c: unit 8c + r of q (and the same unit of the k and v blocks, D/8 units further each)
-					o.u0 = 8 * cid + crank; o.ustride = D / MG_ROWS;
-					o.ucount = headMine ? ( ph == PH_QKV ? 3 : 1 ) : 0;
-					o.xch = ph == PH_QKV ? xchQKV : xchCQ;
-				}
 				return o;
 			};
 			// everything a phase needs that does not depend on the previous phase is requested before the barrier wait
@@ -836,9 +783,9 @@ namespace kern
 			// a layer's cross-attention K/V tile of "my" (chunk, head) starts moving HBM -> L2 several phases ahead of its use (those
 			// phases are latency-bound and leave the DRAM pipe idle); issued while waiting at a barrier, off the critical path
 			auto crossL2 = [ & ]( const MegaLayer& L ) {
-				if( attnUnit < noUnit )
+				if( (int)blockIdx.x < B * a.H )
 				{
-					const size_t cb = (size_t)attnUnit * a.T * 64;
+					const size_t cb = (size_t)blockIdx.x * a.T * 64;
 					const uint8_t* kp = reinterpret_cast<const uint8_t*>( L.crossK + cb );
 					const uint8_t* vp = reinterpret_cast<const uint8_t*>( L.crossV + cb );
 					for( int i = tid; i < a.T; i += MG_THREADS ) { prefetchL2( kp + (size_t)i * 128 ); prefetchL2( vp + (size_t)i * 128 ); }
@@ -857,11 +804,6 @@ namespace kern
 			}
 			grid.arrive();
 			crossL2( a.layers[ 0 ] );
-			if( fused )
-			{
-				selfLoadRows( a, a.layers[ 0 ], D, sm, attnUnit, 0, nkvOld, tid );   // behind the activation rows (SA_BASE)
-				cpAsyncCommit();
-			}
 			mark(); grid.wait(); mark();
 
 			unsigned long long* tmBase = ( a.timing && blockIdx.x == 0 ) ? a.timing + 4000 : nullptr;
@@ -875,13 +817,8 @@ namespace kern
 				for( int ph = 0; ph < PH_COUNT; ph++ )
 				{
 					// ---------------- the phase's work ----------------
-					if( fused && ( ph == PH_SELF || ph == PH_CROSS ) )
-					{
-						mark(); mark();   // (keeps the debug marks aligned with the unfused numbering)
-						continue;         // done inside the projection phase, no barrier of their own
-					}
-					if( ph == PH_SELF ) selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid, attnUnit, attnStride, false );
-					else if( ph == PH_CROSS ) crossAttnPhase( a, L, D, pf, sm, warp, lane, tid, attnUnit, attnStride, nullptr );
+					if( ph == PH_SELF ) selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid );
+					else if( ph == PH_CROSS ) crossAttnPhase( a, L, D, pf, sm, warp, lane, tid );
 					else if( ph == PH_FC2 )
 					{
 						landed();
@@ -911,39 +848,6 @@ namespace kern
 						markId( 1001 + 2 * ph );
 						gemvCompute<D>( op, B, wb, sm, warp, lane, tid, tmBase ? tmBase + ph * 8 : nullptr );
 						markId( 1002 + 2 * ph );
-						if( fused && il < a.L && ph == PH_QKV )
-						{
-							// ---- fused P1+P2: exchange q | k | v of head `cid` inside the cluster, then self attention of (chunk crank, head cid) ----
-							cluster.sync();
-							if( attnUnit < noUnit )
-							{
-								const int nkv = min( nPast + 1, a.nTextCtx );
-								if( tid < 192 )
-								{
-									const int which = tid >> 6, e = tid & 63;
-									const float* peer = cluster.map_shared_rank( xchQKV, e >> 3 );
-									const float val = peer[ ( which * MG_ROWS + ( e & 7 ) ) * 8 + crank ];
-									if( which == 0 ) sm.misc[ e ] = __half2float( __float2half_rn( val ) );
-									else if( which == 1 ) reinterpret_cast<__half*>( sm.a + SA_BASE + (size_t)( nkv - 1 ) * SA_KSTRIDE )[ e ] = __float2half_rn( val );
-									else reinterpret_cast<__half*>( sm.a + SA_BASE + SA_MAXKV * SA_KSTRIDE )[ (size_t)( nkv - 1 ) * 64 + e ] = __float2half_rn( val );
-								}
-								__syncthreads();
-								selfAttnPhase( a, L, D, nPast, sm, warp, lane, tid, attnUnit, attnStride, true );
-							}
-						}
-						else if( fused && il < a.L && ph == PH_CQ )
-						{
-							// ---- fused P4+P5: the V tile and first K rows are requested now (region A is free), q is exchanged, then cross attention ----
-							__syncthreads();
-							crossPrefetch( a, L, pf, sm, attnUnit, warp, lane, tid );
-							cluster.sync();
-							if( attnUnit < noUnit )
-							{
-								if( tid < 64 ) gq[ tid ] = cluster.map_shared_rank( xchCQ, tid >> 3 )[ ( tid & 7 ) * 8 + crank ];
-								__syncthreads();
-								crossAttnPhase( a, L, D, pf, sm, warp, lane, tid, attnUnit, attnStride, gq );
-							}
-						}
 					}
 					if( il == a.L ) break;   // the logits were the last thing to do
 					grid.arrive( tmBase ? tmBase + ph * 8 : nullptr );
@@ -953,7 +857,6 @@ namespace kern
 					{
 					case PH_QKV: nextPh = PH_O; break;          // (self attention does not use the weight registers)
 					case PH_O: nextPh = PH_CQ; break;
-					case PH_CQ: if( fused ) nextPh = PH_CO; break;
 					case PH_CROSS: nextPh = PH_CO; break;
 					case PH_CO: nextPh = PH_FC1; break;
 					case PH_FC2: nextPh = PH_QKV; nextIl = il + 1; break;
@@ -964,30 +867,21 @@ namespace kern
 						op = makeOp( nextIl, nextPh );
 						prepD( op );
 					}
-					if( ph == PH_QKV && !fused )
+					if( ph == PH_QKV )
 					{
 						// earlier tokens' K/V rows of my (chunk, head) -> smem (region A is free: the activations are consumed)
-						selfLoadRows( a, L, D, sm, attnUnit, 0, nkvOld, tid );
+						selfLoadRows( a, L, D, sm, blockIdx.x, 0, nkvOld, tid );
 						cpAsyncCommit();
 					}
-					else if( ph == PH_CQ && !fused )
-						crossPrefetch( a, L, pf, sm, attnUnit, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
+					else if( ph == PH_CQ )
+						crossPrefetch( a, L, pf, sm, blockIdx.x, warp, lane, tid );   // V tile -> smem (region A is free now), first K rows -> registers
 					else if( ph == PH_FC1 )
 					{
 						op = makeOp( il, PH_FC2 );
 						loadBatch<4 * D>( wb, op, 0, myUnits<4 * D>( op ), 0, warp, lane );
 						prefetchParams( op, 4 * D, sm, tid );
 					}
-					else if( ph == PH_FC2 && il + 1 < a.L )
-					{
-						crossL2( a.layers[ il + 1 ] );
-						if( fused )
-						{
-							// fused mode: the next layer's earlier K/V rows go behind the activation rows already now
-							selfLoadRows( a, a.layers[ il + 1 ], D, sm, attnUnit, 0, nkvOld, tid );
-							cpAsyncCommit();
-						}
-					}
+					else if( ph == PH_FC2 && il + 1 < a.L ) crossL2( a.layers[ il + 1 ] );
 					subMark( tmBase ? tmBase + ph * 8 : nullptr, 6 );
 					mark(); grid.wait(); mark();
 					subMark( tmBase ? tmBase + ph * 8 : nullptr, 7 );
@@ -1010,54 +904,13 @@ namespace kern
 			}
 			return cudaSuccess;
 		}
-		// Clusters of 8 that can be co-resident with this kernel's footprint (one CTA per SM): decides whether the fused mode is possible.
 		template<int D>
-		int maxClusters8( int numSMs )
-		{
-			static int cached = -1;
-			if( cached >= 0 ) return cached;
-			cudaLaunchConfig_t cfg{};
-			cfg.gridDim = dim3( ( numSMs / 8 ) * 8 );
-			cfg.blockDim = dim3( MG_THREADS );
-			cfg.dynamicSmemBytes = SMEM;
-			cudaLaunchAttribute at[ 1 ];
-			at[ 0 ].id = cudaLaunchAttributeClusterDimension;
-			at[ 0 ].val.clusterDim.x = 8; at[ 0 ].val.clusterDim.y = 1; at[ 0 ].val.clusterDim.z = 1;
-			cfg.attrs = at;
-			cfg.numAttrs = 1;
-			int n = 0;
-			if( cudaOccupancyMaxActiveClusters( &n, decode_step_kernel<D>, &cfg ) != cudaSuccess ) { cudaGetLastError(); n = 0; }
-			cached = n;
-			if( getenv( "WSP_MEGA_DEBUG" ) ) fprintf( stderr, "whisper_b200: decode_step_kernel<%d>: %d co-resident clusters of 8 (of %d SMs)\n", D, n, numSMs );
-			return n;
-		}
-		template<int D>
-		cudaError_t launchD( const MegaArgs& a0, int numSMs, cudaStream_t s )
+		cudaError_t launchD( const MegaArgs& a, int numSMs, cudaStream_t s )
 		{
 			cudaError_t e = prepareD<D>();
 			if( e != cudaSuccess ) return e;
-			MegaArgs a = a0;
 			e = cudaMemsetAsync( a.barrier, 0, 64 * sizeof( unsigned ), s );
 			if( e != cudaSuccess ) return e;
-			static const bool fusedOff = getenv( "WSP_MEGA_FUSED" ) && getenv( "WSP_MEGA_FUSED" )[ 0 ] == '0';   // A/B switch
-			const int nc = ( !fusedOff && a.B <= 8 ) ? maxClusters8<D>( numSMs ) : 0;
-			if( nc >= a.H && nc >= 8 )
-			{
-				// cluster-fused mode: every CTA belongs to a cluster of 8; all clusters must be co-resident (grid barriers)
-				a.fused = 1;
-				cudaLaunchConfig_t cfg{};
-				cfg.gridDim = dim3( nc * 8 );
-				cfg.blockDim = dim3( MG_THREADS );
-				cfg.dynamicSmemBytes = SMEM;
-				cfg.stream = s;
-				cudaLaunchAttribute at[ 1 ];
-				at[ 0 ].id = cudaLaunchAttributeClusterDimension;
-				at[ 0 ].val.clusterDim.x = 8; at[ 0 ].val.clusterDim.y = 1; at[ 0 ].val.clusterDim.z = 1;
-				cfg.attrs = at;
-				cfg.numAttrs = 1;
-				return cudaLaunchKernelEx( &cfg, decode_step_kernel<D>, a );
-			}
-			a.fused = 0;
 			decode_step_kernel<D><<<numSMs, MG_THREADS, SMEM, s>>>( a );
 			return cudaGetLastError();
 		}

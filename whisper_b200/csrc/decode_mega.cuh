@@ -32,7 +32,6 @@ namespace kern
 		unsigned* barrier = nullptr;        // grid barrier counter (zeroed by the launcher)
 		unsigned long long* timing = nullptr;   // optional: %globaltimer marks of CTA 0 around every barrier (debug)
 		int flags = 0;                      // experiment switches (env WSP_MEGA_FLAGS) for same-box A/B runs; 0 = the shipped configuration
-		int fused = 0;                      // set by decodeStepMega: clusters of 8 CTAs, projection + attention fused per head (B <= 8, H <= clusters)
 	};
 	bool megaSupported( int d, int B, int T );
 	cudaError_t megaPrepare( int d );   // function attributes, outside any stream capture
