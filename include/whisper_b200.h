@@ -123,6 +123,10 @@ wsp_status wsp_decode( wsp_context* c, const int32_t* tokens, int32_t n_tokens, 
 wsp_status wsp_get_logits( wsp_context* c, float* dst, size_t cap_floats );
 wsp_status wsp_get_probs( wsp_context* c, float* dst, size_t cap_floats );
 
+/* whisper_lang_auto_detect (Whisper/source/whisper.cpp:2428-2495): encode slot 0's window at mel frame `offset_frames`, decode [sot],
+ * then — like the reference — a softmax over the language tokens' PROBABILITIES; lang_probs[n_langs] (nullable), *lang_id = the arg-max */
+wsp_status wsp_detect_language( wsp_context* c, int32_t offset_frames, int32_t n_langs, float* lang_probs, int32_t* lang_id );
+
 /* The measured path: for `batch` chunks of host PCM — mel, encode, then n_decode greedy steps (first step samples with
  * is_initial timestamp rules, as whisper_full does, whisper.cpp:2943) entirely on the device with sampled tokens fed back
  * without host round trips.  tokens_out[b*n_decode + i].  stage_ms (nullable): { h2d+mel, encode, decode } from CUDA events. */
@@ -132,6 +136,30 @@ wsp_status wsp_run_chunks( wsp_context* c, const float* const* pcm, const int32_
 wsp_status wsp_upload_pcm( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples );
 /* ... and run the same path from it: mel + encode + decode with no host->device input copy inside (bench.py's `value` leg) */
 wsp_status wsp_run_chunks_resident( wsp_context* c, int32_t batch, const int32_t* prompt, int32_t n_prompt, int32_t n_decode, int32_t* tokens_out, float* stage_ms );
+
+/* ---- several devices in one process (csrc/replicas.cpp) ----
+ * Chunks are independent: one engine + context per listed device (a device may be listed twice: two contexts on one
+ * GPU), the model file read ONCE and its image copied device-to-device from devices[0] (cudaMemcpyPeer over NVLink) — the C++ form of
+ * bench.py's NCCL broadcast; reference analogues: iModel::clone (Whisper/Whisper/ModelImpl.cpp:40-60), whisper_full_parallel
+ * (Whisper/source/whisper.cpp:3127-3268). */
+typedef struct wsp_replicas wsp_replicas;
+typedef struct wsp_replica_stats
+{
+	int32_t device;
+	int32_t batches_done, chunks_done;
+	int32_t failed;          /* the replica returned an error and was retired; its batch went back to the queue */
+	float busy_ms;           /* host wall time spent inside wsp_run_chunks */
+	float load_ms;           /* engine + context creation, including the image copy */
+} wsp_replica_stats;
+wsp_status wsp_replicas_create( const wsp_model* m, const int32_t* devices, int32_t n_devices, int32_t max_batch, wsp_replicas** out );
+int32_t wsp_replicas_count( const wsp_replicas* r );
+/* n_chunks clips through a host work queue: batches of <= max_batch chunks go to whichever replica is free; a batch whose replica fails
+ * is re-queued for the others.  tokens_out[chunk * n_decode + i]; stats (nullable) [n_devices]. */
+wsp_status wsp_replicas_run_chunks( wsp_replicas* r, const float* const* pcm, const int32_t* n_samples, int32_t n_chunks, const int32_t* prompt,
+	int32_t n_prompt, int32_t n_decode, int32_t* tokens_out, wsp_replica_stats* stats );
+/* test hook: replica i fails its next batch (exercises retire + re-queue) */
+wsp_status wsp_replicas_debug_fail_next( wsp_replicas* r, int32_t replica );
+void wsp_replicas_destroy( wsp_replicas* r );
 
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on) */
 wsp_status wsp_timer_start( wsp_context* c );
@@ -151,10 +179,12 @@ wsp_status wsp_debug_set_encoder_layers( wsp_context* c, int32_t n );
 wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n );
 /* debug: 0 = launch the N = 1 decoder step kernel by kernel instead of replaying the captured CUDA graph */
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on );
-/* debug: 0 = run the single-token decoder step as one kernel per op instead of the persistent decoder-step kernel */
-wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on );
-/* debug: %globaltimer marks (ns) of CTA 0 around every grid barrier of the last persistent decoder step (needs WSP_MEGA_TIMING=1) */
-wsp_status wsp_debug_mega_timing( wsp_context* c, uint64_t* dst, int32_t cap );
+/* debug: how the single-token decoder step runs: 2 = one dataflow kernel (decode_flow.cu, default), 1 = round 1's persistent kernel with
+ * grid barriers (decode_mega.cu, kept for same-box A/B runs), 0 = one kernel per op */
+wsp_status wsp_debug_set_step_mode( wsp_context* c, int32_t mode );
+/* debug: record %globaltimer marks (ns) of CTA 0 at every phase boundary of the decoder-step kernel; read them back after a step */
+wsp_status wsp_debug_enable_step_timing( wsp_context* c, int32_t on );
+wsp_status wsp_debug_step_timing( wsp_context* c, uint64_t* dst, int32_t cap );
 /* pinned host memory for callers that want asynchronous H2D copies of PCM (bench.py's e2e leg) */
 void* wsp_host_alloc( size_t bytes );
 void wsp_host_free( void* p );
@@ -168,6 +198,10 @@ wsp_status wsp_test_gemm( int32_t device, int32_t M, int32_t N, int32_t K, const
 wsp_status wsp_test_attention( int32_t device, int32_t BH, int32_t T, const uint16_t* Q, const uint16_t* K, const uint16_t* V, float* out, int32_t iters, float* ms );
 /* skinny GEMM: out[cols][nOut] = x[cols][K] * W[nOut][K]^T */
 wsp_status wsp_test_skinny( int32_t device, int32_t nOut, int32_t K, int32_t cols, const uint16_t* W, const uint16_t* X, float* out, int32_t iters, float* ms );
+/* sampler alone: rows of logits -> probs (softmax with the reference's f16-table exp, may be NULL) and one sampled token per row under
+ * the rules of whisper_sample_best / whisper_sample_timestamp (whisper.cpp:1875-1964); special4 = { beg, sot, solm, not } */
+wsp_status wsp_test_sample( int32_t device, int32_t rows, int32_t n_vocab, const float* logits, const int32_t special4[ 4 ], int32_t force_timestamp,
+	int32_t is_initial, float* probs, wsp_token_data* out );
 /* LayerNorm rows x d f32 -> f16 bit patterns */
 wsp_status wsp_test_layernorm( int32_t device, int32_t rows, int32_t d, const float* x, const float* gamma, const float* beta, uint16_t* out );
 

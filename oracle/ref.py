@@ -42,6 +42,11 @@ def lib():
         L.ora_get_probs.argtypes = [vp, fp]
         L.ora_sample_best.argtypes = [vp, ip, fp]
         L.ora_sample_timestamp.argtypes = [vp, ci, ip, fp]
+        L.ora_sample_from_probs.argtypes = [vp, fp, ci, ci, ip, fp]
+        L.ora_lang_auto_detect.restype = ci; L.ora_lang_auto_detect.argtypes = [vp, ci, ci, fp]
+        L.ora_lang_max_id.restype = ci
+        L.ora_gap_log_enable.argtypes = [vp, ci]
+        L.ora_gap_log_get.argtypes = [fp]
         L.ora_tokenize.restype = ci; L.ora_tokenize.argtypes = [vp, C.c_char_p, ip, ci]
         L.ora_cross_kv_elements.restype = C.c_int64; L.ora_cross_kv_elements.argtypes = [vp]
         L.ora_get_cross_kv.argtypes = [vp, fp, fp]
@@ -53,6 +58,10 @@ def lib():
         L.ora_trace_data.argtypes = [ci, fp]
         L.ora_full.argtypes = [vp, fp, ci, ci, ci, C.c_char_p, ci, ci]
         L.ora_full_ex.argtypes = [vp, fp, ci, ci, ci, C.c_char_p, ci, ci, ci, ci]
+        L.ora_full_ex2.argtypes = [vp, fp, ci, ci, ci, C.c_char_p, ci, ci, ci, ci]
+        L.ora_full_token_t0.restype = C.c_int64; L.ora_full_token_t0.argtypes = [vp, ci, ci]
+        L.ora_full_token_t1.restype = C.c_int64; L.ora_full_token_t1.argtypes = [vp, ci, ci]
+        L.ora_full_token_vlen.restype = C.c_float; L.ora_full_token_vlen.argtypes = [vp, ci, ci]
         L.ora_full_n_segments.argtypes = [vp]
         L.ora_full_segment_t0.restype = C.c_int64; L.ora_full_segment_t0.argtypes = [vp, ci]
         L.ora_full_segment_t1.restype = C.c_int64; L.ora_full_segment_t1.argtypes = [vp, ci]
@@ -147,6 +156,33 @@ class RefOracle:
         else:
             self.L.ora_sample_best(self.ctx, _i(ids), _f(f3))
         return dict(id=int(ids[0]), tid=int(ids[1]), p=float(f3[0]), pt=float(f3[1]), ptsum=float(f3[2]))
+
+    def sample_from_probs(self, probs: np.ndarray, force_timestamp: bool = False, is_initial: bool = False):
+        """whisper_sample_best / whisper_sample_timestamp of the reference on a caller-supplied probability row"""
+        p = np.ascontiguousarray(probs, np.float32)
+        assert p.size == self.n_vocab
+        ids = np.zeros(2, np.int32)
+        f3 = np.zeros(3, np.float32)
+        self.L.ora_sample_from_probs(self.ctx, _f(p), int(force_timestamp), int(is_initial), _i(ids), _f(f3))
+        return dict(id=int(ids[0]), tid=int(ids[1]), p=float(f3[0]), pt=float(f3[1]), ptsum=float(f3[2]))
+
+    def lang_auto_detect(self, offset_ms: int = 0):
+        n = self.L.ora_lang_max_id() + 1
+        pr = np.zeros(n, np.float32)
+        lid = self.L.ora_lang_auto_detect(self.ctx, offset_ms, self.threads, _f(pr))
+        return lid, pr
+
+    def gap_log(self, on: bool | None = None):
+        """on=True/False: start / stop recording the top-2 margin (logit units) of every whisper_decode call, also inside
+        whisper_full; on=None: return what was recorded."""
+        if on is not None:
+            self.L.ora_gap_log_enable(self.ctx, int(on))
+            return None
+        n = self.L.ora_gap_log_count()
+        out = np.zeros(n, np.float32)
+        if n:
+            self.L.ora_gap_log_get(_f(out))
+        return out
 
     def cross_kv(self):
         n = self.L.ora_cross_kv_elements(self.ctx)

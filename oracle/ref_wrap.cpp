@@ -41,6 +41,9 @@ namespace
 	};
 	struct Delayed { std::string name; const ggml_tensor* t; };
 	bool g_traceOn = false;
+	bool g_gapLogOn = false;
+	int g_gapVocab = 0;
+	std::vector<float> g_gapLog;
 	std::vector<TraceItem> g_trace;
 	std::vector<Delayed> g_delayed;
 
@@ -79,6 +82,18 @@ namespace Tracing
 	}
 	void vector( const ItemName& name, const std::vector<float>& v )
 	{
+		if( g_gapLogOn && 0 == strcmp( name.text, "probs" ) && g_gapVocab > 0 && v.size() >= (size_t)g_gapVocab )
+		{
+			// top-2 gap of the last row in logit units: log( p1 / p2 ) — how close the reference's greedy decision was
+			const float* p = v.data() + ( v.size() - (size_t)g_gapVocab );
+			float a = 0, b = 0;
+			for( int i = 0; i < g_gapVocab; i++ )
+			{
+				if( p[ i ] > a ) { b = a; a = p[ i ]; }
+				else if( p[ i ] > b ) b = p[ i ];
+			}
+			g_gapLog.push_back( b > 0 ? logf( a / b ) : 1e9f );
+		}
 		if( !g_traceOn ) return;
 		TraceItem it;
 		it.name = name.text;
@@ -152,6 +167,19 @@ void ora_sample_best( whisper_context* c, int32_t* ids2, float* f3 ) { packToken
 int ora_tokenize( whisper_context* c, const char* text, int32_t* tokens, int cap ) { return whisper_tokenize( c, text, tokens, cap ); }
 void ora_sample_timestamp( whisper_context* c, int is_initial, int32_t* ids2, float* f3 ) { packToken( whisper_sample_timestamp( c, is_initial != 0 ), ids2, f3 ); }
 
+// sampler alone on a caller-supplied probability row: writes it where whisper_sample_best / _timestamp read (the last n_vocab
+// entries of ctx->probs, whisper.cpp:2358-2376) and runs the reference's own rules (whisper.cpp:1875-1964)
+void ora_sample_from_probs( whisper_context* c, const float* probs, int force_timestamp, int is_initial, int32_t* ids2, float* f3 )
+{
+	const int n = c->vocab.n_vocab;
+	if( (int)c->probs.size() < n ) c->probs.resize( n );
+	memcpy( c->probs.data() + ( c->probs.size() - n ), probs, sizeof( float ) * n );
+	packToken( force_timestamp ? whisper_sample_timestamp( c, is_initial != 0 ) : whisper_sample_best( c ), ids2, f3 );
+}
+// language auto-detection (whisper.cpp:2428-2495): returns the language id, fills probs[whisper_lang_max_id()+1] when not null
+int ora_lang_auto_detect( whisper_context* c, int offset_ms, int threads, float* lang_probs ) { return whisper_lang_auto_detect( c, offset_ms, threads, lang_probs ); }
+int ora_lang_max_id() { return whisper_lang_max_id(); }
+
 // f16 cross-attention memories written by whisper_encode (whisper.cpp:1479-1485), as f32: [n_text_layer][n_ctx][n_state]
 int64_t ora_cross_kv_elements( whisper_context* c ) { return ggml_nelements( c->model.memory_cross_k ); }
 void ora_get_cross_kv( whisper_context* c, float* k, float* v )
@@ -169,6 +197,11 @@ void ora_get_self_kv( whisper_context* c, float* k, float* v )
 	const ggml_fp16_t* pv = (const ggml_fp16_t*)c->model.memory_v->data;
 	for( int64_t i = 0; i < n; i++ ) { k[ i ] = ggml_fp16_to_fp32( pk[ i ] ); v[ i ] = ggml_fp16_to_fp32( pv[ i ] ); }
 }
+
+// ---- decision-margin log: one entry per whisper_decode call while enabled (also inside whisper_full) ----
+void ora_gap_log_enable( whisper_context* c, int on ) { g_gapLogOn = on != 0; g_gapVocab = c ? c->vocab.n_vocab : 0; g_gapLog.clear(); }
+int ora_gap_log_count() { return (int)g_gapLog.size(); }
+void ora_gap_log_get( float* dst ) { memcpy( dst, g_gapLog.data(), g_gapLog.size() * sizeof( float ) ); }
 
 // ---- trace access ----
 void ora_trace_enable( int on ) { g_traceOn = on != 0; g_trace.clear(); g_delayed.clear(); }
@@ -212,6 +245,28 @@ int ora_full_ex( whisper_context* c, const float* pcm, int n, int threads, int f
 	p.duration_ms = duration_ms;
 	return whisper_full( c, p, pcm, n );
 }
+// + token-level timestamps (flags bit 8 = eFullParamsFlags::TokenTimestamps) and max_len wrapping (whisper.cpp:3063-3070)
+int ora_full_ex2( whisper_context* c, const float* pcm, int n, int threads, int flags, const char* language, int max_tokens, int offset_ms, int duration_ms, int max_len )
+{
+	whisper_full_params p = whisper_full_default_params( WHISPER_SAMPLING_GREEDY );
+	p.n_threads = threads;
+	p.translate = ( flags & 1 ) != 0;
+	p.no_context = ( flags & 2 ) != 0;
+	p.single_segment = ( flags & 4 ) != 0;
+	p.print_special = ( flags & 8 ) != 0;
+	p.token_timestamps = ( flags & 0x100 ) != 0;
+	p.print_progress = false;
+	p.print_realtime = false;
+	p.language = language;
+	p.max_tokens = max_tokens;
+	p.max_len = max_len;
+	p.offset_ms = offset_ms;
+	p.duration_ms = duration_ms;
+	return whisper_full( c, p, pcm, n );
+}
+int64_t ora_full_token_t0( whisper_context* c, int i, int j ) { return whisper_full_get_token_data( c, i, j ).t0; }
+int64_t ora_full_token_t1( whisper_context* c, int i, int j ) { return whisper_full_get_token_data( c, i, j ).t1; }
+float ora_full_token_vlen( whisper_context* c, int i, int j ) { return whisper_full_get_token_data( c, i, j ).vlen; }
 int ora_full_n_segments( whisper_context* c ) { return whisper_full_n_segments( c ); }
 int64_t ora_full_segment_t0( whisper_context* c, int i ) { return whisper_full_get_segment_t0( c, i ); }
 int64_t ora_full_segment_t1( whisper_context* c, int i ) { return whisper_full_get_segment_t1( c, i ); }

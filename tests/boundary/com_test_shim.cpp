@@ -1,0 +1,190 @@
+// TEST INFRASTRUCTURE — flat C helpers over the COM-style surface (include/whisper_b200_com.h) so that pytest can drive C++ vtables
+// through ctypes.  Built into tests/boundary/_build/libwspc_test.so and linked against libwhisper_b200.so: it uses nothing but the
+// public header, exactly like a client application would (Examples/main/main.cpp:210-318 of the reference).
+#include "whisper_b200_com.h"
+#include <string>
+#include <vector>
+using namespace Whisper;
+
+// every call goes loadModel -> createContext -> fullDefaultParams -> runFull -> getResults exactly as the reference's CLI does
+namespace
+{
+	struct Session
+	{
+		iModel* model = nullptr;
+		iContext* context = nullptr;
+		iTranscribeResult* result = nullptr;
+		std::vector<int> segCallbackCounts;
+		int maxLen = 0;
+	};
+	HRESULT segCallback( iContext*, uint32_t nNew, void* pv ) noexcept
+	{
+		static_cast<Session*>( pv )->segCallbackCounts.push_back( (int)nNew );
+		return S_OK;
+	}
+}
+
+extern "C" {
+
+int32_t wspc_open( const char* modelPathUtf8, int32_t device, void** out )
+{
+	if( !modelPathUtf8 || !out ) return E_POINTER;
+	std::wstring w;
+	for( const char* p = modelPathUtf8; *p; p++ ) w.push_back( (wchar_t)(unsigned char)*p );   // test paths are ASCII
+	std::wstring adapter = std::to_wstring( device );
+	sModelSetup setup;
+	setup.impl = eModelImplementation::B200;
+	setup.adapter = adapter.c_str();
+	Session* s = new Session();
+	HRESULT hr = loadModel( w.c_str(), setup, nullptr, &s->model );
+	if( SUCCEEDED( hr ) ) hr = s->model->createContext( &s->context );
+	if( FAILED( hr ) )
+	{
+		if( s->model ) s->model->Release();
+		delete s;
+		return hr;
+	}
+	*out = s;
+	return S_OK;
+}
+void wspc_close( void* h )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return;
+	if( s->result ) s->result->Release();
+	if( s->context ) s->context->Release();
+	if( s->model ) s->model->Release();
+	delete s;
+}
+// flags = eFullParamsFlags bits; language = code such as "en" or "auto"
+int32_t wspc_run_full( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t maxTokens, int32_t cpuThreads,
+	int32_t offsetMs, int32_t durationMs, const int32_t* promptTokens, int32_t nPromptTokens )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return E_POINTER;
+	sFullParams p;
+	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
+	if( FAILED( hr ) ) return hr;
+	p.flags = (eFullParamsFlags)flags;
+	p.language = ( language && strcmp( language, "auto" ) != 0 ) ? findLanguageKeyA( language ) : makeLanguageKey( "auto" );
+	p.max_tokens = maxTokens;
+	p.max_len = s->maxLen;
+	p.cpuThreads = cpuThreads;
+	p.offset_ms = offsetMs;
+	p.duration_ms = durationMs;
+	p.prompt_tokens = promptTokens;
+	p.prompt_n_tokens = nPromptTokens;
+	p.new_segment_callback = &segCallback;
+	p.new_segment_callback_user_data = s;
+	s->segCallbackCounts.clear();
+	iAudioBuffer* buf = nullptr;
+	hr = createAudioBuffer( pcm, (uint32_t)nSamples, &buf );
+	if( FAILED( hr ) ) return hr;
+	hr = s->context->runFull( p, buf );
+	buf->Release();
+	if( FAILED( hr ) ) return hr;
+	if( s->result ) { s->result->Release(); s->result = nullptr; }
+	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
+	return FAILED( hr2 ) ? hr2 : hr;
+}
+void wspc_set_max_len( void* h, int32_t maxLen ) { static_cast<Session*>( h )->maxLen = maxLen; }
+int64_t wspc_token_t0( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	return (int64_t)s->result->getTokens()[ s->result->getSegments()[ i ].firstToken + j ].time.begin.ticks / 100000;
+}
+int64_t wspc_token_t1( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	return (int64_t)s->result->getTokens()[ s->result->getSegments()[ i ].firstToken + j ].time.end.ticks / 100000;
+}
+int32_t wspc_segment_callback_total( void* h )
+{
+	Session* s = static_cast<Session*>( h );
+	int n = 0;
+	for( int v : s->segCallbackCounts ) n += v;
+	return n;
+}
+int32_t wspc_n_segments( void* h )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s || !s->result ) return 0;
+	sTranscribeLength len;
+	s->result->getSize( len );
+	return (int32_t)len.countSegments;
+}
+int32_t wspc_n_segment_callbacks( void* h ) { Session* s = static_cast<Session*>( h ); return s ? (int32_t)s->segCallbackCounts.size() : 0; }
+int64_t wspc_segment_t0( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.begin.ticks / 100000 ); }
+int64_t wspc_segment_t1( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.end.ticks / 100000 ); }
+const char* wspc_segment_text( void* h, int32_t i ) { return static_cast<Session*>( h )->result->getSegments()[ i ].text; }
+int32_t wspc_segment_n_tokens( void* h, int32_t i ) { return (int32_t) static_cast<Session*>( h )->result->getSegments()[ i ].countTokens; }
+int32_t wspc_token_id( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return s->result->getTokens()[ seg.firstToken + j ].id;
+}
+float wspc_token_p( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return s->result->getTokens()[ seg.firstToken + j ].probability;
+}
+int32_t wspc_token_flags( void* h, int32_t i, int32_t j )
+{
+	Session* s = static_cast<Session*>( h );
+	const sSegment& seg = s->result->getSegments()[ i ];
+	return (int32_t)s->result->getTokens()[ seg.firstToken + j ].flags;
+}
+// iModel surface
+int32_t wspc_tokenize( void* h, const char* text, int32_t* dst, int32_t cap )
+{
+	Session* s = static_cast<Session*>( h );
+	struct Sink { int32_t* dst; int32_t cap; int32_t n; } sink{ dst, cap, 0 };
+	auto cb = []( const int* tokens, int n, void* pv ) {
+		Sink* k = static_cast<Sink*>( pv );
+		for( int i = 0; i < n && k->n < k->cap; i++ ) k->dst[ k->n++ ] = tokens[ i ];
+	};
+	const HRESULT hr = s->model->tokenize( text, cb, &sink );
+	return FAILED( hr ) ? hr : sink.n;
+}
+const char* wspc_string_from_token( void* h, int32_t id ) { return static_cast<Session*>( h )->model->stringFromToken( id ); }
+int32_t wspc_is_multilingual( void* h ) { return static_cast<Session*>( h )->model->isMultilingual() == S_OK ? 1 : 0; }
+int32_t wspc_special_tokens( void* h, int32_t* out8 )
+{
+	SpecialTokens st;
+	const HRESULT hr = static_cast<Session*>( h )->model->getSpecialTokens( st );
+	memcpy( out8, &st, sizeof( st ) );
+	return hr;
+}
+int32_t wspc_query_interfaces( void* h )
+{
+	// IUnknown plumbing: QueryInterface round trips and reference counts behave like COM
+	Session* s = static_cast<Session*>( h );
+	void* p = nullptr;
+	if( s->model->QueryInterface( iModel::iid(), &p ) != S_OK || p != s->model ) return 1;
+	s->model->Release();
+	if( s->model->QueryInterface( ComLight::IUnknown::iid(), &p ) != S_OK ) return 2;
+	s->model->Release();
+	if( s->model->QueryInterface( iContext::iid(), &p ) != E_NOINTERFACE || p != nullptr ) return 3;
+	iModel* m2 = nullptr;
+	if( s->context->getModel( &m2 ) != S_OK || m2 != s->model ) return 4;
+	m2->Release();
+	iModel* clone = nullptr;
+	if( s->model->clone( &clone ) != S_OK || !clone ) return 5;
+	clone->Release();
+	sProgressSink sink{ nullptr, nullptr };
+	sFullParams fp;
+	s->context->fullDefaultParams( eSamplingStrategy::Greedy, &fp );
+	if( s->context->runStreamed( fp, sink, nullptr ) != E_NOTIMPL ) return 6;
+	return 0;
+}
+uint32_t wspc_find_language_key( const char* lang ) { return findLanguageKeyA( lang ); }
+int32_t wspc_language_count( void )
+{
+	sLanguageList l;
+	getSupportedLanguages( l );
+	return (int32_t)l.length;
+}
+
+} // extern "C"

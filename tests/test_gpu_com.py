@@ -1,21 +1,27 @@
 """The COM-style drop-in surface (include/whisper_b200_com.h) on a B200: loadModel -> createContext -> fullDefaultParams -> runFull ->
 getResults, exactly the call sequence of the reference's CLI (Examples/main/main.cpp:210-318), driven through the flat wspc_*
 helpers (ctypes cannot call C++ vtables).  The transcription driver is compared with the reference's whisper_full()
-(Whisper/source/whisper.cpp:2765-3125) via fixtures generated from oracle/_ref (tests/golden/full_micro_en_ts.npz)."""
+(Whisper/source/whisper.cpp:2765-3125) via fixtures generated from oracle/_ref (tests/golden/full_runs.npz, scripted models)."""
 import ctypes as C
 import os
 
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import FULL_MODEL, FULL_RUNS, full_pcm
+from tests.golden.make_golden import FULL_MAX_LEN, FULL_MODEL, FULL_RUNS, full_pcm
 from whisper_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 
 
+SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "boundary", "_build", "libwspc_test.so")
+
+
 def _lib():
-    L = capi.lib()
+    capi.lib()                       # the product library (the shim links against it)
+    if not os.path.exists(SHIM):
+        pytest.fail("tests/boundary/_build/libwspc_test.so is missing: run __graft_entry__.build()")
+    L = C.CDLL(SHIM)
     vp, i32 = C.c_void_p, C.c_int32
     L.wspc_open.restype = i32; L.wspc_open.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     L.wspc_close.argtypes = [vp]
@@ -33,41 +39,67 @@ def _lib():
     L.wspc_tokenize.restype = i32; L.wspc_tokenize.argtypes = [vp, C.c_char_p, C.POINTER(i32), i32]
     L.wspc_string_from_token.restype = C.c_char_p; L.wspc_string_from_token.argtypes = [vp, i32]
     L.wspc_special_tokens.restype = i32; L.wspc_special_tokens.argtypes = [vp, C.POINTER(i32)]
+    L.wspc_set_max_len.argtypes = [vp, i32]
+    for f in ("wspc_token_t0", "wspc_token_t1"):
+        getattr(L, f).restype = C.c_int64; getattr(L, f).argtypes = [vp, i32, i32]
+    L.wspc_segment_callback_total.restype = i32; L.wspc_segment_callback_total.argtypes = [vp]
     L.wspc_find_language_key.restype = C.c_uint32; L.wspc_find_language_key.argtypes = [C.c_char_p]
     L.wspc_language_count.restype = i32
     return L
 
 
+_sessions = {}
+
+
+def open_session(model):
+    L = _lib()
+    if model not in _sessions:
+        h = C.c_void_p()
+        hr = L.wspc_open(synth.model_path(model).encode(), 0, C.byref(h))
+        assert hr == 0, hex(hr & 0xFFFFFFFF)
+        _sessions[model] = h
+    return L, _sessions[model]
+
+
 @pytest.fixture(scope="module")
 def session():
+    yield open_session(FULL_MODEL)
     L = _lib()
-    h = C.c_void_p()
-    hr = L.wspc_open(synth.model_path(FULL_MODEL).encode(), 0, C.byref(h))
-    assert hr == 0, hex(hr & 0xFFFFFFFF)
-    yield L, h
-    L.wspc_close(h)
+    for h in _sessions.values():
+        L.wspc_close(h)
+    _sessions.clear()
 
 
-def run_full(L, h, pcm, flags=0, language=b"en", max_tokens=0, threads=4, off=0, dur=0, prompt=None):
+def run_full(L, h, pcm, flags=0, language=b"en", max_tokens=0, threads=4, off=0, dur=0, prompt=None, max_len=0):
     pcm = np.ascontiguousarray(pcm, np.float32)
     pt = None if prompt is None else np.ascontiguousarray(prompt, np.int32)
+    L.wspc_set_max_len(h, max_len)
     hr = L.wspc_run_full(h, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size, flags, language, max_tokens, threads, off, dur,
                          None if pt is None else pt.ctypes.data_as(C.POINTER(C.c_int32)), 0 if pt is None else pt.size)
     segs = []
     for i in range(L.wspc_n_segments(h)):
         n = L.wspc_segment_n_tokens(h, i)
         segs.append(dict(t0=L.wspc_segment_t0(h, i), t1=L.wspc_segment_t1(h, i), text=L.wspc_segment_text(h, i).decode(errors="replace"),
-                         tokens=[L.wspc_token_id(h, i, j) for j in range(n)], flags=[L.wspc_token_flags(h, i, j) for j in range(n)]))
+                         tokens=[L.wspc_token_id(h, i, j) for j in range(n)], flags=[L.wspc_token_flags(h, i, j) for j in range(n)],
+                         token_t=[[L.wspc_token_t0(h, i, j), L.wspc_token_t1(h, i, j)] for j in range(n)]))
     return hr, segs
 
 
 @pytest.mark.parametrize("name", list(FULL_RUNS))
 def test_run_full_matches_reference_driver(session, name):
-    L, h = session
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "full_micro_en_ts.npz"))
-    flags, max_tokens, off, dur = FULL_RUNS[name]
-    # eFullParamsFlags::NoContext is implied between parametrised runs: the reference fixture was made with a fresh context each time
-    hr, segs = run_full(L, h, full_pcm(), flags=flags | 2, max_tokens=max_tokens, off=off, dur=dur)
+    """whisper_full on 78 s of audio per case: window seeking from timestamp tokens, prompt carry-over between windows (and, for
+    `context_second_call`, between two runFull calls on one context), segment splitting, eFullParamsFlags, language / task tokens of the
+    multilingual model, token-level timestamps and max_len wrapping — segments, tokens, texts and token times equal to the reference's."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "full_runs.npz"))
+    model, flags, max_tokens, off, dur, lang, calls = FULL_RUNS[name]
+    L, h = open_session(model)
+    pcm = full_pcm(int(g[name + "_pcm_base"]))
+    kw = dict(language=lang.encode(), max_tokens=max_tokens, off=off, dur=dur, max_len=FULL_MAX_LEN.get(name, 0))
+    # the fixture ran on a fresh context: NoContext on the first call clears what earlier cases left in this session's context
+    hr, segs = run_full(L, h, pcm, flags=flags | 2, **kw)
+    if calls == 2:
+        assert hr == 0
+        hr, segs = run_full(L, h, pcm, flags=flags, **kw)      # second call WITHOUT NoContext: starts from the first call's text (whisper.cpp:2850-2861)
     assert hr == 0
     ref_t = g[name + "_t"]
     assert len(segs) == len(ref_t)
@@ -75,9 +107,31 @@ def test_run_full_matches_reference_driver(session, name):
     assert [len(s["tokens"]) for s in segs] == g[name + "_ntok"].tolist()
     assert [t for s in segs for t in s["tokens"]] == g[name + "_tokens"].tolist()
     assert [s["text"] for s in segs] == g[name + "_text"].tolist()
-    assert L.wspc_n_segment_callbacks(h) == len(segs)     # new_segment_callback fired once per segment
+    assert L.wspc_segment_callback_total(h) == len(segs)  # new_segment_callback reports every segment (n_new > 1 after a wrap)
+    eot = 50257 if model.startswith("micro-") else 50256
     for s in segs:                                        # eTokenFlags::Special <=> id >= eot (convertThings.cpp:200-203)
-        assert s["flags"] == [1 if t >= 50256 else 0 for t in s["tokens"]]
+        assert s["flags"] == [1 if t >= eot else 0 for t in s["tokens"]]
+    if flags & 0x100:
+        assert [t for s in segs for t in s["token_t"]] == g[name + "_token_t"].tolist()
+    else:
+        assert all(t == [-1, -1] for s in segs for t in s["token_t"])       # not computed: whisper_token_data's initial -1 (whisper.cpp:1880)
+
+
+def test_language_auto_detect_matches_reference():
+    """whisper_lang_auto_detect (whisper.cpp:2428-2495): encode, decode [sot], the reference's softmax over the language tokens'
+    PROBABILITIES (quirk kept), arg-max.  Through the C ABI: wsp_detect_language."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lang_detect.npz"))
+    m = capi.Model(synth.model_path("micro-sc"))
+    e = capi.Engine(m, 0)
+    c = capi.Context(e, 1)
+    try:
+        for i, ch in enumerate(g["chunks"].tolist()):
+            c.pcm_to_mel(0, synth.synth_pcm(ch, 320000))
+            lid, probs = c.detect_language(0, g["lang_probs"].shape[1])
+            assert lid == int(g["lang_id"][i])
+            assert np.abs(probs - g["lang_probs"][i]).max() < 2e-4
+    finally:
+        c.close(); e.close(); m.close()
 
 
 def test_short_audio_is_a_noop(session):

@@ -38,9 +38,10 @@ def golden(name):
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_mel(name):
-    model, chunk, n, off = CASES[name]
+    model, _, n, off = CASES[name]
     m, e, c = open_model(model)
     g = golden(name)
+    chunk = int(g["chunk"])
     c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
     mel = c.get_mel(0)
     assert mel.shape == tuple(g["mel_shape"])
@@ -48,7 +49,7 @@ def test_mel(name):
 
 
 def test_mel_edge_cases():
-    m, e, c = open_model("micro.en")
+    m, e, c = open_model("micro.en-sc")
     # shorter than one FFT window, and an empty buffer: n_len = n_samples / 160 frames, zero-padded frames (whisper.cpp:2080, 2105-2109)
     for n in (0, 100, 160, 399, 400, 16000):
         c.pcm_to_mel(0, synth.synth_pcm(3, n) if n else np.zeros(0, np.float32))
@@ -63,9 +64,10 @@ def test_mel_edge_cases():
 @pytest.mark.parametrize("name", list(CASES))
 def test_encoder_trace_points(name):
     """Same named intermediates the reference traces (whisper.cpp:1121-1432), layer by layer."""
-    model, chunk, n, off = CASES[name]
+    model, _, n, off = CASES[name]
     m, e, c = open_model(model)
     g = golden(name)
+    chunk = int(g["chunk"])
     d, T, L = m.n_audio_state, m.n_audio_ctx, m.n_audio_layer
     c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
     c.set_encoder_layers(0)
@@ -89,9 +91,10 @@ def test_encoder_trace_points(name):
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("threads", [1, 4])
 def test_decoder_logits_teacher_forced(name, threads):
-    model, chunk, n, off = CASES[name]
+    model, _, n, off = CASES[name]
     m, e, c = open_model(model)
     g = golden(name)
+    chunk = int(g["chunk"])
     c.set_reference_threads(threads)
     c.pcm_to_mel(0, synth.synth_pcm(chunk, n))
     c.encode(1, [off])
@@ -124,11 +127,12 @@ def test_decoder_logits_teacher_forced(name, threads):
 def test_greedy_tokens_free_running(name, threads, graph):
     """The measured path (wsp_run_chunks: tokens fed back on the device, CUDA graph per step) reproduces the reference's
     greedy sequence exactly — when the window starts at frame 0, which is what run_chunks encodes."""
-    model, chunk, n, off = CASES[name]
+    model, _, n, off = CASES[name]
     if off != 0:
         pytest.skip("run_chunks always encodes the window at offset 0")
     m, e, c = open_model(model)
     g = golden(name)
+    chunk = int(g["chunk"])
     c.set_reference_threads(threads)
     c.set_graph(graph)
     toks, st = c.run_chunks([synth.synth_pcm(chunk, n)], g["prompt"].tolist(), N_STEPS)
@@ -139,8 +143,8 @@ def test_greedy_tokens_free_running(name, threads, graph):
 
 def test_batch_equals_single():
     """Independent chunks: a chunk's tokens do not depend on which batch slot it sits in or on its neighbours."""
-    m, e, c1 = open_model("micro.en", 1)
-    _, _, c4 = open_model("micro.en", 4)
+    m, e, c1 = open_model("micro.en-sc", 1)
+    _, _, c4 = open_model("micro.en-sc", 4)
     pcms = [synth.synth_pcm(i, 480000 - 16000 * i) for i in range(4)]
     prompt = m.prompt_init()
     t4, _ = c4.run_chunks(pcms, prompt, 12)
@@ -160,8 +164,8 @@ def test_live_reference_when_prebuilt():
     from oracle import ref
     if not ref.available():
         pytest.skip("oracle/_ref not present")
-    m, e, c = open_model("tiny.en")
-    o = ref.RefOracle(synth.model_path("tiny.en"), threads=4)
+    m, e, c = open_model("tiny.en-sc")
+    o = ref.RefOracle(synth.model_path("tiny.en-sc"), threads=4)
     pcm = synth.synth_pcm(5)
     mel_ref = o.pcm_to_mel(pcm)
     c.pcm_to_mel(0, pcm)
@@ -178,26 +182,31 @@ def test_live_reference_when_prebuilt():
     assert toks[0].tolist() == ref_toks.tolist()
 
 
-@pytest.mark.parametrize("model", ["tiny.en", "base.en", "medium"])
+@pytest.mark.parametrize("model", ["tiny.en-sc", "base.en-sc", "medium-sc", "large-sc"])
 def test_real_model_shapes_match_reference_fixture(model):
-    """BASELINE.json's model shapes (synthetic weights): the bench loop's greedy tokens and the last step's logits against the
-    reference's (tests/golden/real_shapes.npz, made by `make_golden.py --real-shapes`); both chunks run as ONE batch here."""
-    from tests.golden.make_golden import REAL_SHAPES, REAL_STEPS
+    """BASELINE.json's model shapes on the scripted weights, all chunks as ONE batch: medium-sc = the bench configuration (8 chunks,
+    32 tokens each), base.en-sc = 12 chunks (the two-tile path of the decoder step, B in 9..16), large-sc = configs[4]'s shape.  Greedy
+    tokens identical to the reference's for every chunk (its margins are >= GAP_SAFE by construction of the fixture), last-step logits
+    within tolerance (tests/golden/real_shapes.npz, made by `make_golden.py --real-shapes`)."""
+    from tests.golden.make_golden import REAL_SHAPES
     g = golden("real_shapes")
-    chunks = REAL_SHAPES[model]
+    key = model.replace(".", "_").replace("-", "_")
+    if key + "_tokens" not in g:
+        pytest.skip("no fixture for " + model)
+    n_chunks, steps = REAL_SHAPES[model]
+    chunks = g[key + "_chunks"].tolist()
+    assert len(chunks) == n_chunks
     m = capi.Model(synth.model_path(model))
     e = capi.Engine(m, 0)
-    c = capi.Context(e, len(chunks))
+    c = capi.Context(e, n_chunks)
     try:
-        key = model.replace(".", "_")
-        prompt = g["%s_c%d_prompt" % (key, chunks[0])].tolist()
+        prompt = g[key + "_prompt"].tolist()
         assert prompt == m.prompt_init()
-        toks, _ = c.run_chunks([synth.synth_pcm(ch) for ch in chunks], prompt, REAL_STEPS)
-        logits = c.logits(len(chunks))
+        toks, _ = c.run_chunks([synth.synth_pcm(ch) for ch in chunks], prompt, steps)
+        logits = c.logits(n_chunks)
         for i, ch in enumerate(chunks):
-            assert toks[i].tolist() == g["%s_c%d_tokens" % (key, ch)].tolist(), (model, ch)
-            ref = g["%s_c%d_last_logits_sub" % (key, ch)]
-            assert np.abs(logits[i][::LOGIT_STEP] - ref).max() < TOL_LOGIT, (model, ch)
+            assert toks[i].tolist() == g[key + "_tokens"][i].tolist(), (model, ch)
+            assert np.abs(logits[i][::LOGIT_STEP] - g[key + "_last_logits_sub"][i]).max() < TOL_LOGIT, (model, ch)
     finally:
         c.close()
         e.close()
@@ -205,7 +214,7 @@ def test_real_model_shapes_match_reference_fixture(model):
 
 
 def test_argument_errors():
-    m, e, c = open_model("micro.en")
+    m, e, c = open_model("micro.en-sc")
     with pytest.raises(capi.WspError) as ex:
         c.encode(2)            # context was created for batch 1
     assert ex.value.status == -7
@@ -219,7 +228,7 @@ def test_argument_errors():
 
 def test_launch_counter_counts_kernels():
     L = capi.lib()
-    m, e, c = open_model("micro.en")
+    m, e, c = open_model("micro.en-sc")
     before = L.wsp_launch_count()
     c.run_chunks([synth.synth_pcm(0)], m.prompt_init(), 4)
     assert L.wsp_launch_count() - before > 40   # encoder ~45 launches + 4 token steps (persistent decoder kernel + sampler)

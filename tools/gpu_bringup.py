@@ -246,10 +246,10 @@ def stage_decoder(model_name="micro.en"):
     c.set_graph(False)
     toks2, st2 = c.run_chunks([pcm], prompt, 16)
     print("  run_chunks (no graph):", "same" if (toks2 == toks).all() else toks2[0].tolist(), st2.tolist(), flush=True)
-    c.set_mega(False)
+    c.set_step_mode(0)
     toks3, st3 = c.run_chunks([pcm], prompt, 16)
     print("  run_chunks (no mega, no graph):", "same" if (toks3 == toks).all() else toks3[0].tolist(), st3.tolist(), flush=True)
-    c.set_mega(True); c.set_graph(True)
+    c.set_step_mode(2); c.set_graph(True)
     ref_s, ref_toks, ref_st = o.bench_chunk(pcm, prompt, 16, threads=th)
     print("  oracle tokens    :", ref_toks.tolist(), flush=True)
 
@@ -301,59 +301,67 @@ def stage_profile(model_name="medium", batch=8, n_decode=3):
     print("  profile run stages", st.tolist(), flush=True)
 
 
-def stage_megatiming(model_name="medium", batch=8):
-    """per-phase time of the persistent decoder step (CTA 0's view): run with WSP_MEGA_TIMING=1"""
-    import ctypes as C
+def stage_flow():
+    """The dataflow decoder-step kernel against round 1's barrier kernel and the kernel-per-op path: same tokens, same logits (the GEMV
+    and cross-attention arithmetic is bit-identical; self-attention scores are summed in a different order), and the decode time of each."""
     from whisper_b200 import capi, synth
-    os.environ["WSP_MEGA_TIMING"] = "1"
+    cases = [("micro.en", 1, 20), ("micro.en", 4, 20), ("tiny.en", 8, 40), ("base.en", 3, 40), ("medium", 8, 100), ("large", 2, 20), ("medium", 12, 24)]
+    only = os.environ.get("FLOW_CASES")
+    if only:
+        cases = [cs for cs in cases if cs[0] in only.split(",")]
+    for (name, batch, n) in cases:
+        path, m, e, c = _open(name, batch=batch)
+        pcms = [synth.synth_pcm(i) for i in range(batch)]
+        prompt = m.prompt_init()
+        res = {}
+        for mode in (2, 1, 0):
+            c.set_step_mode(mode)
+            try:
+                toks, st = c.run_chunks(pcms, prompt, n)
+                toks, st = c.run_chunks(pcms, prompt, n)
+                res[mode] = (toks.copy(), c.logits(batch).copy(), st[2])
+            except Exception as ex:  # noqa: BLE001
+                print("  %s B=%d mode %d FAILED: %s" % (name, batch, mode, ex), flush=True)
+                break
+        if 2 in res and 0 in res:
+            for mode in (1, 0):
+                if mode not in res:
+                    continue
+                same = (res[2][0] == res[mode][0]).all()
+                dl = np.abs(res[2][1] - res[mode][1]).max()
+                print("  %-9s B=%-2d n=%-3d flow vs mode %d: tokens %s, max|dlogit| %.3e | decode ms flow %.2f  mode%d %.2f" % (
+                    name, batch, n, mode, "same" if same else "DIFFER", dl, res[2][2], mode, res[mode][2]), flush=True)
+            print("     tokens[0][:12]", res[2][0][0][:12].tolist(), flush=True)
+        c.set_step_mode(2)
+        c.close(); e.close(); m.close()
+
+
+def stage_steptiming(model_name="medium", batch=8):
+    """per-phase time of the dataflow decoder step as CTA 0 sees it (%globaltimer marks at every phase boundary)"""
+    from whisper_b200 import synth
+    model_name = os.environ.get("STEP_MODEL", model_name)
+    batch = int(os.environ.get("STEP_BATCH", batch))
     path, m, e, c = _open(model_name, batch=batch)
     pcms = [synth.synth_pcm(i) for i in range(batch)]
+    c.step_timing(True)
     c.run_chunks(pcms, m.prompt_init(), 40)
-    buf = (C.c_uint64 * 4608)()
-    capi.check(capi.lib().wsp_debug_mega_timing(c.h, buf, 4608))
-    sub = np.array(buf[4000:4064], dtype=np.int64).reshape(8, 8)
-    print("  sub-marks of the last layer, CTA 0 thread 0 (us): entry->MMA done | ->reduced | ->epilogue | ->end | ->arrived(atomic back) | ->prefetch issued | ->flag seen")
-    for ph in range(8):
-        r = sub[ph]
-        if r[0] == 0 or r[5] == 0:
-            if r[5] and r[7]:
-                print("    P%d: arrive->prefetch issued %.2f | ->flag seen %.2f" % (ph + 1, (r[6] - r[5]) / 1e3, (r[7] - r[6]) / 1e3))
-            continue
-        d = np.diff(r) / 1e3
-        print("    P%d: %.2f | %.2f | %.2f | %.2f | %.2f | %.2f | %.2f" % ((ph + 1,) + tuple(d.tolist())), flush=True)
-    raw = np.array(buf[:4000], dtype=np.int64).reshape(-1, 2)
-    raw = raw[raw[:, 1] > 0]
-    ids, t = raw[:, 0], raw[:, 1]
-    print("  marks", len(ids), "total us", (t[-1] - t[0]) / 1000.0, flush=True)
-    # generic: average interval from each mark id-class to the next mark
-    names = {}
-    for ph in range(8):   # GEMV phases mark 1001 + 2*ph when the activations are staged, 1002 + 2*ph when computed (ph = 0-based phase)
-        names[1001 + 2 * ph] = "P%d staged" % (ph + 1)
-        names[1002 + 2 * ph] = "P%d computed" % (ph + 1)
+    t = c.step_timing().astype(np.int64)
     L = m.n_text_layer
-    acc = {}
-    for k in range(len(ids) - 1):
-        i = int(ids[k])
-        if i >= 1000:
-            key = names[i]
-        else:
-            # barrier marks: phaseId 0 = start, 1 = before embed barrier, 2 = after ...; per layer 16 marks
-            j = i - 2
-            if j < 0 or j >= L * 16:
-                key = "misc %d" % i
-            else:
-                p = (j % 16)
-                key = "P%d %s" % (p // 2 + 1, "after-barrier" if p % 2 == 0 else "before-barrier->after")
-        acc.setdefault(key, []).append((t[k + 1] - t[k]) / 1000.0)
-    for key in sorted(acc):
-        print("  %-34s -> next mark: %.2f us (n=%d)" % (key, np.mean(acc[key]), len(acc[key])), flush=True)
+    n = 1 + 8 * L + 1
+    t = t[:n]
+    d = np.diff(t) / 1e3
+    per = d[:8 * L].reshape(L, 8)
+    names = ["LN1+QKV", "self-attn", "O+res", "LN+CQ", "cross-attn", "CO+res", "LN+FC1", "FC2+res"]
+    print("  %s B=%d: step %.1f us = layers %.1f + logits %.1f" % (model_name, batch, (t[-1] - t[0]) / 1e3, per.sum(), d[8 * L]), flush=True)
+    print("  per layer (mean over %d layers, us): " % L + " | ".join("%s %.2f" % (nm, v) for nm, v in zip(names, per.mean(0))) + " | layer %.2f" % per.sum(1).mean(), flush=True)
+    print("  layer 0: " + " ".join("%.2f" % v for v in per[0]) + "   last layer: " + " ".join("%.2f" % v for v in per[-1]), flush=True)
 
 
 STAGES = {
     "gemm": stage_gemm, "ln": stage_ln, "skinny": stage_skinny, "attn": stage_attn, "mel": stage_mel,
     "encoder": stage_encoder, "decoder": stage_decoder, "batch": stage_batch,
     "encoder_tiny": stage_encoder_tiny, "decoder_tiny": stage_decoder_tiny,
-    "gemm_perf": stage_gemm_perf, "gemm_stress": stage_gemm_stress, "perf": stage_perf, "profile": stage_profile, "megatiming": stage_megatiming,
+    "gemm_perf": stage_gemm_perf, "gemm_stress": stage_gemm_stress, "perf": stage_perf, "profile": stage_profile, "flow": stage_flow, "steptiming": stage_steptiming,
 }
 
 if __name__ == "__main__":

@@ -25,6 +25,10 @@ class TokenData(C.Structure):
     _fields_ = [("id", C.c_int32), ("tid", C.c_int32), ("p", C.c_float), ("pt", C.c_float), ("ptsum", C.c_float)]
 
 
+class ReplicaStats(C.Structure):
+    _fields_ = [("device", C.c_int32), ("batches_done", C.c_int32), ("chunks_done", C.c_int32), ("failed", C.c_int32), ("busy_ms", C.c_float), ("load_ms", C.c_float)]
+
+
 # every symbol include/whisper_b200.h declares (tests/test_abi.py checks the .so exports each one)
 EXPORTS = [
     "wsp_version", "wsp_last_error", "wsp_device_count", "wsp_device_name", "wsp_launch_count",
@@ -33,9 +37,10 @@ EXPORTS = [
     "wsp_engine_create", "wsp_engine_create_from_image", "wsp_engine_destroy", "wsp_engine_weight_bytes",
     "wsp_context_create", "wsp_context_destroy", "wsp_synchronize",
     "wsp_pcm_to_mel", "wsp_set_mel", "wsp_mel_len", "wsp_get_mel", "wsp_encode", "wsp_decode", "wsp_get_logits", "wsp_get_probs",
-    "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_debug_set_mega", "wsp_debug_mega_timing", "wsp_set_reference_threads",
+    "wsp_detect_language", "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_debug_set_step_mode", "wsp_debug_enable_step_timing", "wsp_debug_step_timing", "wsp_set_reference_threads",
     "wsp_host_alloc", "wsp_host_free", "wsp_timings",
-    "wsp_test_gemm", "wsp_test_attention", "wsp_test_skinny", "wsp_test_layernorm",
+    "wsp_replicas_create", "wsp_replicas_count", "wsp_replicas_run_chunks", "wsp_replicas_debug_fail_next", "wsp_replicas_destroy",
+    "wsp_test_gemm", "wsp_test_attention", "wsp_test_skinny", "wsp_test_layernorm", "wsp_test_sample",
 ]
 
 _lib = None
@@ -101,11 +106,19 @@ def lib():
     sig("wsp_debug_set_encoder_layers", i32, [vp, i32])
     sig("wsp_debug_set_graph", i32, [vp, i32])
     sig("wsp_set_reference_threads", i32, [vp, i32])
-    sig("wsp_debug_set_mega", i32, [vp, i32])
-    sig("wsp_debug_mega_timing", i32, [vp, C.POINTER(C.c_uint64), i32])
+    sig("wsp_debug_set_step_mode", i32, [vp, i32])
+    sig("wsp_debug_enable_step_timing", i32, [vp, i32])
+    sig("wsp_debug_step_timing", i32, [vp, C.POINTER(C.c_uint64), i32])
     sig("wsp_host_alloc", vp, [sz])
     sig("wsp_host_free", None, [vp])
     sig("wsp_timings", i32, [vp, fp, ip, i32])
+    sig("wsp_detect_language", i32, [vp, i32, i32, fp, ip])
+    sig("wsp_replicas_create", i32, [vp, ip, i32, i32, C.POINTER(vp)])
+    sig("wsp_replicas_count", i32, [vp])
+    sig("wsp_replicas_run_chunks", i32, [vp, C.POINTER(fp), ip, i32, ip, i32, i32, ip, C.POINTER(ReplicaStats)])
+    sig("wsp_replicas_debug_fail_next", i32, [vp, i32])
+    sig("wsp_replicas_destroy", None, [vp])
+    sig("wsp_test_sample", i32, [i32, i32, i32, fp, ip, i32, i32, fp, C.POINTER(TokenData)])
     sig("wsp_test_gemm", i32, [i32, i32, i32, i32, u16p, u16p, fp, i32, i32, fp])
     sig("wsp_test_attention", i32, [i32, i32, i32, u16p, u16p, u16p, fp, i32, fp])
     sig("wsp_test_skinny", i32, [i32, i32, i32, i32, u16p, u16p, fp, i32, fp])
@@ -324,14 +337,30 @@ class Context:
         check(self.L.wsp_get_tensor(self.h, name.encode(), slot, _f(out), out.size, C.byref(n)))
         return out
 
+    def detect_language(self, offset_frames: int = 0, n_langs: int = 99):
+        probs = np.zeros(n_langs, np.float32)
+        lid = np.zeros(1, np.int32)
+        check(self.L.wsp_detect_language(self.h, offset_frames, n_langs, _f(probs), _i(lid)))
+        return int(lid[0]), probs
+
     def set_encoder_layers(self, n: int):
         check(self.L.wsp_debug_set_encoder_layers(self.h, n))
 
     def set_reference_threads(self, n: int):
         check(self.L.wsp_set_reference_threads(self.h, n))
 
-    def set_mega(self, on: bool):
-        check(self.L.wsp_debug_set_mega(self.h, int(on)))
+    def set_step_mode(self, mode: int):
+        """2 = dataflow decoder-step kernel (default), 1 = round 1's barrier kernel, 0 = one kernel per op."""
+        check(self.L.wsp_debug_set_step_mode(self.h, int(mode)))
+
+    def step_timing(self, enable=None, cap=4608):
+        """enable=True/False switches the %globaltimer marks on/off; enable=None reads the marks of the last step (ns)."""
+        if enable is not None:
+            check(self.L.wsp_debug_enable_step_timing(self.h, int(bool(enable))))
+            return None
+        buf = np.zeros(cap, np.uint64)
+        check(self.L.wsp_debug_step_timing(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap))
+        return buf
 
     def set_graph(self, on: bool):
         check(self.L.wsp_debug_set_graph(self.h, int(on)))
@@ -388,3 +417,43 @@ def test_layernorm(x, gamma, beta, device: int = 0):
     out = np.zeros((rows, d), np.uint16)
     check(lib().wsp_test_layernorm(device, rows, d, _f(x), _f(g), _f(b), _u16(out)))
     return out.view(np.float16).astype(np.float32)
+
+
+def test_sample(logits: np.ndarray, special4, force_timestamp=False, is_initial=False, device: int = 0):
+    """rows of logits -> (probs [rows][n_vocab], list of token dicts) from the GPU sampler alone"""
+    lg = np.ascontiguousarray(logits, np.float32)
+    rows, nv = lg.shape
+    probs = np.empty_like(lg)
+    out = (TokenData * rows)()
+    sp = np.ascontiguousarray(special4, np.int32)
+    check(lib().wsp_test_sample(device, rows, nv, _f(lg), _i(sp), int(force_timestamp), int(is_initial), _f(probs), out))
+    return probs, [dict(id=t.id, tid=t.tid, p=t.p, pt=t.pt, ptsum=t.ptsum) for t in out]
+
+
+class Replicas:
+    """wsp_replicas: one engine + context per listed device inside this process, fed by a host work queue (csrc/replicas.cpp)."""
+
+    def __init__(self, model: Model, devices, max_batch: int):
+        self.L = lib()
+        self.h = C.c_void_p()
+        dv = np.ascontiguousarray(devices, np.int32)
+        check(self.L.wsp_replicas_create(model.h, _i(dv), dv.size, max_batch, C.byref(self.h)))
+        self.n = dv.size
+
+    def run_chunks(self, pcms, prompt, n_decode: int):
+        pcms = [np.ascontiguousarray(p, np.float32) for p in pcms]
+        ptrs = (C.POINTER(C.c_float) * len(pcms))(*[_f(p) for p in pcms])
+        ns = np.array([p.size for p in pcms], np.int32)
+        pr = np.ascontiguousarray(prompt, np.int32)
+        toks = np.zeros((len(pcms), n_decode), np.int32)
+        stats = (ReplicaStats * self.n)()
+        check(self.L.wsp_replicas_run_chunks(self.h, ptrs, _i(ns), len(pcms), _i(pr), pr.size, n_decode, _i(toks), stats))
+        return toks, [dict(device=s.device, batches=s.batches_done, chunks=s.chunks_done, failed=s.failed, busy_ms=s.busy_ms, load_ms=s.load_ms) for s in stats]
+
+    def fail_next(self, replica: int):
+        check(self.L.wsp_replicas_debug_fail_next(self.h, replica))
+
+    def close(self):
+        if self.h:
+            self.L.wsp_replicas_destroy(self.h)
+            self.h = None

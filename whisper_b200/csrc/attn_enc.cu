@@ -11,6 +11,7 @@
 // Rounding points kept from the oracle: Q, K, V and P are f16, all accumulation is f32.  Deliberate difference: exp is
 // exp2f (not the oracle's f16 exp LUT, ggml.c:6065-6067) and P is rounded before the 1/sum normalisation (the oracle rounds after, :6082).
 #include "attn_enc.cuh"
+#include "per_device.h"
 #include "ptx.cuh"
 
 namespace attn
@@ -291,12 +292,10 @@ namespace attn
 
 	cudaError_t launchEnc( const CUtensorMap& mapQ, const CUtensorMap& mapK, const CUtensorMap& mapVt, const EncParams& p, cudaStream_t stream )
 	{
-		static bool attrSet = false;
-		if( !attrSet )
+		static kern::PerDeviceMax attr;
 		{
-			cudaError_t e = cudaFuncSetAttribute( attn_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES );
+			cudaError_t e = attr.raise( SMEM_BYTES, []( size_t n ) { return cudaFuncSetAttribute( attn_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 			if( e != cudaSuccess ) return e;
-			attrSet = true;
 		}
 		dim3 grid( ( p.T + TQ - 1 ) / TQ, p.nBH );
 		attn_enc_kernel<<<grid, 128, SMEM_BYTES, stream>>>( mapQ, mapK, mapVt, p );

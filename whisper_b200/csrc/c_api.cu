@@ -1,5 +1,7 @@
 // extern "C" surface (include/whisper_b200.h) + kernel-level test hooks.
 #include "engine.h"
+#include <algorithm>
+#include <math.h>
 #include <math.h>
 #include <memory>
 #include <string.h>
@@ -325,6 +327,33 @@ wsp_status wsp_get_tensor( wsp_context* cc, const char* name, int32_t slot, floa
 	}
 	return WSP_OK;
 }
+// whisper_lang_auto_detect (Whisper/source/whisper.cpp:2428-2495)
+wsp_status wsp_detect_language( wsp_context* c, int32_t offset_frames, int32_t n_langs, float* lang_probs, int32_t* lang_id )
+{
+	if( !c || !lang_id ) return fail( WSP_E_POINTER, "context/lang_id" );
+	return guarded( [ & ]() -> wsp_status {
+		Context& cx = *c->c;
+		const Engine& e = *cx.e;
+		const int nVocab = e.hp.n_vocab;
+		if( n_langs < 1 || e.tokSot + n_langs >= nVocab ) return fail( WSP_E_INVALIDARG, "n_langs" );
+		const int32_t off = offset_frames;
+		WSP_CHECK( ctxEncode( cx, &off, 1 ) );
+		const int32_t sot = e.tokSot;
+		WSP_CHECK( ctxDecode( cx, &sot, 1, 0, 1, WSP_DECODE_ALL_LOGITS, nullptr ) );
+		std::vector<float> row( (size_t)n_langs );
+		WSP_CUDA( cudaMemcpy( row.data(), cx.probs + ( e.tokSot + 1 ), (size_t)n_langs * 4, cudaMemcpyDeviceToHost ) );
+		// the reference sorts (probability, id) descending, then takes a softmax OVER THE PROBABILITIES (sic), summing in that order
+		std::vector<std::pair<float, int>> pid;
+		for( int i = 0; i < n_langs; i++ ) pid.emplace_back( row[ (size_t)i ], i );
+		std::stable_sort( pid.begin(), pid.end(), []( const std::pair<float, int>& a, const std::pair<float, int>& b ) { return a.first > b.first; } );
+		float sum = 0;
+		for( const auto& kv : pid ) sum += (float)exp( (double)kv.first );
+		if( lang_probs )
+			for( const auto& kv : pid ) lang_probs[ kv.second ] = (float)( exp( (double)kv.first ) / sum );
+		*lang_id = pid[ 0 ].second;
+		return WSP_OK;
+	} );
+}
 wsp_status wsp_debug_set_encoder_layers( wsp_context* c, int32_t n )
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );
@@ -339,18 +368,27 @@ wsp_status wsp_set_reference_threads( wsp_context* c, int32_t n )
 	c->c->refThreads = n;
 	return WSP_OK;
 }
-wsp_status wsp_debug_mega_timing( wsp_context* c, uint64_t* dst, int32_t cap )
+wsp_status wsp_debug_step_timing( wsp_context* c, uint64_t* dst, int32_t cap )
 {
 	if( !c || !dst ) return fail( WSP_E_POINTER, "context/dst" );
 	WSP_CUDA( cudaStreamSynchronize( c->c->stream ) );
 	WSP_CUDA( cudaMemcpy( dst, c->c->megaTiming, sizeof( uint64_t ) * (size_t)( cap < 4608 ? cap : 4608 ), cudaMemcpyDeviceToHost ) );
 	return WSP_OK;
 }
-wsp_status wsp_debug_set_mega( wsp_context* c, int32_t on )
+wsp_status wsp_debug_set_step_mode( wsp_context* c, int32_t on )
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );
-	if( ( on != 0 ) != c->c->useMega && c->c->stepGraph ) { cudaGraphExecDestroy( c->c->stepGraph ); c->c->stepGraph = nullptr; }
-	c->c->useMega = on != 0;
+	// 0 = one kernel per op, 1 = round 1's barrier kernel, 2 = dataflow kernel (default)
+	if( on < 0 || on > 2 ) return fail( WSP_E_INVALIDARG, "step mode" );
+	if( on != c->c->stepMode && c->c->stepGraph ) { cudaGraphExecDestroy( c->c->stepGraph ); c->c->stepGraph = nullptr; }
+	c->c->stepMode = on;
+	return WSP_OK;
+}
+wsp_status wsp_debug_enable_step_timing( wsp_context* c, int32_t on )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	if( ( on != 0 ) != c->c->stepTiming && c->c->stepGraph ) { cudaGraphExecDestroy( c->c->stepGraph ); c->c->stepGraph = nullptr; }
+	c->c->stepTiming = on != 0;
 	return WSP_OK;
 }
 wsp_status wsp_debug_set_graph( wsp_context* c, int32_t on )
@@ -538,6 +576,33 @@ wsp_status wsp_test_layernorm( int32_t device, int32_t rows, int32_t d, const fl
 	WSP_CUDA( cudaDeviceSynchronize() );
 	g_launchCount.fetch_add( 1 );
 	WSP_CUDA( cudaMemcpy( out, dout.p, (size_t)rows * d * 2, cudaMemcpyDeviceToHost ) );
+	return WSP_OK;
+}
+
+// sampler alone: rows of hand-made logits -> softmax + the Whisper sampling rules (whisper_sample_best / _timestamp, whisper.cpp:1875-1964)
+wsp_status wsp_test_sample( int32_t device, int32_t rows, int32_t n_vocab, const float* logits, const int32_t special4[ 4 ], int32_t force_timestamp,
+	int32_t is_initial, float* probs, wsp_token_data* out )
+{
+	if( !logits || !special4 || !out ) return fail( WSP_E_POINTER, "logits/special/out" );
+	if( rows < 1 || rows > 4096 || n_vocab < 8 ) return fail( WSP_E_INVALIDARG, "rows / n_vocab" );
+	WSP_CHECK( requireSm100( device ) );
+	static_assert( sizeof( wsp_token_data ) == sizeof( kern::TokenData ), "token data layout" );
+	DevTmp<float> dl, dp;
+	DevTmp<int> dflags;
+	DevTmp<kern::TokenData> dout;
+	WSP_CUDA( dl.alloc( (size_t)rows * n_vocab ) ); WSP_CUDA( dp.alloc( (size_t)rows * n_vocab ) ); WSP_CUDA( dflags.alloc( 2 ) ); WSP_CUDA( dout.alloc( rows ) );
+	WSP_CUDA( cudaMemcpy( dl.p, logits, (size_t)rows * n_vocab * 4, cudaMemcpyHostToDevice ) );
+	const int fl[ 2 ] = { force_timestamp ? 1 : 0, is_initial ? 1 : 0 };
+	WSP_CUDA( cudaMemcpy( dflags.p, fl, sizeof( fl ), cudaMemcpyHostToDevice ) );
+	kern::SampleArgs sa;
+	sa.logits = dl.p; sa.probs = dp.p; sa.B = rows; sa.nVocab = n_vocab;
+	sa.tokenBeg = special4[ 0 ]; sa.tokenSot = special4[ 1 ]; sa.tokenSolm = special4[ 2 ]; sa.tokenNot = special4[ 3 ];
+	sa.dForceTs = dflags.p; sa.out = dout.p; sa.N = 1;
+	WSP_CUDA( kern::sampleGreedy( sa, 0 ) );
+	WSP_CUDA( cudaDeviceSynchronize() );
+	g_launchCount.fetch_add( 2 );
+	WSP_CUDA( cudaMemcpy( out, dout.p, (size_t)rows * sizeof( wsp_token_data ), cudaMemcpyDeviceToHost ) );
+	if( probs ) WSP_CUDA( cudaMemcpy( probs, dp.p, (size_t)rows * n_vocab * 4, cudaMemcpyDeviceToHost ) );
 	return WSP_OK;
 }
 

@@ -8,7 +8,9 @@
 // The D3D back-end's driver (Whisper/Whisper/ContextImpl.cpp:452-794) differs slightly (it always skips 1 s on failure); the oracle wins.
 #include "../../include/whisper_b200.h"
 #include "../../include/whisper_b200_com.h"
+#include <algorithm>
 #include <atomic>
+#include <math.h>
 #include <map>
 
 #include <memory>
@@ -206,7 +208,9 @@ namespace
 
 	struct ResultData
 	{
-		struct Seg { int64_t t0, t1; std::string text; std::vector<wsp_token_data> tokens; };
+		// whisper_token_data (whisper.h:71-85): t0 / t1 stay -1 unless token-level timestamps were requested
+		struct Tok { wsp_token_data d; int64_t t0 = -1, t1 = -1; float vlen = 0.0f; };
+		struct Seg { int64_t t0, t1; std::string text; std::vector<Tok> tokens; };
 		std::vector<Seg> segs;
 	};
 
@@ -237,12 +241,14 @@ namespace
 				if( makeTokens )
 				{
 					seg.countTokens = (uint32_t)s.tokens.size();
-					for( const auto& t : s.tokens )
+					for( const auto& tok : s.tokens )
 					{
+						const wsp_token_data& t = tok.d;
 						sToken tk;
 						tk.text = wsp_model_token_text( e->model, t.id );
-						tk.time.begin.ticks = 0; tk.time.end.ticks = 0;
-						tk.probability = t.p; tk.probabilityTimestamp = t.pt; tk.ptsum = t.ptsum; tk.vlen = 0;
+						tk.time.begin.ticks = (uint64_t)( tok.t0 * 100000 );   // -1 (not computed) converts like the reference's MFllMulDiv( -1, ... )
+						tk.time.end.ticks = (uint64_t)( tok.t1 * 100000 );
+						tk.probability = t.p; tk.probabilityTimestamp = t.pt; tk.ptsum = t.ptsum; tk.vlen = tok.vlen;
 						tk.id = t.id;
 						tk.flags = t.id >= e->tokEot() ? eTokenFlags::Special : eTokenFlags::None;
 						tokens.push_back( tk );
@@ -271,6 +277,12 @@ namespace
 		std::vector<int32_t> promptPast;       // text context carried across windows and calls (whisper_context::prompt_past)
 		ResultData results;
 		mutable ResultObj* staticResult = nullptr;
+		// token-level timestamps (whisper_context::energy / t_beg / t_last / tid_last, whisper.cpp:425-431)
+		std::vector<float> energy;
+		int64_t tBeg = 0, tLast = 0;
+		int tidLast = 0;
+		void computeTokenTimestamps( size_t iSegment, float tholdPt, float tholdPtsum );
+		int wrapSegment( int maxLen );
 
 		~ContextObj() override;
 
@@ -458,20 +470,215 @@ namespace
 		return S_OK;
 	}
 
+	// ---- token-level timestamps and segment wrapping: restatement of the reference's "experimental" heuristics -------------------
+	// get_signal_energy (whisper.cpp:3356-3372): mean |x| over a window of 2 hw + 1 samples, f32 sums in the same order
+	static std::vector<float> signalEnergy( const float* signal, int nSamples, int hw )
+	{
+		std::vector<float> result( (size_t)( nSamples > 0 ? nSamples : 0 ) );
+		for( int i = 0; i < nSamples; i++ )
+		{
+			float sum = 0;
+			for( int j = -hw; j <= hw; j++ )
+				if( i + j >= 0 && i + j < nSamples ) sum += fabsf( signal[ i + j ] );
+			result[ (size_t)i ] = sum / ( 2 * hw + 1 );
+		}
+		return result;
+	}
+	// voice_length (whisper.cpp:3330-3353): a cost that is high for text that takes longer to pronounce
+	static float voiceLength( const char* text )
+	{
+		float res = 0.0f;
+		for( const char* p = text ? text : ""; *p; p++ )
+		{
+			const char c = *p;
+			if( c == ' ' ) res += 0.01f;
+			else if( c == ',' ) res += 2.00f;
+			else if( c == '.' || c == '!' || c == '?' ) res += 3.00f;
+			else if( c >= '0' && c <= '9' ) res += 3.00f;
+			else res += 1.00f;
+		}
+		return res;
+	}
+	static int timestampToSample( int64_t t, int nSamples ) { return std::max( 0, std::min( nSamples - 1, (int)( ( t * 16000 ) / 100 ) ) ); }   // :3320-3322
+	static int64_t sampleToTimestamp( int iSample ) { return ( 100 * (int64_t)iSample ) / 16000; }                                            // :3324-3326
+
+	// whisper_exp_compute_token_level_timestamps (whisper.cpp:3374-3600), step by step: timestamps from confident timestamp tokens,
+	// the gaps split in proportion to the voice lengths, then every token grown / shrunk against the signal energy
+	void ContextObj::computeTokenTimestamps( size_t iSegment, float tholdPt, float tholdPtsum )
+	{
+		ResultData::Seg& segment = results.segs[ iSegment ];
+		auto& tokens = segment.tokens;
+		const int nSamples = (int)energy.size();
+		if( nSamples == 0 )
+		{
+			logMessage( eLogLevel::Warning, "computeTokenTimestamps: no signal data available" );
+			return;
+		}
+		const int64_t t0 = segment.t0, t1 = segment.t1;
+		const int n = (int)tokens.size();
+		if( n == 0 ) return;
+		if( n == 1 ) { tokens[ 0 ].t0 = t0; tokens[ 0 ].t1 = t1; return; }
+		const int tokBeg = eng->tokBeg(), tokEot = eng->tokEot();
+		for( int j = 0; j < n; ++j )
+		{
+			const wsp_token_data& token = tokens[ j ].d;
+			if( j == 0 )
+			{
+				if( token.id == tokBeg )
+				{
+					tokens[ j ].t0 = t0;
+					tokens[ j ].t1 = t0;
+					tokens[ j + 1 ].t0 = t0;
+					tBeg = t0; tLast = t0; tidLast = tokBeg;
+				}
+				else tokens[ j ].t0 = tLast;
+			}
+			const int64_t tt = tBeg + 2 * ( (int64_t)token.tid - tokBeg );
+			tokens[ j ].vlen = voiceLength( wsp_model_token_text( eng->model, token.id ) );
+			if( token.pt > tholdPt && token.ptsum > tholdPtsum && token.tid > tidLast && tt <= t1 )
+			{
+				if( j > 0 ) tokens[ j - 1 ].t1 = tt;
+				tokens[ j ].t0 = tt;
+				tidLast = token.tid;
+			}
+		}
+		tokens[ n - 2 ].t1 = t1;
+		tokens[ n - 1 ].t0 = t1;
+		tokens[ n - 1 ].t1 = t1;
+		tLast = t1;
+		// intervals of tokens with unknown timestamps: split proportionally to the voice lengths
+		{
+			int p0 = 0, p1 = 0;
+			while( true )
+			{
+				while( p1 < n && tokens[ p1 ].t1 < 0 ) p1++;
+				if( p1 >= n ) p1--;
+				if( p1 > p0 )
+				{
+					double psum = 0.0;
+					for( int j = p0; j <= p1; j++ ) psum += tokens[ j ].vlen;
+					const double dt = (double)( tokens[ p1 ].t1 - tokens[ p0 ].t0 );
+					for( int j = p0 + 1; j <= p1; j++ )
+					{
+						const double ct = tokens[ j - 1 ].t0 + dt * tokens[ j - 1 ].vlen / psum;
+						tokens[ j - 1 ].t1 = (int64_t)ct;
+						tokens[ j ].t0 = (int64_t)ct;
+					}
+				}
+				p1++;
+				p0 = p1;
+				if( p1 >= n ) break;
+			}
+		}
+		// fix up (just in case)
+		for( int j = 0; j < n - 1; j++ )
+		{
+			if( tokens[ j ].t1 < 0 ) tokens[ j + 1 ].t0 = tokens[ j ].t1;
+			if( j > 0 && tokens[ j - 1 ].t1 > tokens[ j ].t0 )
+			{
+				tokens[ j ].t0 = tokens[ j - 1 ].t1;
+				tokens[ j ].t1 = std::max( tokens[ j ].t0, tokens[ j ].t1 );
+			}
+		}
+		// VAD: expand or contract tokens based on voice activity
+		{
+			const int hw = 16000 / 8;
+			for( int j = 0; j < n; j++ )
+			{
+				if( tokens[ j ].d.id >= tokEot ) continue;
+				int s0 = timestampToSample( tokens[ j ].t0, nSamples );
+				int s1 = timestampToSample( tokens[ j ].t1, nSamples );
+				const int ss0 = std::max( s0 - hw, 0 );
+				const int ss1 = std::min( s1 + hw, nSamples );
+				const int ns = ss1 - ss0;
+				float sum = 0.0f;
+				for( int k = ss0; k < ss1; k++ ) sum += energy[ (size_t)k ];
+				const float thold = (float)( 0.5 * sum / ns );
+				{
+					int k = s0;
+					if( energy[ (size_t)k ] > thold && j > 0 )
+					{
+						while( k > 0 && energy[ (size_t)k ] > thold ) k--;
+						tokens[ j ].t0 = sampleToTimestamp( k );
+						if( tokens[ j ].t0 < tokens[ j - 1 ].t1 ) tokens[ j ].t0 = tokens[ j - 1 ].t1;
+						else s0 = k;
+					}
+					else
+					{
+						while( energy[ (size_t)k ] < thold && k < s1 ) k++;
+						s0 = k;
+						tokens[ j ].t0 = sampleToTimestamp( k );
+					}
+				}
+				{
+					int k = s1;
+					if( energy[ (size_t)k ] > thold )
+					{
+						while( k < nSamples - 1 && energy[ (size_t)k ] > thold ) k++;
+						tokens[ j ].t1 = sampleToTimestamp( k );
+						// (the reference tests `j < ns - 1` and then reads tokens[j + 1]: past the end for the last token of a segment
+						// that does not close with a timestamp — undefined there, skipped here)
+						if( j < ns - 1 && j + 1 < n && tokens[ j ].t1 > tokens[ j + 1 ].t0 ) tokens[ j ].t1 = tokens[ j + 1 ].t0;
+						else s1 = k;
+					}
+					else
+					{
+						while( energy[ (size_t)k ] < thold && k > s0 ) k--;
+						s1 = k;
+						tokens[ j ].t1 = sampleToTimestamp( k );
+					}
+				}
+			}
+		}
+	}
+
+	// whisper_wrap_segment (whisper.cpp:2713-2763): wrap the last segment to max_len characters; returns the number of new segments
+	int ContextObj::wrapSegment( int maxLen )
+	{
+		ResultData::Seg segment = results.segs.back();
+		int res = 1, acc = 0;
+		std::string text;
+		const int tokEot = eng->tokEot();
+		for( int i = 0; i < (int)segment.tokens.size(); i++ )
+		{
+			const ResultData::Tok& token = segment.tokens[ (size_t)i ];
+			if( token.d.id >= tokEot ) continue;
+			const char* txt = wsp_model_token_text( eng->model, token.d.id );
+			if( !txt ) txt = "";
+			const int cur = (int)strlen( txt );
+			if( acc + cur > maxLen && i > 0 )
+			{
+				// split here
+				results.segs.back().text = std::move( text );
+				results.segs.back().t1 = token.t0;
+				results.segs.back().tokens.resize( (size_t)i );
+				ResultData::Seg next;
+				next.t0 = token.t0;
+				next.t1 = segment.t1;
+				next.tokens.assign( segment.tokens.begin() + i, segment.tokens.end() );
+				results.segs.push_back( std::move( next ) );
+				acc = 0;
+				text.clear();
+				segment = results.segs.back();
+				i = -1;
+				res++;
+			}
+			else
+			{
+				acc += cur;
+				text += txt;
+			}
+		}
+		results.segs.back().text = std::move( text );
+		return res;
+	}
+
 	// whisper_lang_auto_detect (whisper.cpp:2428-2495): encode at offset 0, decode [sot], most probable language token
 	HRESULT ContextObj::detectLanguage( int& langId )
 	{
-		const int32_t off = 0;
-		HR( check( wsp_encode( ctx, &off, 1 ), "wsp_encode" ) );
-		const int32_t sot = eng->tokSot();
-		HR( check( wsp_decode( ctx, &sot, 1, 0, 1, WSP_DECODE_ALL_LOGITS, nullptr ), "wsp_decode" ) );
-		std::vector<float> probs( (size_t)eng->nVocab() );
-		HR( check( wsp_get_probs( ctx, probs.data(), probs.size() ), "wsp_get_probs" ) );
-		const int n = (int)languages().codes.size();
-		int best = 0;
-		for( int i = 1; i < n; i++ )
-			if( sot + 1 + i < eng->nVocab() && probs[ sot + 1 + i ] > probs[ sot + 1 + best ] ) best = i;
-		langId = best;
+		int32_t id = 0;
+		HR( check( wsp_detect_language( ctx, 0, (int32_t)languages().codes.size(), nullptr, &id ), "wsp_detect_language" ) );
+		langId = id;
 		return S_OK;
 	}
 
@@ -489,8 +696,6 @@ namespace
 			logMessage( eLogLevel::Error, "whisper_b200: audio_ctx override is not supported" );
 			return E_NOTIMPL;
 		}
-		if( params.flag( eFullParamsFlags::TokenTimestamps ) )
-			logMessage( eLogLevel::Warning, "whisper_b200: token-level timestamps are not computed (segment timestamps are)" );
 		// the reference's decoder arithmetic depends on its thread count; follow the caller's cpuThreads
 		const int threads = params.cpuThreads < 1 ? 1 : ( params.cpuThreads > 16 ? 16 : params.cpuThreads );
 		HR( check( wsp_set_reference_threads( ctx, threads ), "wsp_set_reference_threads" ) );
@@ -500,6 +705,12 @@ namespace
 		const int nSamples = (int)buffer->countSamples();
 		if( !pcm && nSamples > 0 ) return E_POINTER;
 		HR( check( wsp_pcm_to_mel( ctx, 0, pcm, nSamples ), "wsp_pcm_to_mel" ) );                 // :2782
+		const bool tokenTimestamps = params.flag( eFullParamsFlags::TokenTimestamps );
+		if( tokenTimestamps )                                                                      // :2803-2808
+		{
+			tBeg = 0; tLast = 0; tidLast = 0;
+			energy = signalEnergy( pcm, nSamples, 32 );
+		}
 		const int nLen = wsp_mel_len( ctx, 0 );
 
 		const int tokEot = eng->tokEot(), tokSot = eng->tokSot(), tokPrev = eng->tokPrev(), tokBeg = eng->tokBeg();
@@ -626,11 +837,17 @@ namespace
 			auto emit = [ & ]( int64_t t0, int64_t t1, const std::string& text, int i0, int i1 ) -> HRESULT {
 				ResultData::Seg s;
 				s.t0 = t0; s.t1 = t1; s.text = text;
-				s.tokens.assign( tokensCur.begin() + i0, tokensCur.begin() + i1 );
+				for( int k = i0; k < i1; k++ ) { ResultData::Tok tk; tk.d = tokensCur[ k ]; s.tokens.push_back( tk ); }
 				results.segs.push_back( std::move( s ) );
+				int nNew = 1;
+				if( tokenTimestamps )                                                              // :3063-3070, 3107-3114
+				{
+					computeTokenTimestamps( results.segs.size() - 1, params.thold_pt, params.thold_ptsum );
+					if( params.max_len > 0 ) nNew = wrapSegment( params.max_len );
+				}
 				if( params.new_segment_callback )
 				{
-					const HRESULT hr = params.new_segment_callback( this, 1, params.new_segment_callback_user_data );
+					const HRESULT hr = params.new_segment_callback( this, (uint32_t)nNew, params.new_segment_callback_user_data );
 					if( FAILED( hr ) ) return hr;
 				}
 				return S_OK;
@@ -790,169 +1007,3 @@ namespace Whisper
 		return S_OK;
 	}
 }
-
-// ===================================================================================================================
-// flat C helpers over the COM surface, for tests/ (ctypes cannot call C++ vtables): every call goes loadModel -> createContext ->
-// fullDefaultParams -> runFull -> getResults exactly as Examples/main/main.cpp:210-318 does.
-// ===================================================================================================================
-namespace
-{
-	struct Session
-	{
-		iModel* model = nullptr;
-		iContext* context = nullptr;
-		iTranscribeResult* result = nullptr;
-		std::vector<int> segCallbackCounts;
-	};
-	HRESULT segCallback( iContext*, uint32_t nNew, void* pv ) noexcept
-	{
-		static_cast<Session*>( pv )->segCallbackCounts.push_back( (int)nNew );
-		return S_OK;
-	}
-}
-
-extern "C" {
-
-int32_t wspc_open( const char* modelPathUtf8, int32_t device, void** out )
-{
-	if( !modelPathUtf8 || !out ) return E_POINTER;
-	std::wstring w;
-	for( const char* p = modelPathUtf8; *p; p++ ) w.push_back( (wchar_t)(unsigned char)*p );   // test paths are ASCII
-	std::wstring adapter = std::to_wstring( device );
-	sModelSetup setup;
-	setup.impl = eModelImplementation::B200;
-	setup.adapter = adapter.c_str();
-	Session* s = new Session();
-	HRESULT hr = loadModel( w.c_str(), setup, nullptr, &s->model );
-	if( SUCCEEDED( hr ) ) hr = s->model->createContext( &s->context );
-	if( FAILED( hr ) )
-	{
-		if( s->model ) s->model->Release();
-		delete s;
-		return hr;
-	}
-	*out = s;
-	return S_OK;
-}
-void wspc_close( void* h )
-{
-	Session* s = static_cast<Session*>( h );
-	if( !s ) return;
-	if( s->result ) s->result->Release();
-	if( s->context ) s->context->Release();
-	if( s->model ) s->model->Release();
-	delete s;
-}
-// flags = eFullParamsFlags bits; language = code such as "en" or "auto"
-int32_t wspc_run_full( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t maxTokens, int32_t cpuThreads,
-	int32_t offsetMs, int32_t durationMs, const int32_t* promptTokens, int32_t nPromptTokens )
-{
-	Session* s = static_cast<Session*>( h );
-	if( !s ) return E_POINTER;
-	sFullParams p;
-	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
-	if( FAILED( hr ) ) return hr;
-	p.flags = (eFullParamsFlags)flags;
-	p.language = ( language && strcmp( language, "auto" ) != 0 ) ? findLanguageKeyA( language ) : makeLanguageKey( "auto" );
-	p.max_tokens = maxTokens;
-	p.cpuThreads = cpuThreads;
-	p.offset_ms = offsetMs;
-	p.duration_ms = durationMs;
-	p.prompt_tokens = promptTokens;
-	p.prompt_n_tokens = nPromptTokens;
-	p.new_segment_callback = &segCallback;
-	p.new_segment_callback_user_data = s;
-	s->segCallbackCounts.clear();
-	iAudioBuffer* buf = nullptr;
-	hr = createAudioBuffer( pcm, (uint32_t)nSamples, &buf );
-	if( FAILED( hr ) ) return hr;
-	hr = s->context->runFull( p, buf );
-	buf->Release();
-	if( FAILED( hr ) ) return hr;
-	if( s->result ) { s->result->Release(); s->result = nullptr; }
-	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
-	return FAILED( hr2 ) ? hr2 : hr;
-}
-int32_t wspc_n_segments( void* h )
-{
-	Session* s = static_cast<Session*>( h );
-	if( !s || !s->result ) return 0;
-	sTranscribeLength len;
-	s->result->getSize( len );
-	return (int32_t)len.countSegments;
-}
-int32_t wspc_n_segment_callbacks( void* h ) { Session* s = static_cast<Session*>( h ); return s ? (int32_t)s->segCallbackCounts.size() : 0; }
-int64_t wspc_segment_t0( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.begin.ticks / 100000 ); }
-int64_t wspc_segment_t1( void* h, int32_t i ) { return (int64_t)( static_cast<Session*>( h )->result->getSegments()[ i ].time.end.ticks / 100000 ); }
-const char* wspc_segment_text( void* h, int32_t i ) { return static_cast<Session*>( h )->result->getSegments()[ i ].text; }
-int32_t wspc_segment_n_tokens( void* h, int32_t i ) { return (int32_t) static_cast<Session*>( h )->result->getSegments()[ i ].countTokens; }
-int32_t wspc_token_id( void* h, int32_t i, int32_t j )
-{
-	Session* s = static_cast<Session*>( h );
-	const sSegment& seg = s->result->getSegments()[ i ];
-	return s->result->getTokens()[ seg.firstToken + j ].id;
-}
-float wspc_token_p( void* h, int32_t i, int32_t j )
-{
-	Session* s = static_cast<Session*>( h );
-	const sSegment& seg = s->result->getSegments()[ i ];
-	return s->result->getTokens()[ seg.firstToken + j ].probability;
-}
-int32_t wspc_token_flags( void* h, int32_t i, int32_t j )
-{
-	Session* s = static_cast<Session*>( h );
-	const sSegment& seg = s->result->getSegments()[ i ];
-	return (int32_t)s->result->getTokens()[ seg.firstToken + j ].flags;
-}
-// iModel surface
-int32_t wspc_tokenize( void* h, const char* text, int32_t* dst, int32_t cap )
-{
-	Session* s = static_cast<Session*>( h );
-	struct Sink { int32_t* dst; int32_t cap; int32_t n; } sink{ dst, cap, 0 };
-	auto cb = []( const int* tokens, int n, void* pv ) {
-		Sink* k = static_cast<Sink*>( pv );
-		for( int i = 0; i < n && k->n < k->cap; i++ ) k->dst[ k->n++ ] = tokens[ i ];
-	};
-	const HRESULT hr = s->model->tokenize( text, cb, &sink );
-	return FAILED( hr ) ? hr : sink.n;
-}
-const char* wspc_string_from_token( void* h, int32_t id ) { return static_cast<Session*>( h )->model->stringFromToken( id ); }
-int32_t wspc_is_multilingual( void* h ) { return static_cast<Session*>( h )->model->isMultilingual() == S_OK ? 1 : 0; }
-int32_t wspc_special_tokens( void* h, int32_t* out8 )
-{
-	SpecialTokens st;
-	const HRESULT hr = static_cast<Session*>( h )->model->getSpecialTokens( st );
-	memcpy( out8, &st, sizeof( st ) );
-	return hr;
-}
-int32_t wspc_query_interfaces( void* h )
-{
-	// IUnknown plumbing: QueryInterface round trips and reference counts behave like COM
-	Session* s = static_cast<Session*>( h );
-	void* p = nullptr;
-	if( s->model->QueryInterface( iModel::iid(), &p ) != S_OK || p != s->model ) return 1;
-	s->model->Release();
-	if( s->model->QueryInterface( ComLight::IUnknown::iid(), &p ) != S_OK ) return 2;
-	s->model->Release();
-	if( s->model->QueryInterface( iContext::iid(), &p ) != E_NOINTERFACE || p != nullptr ) return 3;
-	iModel* m2 = nullptr;
-	if( s->context->getModel( &m2 ) != S_OK || m2 != s->model ) return 4;
-	m2->Release();
-	iModel* clone = nullptr;
-	if( s->model->clone( &clone ) != S_OK || !clone ) return 5;
-	clone->Release();
-	sProgressSink sink{ nullptr, nullptr };
-	sFullParams fp;
-	s->context->fullDefaultParams( eSamplingStrategy::Greedy, &fp );
-	if( s->context->runStreamed( fp, sink, nullptr ) != E_NOTIMPL ) return 6;
-	return 0;
-}
-uint32_t wspc_find_language_key( const char* lang ) { return findLanguageKeyA( lang ); }
-int32_t wspc_language_count( void )
-{
-	sLanguageList l;
-	getSupportedLanguages( l );
-	return (int32_t)l.length;
-}
-
-} // extern "C"

@@ -34,7 +34,7 @@ namespace wsp
 		for( auto& s : slots ) { if( s.mel ) cudaFree( s.mel ); if( s.pcm ) cudaFree( s.pcm ); }
 		for( auto& v : prof.pool ) cudaEventDestroy( v );
 		for( auto& v : timerEv ) if( v ) cudaEventDestroy( v );
-		void* bufs[] = { megaLayers, megaBarrier, megaTiming, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
+		void* bufs[] = { flowLayers, flowBias, flowExch, flowCtrl, megaLayers, megaBarrier, megaTiming, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
 			tokensDev, dNPast, sampled, history };
 		for( void* b : bufs ) if( b ) cudaFree( b );
 		for( auto& v : ev ) if( v ) cudaEventDestroy( v );
@@ -133,11 +133,39 @@ namespace wsp
 			WSP_CUDA( cudaMemcpy( c.megaLayers, ml.data(), ml.size() * sizeof( kern::MegaLayer ), cudaMemcpyHostToDevice ) );
 			WSP_CHECK( devAlloc( c.megaBarrier, 64, true ) );
 			WSP_CHECK( devAlloc( c.megaTiming, 4608, true ) );
-			const char* env = getenv( "WSP_MEGA" );
-			c.useMega = !( env && env[ 0 ] == '0' );
+		}
+		// dataflow decoder-step kernel: pointer table, per-CTA bias slabs, sentinel-filled exchange buffers (decode_flow.cu)
+		{
+			const kern::FlowGeom g = kern::flowGeometry( d, hp.n_vocab, e->numSMs );
+			c.flowGeom = g;
+			const size_t slabLayer = (size_t)g.grid * g.slabFloats;
+			WSP_CHECK( devAlloc( c.flowBias, slabLayer * L ) );
+			std::vector<kern::FlowLayer> fl( (size_t)L );
+			for( int i = 0; i < L; i++ )
+			{
+				const DecLayerW& W = e->dec[ i ];
+				kern::FlowLayer& m = fl[ i ];
+				m.ln1g = W.ln1.g; m.ln1b = W.ln1.b; m.lncg = W.lnc.g; m.lncb = W.lnc.b; m.ln3g = W.ln3.g; m.ln3b = W.ln3.b;
+				m.wqkv = W.wqkv; m.wo = W.wo; m.wcq = W.wcq; m.wco = W.wco; m.w1 = W.w1; m.w2 = W.w2;
+				m.biasSlab = c.flowBias + (size_t)i * slabLayer;
+				m.kCache = c.selfK + (size_t)i * B * hp.n_text_ctx * d;
+				m.vCache = c.selfV + (size_t)i * B * hp.n_text_ctx * d;
+				m.crossK = c.crossK + (size_t)i * B * T * d;
+				m.crossV = c.crossV + (size_t)i * B * T * d;
+				WSP_CUDA( kern::flowBuildBiasSlab( c.flowBias + (size_t)i * slabLayer, g, d, W.bqkv, W.bo, W.bcq, W.bco, W.b1, W.b2, c.stream ) );
+			}
+			WSP_CHECK( devAlloc( c.flowLayers, (size_t)L ) );
+			WSP_CUDA( cudaMemcpy( c.flowLayers, fl.data(), fl.size() * sizeof( kern::FlowLayer ), cudaMemcpyHostToDevice ) );
+			const size_t exBytes = kern::flowExchangeBytes( d, maxBatch, L );
+			WSP_CHECK( devAlloc( c.flowExch, exBytes ) );
+			WSP_CUDA( cudaMemset( c.flowExch, 0xFF, exBytes ) );
+			WSP_CHECK( devAlloc( c.flowCtrl, 8, true ) );
+			const char* env = getenv( "WSP_STEP_MODE" );
+			if( env && env[ 0 ] >= '0' && env[ 0 ] <= '2' ) c.stepMode = env[ 0 ] - '0';
 		}
 		WSP_CUDA( kern::prepare( 4 * d ) );
 		WSP_CUDA( kern::megaPrepare( d ) );
+		WSP_CUDA( kern::flowPrepare( d ) );
 		WSP_CUDA( cudaDeviceSynchronize() );
 		*out = cp.release();
 		return WSP_OK;
@@ -350,7 +378,30 @@ namespace wsp
 		const int cols = batch * N;
 		const float qkScale = (float)pow( 64.0, -0.25 );   // whisper.cpp:1588, 1595, 1700
 		int n = 0;
-		if( N == 1 && !allLogits && c.useMega && kern::megaSupported( d, batch, T ) )
+		if( N == 1 && !allLogits && c.stepMode == 2 && kern::flowSupported( d, batch, T, H, nCtx, c.refThreads, e.numSMs ) )
+		{
+			// steady state: ONE dataflow kernel for embedding + all layers + logits (decode_flow.cu), then the sampler
+			kern::FlowArgs fa;
+			fa.layers = c.flowLayers; fa.L = hp.n_text_layer; fa.B = batch; fa.maxB = c.maxB; fa.H = H; fa.nTextCtx = nCtx; fa.T = T; fa.nVocab = hp.n_vocab;
+			fa.refThreads = c.refThreads;
+			fa.tokEmb = e.tokEmb; fa.decPos = e.decPos; fa.lnfg = e.decLn.g; fa.lnfb = e.decLn.b;
+			fa.tokens = c.tokensDev; fa.dNPast = c.dNPast;
+			fa.exch = c.flowExch; fa.ctrl = c.flowCtrl; fa.logits = c.logits; fa.timing = c.stepTiming ? c.megaTiming : nullptr;
+			fa.g = c.flowGeom;
+			WSP_KERNEL( KK_SKINNY, kern::decodeStepFlow( fa, d, e.numSMs, s ) ); n++;
+			if( sample )
+			{
+				kern::SampleArgs sa;
+				sa.logits = c.logits; sa.probs = c.probs; sa.B = batch; sa.nVocab = hp.n_vocab;
+				sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
+				sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
+				sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;
+				WSP_KERNEL( KK_OTHER, kern::sampleGreedy( sa, s ) ); n += 2;
+			}
+			if( launchesOut ) *launchesOut = n;
+			return WSP_OK;
+		}
+		if( N == 1 && !allLogits && c.stepMode == 1 && kern::megaSupported( d, batch, T ) )
 		{
 			// steady state: one persistent kernel for embedding + all layers + logits (decode_mega.cu), then the sampler
 			kern::MegaArgs ma;
@@ -358,11 +409,7 @@ namespace wsp
 			ma.refThreads = c.refThreads;
 			ma.tokEmb = e.tokEmb; ma.decPos = e.decPos; ma.lnfg = e.decLn.g; ma.lnfb = e.decLn.b;
 			ma.tokens = c.tokensDev; ma.dNPast = c.dNPast;
-			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier; ma.timing = getenv( "WSP_MEGA_TIMING" ) ? c.megaTiming : nullptr;
-			{
-				const char* mf = getenv( "WSP_MEGA_FLAGS" );
-				ma.flags = mf ? atoi( mf ) : 0;
-			}
+			ma.x = c.xd; ma.q = c.qd; ma.attn = c.attnD; ma.h = c.hD; ma.logits = c.logits; ma.barrier = c.megaBarrier; ma.timing = c.stepTiming ? c.megaTiming : nullptr;
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepMega( ma, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

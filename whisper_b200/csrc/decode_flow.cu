@@ -1,0 +1,1071 @@
+// Dataflow decoder-step kernel: one launch runs a whole single-token decoder step (embedding, every layer, final LayerNorm and
+// logits) for up to 16 chunks.  Reference: whisper_decode, Whisper/source/whisper.cpp:1508-1872 (what one step must compute);
+// it replaces the per-token dispatch chain around ComputeShaders/mulMatByRowTiled.hlsl (Whisper/Whisper/WhisperContext.cpp:578-639).
+//
+// Round 1 ran the step as a persistent kernel with a grid-wide counter barrier between the ~190 data-dependent phases; it sat at
+// 20 % of the HBM rate because every phase paid  arrive (block barrier + release fence + atomic round trip) + flag poll + an L2
+// round trip for the activations + a burst of weight loads that the in-order load queue put in front of everything else.
+// This kernel removes both costs:
+//
+//  * Weights, LayerNorm parameters and the self / cross K,V rows never depend on the current step.  A PRODUCER WARP streams them
+//    in consumption order into a shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), as far ahead as
+//    the ring allows (~180 KB per SM), so the HBM pipe is busy for the whole step and the consumers' loads never queue behind it.
+//  * There is NO grid barrier.  Every (layer, phase) output has its own exchange buffer, pre-filled with a sentinel that the
+//    arithmetic cannot produce (all-ones: a NaN payload no FP instruction generates).  Producers of a phase simply store their
+//    results; consumers poll the data itself (ld.relaxed.gpu) until no sentinel is left.  One L2 write + one L2 read is the
+//    whole exchange; a 4-byte (f32) or 2-byte (f16) element is its own flag, so no fences or ordering between stores are needed.
+//    Two buffer sets alternate between launches; each step re-arms the idle set (whose readers finished with the previous launch).
+//
+// Arithmetic is identical to round 1's kernels: f16 x f16 -> f32 through mma.sync.m16n8k16 with k-permuted fragments, 8 warps
+// splitting K in the same order, LayerNorm / bias / scale / residual / GELU fused, reference-exact f16 V^T*P chains.
+#include "decode_flow.cuh"
+#include "per_device.h"
+#include "ptx.cuh"
+#include <math.h>
+
+namespace kern
+{
+	namespace
+	{
+		constexpr int FL_WARPS = 8;                    // consumer warps
+		constexpr int FL_CONSUMERS = FL_WARPS * 32;
+		constexpr int FL_THREADS = FL_CONSUMERS + 32;  // + the producer warp
+		constexpr int FL_NSMAX = 32;
+		constexpr int FL_MAXT = 1536;
+		constexpr int FL_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA on sm_100
+		constexpr uint32_t SENT32 = 0xFFFFFFFFu;
+
+		template<int D>
+		struct Cfg
+		{
+			static constexpr int RS = 2 * D + 64;                                  // bytes per weight / activation row in shared memory (conflict-free LDS.128)
+			static constexpr int SLOT = ( 8 * RS > 16384 ) ? 8 * RS : 16384;       // one ring slot: 8 weight rows x D, or a run of K/V rows
+			static constexpr int CR = ( SLOT / 128 ) & ~7;                         // K/V rows (128 bytes each) per slot
+			static constexpr int STEPS = D / 32;
+			static constexpr int SPW = ( STEPS + FL_WARPS - 1 ) / FL_WARPS;
+			static constexpr int N4 = D / 128;
+		};
+
+		struct SmemLayout
+		{
+			int act, red, sp, bias, xres, so, sred, qkv, bars, total;
+		};
+		__host__ __device__ inline SmemLayout smemLayout( int slot, int rs, int NS, int ncols )
+		{
+			SmemLayout l;
+			int o = NS * slot;
+			l.act = o; o += ncols * rs;
+			l.red = o; o += 4 * FL_WARPS * 8 * ncols * 4;
+			l.sp = o; o += FL_MAXT * 4;
+			l.bias = o; o += 256 * 4;
+			l.xres = o; o += 16 * 16 * 4;
+			l.so = o; o += 256 * 4;
+			l.sred = o; o += 64;
+			l.qkv = o; o += 3 * 128;
+			l.bars = o; o += 2 * FL_NSMAX * 8;
+			l.total = o;
+			return l;
+		}
+		inline int ringSlots( int slot, int rs, int ncols )
+		{
+			const int fixed = smemLayout( slot, rs, 0, ncols ).total;
+			int ns = ( FL_SMEM_MAX - fixed ) / slot;
+			return ns > FL_NSMAX ? FL_NSMAX : ns;
+		}
+
+		// ---- small device helpers ------------------------------------------------------------------------------------
+		__device__ __forceinline__ float warpSumF( float v )
+		{
+			for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync( 0xffffffffu, v, o );
+			return v;
+		}
+		__device__ __forceinline__ float warpMaxF( float v )
+		{
+			for( int o = 16; o > 0; o >>= 1 ) v = fmaxf( v, __shfl_xor_sync( 0xffffffffu, v, o ) );
+			return v;
+		}
+		__device__ __forceinline__ void mmaF( float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1 )
+		{
+			// rows 8..15 of the A tile are unused (registers a1, a3 = 0): a unit is 8 weight rows
+			const uint32_t z = 0;
+			asm volatile(
+				"mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+				: "+f"( c[ 0 ] ), "+f"( c[ 1 ] ), "+f"( c[ 2 ] ), "+f"( c[ 3 ] )
+				: "r"( a0 ), "r"( z ), "r"( a2 ), "r"( z ), "r"( b0 ), "r"( b1 ) );
+		}
+		__device__ __forceinline__ void consumerSync() { asm volatile( "bar.sync 1, 256;" ::: "memory" ); }
+
+		// exchange accesses: performed at L2 (gpu scope), never through a possibly stale L1 line
+		__device__ __forceinline__ uint4 ldPoll( const void* p )
+		{
+			uint4 r;
+			asm volatile( "ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( r.x ), "=r"( r.y ), "=r"( r.z ), "=r"( r.w ) : "l"( p ) : "memory" );
+			return r;
+		}
+		__device__ __forceinline__ bool hasSent32( const uint4& v ) { return v.x == SENT32 || v.y == SENT32 || v.z == SENT32 || v.w == SENT32; }
+		__device__ __forceinline__ bool hasSent16w( uint32_t w ) { return ( w & 0xFFFFu ) == 0xFFFFu || ( w >> 16 ) == 0xFFFFu; }
+		__device__ __forceinline__ bool hasSent16( const uint4& v ) { return hasSent16w( v.x ) || hasSent16w( v.y ) || hasSent16w( v.z ) || hasSent16w( v.w ); }
+		__device__ __forceinline__ void stX32( float* p, float v )
+		{
+			uint32_t b = __float_as_uint( v );
+			if( b == SENT32 ) b = 0x7FFFFFFFu;   // a NaN stays a NaN, but never looks like "not written yet"
+			asm volatile( "st.relaxed.gpu.global.u32 [%0], %1;" ::"l"( p ), "r"( b ) : "memory" );
+		}
+		__device__ __forceinline__ void stX16( __half* p, __half v )
+		{
+			unsigned short b = __half_as_ushort( v );
+			if( b == 0xFFFFu ) b = 0x7FFFu;
+			asm volatile( "st.relaxed.gpu.global.u16 [%0], %1;" ::"l"( p ), "h"( b ) : "memory" );
+		}
+		// a protocol bug must not hang the GPU: every wait gives up (trap = launch failure) after ~2 s of wall time
+		__device__ __forceinline__ unsigned long long globalNs()
+		{
+			unsigned long long t;
+			asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
+			return t;
+		}
+		__device__ __noinline__ void spinCheck( unsigned long long& t0 )
+		{
+			const unsigned long long t = globalNs();
+			if( t0 == 0 ) t0 = t;
+			else if( t - t0 > 2000000000ull ) __trap();
+		}
+		struct SpinGuard
+		{
+			unsigned spins = 0;
+			unsigned long long t0 = 0;
+			__device__ __forceinline__ void tick()
+			{
+				if( ( ++spins & 1023u ) == 0 ) spinCheck( t0 );
+			}
+		};
+		__device__ __forceinline__ void mbarWaitLong( uint64_t* bar, uint32_t parity )
+		{
+			SpinGuard g;
+			while( !ptx::mbar_try_wait( bar, parity ) ) g.tick();
+		}
+
+		__device__ __forceinline__ float expTabF( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
+
+		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key
+		template<bool F16>
+		__device__ __forceinline__ float chainRows( float y, const float* __restrict__ sp, const __half* __restrict__ v, int n )
+		{
+			int j = 0;
+			for( ; j + 4 <= n; j += 4 )
+			{
+				const float x0 = __half2float( v[ j * 64 ] );
+				const float x1 = __half2float( v[ ( j + 1 ) * 64 ] );
+				const float x2 = __half2float( v[ ( j + 2 ) * 64 ] );
+				const float x3 = __half2float( v[ ( j + 3 ) * 64 ] );
+				if( F16 )
+				{
+					y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
+				}
+				else
+				{
+					y = __fmaf_rn( sp[ j ], x0, y );
+					y = __fmaf_rn( sp[ j + 1 ], x1, y );
+					y = __fmaf_rn( sp[ j + 2 ], x2, y );
+					y = __fmaf_rn( sp[ j + 3 ], x3, y );
+				}
+			}
+			for( ; j < n; j++ )
+			{
+				const float x = __half2float( v[ j * 64 ] );
+				if( F16 ) y = __half2float( __float2half_rn( __fmaf_rn( x, sp[ j ], y ) ) );
+				else y = __fmaf_rn( sp[ j ], x, y );
+			}
+			return y;
+		}
+
+		// scores of n K rows (128 bytes each, contiguous in shared memory) against the query held in registers: 8 lanes per row,
+		// 4 rows per warp instruction (512 contiguous bytes: conflict-free); returns the updated running maximum
+		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const float* qf, float* sp, int warp, int lane, float lmax )
+		{
+			const int sub = lane & 7, rgrp = lane >> 3;
+			for( int r0 = warp * 4; r0 < n; r0 += FL_WARPS * 4 )
+			{
+				const int r = r0 + rgrp;
+				uint4 u = make_uint4( 0, 0, 0, 0 );
+				if( r < n ) u = *reinterpret_cast<const uint4*>( kc + (size_t)r * 128 + sub * 16 );
+				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
+				float s = 0.0f;
+#pragma unroll
+				for( int e = 0; e < 4; e++ )
+				{
+					const float2 f = __half22float2( h2[ e ] );
+					s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
+				}
+				s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+				s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+				s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+				if( r < n )
+				{
+					if( sub == 0 ) sp[ jBase + r ] = s;
+					lmax = fmaxf( lmax, s );
+				}
+			}
+			return lmax;
+		}
+
+		// softmax over sp[0, n) exactly as the reference does it: max in f32, e = f16-table exp, sum, scale by 1/sum (ggml.c:5026-5095)
+		__device__ __forceinline__ void softmaxRow( float* sp, int n, float lmax, float* sred, int tid, int warp, int lane )
+		{
+			lmax = warpMaxF( lmax );
+			if( lane == 0 ) sred[ warp ] = lmax;
+			consumerSync();
+			float mx = sred[ 0 ];
+			for( int w = 1; w < FL_WARPS; w++ ) mx = fmaxf( mx, sred[ w ] );
+			consumerSync();
+			float lsum = 0.0f;
+			for( int j = tid; j < n; j += FL_CONSUMERS )
+			{
+				const float e = expTabF( sp[ j ] - mx );
+				sp[ j ] = e;
+				lsum += e;
+			}
+			lsum = warpSumF( lsum );
+			if( lane == 0 ) sred[ warp ] = lsum;
+			consumerSync();
+			float tot = 0.0f;
+			for( int w = 0; w < FL_WARPS; w++ ) tot += sred[ w ];
+			const float inv = 1.0f / tot;
+			for( int j = tid; j < n; j += FL_CONSUMERS ) sp[ j ] *= inv;
+			consumerSync();
+		}
+
+		// one f32 row of D elements from an exchange buffer: every lane polls its N4 16-byte pieces until no sentinel is left
+		template<int D>
+		__device__ __forceinline__ void pollRowF32( const float* row, float4* v, int lane )
+		{
+			constexpr int N4 = Cfg<D>::N4;
+			const uint4* src = reinterpret_cast<const uint4*>( row );
+			uint4 u[ N4 ];
+#pragma unroll
+			for( int i = 0; i < N4; i++ ) u[ i ] = ldPoll( src + i * 32 + lane );
+			SpinGuard guard;
+			while( true )
+			{
+				bool miss = false;
+#pragma unroll
+				for( int i = 0; i < N4; i++ )
+					if( hasSent32( u[ i ] ) )
+					{
+						u[ i ] = ldPoll( src + i * 32 + lane );
+						miss = true;
+					}
+				if( !miss ) break;
+				guard.tick();
+			}
+#pragma unroll
+			for( int i = 0; i < N4; i++ )
+				v[ i ] = make_float4( __uint_as_float( u[ i ].x ), __uint_as_float( u[ i ].y ), __uint_as_float( u[ i ].z ), __uint_as_float( u[ i ].w ) );
+		}
+		// token + positional embedding row (a13: whisper.cpp:1536-1548), computed by every CTA for itself: no exchange for layer 0's input
+		template<int D>
+		__device__ __forceinline__ void embedRow( const __half* te, const float* pe, float4* v, int lane )
+		{
+			constexpr int N4 = Cfg<D>::N4;
+#pragma unroll
+			for( int i = 0; i < N4; i++ )
+			{
+				const uint2 h = *reinterpret_cast<const uint2*>( te + ( i * 32 + lane ) * 4 );
+				const float4 p = *reinterpret_cast<const float4*>( pe + ( i * 32 + lane ) * 4 );
+				const float2 a = __half22float2( *reinterpret_cast<const __half2*>( &h.x ) );
+				const float2 b = __half22float2( *reinterpret_cast<const __half2*>( &h.y ) );
+				v[ i ] = make_float4( a.x + p.x, a.y + p.y, b.x + p.z, b.y + p.w );
+			}
+		}
+		// LayerNorm of one row held in registers (one warp per row) -> f16 activations; keeps this CTA's residual rows
+		template<int D>
+		__device__ __forceinline__ void normRow( float4* v, const float* gamma, const float* beta, __half* dst, float* xresRow, int r0, int nr, int lane )
+		{
+			constexpr int N4 = Cfg<D>::N4;
+			if( nr > 0 )
+			{
+#pragma unroll
+				for( int i = 0; i < N4; i++ )
+				{
+					const int e0 = ( i * 32 + lane ) * 4;
+					if( e0 + 3 >= r0 && e0 < r0 + nr )
+					{
+						const float f[ 4 ] = { v[ i ].x, v[ i ].y, v[ i ].z, v[ i ].w };
+#pragma unroll
+						for( int k = 0; k < 4; k++ )
+						{
+							const int r = e0 + k - r0;
+							if( r >= 0 && r < nr ) xresRow[ r ] = f[ k ];
+						}
+					}
+				}
+			}
+			float s = 0.0f;
+#pragma unroll
+			for( int i = 0; i < N4; i++ ) s += v[ i ].x + v[ i ].y + v[ i ].z + v[ i ].w;
+			const float mean = warpSumF( s ) / (float)D;
+			float sq = 0.0f;
+#pragma unroll
+			for( int i = 0; i < N4; i++ )
+			{
+				v[ i ].x -= mean; v[ i ].y -= mean; v[ i ].z -= mean; v[ i ].w -= mean;
+				sq += v[ i ].x * v[ i ].x + v[ i ].y * v[ i ].y + v[ i ].z * v[ i ].z + v[ i ].w * v[ i ].w;
+			}
+			const float rstd = 1.0f / sqrtf( warpSumF( sq ) / (float)D + 1e-5f );
+			const float4* g4 = reinterpret_cast<const float4*>( gamma );
+			const float4* b4 = reinterpret_cast<const float4*>( beta );
+			uint2* d2 = reinterpret_cast<uint2*>( dst );
+#pragma unroll
+			for( int i = 0; i < N4; i++ )
+			{
+				const float4 gg = g4[ i * 32 + lane ];
+				const float4 bb = b4[ i * 32 + lane ];
+				__half2 h0 = __floats2half2_rn( v[ i ].x * rstd * gg.x + bb.x, v[ i ].y * rstd * gg.y + bb.y );
+				__half2 h1 = __floats2half2_rn( v[ i ].z * rstd * gg.z + bb.z, v[ i ].w * rstd * gg.w + bb.w );
+				uint2 u;
+				u.x = *reinterpret_cast<uint32_t*>( &h0 );
+				u.y = *reinterpret_cast<uint32_t*>( &h1 );
+				d2[ i * 32 + lane ] = u;
+			}
+		}
+		// B rows of D ready f16 activations (attention output, GELU output) from an exchange buffer -> shared memory
+		template<int D>
+		__device__ __forceinline__ void stageF16( const __half* src, size_t colStride, int B, uint8_t* act, int tid )
+		{
+			constexpr int V8 = D / 8;
+			constexpr int RS = Cfg<D>::RS;
+			constexpr int U = 4;
+			const int total = B * V8;
+			for( int base = 0; base < total; base += FL_CONSUMERS * U )
+			{
+				uint4 u[ U ];
+				const __half* p[ U ];
+#pragma unroll
+				for( int k = 0; k < U; k++ )
+				{
+					const int i = base + k * FL_CONSUMERS + tid;
+					const int c = i / V8, kk = i - c * V8;
+					p[ k ] = i < total ? src + (size_t)c * colStride + kk * 8 : nullptr;
+					u[ k ] = make_uint4( 0, 0, 0, 0 );
+					if( p[ k ] ) u[ k ] = ldPoll( p[ k ] );
+				}
+				SpinGuard guard;
+				while( true )
+				{
+					bool miss = false;
+#pragma unroll
+					for( int k = 0; k < U; k++ )
+						if( p[ k ] && hasSent16( u[ k ] ) )
+						{
+							u[ k ] = ldPoll( p[ k ] );
+							miss = true;
+						}
+					if( !miss ) break;
+					guard.tick();
+				}
+#pragma unroll
+				for( int k = 0; k < U; k++ )
+				{
+					const int i = base + k * FL_CONSUMERS + tid;
+					const int c = i / V8, kk = i - c * V8;
+					if( i < total ) *reinterpret_cast<uint4*>( act + (size_t)c * RS + kk * 16 ) = u[ k ];
+				}
+			}
+		}
+
+		enum { EP_QKV = 0, EP_RESID = 1, EP_QSCALE = 2, EP_GELU = 3, EP_LOGITS = 4 };
+		struct GemvOut
+		{
+			int epi;
+			int nOut, R;             // rows of the whole phase, rows per CTA
+			const float* bias;       // shared memory: this CTA's rows
+			float scale;
+			float* outF32;           // x (exchange) / logits
+			__half* outF16;          // q / cq / h (exchange)
+			__half* knew; __half* vnew;
+			__half* kCache; __half* vCache;
+			int ld;
+		};
+
+		// -----------------------------------------------------------------------------------------------------------
+		template<int D>
+		__global__ void __launch_bounds__( FL_THREADS, 1 )
+			decode_flow_kernel( const FlowArgs a )
+		{
+			using C = Cfg<D>;
+			constexpr int RS = C::RS, SLOT = C::SLOT, CR = C::CR;
+			extern __shared__ __align__( 128 ) uint8_t fl_smem[];
+			const int NS = a.NS, ncols = a.ncols;
+			const SmemLayout lay = smemLayout( SLOT, RS, NS, ncols );
+			uint8_t* const ring = fl_smem;
+			uint8_t* const act = fl_smem + lay.act;
+			float* const red = reinterpret_cast<float*>( fl_smem + lay.red );
+			float* const sp = reinterpret_cast<float*>( fl_smem + lay.sp );
+			float* const sbias = reinterpret_cast<float*>( fl_smem + lay.bias );
+			float* const xres = reinterpret_cast<float*>( fl_smem + lay.xres );
+			float* const so = reinterpret_cast<float*>( fl_smem + lay.so );
+			float* const sred = reinterpret_cast<float*>( fl_smem + lay.sred );
+			uint8_t* const sqkv = fl_smem + lay.qkv;
+			uint64_t* const full = reinterpret_cast<uint64_t*>( fl_smem + lay.bars );
+			uint64_t* const empty = full + FL_NSMAX;
+
+			const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+			const int cta = blockIdx.x, G = gridDim.x;
+			if( tid == 0 )
+			{
+				for( int i = 0; i < NS; i++ )
+				{
+					ptx::mbar_init( full + i, 1 );
+					ptx::mbar_init( empty + i, FL_WARPS );
+				}
+				ptx::fence_barrier_init();
+			}
+			__syncthreads();
+
+			const unsigned epoch = *reinterpret_cast<const volatile unsigned*>( a.ctrl + 1 );
+			const int set = (int)( epoch & 1u );
+			const int B = a.B, H = a.H, T = a.T, L = a.L;
+			int nPast = *a.dNPast;              // read once: the sampler advances it after this launch
+			nPast = max( 0, min( nPast, a.nTextCtx - 1 ) );
+			const int nkvOld = nPast;           // rows of earlier tokens in the self-KV cache
+			const int parts = a.refThreads > 0 ? a.refThreads : 4;
+			const size_t colsD = (size_t)a.maxB * D;
+			const size_t exLayer = colsD * 32;
+			const FlowGeom& g = a.g;
+			const int r1 = cta * g.R1, n1 = max( 0, min( g.R1, D - r1 ) );
+			const int r3 = cta * g.R3, n3 = max( 0, min( g.R3, 3 * D - r3 ) );
+			const int r4 = cta * g.R4, n4 = max( 0, min( g.R4, 4 * D - r4 ) );
+			const int rv = cta * g.RV, nv = max( 0, min( g.RV, a.nVocab - rv ) );
+			const int nKcSelf = ( nkvOld + CR - 1 ) / CR;
+			const int nKcCross = ( T + CR - 1 ) / CR;
+			const int dcCross = ( T + parts - 1 ) / parts;
+			const int roundsCross = ( dcCross + CR - 1 ) / CR;
+
+			// =========================================================================================================
+			// producer warp: everything that does not depend on this step, in consumption order, as far ahead as the ring allows
+			// =========================================================================================================
+			if( warp == FL_WARPS )
+			{
+				int pSlot = 0;
+				uint32_t pPar = 0;
+				bool wrapped = false;
+				uint64_t* bar = nullptr;
+				auto begin = [ & ]( uint32_t bytes ) -> uint8_t* {
+					uint8_t* dst = ring + (size_t)pSlot * SLOT;
+					bar = full + pSlot;
+					if( lane == 0 )
+					{
+						if( wrapped ) mbarWaitLong( empty + pSlot, pPar ^ 1u );
+						if( bytes ) ptx::mbar_expect_tx( bar, bytes );
+						else ptx::mbar_arrive( bar );
+					}
+					__syncwarp();
+					if( ++pSlot == NS ) { pSlot = 0; pPar ^= 1u; wrapped = true; }
+					return dst;
+				};
+				auto sendParams = [ & ]( const float* gm, const float* bt, const float* slab, int slabFloats ) {
+					uint8_t* dst = begin( (uint32_t)( 2 * D * 4 + slabFloats * 4 ) );
+					if( lane == 0 ) ptx::bulk_load_1d( dst, gm, D * 4, bar );
+					if( lane == 1 ) ptx::bulk_load_1d( dst + D * 4, bt, D * 4, bar );
+					if( lane == 2 && slabFloats ) ptx::bulk_load_1d( dst + 2 * D * 4, slab, (uint32_t)slabFloats * 4, bar );
+				};
+				auto sendWeights = [ & ]( const __half* W, int K, int row0, int nRows, int kChunks ) {
+					const int nUnits = ( nRows + 7 ) >> 3;
+					for( int u0 = 0; u0 < nUnits; u0 += 4 )
+					{
+						const int nb = min( 4, nUnits - u0 );
+						for( int kc = 0; kc < kChunks; kc++ )
+							for( int u = 0; u < nb; u++ )
+							{
+								const int rows = min( 8, nRows - ( u0 + u ) * 8 );
+								uint8_t* dst = begin( (uint32_t)rows * D * 2 );
+								if( lane < rows )
+									ptx::bulk_load_1d( dst + lane * RS, W + (size_t)( row0 + ( u0 + u ) * 8 + lane ) * K + (size_t)kc * D, D * 2, bar );
+							}
+					}
+				};
+				auto sendKv = [ & ]( const __half* base, int j0, int n ) {
+					uint8_t* dst = begin( (uint32_t)( n > 0 ? n * 128 : 0 ) );
+					if( lane == 0 && n > 0 ) ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, bar );
+				};
+				for( int il = 0; il < L; il++ )
+				{
+					const FlowLayer& Lr = a.layers[ il ];
+					sendParams( Lr.ln1g, Lr.ln1b, Lr.biasSlab + (size_t)cta * g.slabFloats, g.slabFloats );
+					sendWeights( Lr.wqkv, D, r3, n3, 1 );
+					for( int unit = cta; unit < B * H; unit += G )
+					{
+						const size_t hb = (size_t)unit * a.nTextCtx * 64;   // unit = b * H + h
+						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
+						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.vCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
+					}
+					sendWeights( Lr.wo, D, r1, n1, 1 );
+					sendParams( Lr.lncg, Lr.lncb, nullptr, 0 );
+					sendWeights( Lr.wcq, D, r1, n1, 1 );
+					for( int unit = cta; unit < B * H; unit += G )
+					{
+						const size_t hb = (size_t)unit * T * 64;
+						for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
+						for( int i = 0; i < roundsCross; i++ )
+							for( int p = 0; p < parts; p++ )
+							{
+								const int j0 = p * dcCross + i * CR;
+								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcCross, T ) );
+								sendKv( Lr.crossV + hb, j0, j1 - j0 );
+							}
+					}
+					sendWeights( Lr.wco, D, r1, n1, 1 );
+					sendParams( Lr.ln3g, Lr.ln3b, nullptr, 0 );
+					sendWeights( Lr.w1, D, r4, n4, 1 );
+					sendWeights( Lr.w2, 4 * D, r1, n1, 4 );
+				}
+				sendParams( a.lnfg, a.lnfb, nullptr, 0 );
+				sendWeights( a.tokEmb, D, rv, nv, 1 );
+				return;
+			}
+
+			// =========================================================================================================
+			// consumer warps
+			// =========================================================================================================
+			int cSlot = 0;
+			uint32_t cPar = 0;
+			auto slotAt = [ & ]( int k, uint32_t& par ) -> int {
+				int idx = cSlot + k;
+				par = cPar;
+				if( idx >= NS ) { idx -= NS; par ^= 1u; }
+				return idx;
+			};
+			auto waitSlot = [ & ]( int k ) -> uint8_t* {
+				uint32_t par;
+				const int idx = slotAt( k, par );
+				mbarWaitLong( full + idx, par );
+				return ring + (size_t)idx * SLOT;
+			};
+			// Every consumer warp releases every slot exactly once, after its last read.  `observe`: this warp may not have waited for
+			// the slot's data itself (V rows are read by the two warps of one chain only) — it does so now, so that every warp sees
+			// every phase of every `full` barrier complete and a later parity wait can never match a phase it skipped.
+			auto releaseSlots = [ & ]( int n, bool observe = false ) {
+				__syncwarp();
+				if( lane == 0 )
+					for( int k = 0; k < n; k++ )
+					{
+						uint32_t par;
+						const int idx = slotAt( k, par );
+						if( observe ) mbarWaitLong( full + idx, par );
+						ptx::mbar_arrive( empty + idx );
+					}
+				cSlot += n;
+				if( cSlot >= NS ) { cSlot -= NS; cPar ^= 1u; }
+			};
+			int markIdx = 0;
+			auto mark = [ & ]() {
+				if( a.timing && cta == 0 && tid == 0 && markIdx < 1024 )
+				{
+					unsigned long long t;
+					asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
+					a.timing[ markIdx ] = t;
+				}
+				markIdx++;
+			};
+			mark();
+
+			const int gq = lane >> 2, tq = lane & 3;
+			const bool twoTiles = B > 8;
+			const float qkScale = 0.35355339059327379f;   // 64^-1/4 (whisper.cpp:1588, 1595, 1700)
+
+			// LayerNorm staging of all B columns (one warp per column); src == nullptr: layer 0's input, embedded on the spot
+			auto stageLN = [ & ]( const float* src, const uint8_t* params ) {
+				const float* gamma = reinterpret_cast<const float*>( params );
+				const float* beta = gamma + D;
+				for( int c = warp; c < B; c += FL_WARPS )
+				{
+					float4 v[ C::N4 ];
+					if( src ) pollRowF32<D>( src + (size_t)c * D, v, lane );
+					else embedRow<D>( a.tokEmb + (size_t)a.tokens[ c ] * D, a.decPos + (size_t)nPast * D, v, lane );
+					normRow<D>( v, gamma, beta, reinterpret_cast<__half*>( act + (size_t)c * RS ), xres + c * 16, r1, n1, lane );
+				}
+			};
+
+			// weight-streaming GEMV of this CTA's rows: out[col][n] = sum_k W[n][k] * act[col][k].  KC = 1: the activations are staged
+			// already; KC = 4 (fc2): K = 4D is walked in four D-wide chunks, each staged from the exchange buffer `hsrc` first.
+			auto gemv = [ & ]( const GemvOut& o, int row0, int nRows, int KC, const __half* hsrc ) {
+				const int nUnits = ( nRows + 7 ) >> 3;
+				for( int u0 = 0; u0 < nUnits; u0 += 4 )
+				{
+					const int nb = min( 4, nUnits - u0 );
+					float acc0[ 4 ][ 4 ], acc1[ 4 ][ 4 ];
+#pragma unroll
+					for( int u = 0; u < 4; u++ )
+#pragma unroll
+						for( int i = 0; i < 4; i++ ) { acc0[ u ][ i ] = 0.0f; acc1[ u ][ i ] = 0.0f; }
+					for( int kc = 0; kc < KC; kc++ )
+					{
+						if( KC > 1 )
+						{
+							if( kc > 0 ) consumerSync();   // the previous chunk's MMAs have read `act`
+							stageF16<D>( hsrc + (size_t)kc * D, (size_t)4 * D, B, act, tid );
+							consumerSync();
+						}
+#pragma unroll
+						for( int u = 0; u < 4; u++ )
+						{
+							if( u < nb )
+							{
+								const uint8_t* w = waitSlot( 0 );
+								const uint8_t* wb = w + (size_t)gq * RS + tq * 16;
+								const uint8_t* xb0 = act + (size_t)gq * RS + tq * 16;
+								const uint8_t* xb1 = act + (size_t)( gq + 8 ) * RS + tq * 16;
+#pragma unroll
+								for( int s = 0; s < C::SPW; s++ )
+								{
+									const int st = warp + FL_WARPS * s;
+									if( st < C::STEPS )
+									{
+										const uint4 wv = *reinterpret_cast<const uint4*>( wb + st * 64 );
+										const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 64 );
+										mmaF( acc0[ u ], wv.x, wv.y, x0.x, x0.y );
+										mmaF( acc0[ u ], wv.z, wv.w, x0.z, x0.w );
+										if( twoTiles )
+										{
+											const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 64 );
+											mmaF( acc1[ u ], wv.x, wv.y, x1.x, x1.y );
+											mmaF( acc1[ u ], wv.z, wv.w, x1.z, x1.w );
+										}
+									}
+								}
+								releaseSlots( 1 );
+							}
+						}
+					}
+					// cross-warp reduction: red[u][warp][row g][col]
+#pragma unroll
+					for( int u = 0; u < 4; u++ )
+					{
+						if( u < nb )
+						{
+							float* my = red + ( ( u * FL_WARPS + warp ) * 8 + gq ) * ncols;
+							my[ 2 * tq ] = acc0[ u ][ 0 ];
+							my[ 2 * tq + 1 ] = acc0[ u ][ 1 ];
+							if( twoTiles ) { my[ 8 + 2 * tq ] = acc1[ u ][ 0 ]; my[ 8 + 2 * tq + 1 ] = acc1[ u ][ 1 ]; }
+						}
+					}
+					consumerSync();
+					for( int idx = tid; idx < nb * B * 8; idx += FL_CONSUMERS )
+					{
+						const int u = idx / ( B * 8 );
+						const int rem = idx - u * B * 8;
+						const int c = rem >> 3, r = rem & 7;
+						const int rl = ( u0 + u ) * 8 + r;     // row within this CTA's range
+						if( rl >= nRows ) continue;
+						const int n = row0 + rl;
+						float v = 0.0f;
+#pragma unroll
+						for( int w = 0; w < FL_WARPS; w++ ) v += red[ ( ( u * FL_WARPS + w ) * 8 + r ) * ncols + c ];
+						const float bs = o.bias ? o.bias[ rl ] : 0.0f;
+						switch( o.epi )
+						{
+						case EP_QKV:
+						{
+							const int which = n / D;
+							const int nn = n - which * D;
+							if( which == 0 ) stX16( o.outF16 + (size_t)c * D + nn, __float2half_rn( ( v + bs ) * o.scale ) );
+							else
+							{
+								const int h = nn >> 6, e = nn & 63;
+								const size_t off = ( ( (size_t)c * H + h ) * a.nTextCtx + nPast ) * 64 + e;
+								if( which == 1 )
+								{
+									const __half kv = __float2half_rn( v * o.scale );
+									o.kCache[ off ] = kv;
+									stX16( o.knew + (size_t)c * D + nn, kv );
+								}
+								else
+								{
+									const __half vv = __float2half_rn( v + bs );
+									o.vCache[ off ] = vv;
+									stX16( o.vnew + (size_t)c * D + nn, vv );
+								}
+							}
+							break;
+						}
+						case EP_RESID:
+							stX32( o.outF32 + (size_t)c * D + n, v + bs + xres[ c * 16 + rl ] );
+							break;
+						case EP_QSCALE:
+							stX16( o.outF16 + (size_t)c * D + n, __float2half_rn( ( v + bs ) * o.scale ) );
+							break;
+						case EP_GELU:
+							stX16( o.outF16 + (size_t)c * o.ld + n, __float2half_rn( ptx::gelu_f16_semantics( v + bs ) ) );
+							break;
+						default:
+							o.outF32[ (size_t)c * o.ld + n ] = v;
+							break;
+						}
+					}
+					if( u0 + 4 < nUnits ) consumerSync();   // `red` is rewritten by the next batch
+				}
+			};
+
+			for( int il = 0; il < L; il++ )
+			{
+				const FlowLayer& Lr = a.layers[ il ];
+				uint8_t* const exb = a.exch + ( (size_t)set * L + il ) * exLayer;
+				float* const x1 = reinterpret_cast<float*>( exb );
+				float* const x2 = x1 + colsD;
+				float* const x3 = x2 + colsD;
+				__half* const hbase = reinterpret_cast<__half*>( exb + colsD * 12 );
+				__half* const qh = hbase;
+				__half* const knew = hbase + colsD;
+				__half* const vnew = hbase + 2 * colsD;
+				__half* const attn1 = hbase + 3 * colsD;
+				__half* const cq = hbase + 4 * colsD;
+				__half* const attn2 = hbase + 5 * colsD;
+				__half* const hbuf = hbase + 6 * colsD;
+				const float* xin = nullptr;
+				if( il > 0 ) xin = reinterpret_cast<const float*>( a.exch + ( (size_t)set * L + il - 1 ) * exLayer ) + 2 * colsD;
+
+				GemvOut o{};
+				o.scale = 1.0f; o.ld = D;
+
+				// ---- LN1 + (Q | K | V): K/V rows appended to the f16 cache (a14) ----
+				{
+					const uint8_t* pr = waitSlot( 0 );
+					for( int i = tid; i < g.slabFloats; i += FL_CONSUMERS ) sbias[ i ] = reinterpret_cast<const float*>( pr + 2 * D * 4 )[ i ];
+					if( n3 > 0 ) stageLN( xin, pr );
+					consumerSync();
+					releaseSlots( 1 );
+					o.epi = EP_QKV; o.nOut = 3 * D; o.R = g.R3; o.bias = sbias + g.oQkv; o.scale = qkScale;
+					o.outF16 = qh; o.knew = knew; o.vnew = vnew; o.kCache = Lr.kCache; o.vCache = Lr.vCache;
+					gemv( o, r3, n3, 1, nullptr );
+					o.scale = 1.0f;
+				}
+				mark();
+				// ---- self attention over the cache (reference-exact f16 V^T*P chains), units = (chunk, head) ----
+				for( int unit = cta; unit < B * H; unit += G )
+				{
+					const int b = unit / H, h = unit - b * H;
+					const size_t vo = (size_t)b * D + h * 64;
+					if( tid < 24 )
+					{
+						const int arr = tid >> 3, piece = tid & 7;
+						const __half* src = ( arr == 0 ? qh : arr == 1 ? knew : vnew ) + vo + piece * 8;
+						uint4 u = ldPoll( src );
+						SpinGuard guard;
+						while( hasSent16( u ) ) { u = ldPoll( src ); guard.tick(); }
+						reinterpret_cast<uint4*>( sqkv )[ tid ] = u;
+					}
+					consumerSync();
+					float qf[ 8 ];
+					{
+						const __half* qs = reinterpret_cast<const __half*>( sqkv ) + ( lane & 7 ) * 8;
+#pragma unroll
+						for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( qs[ e ] );
+					}
+					float lmax = -INFINITY;
+					for( int ci = 0; ci < nKcSelf; ci++ )
+					{
+						const uint8_t* kc = waitSlot( 0 );
+						lmax = scoreRows( kc, min( CR, nkvOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+						releaseSlots( 1 );
+					}
+					lmax = scoreRows( sqkv + 128, 1, nkvOld, qf, sp, warp, lane, lmax );   // this step's own K row
+					const int nkv = nkvOld + 1;
+					softmaxRow( sp, nkv, lmax, sred, tid, warp, lane );
+					{
+						const int dc = ( nkv + parts - 1 ) / parts;
+						const int p = tid >> 6, e = tid & 63;
+						if( p < parts )
+						{
+							const int j0 = min( p * dc, nkv ), j1 = min( ( p + 1 ) * dc, nkv );
+							float y = 0.0f;
+							int j = j0;
+							while( j < j1 )
+							{
+								int n;
+								const __half* vp;
+								if( j < nkvOld )
+								{
+									const int ci = j / CR;
+									n = min( j1, min( nkvOld, ( ci + 1 ) * CR ) ) - j;
+									vp = reinterpret_cast<const __half*>( waitSlot( ci ) ) + (size_t)( j - ci * CR ) * 64 + e;
+								}
+								else
+								{
+									n = 1;
+									vp = reinterpret_cast<const __half*>( sqkv + 256 ) + e;   // this step's own V row
+								}
+								y = a.refThreads > 0 ? chainRows<true>( y, sp + j, vp, n ) : chainRows<false>( y, sp + j, vp, n );
+								j += n;
+							}
+							so[ tid ] = y;
+						}
+						releaseSlots( nKcSelf, true );
+					}
+					consumerSync();
+					if( tid < 64 )
+					{
+						float acc = so[ tid ];
+						for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
+						stX16( attn1 + vo + tid, __float2half_rn( acc ) );
+					}
+					consumerSync();
+				}
+				mark();
+				// ---- self-attention out projection + residual ----
+				o.epi = EP_RESID; o.nOut = D; o.R = g.R1; o.bias = sbias + g.oO; o.outF32 = x1;
+				if( n1 > 0 )
+				{
+					stageF16<D>( attn1, D, B, act, tid );
+					consumerSync();
+					gemv( o, r1, n1, 1, nullptr );
+				}
+				mark();
+				// ---- LN + cross-attention query (a15) ----
+				{
+					const uint8_t* pr = waitSlot( 0 );
+					if( n1 > 0 ) stageLN( x1, pr );
+					consumerSync();
+					releaseSlots( 1 );
+					o.epi = EP_QSCALE; o.bias = sbias + g.oCq; o.scale = qkScale; o.outF16 = cq;
+					gemv( o, r1, n1, 1, nullptr );
+					o.scale = 1.0f;
+				}
+				mark();
+				// ---- cross attention over the encoder's f16 K/V memories, units = (chunk, head) ----
+				for( int unit = cta; unit < B * H; unit += G )
+				{
+					const int b = unit / H, h = unit - b * H;
+					const size_t vo = (size_t)b * D + h * 64;
+					float qf[ 8 ];
+					{
+						const __half* src = cq + vo + ( lane & 7 ) * 8;
+						uint4 u = ldPoll( src );
+						SpinGuard guard;
+						while( hasSent16( u ) ) { u = ldPoll( src ); guard.tick(); }
+						const __half* qs = reinterpret_cast<const __half*>( &u );
+#pragma unroll
+						for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( qs[ e ] );
+					}
+					float lmax = -INFINITY;
+					for( int ci = 0; ci < nKcCross; ci++ )
+					{
+						const uint8_t* kc = waitSlot( 0 );
+						lmax = scoreRows( kc, min( CR, T - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+						releaseSlots( 1 );
+					}
+					softmaxRow( sp, T, lmax, sred, tid, warp, lane );
+					{
+						const int p = tid >> 6, e = tid & 63;
+						float y = 0.0f;
+						for( int i = 0; i < roundsCross; i++ )
+						{
+							if( p < parts )
+							{
+								const int j0 = p * dcCross + i * CR;
+								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcCross, T ) );
+								if( j1 > j0 )
+								{
+									const __half* vp = reinterpret_cast<const __half*>( waitSlot( p ) ) + e;
+									y = a.refThreads > 0 ? chainRows<true>( y, sp + j0, vp, j1 - j0 ) : chainRows<false>( y, sp + j0, vp, j1 - j0 );
+								}
+							}
+							releaseSlots( parts, true );
+						}
+						if( p < parts ) so[ tid ] = y;
+					}
+					consumerSync();
+					if( tid < 64 )
+					{
+						float acc = so[ tid ];
+						for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
+						stX16( attn2 + vo + tid, __float2half_rn( acc ) );
+					}
+					consumerSync();
+				}
+				mark();
+				// ---- cross-attention out projection + residual ----
+				o.epi = EP_RESID; o.bias = sbias + g.oCo; o.outF32 = x2;
+				if( n1 > 0 )
+				{
+					stageF16<D>( attn2, D, B, act, tid );
+					consumerSync();
+					gemv( o, r1, n1, 1, nullptr );
+				}
+				mark();
+				// ---- LN + fc1 + GELU (a16) ----
+				{
+					const uint8_t* pr = waitSlot( 0 );
+					if( n4 > 0 ) stageLN( x2, pr );
+					consumerSync();
+					releaseSlots( 1 );
+					o.epi = EP_GELU; o.nOut = 4 * D; o.R = g.R4; o.bias = sbias + g.oFc1; o.outF16 = hbuf; o.ld = 4 * D;
+					gemv( o, r4, n4, 1, nullptr );
+				}
+				mark();
+				// ---- fc2 + residual ----
+				o.epi = EP_RESID; o.nOut = D; o.R = g.R1; o.bias = sbias + g.oFc2; o.outF32 = x3; o.ld = D;
+				gemv( o, r1, n1, 4, hbuf );
+				mark();
+				// ---- re-arm this layer's buffers of the idle set (their readers finished with the previous launch) ----
+				{
+					uint4* dst = reinterpret_cast<uint4*>( a.exch + ( (size_t)( set ^ 1 ) * L + il ) * exLayer );
+					const size_t n16 = exLayer / 16;
+					const size_t per = ( n16 + G - 1 ) / G;
+					const size_t lo = (size_t)cta * per;
+					for( size_t i = tid; i < per && lo + i < n16; i += FL_CONSUMERS ) dst[ lo + i ] = make_uint4( SENT32, SENT32, SENT32, SENT32 );
+				}
+			}
+			// ---- final LayerNorm + logits = tok_emb^T x (a17) ----
+			{
+				const float* xin = reinterpret_cast<const float*>( a.exch + ( (size_t)set * L + L - 1 ) * exLayer ) + 2 * colsD;
+				const uint8_t* pr = waitSlot( 0 );
+				if( nv > 0 ) stageLN( xin, pr );
+				consumerSync();
+				releaseSlots( 1 );
+				GemvOut o{};
+				o.epi = EP_LOGITS; o.nOut = a.nVocab; o.R = g.RV; o.bias = nullptr; o.scale = 1.0f; o.outF32 = a.logits; o.ld = a.nVocab;
+				gemv( o, rv, nv, 1, nullptr );
+			}
+			mark();
+			// the last CTA to finish flips the exchange set for the next launch
+			consumerSync();
+			if( tid == 0 )
+			{
+				const unsigned old = atomicAdd( a.ctrl, 1u );
+				if( old == (unsigned)G - 1u )
+				{
+					a.ctrl[ 0 ] = 0u;
+					a.ctrl[ 1 ] = epoch + 1u;
+				}
+			}
+		}
+
+		__global__ void flow_bias_slab_kernel( float* slab, FlowGeom g, int d, const float* bqkv, const float* bo, const float* bcq, const float* bco,
+			const float* b1, const float* b2 )
+		{
+			const int c = blockIdx.x;
+			for( int i = threadIdx.x; i < g.slabFloats; i += blockDim.x )
+			{
+				const float* src;
+				int r, R, nOut;
+				if( i < g.oO ) { src = bqkv; r = i - g.oQkv; R = g.R3; nOut = 3 * d; }
+				else if( i < g.oCq ) { src = bo; r = i - g.oO; R = g.R1; nOut = d; }
+				else if( i < g.oCo ) { src = bcq; r = i - g.oCq; R = g.R1; nOut = d; }
+				else if( i < g.oFc1 ) { src = bco; r = i - g.oCo; R = g.R1; nOut = d; }
+				else if( i < g.oFc2 ) { src = b1; r = i - g.oFc1; R = g.R4; nOut = 4 * d; }
+				else { src = b2; r = i - g.oFc2; R = g.R1; nOut = d; }
+				const int n = c * R + r;
+				slab[ (size_t)c * g.slabFloats + i ] = ( r < R && n < nOut ) ? src[ n ] : 0.0f;
+			}
+		}
+
+		template<int D>
+		int smemBytes( int ncols, int* nsOut )
+		{
+			using C = Cfg<D>;
+			const int ns = ringSlots( C::SLOT, C::RS, ncols );
+			if( nsOut ) *nsOut = ns;
+			return smemLayout( C::SLOT, C::RS, ns, ncols ).total;
+		}
+		template<int D>
+		cudaError_t prepareD()
+		{
+			static PerDeviceMax attr;
+			return attr.raise( FL_SMEM_MAX, []( size_t n ) { return cudaFuncSetAttribute( decode_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
+		}
+		template<int D>
+		cudaError_t launchD( FlowArgs& a, int numSMs, cudaStream_t s )
+		{
+			a.ncols = a.B > 8 ? 16 : 8;
+			int ns = 0;
+			const int smem = smemBytes<D>( a.ncols, &ns );
+			a.NS = ns;
+			cudaLaunchConfig_t cfg{};
+			cfg.gridDim = dim3( (unsigned)numSMs );
+			cfg.blockDim = dim3( FL_THREADS );
+			cfg.dynamicSmemBytes = (size_t)smem;
+			cfg.stream = s;
+			cudaLaunchAttribute at[ 1 ];
+			at[ 0 ].id = cudaLaunchAttributeCooperative;   // co-residency of all CTAs is a correctness requirement of the exchange
+			at[ 0 ].val.cooperative = 1;
+			cfg.attrs = at;
+			cfg.numAttrs = 1;
+			return cudaLaunchKernelEx( &cfg, decode_flow_kernel<D>, (const FlowArgs)a );
+		}
+		inline int pad4( int x ) { return ( x + 3 ) & ~3; }
+	}
+
+	FlowGeom flowGeometry( int d, int nVocab, int grid )
+	{
+		FlowGeom g;
+		g.grid = grid;
+		g.R1 = ( d + grid - 1 ) / grid;
+		g.R3 = ( 3 * d + grid - 1 ) / grid;
+		g.R4 = ( 4 * d + grid - 1 ) / grid;
+		g.RV = ( nVocab + grid - 1 ) / grid;
+		g.oQkv = 0;
+		g.oO = g.oQkv + pad4( g.R3 );
+		g.oCq = g.oO + pad4( g.R1 );
+		g.oCo = g.oCq + pad4( g.R1 );
+		g.oFc1 = g.oCo + pad4( g.R1 );
+		g.oFc2 = g.oFc1 + pad4( g.R4 );
+		g.slabFloats = g.oFc2 + pad4( g.R1 );
+		return g;
+	}
+
+	bool flowSupported( int d, int B, int T, int H, int nTextCtx, int refThreads, int grid )
+	{
+		if( B < 1 || B > 16 || T > FL_MAXT || T < 1 || H * 64 != d || nTextCtx > FL_MAXT ) return false;
+		if( refThreads < 0 || refThreads > 4 ) return false;
+		if( !( d == 128 || d == 384 || d == 512 || d == 768 || d == 1024 || d == 1280 ) ) return false;
+		const FlowGeom g = flowGeometry( d, 51865, grid );
+		if( g.R1 > 16 || g.slabFloats > 256 ) return false;
+		// the self-attention V rows of one head are held in the ring all at once
+		const int rs = 2 * d + 64;
+		const int slot = 8 * rs > 16384 ? 8 * rs : 16384;
+		const int cr = ( slot / 128 ) & ~7;
+		const int ns = ringSlots( slot, rs, B > 8 ? 16 : 8 );
+		if( ( nTextCtx + cr - 1 ) / cr + 1 > ns || 4 + 1 > ns ) return false;
+		return true;
+	}
+
+	size_t flowExchangeBytes( int d, int maxB, int L ) { return (size_t)2 * L * maxB * d * 32; }
+
+	cudaError_t flowPrepare( int d )
+	{
+		switch( d )
+		{
+		case 128: return prepareD<128>();
+		case 384: return prepareD<384>();
+		case 512: return prepareD<512>();
+		case 768: return prepareD<768>();
+		case 1024: return prepareD<1024>();
+		case 1280: return prepareD<1280>();
+		default: return cudaSuccess;
+		}
+	}
+
+	cudaError_t flowBuildBiasSlab( float* slab, const FlowGeom& g, int d, const float* bqkv, const float* bo, const float* bcq, const float* bco,
+		const float* b1, const float* b2, cudaStream_t s )
+	{
+		flow_bias_slab_kernel<<<g.grid, 128, 0, s>>>( slab, g, d, bqkv, bo, bcq, bco, b1, b2 );
+		return cudaGetLastError();
+	}
+
+	cudaError_t decodeStepFlow( FlowArgs a, int d, int numSMs, cudaStream_t s )
+	{
+		switch( d )
+		{
+		case 128: return launchD<128>( a, numSMs, s );
+		case 384: return launchD<384>( a, numSMs, s );
+		case 512: return launchD<512>( a, numSMs, s );
+		case 768: return launchD<768>( a, numSMs, s );
+		case 1024: return launchD<1024>( a, numSMs, s );
+		case 1280: return launchD<1280>( a, numSMs, s );
+		default: return cudaErrorInvalidValue;
+		}
+	}
+}

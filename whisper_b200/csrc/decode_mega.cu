@@ -10,6 +10,7 @@
 // Arithmetic is identical to the kernel-per-op path (kernels_decode.cu): f16 x f16 -> f32 through mma.sync.m16n8k16 with the
 // k-permuted fragments, LayerNorm / bias / scale / residual / GELU fused, reference-exact f16 V^T*P chains (pvChainF16).
 #include "decode_mega.cuh"
+#include "per_device.h"
 #include "ptx.cuh"
 #include <math.h>
 
@@ -339,7 +340,7 @@ namespace kern
 				if( which == 0 ) op.outF32[ (size_t)col * op.ld + nn ] = ( v + biasN ) * op.scale;
 				else
 				{
-					const size_t off = ( (size_t)col * op.nTextCtx + op.nPast ) * op.d + nn;
+					const size_t off = ( ( (size_t)col * ( op.d >> 6 ) + ( nn >> 6 ) ) * op.nTextCtx + op.nPast ) * 64 + ( nn & 63 );
 					if( which == 1 ) op.kCache[ off ] = __float2half_rn( v * op.scale );
 					else op.vCache[ off ] = __float2half_rn( v + biasN );
 				}
@@ -456,8 +457,8 @@ namespace kern
 		{
 			if( unit >= a.B * a.H ) return;
 			const int b = unit / a.H, h = unit - b * a.H;
-			const __half* kb = L.kCache + (size_t)b * a.nTextCtx * d + h * 64;
-			const __half* vb = L.vCache + (size_t)b * a.nTextCtx * d + h * 64;
+			const __half* kb = L.kCache + ( (size_t)b * a.H + h ) * a.nTextCtx * 64;
+			const __half* vb = L.vCache + ( (size_t)b * a.H + h ) * a.nTextCtx * 64;
 			uint8_t* sK = sm.a;
 			uint8_t* sV = sm.a + SA_MAXKV * SA_KSTRIDE;
 			const int n = ( j1 - j0 ) * 8;   // 16-byte chunks per matrix
@@ -466,8 +467,8 @@ namespace kern
 				const bool isV = i >= n;
 				const int k = isV ? i - n : i;
 				const int j = j0 + ( k >> 3 ), c = k & 7;
-				if( isV ) cpAsync16( sV + j * 128 + c * 16, vb + (size_t)j * d + c * 8 );
-				else cpAsync16( sK + j * SA_KSTRIDE + c * 16, kb + (size_t)j * d + c * 8 );
+				if( isV ) cpAsync16( sV + j * 128 + c * 16, vb + (size_t)j * 64 + c * 8 );
+				else cpAsync16( sK + j * SA_KSTRIDE + c * 16, kb + (size_t)j * 64 + c * 8 );
 			}
 		}
 		__device__ void selfAttnPhase( const MegaArgs& a, const MegaLayer& L, int d, int nPast, const Smem& sm, int warp, int lane, int tid )
@@ -895,14 +896,8 @@ namespace kern
 		cudaError_t prepareD()
 		{
 			static_assert( 16 * ( 4 * D + MG_PAD ) * 2 <= MG_SMEM_A, "activation rows must fit region A" );
-			static bool attr = false;
-			if( !attr )
-			{
-				cudaError_t e = cudaFuncSetAttribute( decode_step_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
-				if( e != cudaSuccess ) return e;
-				attr = true;
-			}
-			return cudaSuccess;
+			static PerDeviceMax attr;
+			return attr.raise( SMEM, []( size_t n ) { return cudaFuncSetAttribute( decode_step_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 		}
 		template<int D>
 		cudaError_t launchD( const MegaArgs& a, int numSMs, cudaStream_t s )

@@ -11,7 +11,7 @@ namespace kern
 		const float *ln1g, *ln1b, *lncg, *lncb, *ln3g, *ln3b;
 		const __half *wqkv, *wo, *wcq, *wco, *w1, *w2;
 		const float *bqkv, *bo, *bcq, *bco, *b1, *b2;
-		__half *kCache, *vCache;            // [maxB][nTextCtx][d] of this layer
+		__half *kCache, *vCache;            // [maxB][H][nTextCtx][64] of this layer (head-major)
 		const __half *crossK, *crossV;      // [maxB][H][T][64] of this layer
 	};
 	struct MegaArgs
@@ -31,7 +31,6 @@ namespace kern
 		float* logits = nullptr;            // [B][nVocab]
 		unsigned* barrier = nullptr;        // grid barrier counter (zeroed by the launcher)
 		unsigned long long* timing = nullptr;   // optional: %globaltimer marks of CTA 0 around every barrier (debug)
-		int flags = 0;                      // experiment switches (env WSP_MEGA_FLAGS) for same-box A/B runs; 0 = the shipped configuration
 	};
 	bool megaSupported( int d, int B, int T );
 	cudaError_t megaPrepare( int d );   // function attributes, outside any stream capture

@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/whisper_b200.h"
 #include "attn_enc.cuh"
+#include "decode_flow.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -128,7 +129,7 @@ namespace wsp
 		int Tp = 0;
 
 		// decoder state
-		__half* selfK = nullptr;        // [L][maxB][n_text_ctx][d]
+		__half* selfK = nullptr;        // [L][maxB][H][n_text_ctx][64] (head-major rows)
 		__half* selfV = nullptr;
 		float* xd = nullptr;            // [maxB*kMaxDecodeTokens][d]
 		float* qd = nullptr;
@@ -158,7 +159,15 @@ namespace wsp
 		kern::MegaLayer* megaLayers = nullptr;
 		unsigned* megaBarrier = nullptr;
 		unsigned long long* megaTiming = nullptr;   // [4096] debug marks
-		bool useMega = true;
+		// dataflow decoder-step kernel (decode_flow.cu): per-layer pointer table, per-CTA bias slabs, exchange buffers, launch epoch
+		kern::FlowLayer* flowLayers = nullptr;
+		float* flowBias = nullptr;
+		uint8_t* flowExch = nullptr;
+		unsigned* flowCtrl = nullptr;
+		kern::FlowGeom flowGeom;
+		// N = 1 decoder step: 2 = dataflow kernel (default), 1 = round 1's barrier kernel, 0 = one kernel per op
+		int stepMode = 2;
+		bool stepTiming = false;        // record %globaltimer marks of CTA 0 into megaTiming (wsp_debug_step_timing)
 
 		// decode CUDA graph (N = 1 steady state)
 		cudaGraphExec_t stepGraph = nullptr;

@@ -1,5 +1,6 @@
 // tcgen05 + TMA GEMM for sm_100a — see gemm_tc.cuh for the design notes.
 #include "gemm_tc.cuh"
+#include "per_device.h"
 #include <stdio.h>
 #include <mutex>
 
@@ -555,12 +556,10 @@ namespace gemm
 	{
 		using SL = SmemLayout<BN, STAGES>;
 		auto kfn = gemm_tc_kernel<BN, STAGES, MODE, AMODE>;
-		static bool attrSet = false;
-		if( !attrSet )
+		static kern::PerDeviceMax attr;
 		{
-			cudaError_t e = cudaFuncSetAttribute( kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL );
+			cudaError_t e = attr.raise( SL::TOTAL, [ & ]( size_t n ) { return cudaFuncSetAttribute( kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 			if( e != cudaSuccess ) return e;
-			attrSet = true;
 		}
 		const int num_tiles = ( ( L.M + BM - 1 ) / BM ) * ( ( L.N + BN - 1 ) / BN );
 		const int grid = num_tiles < numSMs ? num_tiles : numSMs;

@@ -74,7 +74,7 @@ namespace kern
 		float* outF32 = nullptr;       // q / x / logits  [col][ld]
 		__half* outF16 = nullptr;      // h             [col][ld]
 		int ld = 0;
-		__half* kCache = nullptr;      // [B][nTextCtx][d] for this layer
+		__half* kCache = nullptr;      // [B][H][nTextCtx][64] for this layer (head-major)
 		__half* vCache = nullptr;
 		int d = 0, N = 0, nTextCtx = 0;
 		const int* dNPast = nullptr;

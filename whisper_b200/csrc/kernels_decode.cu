@@ -1,5 +1,6 @@
 // Decoder per-token kernels (weight/KV streaming, HBM-bound): skinny GEMM, self/cross attention over f16 KV, sampler.
 #include "kernels.cuh"
+#include "per_device.h"
 #include "ptx.cuh"
 #include <math.h>
 #include <cooperative_groups.h>
@@ -236,7 +237,9 @@ namespace kern
 			else
 			{
 				const int b = col / a.N, i = col - b * a.N;
-				const size_t off = ( (size_t)b * a.nTextCtx + ( *a.dNPast + i ) ) * a.d + nn;
+				// self-KV cache rows are head-major [b][h][pos][64]: one head's rows are contiguous (bulk-copied by decode_flow.cu)
+				const int pos = min( *a.dNPast + i, a.nTextCtx - 1 );
+				const size_t off = ( ( (size_t)b * ( a.d >> 6 ) + ( nn >> 6 ) ) * a.nTextCtx + pos ) * 64 + ( nn & 63 );
 				if( which == 1 ) a.kCache[ off ] = __float2half_rn( v * a.scale );
 				else a.vCache[ off ] = __float2half_rn( v + a.bias[ n ] );
 			}
@@ -261,27 +264,19 @@ namespace kern
 	}
 
 	static size_t skinnySmem( int K ) { return (size_t)SK_COLS * ( K + SK_PAD ) * sizeof( __half ) + (size_t)SK_WARPS * SK_ROWS * SK_COLS * sizeof( float ); }
-	static size_t g_skinnySmemSet = 0;
+	static PerDeviceMax g_skinnyAttr;
 	static cudaError_t crossPrepare( int T );
 	cudaError_t prepare( int maxK )
 	{
 		cudaError_t ce = crossPrepare( 1500 );
 		if( ce != cudaSuccess ) return ce;
-		const size_t smem = skinnySmem( maxK );
-		if( smem > g_skinnySmemSet )
-		{
-			cudaError_t e = cudaFuncSetAttribute( skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
-			if( e != cudaSuccess ) return e;
-			g_skinnySmemSet = smem;
-		}
-		return cudaSuccess;
+		return g_skinnyAttr.raise( skinnySmem( maxK ), []( size_t n ) { return cudaFuncSetAttribute( skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 	}
 	cudaError_t skinnyGemm( const SkinnyArgs& a, cudaStream_t s )
 	{
 		if( a.K % 32 != 0 ) return cudaErrorInvalidValue;
 		if( a.gamma && ( a.K % 128 != 0 || a.K > 1280 ) ) return cudaErrorInvalidValue;   // fused LayerNorm keeps the row in registers
 		const size_t smem = skinnySmem( a.K );
-		if( smem > g_skinnySmemSet )
 		{
 			cudaError_t e = prepare( a.K );
 			if( e != cudaSuccess ) return e;
@@ -327,7 +322,7 @@ namespace kern
 
 	// ---------------------------------------------------------------------------------------------------------------
 	// Decoder self-attention, one CTA per (chunk, head, query).  Oracle: whisper.cpp:1616-1661 — K*Q (Q rounded to f16 by the
-	// mul_mat, ggml.c:4599), causal mask, softmax, V^T * P.  KV cache rows are [b][pos][d] f16.
+	// mul_mat, ggml.c:4599), causal mask, softmax, V^T * P.  KV cache rows are head-major [b][h][pos][64] f16.
 	constexpr int SA_THREADS = 128;
 	constexpr int SA_MAXKV = 448;
 
@@ -351,12 +346,12 @@ namespace kern
 		if( tid < 64 )
 			sq[ tid ] = __half2float( __float2half_rn( q[ (size_t)col * d + h * 64 + tid ] ) );
 		__syncthreads();
-		const __half* kb = kCache + (size_t)b * nTextCtx * d + h * 64;
-		const __half* vb = vCache + (size_t)b * nTextCtx * d + h * 64;
+		const __half* kb = kCache + ( (size_t)b * H + h ) * nTextCtx * 64;
+		const __half* vb = vCache + ( (size_t)b * H + h ) * nTextCtx * 64;
 		float lmax = -INFINITY;
 		for( int j = tid; j < nkv; j += SA_THREADS )
 		{
-			const uint4* kr = reinterpret_cast<const uint4*>( kb + (size_t)j * d );
+			const uint4* kr = reinterpret_cast<const uint4*>( kb + (size_t)j * 64 );
 			float s = 0.0f;
 #pragma unroll
 			for( int c = 0; c < 8; c++ )
@@ -402,7 +397,7 @@ namespace kern
 			for( int part = tid >> 6; part < refThreads; part += SA_THREADS / 64 )
 			{
 				const int j0 = min( part * dc, nkv ), j1 = min( ( part + 1 ) * dc, nkv );   // masked keys contribute exactly 0
-				so[ part ][ e ] = pvChainF16( sp, vb + e, (size_t)d, j0, j1 );
+				so[ part ][ e ] = pvChainF16( sp, vb + e, (size_t)64, j0, j1 );
 			}
 			__syncthreads();
 			if( tid < 64 )
@@ -417,7 +412,7 @@ namespace kern
 			const int half = tid >> 6;
 			float o = 0.0f;
 			for( int j = half; j < nkv; j += 2 )
-				o += sp[ j ] * __half2float( vb[ (size_t)j * d + e ] );
+				o += sp[ j ] * __half2float( vb[ (size_t)j * 64 + e ] );
 			so[ half ][ e ] = o;
 			__syncthreads();
 			if( tid < 64 )
@@ -598,17 +593,10 @@ namespace kern
 			out[ (size_t)col * d + h * 64 + tid ] = __float2half_rn( acc );
 		}
 	}
-	static size_t g_crossSmemSet = 0;
+	static PerDeviceMax g_crossAttr;
 	static cudaError_t crossPrepare( int T )
 	{
-		const size_t smem = (size_t)T * 128;
-		if( smem > g_crossSmemSet )
-		{
-			cudaError_t e = cudaFuncSetAttribute( cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
-			if( e != cudaSuccess ) return e;
-			g_crossSmemSet = smem;
-		}
-		return cudaSuccess;
+		return g_crossAttr.raise( (size_t)T * 128, []( size_t n ) { return cudaFuncSetAttribute( cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 	}
 	cudaError_t crossAttnDecode( const float* q, const __half* kMem, const __half* vMem, __half* out, int B, int N, int H, int d, int T, int refThreads, cudaStream_t s )
 	{
@@ -922,14 +910,15 @@ namespace kern
 		{
 			const int cl = clusterSize;
 			const size_t sliceBytes = (size_t)( ( a.nVocab + cl - 1 ) / cl ) * sizeof( float );
-			static size_t sliceSet = 0;
-			if( sliceBytes > sliceSet )
+			static PerDeviceMax sliceAttr;
 			{
-				cudaError_t ea = cudaFuncSetAttribute( sample_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)( (size_t)( ( a.nVocab + 3 ) / 4 ) * sizeof( float ) ) );
+				const int nv = a.nVocab;
+				cudaError_t ea = sliceAttr.raise( (size_t)( ( nv + 3 ) / 4 ) * sizeof( float ), [ nv ]( size_t n4 ) {
+					cudaError_t e4 = cudaFuncSetAttribute( sample_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n4 );
+					if( e4 != cudaSuccess ) return e4;
+					return cudaFuncSetAttribute( sample_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)( (size_t)( ( nv + 7 ) / 8 ) * sizeof( float ) ) );
+				} );
 				if( ea != cudaSuccess ) return ea;
-				ea = cudaFuncSetAttribute( sample_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)( (size_t)( ( a.nVocab + 7 ) / 8 ) * sizeof( float ) ) );
-				if( ea != cudaSuccess ) return ea;
-				sliceSet = sliceBytes;
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3( cl, a.B );
@@ -948,12 +937,11 @@ namespace kern
 		const size_t rowBytes = (size_t)a.nVocab * sizeof( float );
 		static const bool forceGlobal = getenv( "WSP_SAMPLER_GLOBAL" ) != nullptr;   // A/B switch for measurements
 		sa.rowInSmem = ( rowBytes <= 220 * 1024 && !forceGlobal ) ? 1 : 0;
-		static size_t smemSet = 0;
-		if( sa.rowInSmem && rowBytes > smemSet )
+		static PerDeviceMax rowAttr;
+		if( sa.rowInSmem )
 		{
-			cudaError_t ea = cudaFuncSetAttribute( sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowBytes );
+			cudaError_t ea = rowAttr.raise( rowBytes, []( size_t n ) { return cudaFuncSetAttribute( sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
 			if( ea != cudaSuccess ) return ea;
-			smemSet = rowBytes;
 		}
 		cudaError_t e = launchPdl( sample_kernel, dim3( a.B ), dim3( SM_THREADS ), sa.rowInSmem ? rowBytes : 0, s, sa );
 		if( e != cudaSuccess ) return e;

@@ -138,7 +138,192 @@ def tokenizer_test_words(i: int) -> bytes:
     return (" t%d" % i).encode() if i != 50256 else b""
 
 
-def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0, ts_boost: float = 1.0, eot_boost: float = 1.0, words=None) -> HParams:
+# ---------------------------------------------------------------------------------------------------------------------
+# "Scripted" synthetic models (name suffix "-sc").
+#
+# A decoder with purely random weights is useless as a parity fixture: whatever the audio and the history, it collapses onto one
+# repeated token (a fixed point of token -> next token), so "identical greedy tokens" proves little.  A scripted model keeps
+# random weights everywhere (every kernel still chews on generic data) but confines them to the last d-64 "noise" dimensions of
+# the decoder's residual stream and uses the first 64 dimensions as a clean CODE channel:
+#
+#   * every ACTIVE token (64 text tokens, timestamps, EOT, sot / transcribe / translate) carries an orthogonal code in its
+#     embedding row; all other rows have no code and can never win;
+#   * the first hidden units of the LAST decoder layer's MLP are a lookup keyed on the input token's code: they erase it and
+#     write the code of the SUCCESSOR — a Markov chain  init-timestamp -> 2-4 text tokens -> end timestamp -> start timestamp
+#     -> text ... -> EOT  with increasing timestamps, i.e. what whisper_full's segment / seek logic expects (whisper.cpp:2926-3016);
+#   * every text step writes the codes of TWO equally scored candidates; which one wins is decided by the ordinary random part of
+#     the logits, which depends on the audio (cross-attention) and on the whole history (self-attention over the KV cache).
+#
+# Logits are therefore peaked (successor vs everything else: ~10), sequences vary from chunk to chunk, and a wrong KV cache or
+# cross-attention flips branch decisions.  The branch margins are Gaussian (std ~3): fixtures record the reference's top-2 gap at
+# every step, and the generator only keeps inputs whose gaps stay clear of the parity tolerance.
+SC_NC = 64                      # code dimensions: [0,16) segment code, [16,32) step code, [32,64) special-token code
+SC_SEG_LEN = (4, 3, 4, 2, 4, 3, 4, 4)
+SC_GAMMA_NOISE = 3.0
+# Calibration (tools/calibrate_script.py, stored in whisper_b200/script_calib.npz): a random network's outputs are ~95 % one constant
+# vector.  The scripted models subtract the measured constant from the encoder's ln_post output and from the decoder's final
+# LayerNorm output (noise dimensions) and amplify what is left — the part that depends on the audio, the position and the history.
+SC_CENTER = None                # mean of the decoder's final LayerNorm output at unit gain, [d]
+SC_GAIN = 1.0
+SC_ENC_CENTER = None            # mean of the encoder's ln_post output at unit gain, [d]
+SC_ENC_GAIN = 1.0
+SC_NOISE_LOGIT_RMS = 0.9
+SC_ENC_GAIN_CALIBRATED = 10.0
+
+
+def _hadamard(n):
+    h = np.array([[1.0]])
+    while h.shape[0] < n:
+        h = np.block([[h, h], [h, -h]])
+    return h
+
+
+SC_SPARSE = False               # "-sc1" models: only the first text token of segments 0, 3 and 6 is a branch (long whisper_full runs)
+
+
+def script_tokens(n_vocab: int):
+    """The active tokens of a scripted model and the successor table.  Returns (codes, succ):
+    codes: {token_id: unit-norm float64[64] code},  succ: {token_id: [successor ids]} (two entries = a branch)."""
+    sh = 1 if n_vocab == 51865 else 0
+    eot, sot, beg = 50256 + sh, 50257 + sh, 50363 + sh      # multilingual files shift the specials by one (whisper.cpp:575-583)
+    translate, transcribe = 50358, 50359
+    h16 = _hadamard(16) / 4.0
+    h32 = _hadamard(32) / np.sqrt(32.0)
+    codes, succ = {}, {}
+
+    def text_id(k, j, v):
+        return 1000 + 400 * k + 50 * j + 7 * v + 3 * k * j
+
+    def text_code(k, j, v):
+        c = np.zeros(SC_NC)
+        c[0:16] = h16[1 + k]
+        c[16:32] = h16[1 + 2 * j + v]
+        return c / np.sqrt(2.0)
+
+    def special_code(i):
+        c = np.zeros(SC_NC)
+        c[32:64] = h32[1 + i]
+        return c
+
+    ts_end = [beg + 100 * (k + 1) for k in range(8)]
+    ts_start = [t + 1 for t in ts_end[:7]]
+    init, init2 = beg, beg + 4
+    specials = [eot, sot, transcribe, translate, init, init2] + ts_end + ts_start
+    for i, t in enumerate(specials):
+        codes[t] = special_code(i)
+    for k in range(8):
+        for j in range(4):
+            for v in range(2):
+                codes[text_id(k, j, v)] = text_code(k, j, v)
+    assert len(set(codes)) == len(specials) + 64
+
+    def seg_first(k):
+        if SC_SPARSE and k not in (0, 3, 6):
+            return [text_id(k, 0, k & 1)]
+        return [text_id(k, 0, 0), text_id(k, 0, 1)]
+    for t in (sot, transcribe):
+        succ[t] = [init]
+    succ[translate] = [init2]
+    succ[init] = seg_first(0)
+    succ[init2] = seg_first(4)
+    succ[eot] = seg_first(0)          # never used by whisper_full (it stops at EOT); keeps fixed-length benchmark loops varied
+    for k in range(8):
+        for j in range(4):
+            for v in range(2):
+                if j >= SC_SEG_LEN[k] - 1:
+                    succ[text_id(k, j, v)] = [ts_end[k]]
+                elif SC_SPARSE:
+                    succ[text_id(k, j, v)] = [text_id(k, j + 1, v ^ (j & 1))]     # no branch: the variant follows from the segment's first token
+                else:
+                    succ[text_id(k, j, v)] = [text_id(k, j + 1, 0), text_id(k, j + 1, 1)]
+        succ[ts_end[k]] = [ts_start[k]] if k < 7 else [eot]
+        if k < 7:
+            succ[ts_start[k]] = seg_first(k + 1)
+    return codes, succ
+
+
+def _script_patch(name: str, ne, kind: str, data: np.ndarray, hp: "HParams") -> np.ndarray:
+    """Turn one freshly drawn random decoder tensor into its scripted form (see above).  `data` is flat, ne[0] fastest."""
+    if not name.startswith("decoder."):
+        # a random encoder collapses too: its output is ~95 % one constant vector.  Centre ln_post on the calibrated mean and
+        # amplify what is left, so that the cross-attention memories really depend on the audio and on the position
+        if name == "encoder.ln_post.weight":
+            return data * np.float32(SC_ENC_GAIN)
+        if name == "encoder.ln_post.bias" and SC_ENC_CENTER is not None:
+            return (-SC_ENC_GAIN * SC_ENC_CENTER).astype(np.float32)
+        return data
+    d, L = hp.n_text_state, hp.n_text_layer
+    # code amplitude in the embedding: it has to dominate the noise part of the residual stream, whose norm grows like a random walk
+    # over the 3 L sub-layers (~2 sqrt(d) for the 4-layer models)
+    ge = 3.0 * np.sqrt(d) * max(1.0, np.sqrt(L / 4.0))
+    if name == "decoder.token_embedding.weight":
+        rows = data.reshape(ne[1], ne[0])
+        rows[:, :SC_NC] = 0.0
+        codes, _ = script_tokens(hp.n_vocab)
+        for t, c in codes.items():
+            rows[t, :SC_NC] = (ge * np.sqrt(2.0) * c).astype(np.float32)
+        return rows.reshape(-1)
+    if name == "decoder.positional_embedding":
+        rows = data.reshape(ne[1], ne[0])
+        rows[:, :SC_NC] = 0.0
+        return rows.reshape(-1)
+    if name == "decoder.ln.weight":
+        data = data * np.float32(SC_GAMMA_NOISE * SC_GAIN)           # noise logits: rms ~3
+        data[:SC_NC] = np.float32(27.5 / (ge * np.sqrt(d)))   # code logits: successor ~25, same-segment runners-up ~10, everything else ~0
+        return data
+    if name == "decoder.ln.bias":
+        if SC_CENTER is not None:
+            data[SC_NC:] = (-SC_GAMMA_NOISE * SC_GAIN * SC_CENTER[SC_NC:]).astype(np.float32)
+        data[:SC_NC] = 0.0
+        return data
+    if not name.startswith("decoder.blocks."):
+        return data
+    il = int(name.split(".")[2])
+    leaf = name.split(".", 3)[3]
+    last = il == L - 1
+    if kind == "mat":
+        w = data.reshape(ne[1], ne[0])           # [out][in]
+        reads_stream = leaf in ("cross_attn.query.weight", "mlp.0.weight")     # self-attention reads the token codes too: history matters
+        writes_stream = leaf in ("attn.out.weight", "cross_attn.out.weight", "mlp.2.weight")
+        if reads_stream:
+            w[:, :SC_NC] = 0.0
+        if writes_stream:
+            w[:SC_NC, :] = 0.0
+        if last and leaf in ("mlp.0.weight", "mlp.2.weight"):
+            codes, succ = script_tokens(hp.n_vocab)
+            toks = sorted(codes)
+            kappa = 26.7 / np.sqrt(d)          # full match: kappa * ge sqrt(2) / sigma ~ 24 with sigma ~ 1.1 ge sqrt(2 / d), whatever ge is
+            for u, t in enumerate(toks):
+                if leaf == "mlp.0.weight":
+                    w[u, :] = 0.0
+                    w[u, :SC_NC] = (kappa * codes[t]).astype(np.float32)
+                else:
+                    target = np.zeros(SC_NC)
+                    for s_ in succ[t]:
+                        target += codes[s_]
+                    if len(succ[t]) == 2:      # both branch candidates share the segment code: count it once
+                        target[0:16] *= 0.5
+                    col = (ge * np.sqrt(2.0) / 3.0) * (target - codes[t])
+                    w[:, u] = 0.0
+                    w[:SC_NC, u] = col.astype(np.float32)
+        return w.reshape(-1)
+    if leaf in ("attn.out.bias", "cross_attn.out.bias", "mlp.2.bias"):
+        data[:SC_NC] = 0.0
+        return data
+    if last and leaf == "mlp.0.bias":
+        codes, _ = script_tokens(hp.n_vocab)
+        data[:len(codes)] = np.float32(-18.0)
+        return data
+    if leaf.endswith("_ln.weight"):
+        data[:SC_NC] = 1.0
+        return data
+    if leaf.endswith("_ln.bias"):
+        data[:SC_NC] = 0.0
+        return data
+    return data
+
+
+def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0, ts_boost: float = 1.0, eot_boost: float = 1.0, words=None, script: bool = False) -> HParams:
     """Write a synthetic ggml model file.  Matrices ~ N(0, 1/fan_in) stored f16; LN gamma = 1 + N(0, 0.01);
     biases N(0, 0.01); positional embeddings N(0, 0.01); the token embedding is scaled by
     `emb_scale` so that greedy decisions are not near-ties on random weights (SURVEY.md §7 "Parity definition")."""
@@ -178,6 +363,8 @@ def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0,
                 data = rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
             else:
                 data = rng.standard_normal(n, dtype=np.float32) * np.float32(0.01)
+            if script:
+                data = _script_patch(name, ne, kind, data, hp)
             nb = name.encode()
             f.write(struct.pack("<3i", len(ne), len(nb), 1 if is_f16 else 0))
             f.write(struct.pack("<%di" % len(ne), *ne))
@@ -187,13 +374,47 @@ def write_model(path: str, name_or_hp, seed: int = 1234, emb_scale: float = 3.0,
     return hp
 
 
+CALIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "script_calib.npz")
+
+
+def write_script_model(path: str, base: str, seed: int = 1234, stage: int = 2, calib: dict | None = None, sparse: bool = False):
+    """Write the scripted variant of model `base`.  stage 0: no centring (calibration pass 1), 1: encoder centred (pass 2),
+    2: final model — needs the calibration entries of (base, seed) in script_calib.npz (or `calib`)."""
+    global SC_CENTER, SC_GAIN, SC_ENC_CENTER, SC_ENC_GAIN, SC_SPARSE
+    if calib is None and stage > 0:
+        if not os.path.exists(CALIB_PATH):
+            raise RuntimeError("no %s: run tools/calibrate_script.py (needs oracle/_ref)" % CALIB_PATH)
+        z = np.load(CALIB_PATH)
+        key = "%s_%d" % (base, seed)
+        if key + "_enc" not in z:
+            raise RuntimeError("scripted model %s (seed %d) has no calibration entry: run tools/calibrate_script.py %s" % (base, seed, base))
+        calib = {"enc": z[key + "_enc"], "dec": z[key + "_dec"], "var": float(z[key + "_var"])}
+    SC_ENC_CENTER, SC_ENC_GAIN = (calib["enc"], SC_ENC_GAIN_CALIBRATED) if stage >= 1 else (None, 1.0)
+    if stage >= 2:
+        # gain such that the variable ("noise") part of the logits has rms ~SC_NOISE_LOGIT_RMS: branch margins of a few units against
+        # code margins of ~10.  noise logit rms = (emb_scale / sqrt(d)) * |variable part of z| * gamma
+        d = MODELS[base].n_text_state
+        SC_CENTER, SC_GAIN = calib["dec"], SC_NOISE_LOGIT_RMS * np.sqrt(d) / (3.0 * SC_GAMMA_NOISE * calib["var"])
+    else:
+        SC_CENTER, SC_GAIN = None, 1.0
+    SC_SPARSE = sparse
+    try:
+        return write_model(path, base, seed, script=True)
+    finally:
+        SC_CENTER, SC_GAIN, SC_ENC_CENTER, SC_ENC_GAIN, SC_SPARSE = None, 1.0, None, 1.0, False
+
+
 def model_path(name: str, seed: int = 1234, cache_dir: str | None = None) -> str:
     """Return (creating on first use) the cached synthetic model file for `name`."""
     cache_dir = cache_dir or os.environ.get("WSP_MODEL_CACHE", "/tmp/wsp_models")
     os.makedirs(cache_dir, exist_ok=True)
-    p = os.path.join(cache_dir, "ggml-%s-synth%d.bin" % (name, seed))
+    p = os.path.join(cache_dir, "ggml-%s-synth%d%s.bin" % (name, seed, "-r2" if name.endswith(("-sc", "-sc1")) else ""))
     if not os.path.exists(p):
-        if name.endswith("-ts"):
+        if name.endswith("-sc"):
+            write_script_model(p, name[:-3], seed)
+        elif name.endswith("-sc1"):
+            write_script_model(p, name[:-4], seed, sparse=True)
+        elif name.endswith("-ts"):
             write_model(p, name[:-3], seed, ts_boost=1.3, eot_boost=2.2)
         elif name.endswith("-words"):
             write_model(p, name[:-6], seed, words=tokenizer_test_words)
