@@ -1,0 +1,281 @@
+// whisper_b200_main — command-line transcriber over the COM-style surface of libwhisper_b200.so.
+//
+// Same role, option names and output formats as the reference's Examples/main (main.cpp:174-353, params.cpp, textWriter.cpp):
+//   loadModel -> createContext -> fullDefaultParams -> runFull -> getResults -> txt / srt / vtt next to the input file.
+// Media Foundation is replaced by a small RIFF/WAVE reader: 16-bit PCM or 32-bit float, any channel count (mixed down), resampled to
+// 16 kHz by linear interpolation when the file has another rate.  Options of the reference that need its GPU/MF back-ends
+// (-la/-gpu adapters, -di diarize, -owts karaoke script, -su speed-up) are accepted where harmless and rejected otherwise.
+#include "whisper_b200_com.h"
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+using namespace Whisper;
+
+namespace
+{
+	struct Params
+	{
+		int nThreads = 4, offsetMs = 0, durationMs = 0, maxContext = -1, maxLen = 0, device = 0;
+		float wordThold = 0.01f;
+		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false;
+		std::string language = "en", model = "models/ggml-base.en.bin", prompt;
+		std::vector<std::string> inputs;
+	};
+
+	void usage( const char* exe, const Params& p )
+	{
+		fprintf( stderr, "\nusage: %s [options] file0.wav file1.wav ...\n\noptions:\n", exe );
+		fprintf( stderr, "  -h,       --help          show this help message and exit\n" );
+		fprintf( stderr, "  -la,      --list-adapters list the CUDA devices and exit\n" );
+		fprintf( stderr, "  -gpu N,   --use-gpu N     [%-7d] CUDA device to use\n", p.device );
+		fprintf( stderr, "  -t N,     --threads N     [%-7d] reference thread count whose arithmetic is reproduced (sFullParams::cpuThreads)\n", p.nThreads );
+		fprintf( stderr, "  -ot N,    --offset-t N    [%-7d] time offset in milliseconds\n", p.offsetMs );
+		fprintf( stderr, "  -d  N,    --duration N    [%-7d] duration of audio to process in milliseconds\n", p.durationMs );
+		fprintf( stderr, "  -mc N,    --max-context N [%-7d] maximum number of text context tokens to store\n", p.maxContext );
+		fprintf( stderr, "  -ml N,    --max-len N     [%-7d] maximum segment length in characters\n", p.maxLen );
+		fprintf( stderr, "  -wt N,    --word-thold N  [%-7.2f] word timestamp probability threshold\n", p.wordThold );
+		fprintf( stderr, "  -tr,      --translate     translate from source language to english\n" );
+		fprintf( stderr, "  -otxt,    --output-txt    output result in a text file\n" );
+		fprintf( stderr, "  -ovtt,    --output-vtt    output result in a vtt file\n" );
+		fprintf( stderr, "  -osrt,    --output-srt    output result in a srt file\n" );
+		fprintf( stderr, "  -ps,      --print-special print special tokens\n" );
+		fprintf( stderr, "  -nt,      --no-timestamps do not print timestamps\n" );
+		fprintf( stderr, "  -l LANG,  --language LANG [%-7s] spoken language (\"auto\" = detect)\n", p.language.c_str() );
+		fprintf( stderr, "  -m FNAME, --model FNAME   [%-7s] model path\n", p.model.c_str() );
+		fprintf( stderr, "  -f FNAME, --file FNAME    path of the input audio file (16-bit or float WAV)\n" );
+		fprintf( stderr, "  --prompt TEXT             initial prompt for the model\n\n" );
+	}
+
+	void WSPCALL listAdapter( const wchar_t* name, void* ) { printf( "\"%ls\"\n", name ); }
+
+	bool parse( int argc, char** argv, Params& p )
+	{
+		for( int i = 1; i < argc; i++ )
+		{
+			const std::string a = argv[ i ];
+			auto next = [ & ]() -> const char* { if( i + 1 >= argc ) { fprintf( stderr, "error: %s needs a value\n", a.c_str() ); exit( 1 ); } return argv[ ++i ]; };
+			if( a.empty() || a[ 0 ] != '-' ) { p.inputs.push_back( a ); continue; }
+			if( a == "-h" || a == "--help" ) { usage( argv[ 0 ], p ); return false; }
+			if( a == "-la" || a == "--list-adapters" ) { listGPUs( &listAdapter, nullptr ); return false; }
+			else if( a == "-t" || a == "--threads" ) p.nThreads = atoi( next() );
+			else if( a == "-ot" || a == "--offset-t" ) p.offsetMs = atoi( next() );
+			else if( a == "-d" || a == "--duration" ) p.durationMs = atoi( next() );
+			else if( a == "-mc" || a == "--max-context" ) p.maxContext = atoi( next() );
+			else if( a == "-ml" || a == "--max-len" ) p.maxLen = atoi( next() );
+			else if( a == "-wt" || a == "--word-thold" ) p.wordThold = (float)atof( next() );
+			else if( a == "-tr" || a == "--translate" ) p.translate = true;
+			else if( a == "-otxt" || a == "--output-txt" ) p.outTxt = true;
+			else if( a == "-ovtt" || a == "--output-vtt" ) p.outVtt = true;
+			else if( a == "-osrt" || a == "--output-srt" ) p.outSrt = true;
+			else if( a == "-ps" || a == "--print-special" ) p.printSpecial = true;
+			else if( a == "-nt" || a == "--no-timestamps" ) p.noTimestamps = true;
+			else if( a == "-nc" || a == "--no-colors" ) {}
+			else if( a == "-l" || a == "--language" ) p.language = next();
+			else if( a == "-m" || a == "--model" ) p.model = next();
+			else if( a == "-f" || a == "--file" ) p.inputs.push_back( next() );
+			else if( a == "-gpu" || a == "--use-gpu" ) p.device = atoi( next() );
+			else if( a == "--prompt" ) p.prompt = next();
+			else if( a == "-p" || a == "--processors" || a == "-on" || a == "--offset-n" ) next();
+			else { fprintf( stderr, "error: unknown or unsupported argument: %s\n", a.c_str() ); usage( argv[ 0 ], p ); return false; }
+		}
+		return true;
+	}
+
+	// ---- RIFF/WAVE -> 16 kHz mono f32 -------------------------------------------------------------------------------
+	bool readWav( const std::string& path, std::vector<float>& mono16k )
+	{
+		FILE* f = fopen( path.c_str(), "rb" );
+		if( !f ) { fprintf( stderr, "error: cannot open %s\n", path.c_str() ); return false; }
+		std::vector<uint8_t> buf;
+		fseek( f, 0, SEEK_END ); const long sz = ftell( f ); fseek( f, 0, SEEK_SET );
+		buf.resize( sz > 0 ? (size_t)sz : 0 );
+		const bool ok = sz > 12 && fread( buf.data(), 1, buf.size(), f ) == buf.size();
+		fclose( f );
+		if( !ok || memcmp( buf.data(), "RIFF", 4 ) != 0 || memcmp( buf.data() + 8, "WAVE", 4 ) != 0 ) { fprintf( stderr, "error: %s is not a RIFF/WAVE file\n", path.c_str() ); return false; }
+		auto u16 = [ & ]( size_t o ) { return (uint32_t)buf[ o ] | ( (uint32_t)buf[ o + 1 ] << 8 ); };
+		auto u32 = [ & ]( size_t o ) { return u16( o ) | ( u16( o + 2 ) << 16 ); };
+		uint32_t format = 0, channels = 0, rate = 0, bits = 0;
+		size_t dataOff = 0, dataLen = 0;
+		for( size_t o = 12; o + 8 <= buf.size(); )
+		{
+			const uint32_t len = u32( o + 4 );
+			if( memcmp( buf.data() + o, "fmt ", 4 ) == 0 && len >= 16 )
+			{
+				format = u16( o + 8 ); channels = u16( o + 10 ); rate = u32( o + 12 ); bits = u16( o + 22 );
+				if( format == 0xFFFE && len >= 26 ) format = u16( o + 32 );   // WAVE_FORMAT_EXTENSIBLE: the sub-format's first word
+			}
+			else if( memcmp( buf.data() + o, "data", 4 ) == 0 ) { dataOff = o + 8; dataLen = std::min<size_t>( len, buf.size() - dataOff ); break; }
+			o += 8 + (size_t)len + ( len & 1 );
+		}
+		if( !dataOff || !channels || !rate || !( ( format == 1 && bits == 16 ) || ( format == 3 && bits == 32 ) ) )
+		{
+			fprintf( stderr, "error: %s: only 16-bit PCM and 32-bit float WAV files are supported\n", path.c_str() );
+			return false;
+		}
+		const size_t frame = (size_t)channels * bits / 8, n = dataLen / frame;
+		std::vector<float> mono( n );
+		for( size_t i = 0; i < n; i++ )
+		{
+			float acc = 0;
+			for( uint32_t c = 0; c < channels; c++ )
+			{
+				const uint8_t* p = buf.data() + dataOff + i * frame + (size_t)c * bits / 8;
+				if( bits == 16 ) acc += (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
+				else { float v; memcpy( &v, p, 4 ); acc += v; }
+			}
+			mono[ i ] = acc / (float)channels;
+		}
+		if( rate == 16000 ) { mono16k.swap( mono ); return true; }
+		const size_t m = (size_t)( (double)n * 16000.0 / rate );
+		mono16k.resize( m );
+		for( size_t i = 0; i < m; i++ )
+		{
+			const double x = (double)i * rate / 16000.0;
+			const size_t i0 = (size_t)x, i1 = std::min( i0 + 1, n - 1 );
+			const float t = (float)( x - (double)i0 );
+			mono16k[ i ] = mono[ i0 ] * ( 1.0f - t ) + mono[ i1 ] * t;
+		}
+		return true;
+	}
+
+	// ---- writers: txt / srt / vtt as Examples/main/textWriter.cpp produces them (UTF-8 BOM, CRLF, leading blanks of a segment dropped)
+	std::string fmtTime( uint64_t ticks, bool comma )
+	{
+		const uint64_t ms = ticks / 10000;
+		char b[ 64 ];
+		snprintf( b, sizeof( b ), "%02d:%02d:%02d%c%03d", (int)( ms / 3600000 ), (int)( ms / 60000 % 60 ), (int)( ms / 1000 % 60 ), comma ? ',' : '.', (int)( ms % 1000 ) );
+		return b;
+	}
+	const char* skipBlank( const char* s ) { while( *s == ' ' || *s == '\t' ) s++; return s; }
+	std::string replaceExt( const std::string& path, const char* ext )
+	{
+		const size_t slash = path.find_last_of( "/\\" ), dot = path.find_last_of( '.' );
+		return ( dot != std::string::npos && ( slash == std::string::npos || dot > slash ) ? path.substr( 0, dot ) : path ) + ext;
+	}
+	enum class Fmt { Txt, Srt, Vtt };
+	bool writeResult( iContext* ctx, const std::string& audioPath, Fmt fmt, bool timestamps )
+	{
+		iTranscribeResult* res = nullptr;
+		if( FAILED( ctx->getResults( (eResultFlags)( (uint32_t)eResultFlags::Timestamps | (uint32_t)eResultFlags::Tokens ), &res ) ) ) return false;
+		sTranscribeLength len{};
+		res->getSize( len );
+		const sSegment* segs = res->getSegments();
+		const std::string path = replaceExt( audioPath, fmt == Fmt::Txt ? ".txt" : fmt == Fmt::Srt ? ".srt" : ".vtt" );
+		FILE* f = fopen( path.c_str(), "wb" );
+		if( !f ) { res->Release(); return false; }
+		fputs( "\xEF\xBB\xBF", f );
+		if( fmt == Fmt::Vtt ) fputs( "WEBVTT\r\n\r\n", f );
+		for( uint32_t i = 0; i < len.countSegments; i++ )
+		{
+			const sSegment& s = segs[ i ];
+			const std::string t0 = fmtTime( s.time.begin.ticks, fmt == Fmt::Srt ), t1 = fmtTime( s.time.end.ticks, fmt == Fmt::Srt );
+			if( fmt == Fmt::Txt )
+			{
+				if( timestamps ) fprintf( f, "[%s --> %s]  ", t0.c_str(), t1.c_str() );
+				fprintf( f, "%s\r\n", skipBlank( s.text ) );
+			}
+			else
+			{
+				if( fmt == Fmt::Srt ) fprintf( f, "%u\r\n", i + 1 );
+				fprintf( f, "%s --> %s\r\n%s\r\n\r\n", t0.c_str(), t1.c_str(), skipBlank( s.text ) );
+			}
+		}
+		fclose( f );
+		res->Release();
+		return true;
+	}
+
+	struct SegmentPrinter { bool noTimestamps; uint32_t printed = 0; };
+	HRESULT onNewSegment( iContext* ctx, uint32_t nNew, void* pv ) noexcept
+	{
+		SegmentPrinter* sp = static_cast<SegmentPrinter*>( pv );
+		iTranscribeResult* res = nullptr;
+		if( FAILED( ctx->getResults( eResultFlags::Timestamps, &res ) ) ) return S_OK;
+		sTranscribeLength len{};
+		res->getSize( len );
+		const sSegment* segs = res->getSegments();
+		for( uint32_t i = len.countSegments - std::min( nNew, len.countSegments ); i < len.countSegments; i++ )
+		{
+			if( sp->noTimestamps ) printf( "%s", segs[ i ].text );
+			else printf( "[%s --> %s]  %s\n", fmtTime( segs[ i ].time.begin.ticks, false ).c_str(), fmtTime( segs[ i ].time.end.ticks, false ).c_str(), segs[ i ].text );
+		}
+		fflush( stdout );
+		return S_OK;
+	}
+	void WSPCALL collectPrompt( const int* tokens, int n, void* pv ) { static_cast<std::vector<int>*>( pv )->assign( tokens, tokens + n ); }
+}
+
+int main( int argc, char** argv )
+{
+	sLoggerSetup ls;
+	ls.flags = eLoggerFlags::UseStandardError;
+	ls.level = eLogLevel::Info;
+	setupLogger( ls );
+	Params params;
+	if( !parse( argc, argv, params ) ) return 1;
+	if( params.inputs.empty() ) { fprintf( stderr, "error: no input files specified\n" ); usage( argv[ 0 ], params ); return 2; }
+	if( params.language != "auto" && findLanguageKeyA( params.language.c_str() ) == UINT32_MAX ) { fprintf( stderr, "error: unknown language '%s'\n", params.language.c_str() ); return 3; }
+
+	std::wstring wmodel( params.model.begin(), params.model.end() );
+	const std::wstring adapter = std::to_wstring( params.device );
+	sModelSetup setup;
+	setup.impl = eModelImplementation::B200;
+	setup.adapter = adapter.c_str();
+	iModel* model = nullptr;
+	HRESULT hr = loadModel( wmodel.c_str(), setup, nullptr, &model );
+	if( FAILED( hr ) ) { fprintf( stderr, "failed to load the model: 0x%08x\n", (unsigned)hr ); return 4; }
+	std::vector<int> prompt;
+	if( !params.prompt.empty() && FAILED( model->tokenize( params.prompt.c_str(), &collectPrompt, &prompt ) ) ) { fprintf( stderr, "failed to tokenize the initial prompt\n" ); return 5; }
+	iContext* context = nullptr;
+	hr = model->createContext( &context );
+	if( FAILED( hr ) ) { fprintf( stderr, "failed to initialize whisper context: 0x%08x\n", (unsigned)hr ); return 6; }
+
+	for( const std::string& fname : params.inputs )
+	{
+		if( model->isMultilingual() == S_FALSE && ( params.language != "en" || params.translate ) )
+		{
+			params.language = "en";
+			params.translate = false;
+			fprintf( stderr, "main: WARNING: model is not multilingual, ignoring language and translation options\n" );
+		}
+		std::vector<float> pcm;
+		if( !readWav( fname, pcm ) ) return 8;
+		iAudioBuffer* buffer = nullptr;
+		if( FAILED( createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer ) ) ) return 9;
+
+		sFullParams wp;
+		context->fullDefaultParams( eSamplingStrategy::Greedy, &wp );
+		uint32_t flags = (uint32_t)eFullParamsFlags::NoContext;   // several input files are independent clips (main.cpp:262-263)
+		if( !params.noTimestamps ) flags |= (uint32_t)eFullParamsFlags::PrintTimestamps;
+		if( params.printSpecial ) flags |= (uint32_t)eFullParamsFlags::PrintSpecial;
+		if( params.translate ) flags |= (uint32_t)eFullParamsFlags::Translate;
+		if( params.maxLen > 0 ) flags |= (uint32_t)eFullParamsFlags::TokenTimestamps;
+		wp.flags = (eFullParamsFlags)flags;
+		wp.language = params.language == "auto" ? makeLanguageKey( "auto" ) : makeLanguageKey( params.language.c_str() );
+		wp.cpuThreads = params.nThreads;
+		if( params.maxContext >= 0 ) wp.n_max_text_ctx = params.maxContext;
+		wp.offset_ms = params.offsetMs;
+		wp.duration_ms = params.durationMs;
+		wp.thold_pt = params.wordThold;
+		wp.max_len = params.maxLen;
+		if( !prompt.empty() ) { wp.prompt_tokens = prompt.data(); wp.prompt_n_tokens = (int)prompt.size(); }
+		SegmentPrinter printer{ params.noTimestamps };
+		wp.new_segment_callback = &onNewSegment;
+		wp.new_segment_callback_user_data = &printer;
+		hr = context->runFull( wp, buffer );
+		buffer->Release();
+		if( FAILED( hr ) ) { fprintf( stderr, "Unable to process audio: 0x%08x\n", (unsigned)hr ); return 10; }
+		if( params.noTimestamps ) printf( "\n" );
+		if( params.outTxt && !writeResult( context, fname, Fmt::Txt, !params.noTimestamps ) ) fprintf( stderr, "Unable to produce the text file\n" );
+		if( params.outSrt && !writeResult( context, fname, Fmt::Srt, true ) ) fprintf( stderr, "Unable to produce the srt file\n" );
+		if( params.outVtt && !writeResult( context, fname, Fmt::Vtt, true ) ) fprintf( stderr, "Unable to produce the vtt file\n" );
+	}
+	context->timingsPrint();
+	context->Release();
+	model->Release();
+	return 0;
+}

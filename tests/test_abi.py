@@ -98,3 +98,50 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(capi.WspError) as e:
         capi.test_gemm(a, a)
     assert e.value.status == -5
+
+
+def _first_tensor_header(data: bytes):
+    """byte offset of the first tensor record: magic, 11 hparams, filters, vocabulary (whisper.cpp:451-607)"""
+    import struct
+    pos = 4 + 44
+    n_mel, n_fft = struct.unpack_from("<2i", data, pos)
+    pos += 8 + n_mel * n_fft * 4
+    (n_words,) = struct.unpack_from("<i", data, pos)
+    pos += 4
+    for _ in range(n_words):
+        (ln,) = struct.unpack_from("<I", data, pos)
+        pos += 4 + ln
+    return pos
+
+
+def test_corrupt_tensor_headers_are_rejected(tmp_path):
+    """a negative dimension must not turn into a huge byte count that wraps the cursor; unknown tensor types are refused."""
+    import struct
+    data = bytearray(open(synth.model_path("micro.en"), "rb").read())
+    pos = _first_tensor_header(data)
+    n_dims, name_len, ftype = struct.unpack_from("<3i", data, pos)
+    assert 1 <= n_dims <= 3 and 0 < name_len < 64 and ftype in (0, 1)
+    for patch, what in (((pos + 12, struct.pack("<i", -5)), "negative ne[0]"), ((pos + 12, struct.pack("<i", 0)), "zero ne[0]"),
+                        ((pos + 8, struct.pack("<i", 7)), "ftype 7")):
+        bad = bytearray(data)
+        bad[patch[0]:patch[0] + 4] = patch[1]
+        p = tmp_path / "bad.bin"
+        p.write_bytes(bytes(bad))
+        with pytest.raises(capi.WspError) as e:
+            capi.Model(str(p))
+        assert e.value.status == -4, what  # WSP_E_FORMAT
+
+
+def test_inconsistent_meta_blob_is_rejected():
+    """A meta blob is not trusted: tensor offsets / sizes must stay inside the image it describes."""
+    import struct
+    m = capi.Model(synth.model_path("micro.en"))
+    blob = bytearray(m.meta())
+    size = struct.unpack_from("<Q", blob, len(blob) - 8)[0]      # imageSize is the last field
+    assert size == os.path.getsize(synth.model_path("micro.en"))
+    shrunk = bytearray(blob)
+    shrunk[len(blob) - 8:] = struct.pack("<Q", size // 2)        # now most tensors end past the image
+    with pytest.raises(capi.WspError) as e:
+        capi.Model.from_meta(bytes(shrunk))
+    assert e.value.status == -4
+    m.close()

@@ -126,7 +126,7 @@ def test_language_auto_detect_matches_reference():
     c = capi.Context(e, 1)
     try:
         for i, ch in enumerate(g["chunks"].tolist()):
-            c.pcm_to_mel(0, synth.synth_pcm(ch, 320000))
+            c.pcm_to_mel(0, synth.synth_pcm(ch, 480000))
             lid, probs = c.detect_language(0, g["lang_probs"].shape[1])
             assert lid == int(g["lang_id"][i])
             assert np.abs(probs - g["lang_probs"][i]).max() < 2e-4

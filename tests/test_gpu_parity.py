@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import CASES, LOGIT_STEP, MEL_STEP, N_STEPS, ROW_STEP
+from tests.golden.make_golden import CASES, LOGIT_STEP, MEL_STEP, N_STEPS, ROW_STEP, case_padded
 from whisper_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
@@ -81,11 +81,13 @@ def test_encoder_trace_points(name):
     c.set_encoder_layers(-1)
     c.encode(1, [off])
     assert np.abs(c.get_tensor("enc.x").reshape(T, d)[::ROW_STEP] - g["enc_layers"]).max() < TOL_ENC
-    assert np.abs(c.get_tensor("encode-out").reshape(T, d)[::ROW_STEP] - g["encode_out"]).max() < TOL_ENC
+    # ln_post of the scripted models amplifies by SC_ENC_GAIN_CALIBRATED (synth.py): encode-out and the cross-KV carry that factor
+    gain = synth.SC_ENC_GAIN_CALIBRATED
+    assert np.abs(c.get_tensor("encode-out").reshape(T, d)[::ROW_STEP] - g["encode_out"]).max() < TOL_ENC * gain
     H, Ld = m.n_audio_head, m.n_text_layer
     for nm in ("cross_k", "cross_v"):
         got = c.get_tensor(nm).reshape(Ld, H, T, 64).transpose(0, 2, 1, 3).reshape(Ld, T, d)
-        assert np.abs(got[:, ::ROW_STEP] - g[nm].astype(np.float32)).max() < TOL_KV
+        assert np.abs(got[:, ::ROW_STEP] - g[nm].astype(np.float32)).max() < TOL_KV * gain
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -102,22 +104,27 @@ def test_decoder_logits_teacher_forced(name, threads):
     idx = np.arange(0, m.n_vocab, LOGIT_STEP)
     c.decode([prompt], 0, 1, capi.DECODE_ALL_LOGITS)
     lg = c.logits(len(prompt))
-    assert np.abs(lg[:, idx] - g["t%d_prompt_logits" % threads]).max() < TOL_LOGIT
-    assert np.abs(lg.max(-1) - g["t%d_prompt_logits_max" % threads]).max() < TOL_LOGIT
+    # logits of rms ~3 in every regular case; the zero-padded case runs at rms ~25 (see make_golden.CASES): the tolerance scales with it
+    tol = TOL_LOGIT * max(1.0, float(g["t%d_prompt_logits" % threads].std()) / 3.0)
+    assert np.abs(lg[:, idx] - g["t%d_prompt_logits" % threads]).max() < tol
+    assert np.abs(lg.max(-1) - g["t%d_prompt_logits_max" % threads]).max() < tol
     pr = c.probs(len(prompt))
     assert np.allclose(pr.sum(-1), 1.0, atol=1e-4)
     toks = g["t%d_tokens" % threads]
     s = c.decode([prompt], 0, 1, capi.DECODE_FORCE_TIMESTAMP | capi.DECODE_INITIAL)[0]
-    assert s["id"] == toks[0] and s["tid"] == g["t%d_tids" % threads][0]
-    assert abs(s["p"] - g["t%d_token_p" % threads][0]) < 1e-3
+    pinned = not case_padded(name)     # the zero-padded case pins logits only: its decisions are not protected by GAP_SAFE
+    if pinned:
+        assert s["id"] == toks[0] and s["tid"] == g["t%d_tids" % threads][0]
+        assert abs(s["p"] - g["t%d_token_p" % threads][0]) < 1e-3
     n_past = len(prompt)
     for i in range(1, N_STEPS):
         s = c.decode([[int(toks[i - 1])]], n_past, 1, 0)[0]
         n_past += 1
         lg = c.logits(1)
-        assert np.abs(lg[0, idx] - g["t%d_step_logits" % threads][i - 1]).max() < TOL_LOGIT, "step %d" % i
-        assert s["id"] == toks[i], "step %d" % i
-        assert abs(s["p"] - g["t%d_token_p" % threads][i]) < 5e-3
+        assert np.abs(lg[0, idx] - g["t%d_step_logits" % threads][i - 1]).max() < tol, "step %d" % i
+        if pinned:
+            assert s["id"] == toks[i], "step %d" % i
+            assert abs(s["p"] - g["t%d_token_p" % threads][i]) < 5e-3
     c.set_reference_threads(4)
 
 
@@ -130,6 +137,8 @@ def test_greedy_tokens_free_running(name, threads, graph):
     model, _, n, off = CASES[name]
     if off != 0:
         pytest.skip("run_chunks always encodes the window at offset 0")
+    if case_padded(name):
+        pytest.skip("zero-padded window: decisions are not pinned (make_golden.CASES)")
     m, e, c = open_model(model)
     g = golden(name)
     chunk = int(g["chunk"])
@@ -175,7 +184,7 @@ def test_live_reference_when_prebuilt():
     ck, cv = o.cross_kv()
     d, T, H, L = m.n_audio_state, m.n_audio_ctx, m.n_audio_head, m.n_text_layer
     got = c.get_tensor("cross_k").reshape(L, H, T, 64).transpose(0, 2, 1, 3).reshape(L, T, d)
-    assert np.abs(got - ck).max() < TOL_KV
+    assert np.abs(got - ck).max() < TOL_KV * synth.SC_ENC_GAIN_CALIBRATED
     prompt = m.prompt_init()
     ref_s, ref_toks, _ = o.bench_chunk(pcm, prompt, 20)
     toks, _ = c.run_chunks([pcm], prompt, 20)

@@ -4,9 +4,11 @@
 // (Whisper/ML/Context.ops.cpp:194-227) and the CPU oracle's ggml_compute_forward_flash_attn_f16 (Whisper/source/ggml.c:5912-6097):
 //   S = (K q) / sqrt(64)  (f16 x f16 -> f32),  P = softmax(S),  P rounded to f16,  O = V^T P  (f16 x f16 -> f32).
 // Here: one CTA = 128 queries of one (chunk, head); K/V^T tiles of 128 keys arrive by TMA; S = Q K^T and O_tile = P V are
-// tcgen05.mma with accumulators in TMEM; the online softmax runs one query row per thread (no shuffles) and the running
-// output lives in registers (rescaled per tile), so TMEM is never stored to.  Two CTAs co-reside per SM (80 KB smem, 256
-// TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// tcgen05.mma with accumulators in TMEM; the online softmax runs one query row per thread (no shuffles): the whole 128-wide score row
+// is pulled into registers with four TMEM loads in flight and handled in ONE pass; the running output lives in registers (rescaled
+// per tile), so TMEM is never stored to.  The scores of tile j+1 are issued right behind P*V of tile j, so they are ready before the
+// threads come back from reading O.  Two CTAs co-reside per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax also
+// overlaps the other's MMAs.
 //
 // Rounding points kept from the oracle: Q, K, V and P are f16, all accumulation is f32.  Deliberate difference: exp is
 // exp2f (not the oracle's f16 exp LUT, ggml.c:6065-6067) and P is rounded before the 1/sum normalisation (the oracle rounds after, :6082).
@@ -109,27 +111,29 @@ namespace attn
 		const int r = tid;                                          // my query row inside the tile
 		const float c = p.scale_log2;
 
+		// first S tile; every later one is issued right behind the previous tile's P*V (see below)
+		if( tid == 0 )
+		{
+			ptx::mbar_wait( bar_q, 0 );
+			ptx::mbar_wait( bar_k, 0 );
+			ptx::tc_fence_after();
+			const uint64_t da = ptx::umma_desc_sw128( ptx::smem_u32( sQ ) );
+			const uint64_t db = ptx::umma_desc_sw128( ptx::smem_u32( sK ) );
+#pragma unroll
+			for( int k = 0; k < HD / 16; k++ )
+				ptx::umma_f16( tmem_S, da + (uint64_t)( k * 2 ), db + (uint64_t)( k * 2 ), idescS, k != 0 ? 1u : 0u );
+			ptx::umma_commit( bar_s );
+		}
+		__syncwarp();
+
 		for( int j = 0; j < nkv; j++ )
 		{
 			const uint32_t ph = (uint32_t)( j & 1 );
-			if( tid == 0 )
-			{
-				if( j == 0 ) ptx::mbar_wait( bar_q, 0 );
-				ptx::mbar_wait( bar_k, ph );
-				ptx::tc_fence_after();
-				const uint64_t da = ptx::umma_desc_sw128( ptx::smem_u32( sQ ) );
-				const uint64_t db = ptx::umma_desc_sw128( ptx::smem_u32( sK ) );
-#pragma unroll
-				for( int k = 0; k < HD / 16; k++ )
-					ptx::umma_f16( tmem_S, da + (uint64_t)( k * 2 ), db + (uint64_t)( k * 2 ), idescS, k != 0 ? 1u : 0u );
-				ptx::umma_commit( bar_s );
-			}
-			__syncwarp();
 			ptx::mbar_wait( bar_s, ph );
 			ptx::tc_fence_after();
 			if( tid == 0 && j + 1 < nkv )
 			{
-				// K tile consumed: prefetch the next one behind this tile's softmax
+				// K tile consumed: fetch the next one behind this tile's softmax
 				ptx::mbar_expect_tx( bar_k, SK_BYTES );
 				ptx::tma_load_2d( sK, &mapK, bar_k, 0, bh * p.T + ( j + 1 ) * TK );
 			}
@@ -137,74 +141,53 @@ namespace attn
 
 			const int kv_base = j * TK;
 			const int nvalid = p.T - kv_base;   // columns >= nvalid are padding / the next head's rows
+			const bool fullTile = nvalid >= TK; // only the last tile of a head has padding columns
 
-			// pass 1: row maximum (full tiles take the predicate-free path; only the last tile of a head has padding columns)
-			const bool fullTile = nvalid >= TK;
+			// the whole score row of this thread's query in registers: four TMEM loads in flight, ONE wait, one pass
+			// (round 1 read the row twice, 32 columns at a time with a wait each: TMEM latency x 8 on the critical path of every tile)
+			uint32_t sc[ TK ];
+#pragma unroll
+			for( int ch = 0; ch < TK / 32; ch++ ) ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), sc + ch * 32 );
+			ptx::tmem_ld_wait();
 			float mx = m_run;
-#pragma unroll 1
-			for( int ch = 0; ch < TK / 32; ch++ )
+			if( fullTile )
 			{
-				uint32_t rg[ 32 ];
-				ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), rg );
-				ptx::tmem_ld_wait();
-				if( fullTile )
-				{
 #pragma unroll
-					for( int i = 0; i < 32; i += 2 )
-						mx = max3( mx, __uint_as_float( rg[ i ] ), __uint_as_float( rg[ i + 1 ] ) );
-				}
-				else
-				{
+				for( int i = 0; i < TK; i += 2 ) mx = max3( mx, __uint_as_float( sc[ i ] ), __uint_as_float( sc[ i + 1 ] ) );
+			}
+			else
+			{
 #pragma unroll
-					for( int i = 0; i < 32; i++ )
-					{
-						const float s = __uint_as_float( rg[ i ] );
-						if( ch * 32 + i < nvalid ) mx = fmaxf( mx, s );
-					}
-				}
+				for( int i = 0; i < TK; i++ )
+					if( i < nvalid ) mx = fmaxf( mx, __uint_as_float( sc[ i ] ) );
 			}
 			const float alpha = m_run == -INFINITY ? 0.0f : ex2Approx( ( m_run - mx ) * c );   // first tile: nothing to rescale
 			m_run = mx;
 			const float nmc = -mx * c;
 
-			// pass 2: probabilities -> f16 -> swizzled smem (A operand of P*V)
+			// probabilities -> f16 -> swizzled smem (A operand of P*V)
 			float lsum = 0.0f;
-#pragma unroll 1
+#pragma unroll
 			for( int ch = 0; ch < TK / 32; ch++ )
 			{
-				uint32_t rg[ 32 ];
-				ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), rg );
-				ptx::tmem_ld_wait();
-				float pv[ 32 ];
-				if( fullTile )
-				{
-#pragma unroll
-					for( int i = 0; i < 32; i++ )
-					{
-						const float e = ex2Approx( fmaf( __uint_as_float( rg[ i ] ), c, nmc ) );
-						pv[ i ] = e;
-						lsum += e;
-					}
-				}
-				else
-				{
-#pragma unroll
-					for( int i = 0; i < 32; i++ )
-					{
-						const float e = ( ch * 32 + i < nvalid ) ? ex2Approx( fmaf( __uint_as_float( rg[ i ] ), c, nmc ) ) : 0.0f;
-						pv[ i ] = e;
-						lsum += e;
-					}
-				}
 				uint8_t* sub = sP + ( ch >> 1 ) * ( SP_BYTES / 2 ) + r * 128;
 #pragma unroll
 				for( int g = 0; g < 4; g++ )
 				{
+					float e[ 8 ];
+#pragma unroll
+					for( int i = 0; i < 8; i++ )
+					{
+						const int col = ch * 32 + g * 8 + i;
+						const float v = ex2Approx( fmaf( __uint_as_float( sc[ col ] ), c, nmc ) );
+						e[ i ] = ( fullTile || col < nvalid ) ? v : 0.0f;
+						lsum += e[ i ];
+					}
 					const int chunk16 = ( ( ch & 1 ) * 4 + g ) ^ ( r & 7 );
-					__half2 h0 = __floats2half2_rn( pv[ g * 8 + 0 ], pv[ g * 8 + 1 ] );
-					__half2 h1 = __floats2half2_rn( pv[ g * 8 + 2 ], pv[ g * 8 + 3 ] );
-					__half2 h2 = __floats2half2_rn( pv[ g * 8 + 4 ], pv[ g * 8 + 5 ] );
-					__half2 h3 = __floats2half2_rn( pv[ g * 8 + 6 ], pv[ g * 8 + 7 ] );
+					__half2 h0 = __floats2half2_rn( e[ 0 ], e[ 1 ] );
+					__half2 h1 = __floats2half2_rn( e[ 2 ], e[ 3 ] );
+					__half2 h2 = __floats2half2_rn( e[ 4 ], e[ 5 ] );
+					__half2 h3 = __floats2half2_rn( e[ 6 ], e[ 7 ] );
 					uint4 u;
 					u.x = *reinterpret_cast<uint32_t*>( &h0 );
 					u.y = *reinterpret_cast<uint32_t*>( &h1 );
@@ -217,7 +200,7 @@ namespace attn
 
 			ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
 			ptx::tc_fence_before();
-			__syncthreads();
+			__syncthreads();            // P complete, and every thread has its S row in registers: the S columns are free again
 
 			if( tid == 0 )
 			{
@@ -232,6 +215,19 @@ namespace attn
 					ptx::umma_f16( tmem_O, da, db, idescO, k != 0 ? 1u : 0u );
 				}
 				ptx::umma_commit( bar_o );
+				if( j + 1 < nkv )
+				{
+					// the NEXT tile's scores right behind this P*V: the tensor core computes them while the threads read O back and
+					// rescale, so no tile waits for its own Q*K^T any more
+					ptx::mbar_wait( bar_k, ph ^ 1u );
+					ptx::tc_fence_after();
+					const uint64_t dq = ptx::umma_desc_sw128( ptx::smem_u32( sQ ) );
+					const uint64_t dk = ptx::umma_desc_sw128( ptx::smem_u32( sK ) );
+#pragma unroll
+					for( int k = 0; k < HD / 16; k++ )
+						ptx::umma_f16( tmem_S, dq + (uint64_t)( k * 2 ), dk + (uint64_t)( k * 2 ), idescS, k != 0 ? 1u : 0u );
+					ptx::umma_commit( bar_s );
+				}
 			}
 			__syncwarp();
 			ptx::mbar_wait( bar_o, ph );
@@ -244,15 +240,13 @@ namespace attn
 			}
 			__syncwarp();
 
-#pragma unroll
-			for( int ch = 0; ch < HD / 32; ch++ )
 			{
-				uint32_t rg[ 32 ];
-				ptx::tmem_ld_32x32( tmem_O + lane_base + (uint32_t)( ch * 32 ), rg );
+				uint32_t rg[ HD ];
+				ptx::tmem_ld_32x32( tmem_O + lane_base, rg );
+				ptx::tmem_ld_32x32( tmem_O + lane_base + 32u, rg + 32 );
 				ptx::tmem_ld_wait();
 #pragma unroll
-				for( int i = 0; i < 32; i++ )
-					o_acc[ ch * 32 + i ] = o_acc[ ch * 32 + i ] * alpha + __uint_as_float( rg[ i ] );
+				for( int i = 0; i < HD; i++ ) o_acc[ i ] = o_acc[ i ] * alpha + __uint_as_float( rg[ i ] );
 			}
 			ptx::tc_fence_before();
 		}

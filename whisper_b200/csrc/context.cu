@@ -533,6 +533,8 @@ namespace wsp
 		if( devTokens && nTokens != 1 ) return fail( WSP_E_INVALIDARG, "DEVICE_TOKENS implies n_tokens == 1" );
 		if( !devTokens && !tokensHost ) return fail( WSP_E_POINTER, "tokens" );
 		if( !devTokens && ( nPast < 0 || nPast + nTokens > hp.n_text_ctx ) ) return fail( WSP_E_BOUNDS, "n_past + n_tokens exceeds n_text_ctx" );
+		// device-fed tokens continue from the device's n_past: its host mirror guards the KV cache and the positional table
+		if( devTokens && c.nPastHost + nTokens > hp.n_text_ctx ) return fail( WSP_E_BOUNDS, "n_past + n_tokens exceeds n_text_ctx" );
 		WSP_CUDA( cudaSetDevice( c.e->device ) );
 		cudaStream_t s = c.stream;
 		WSP_CUDA( cudaEventRecord( c.ev[ 0 ], s ) );
@@ -546,6 +548,9 @@ namespace wsp
 			launched( 2 );
 		}
 		WSP_CHECK( decodeSubmit( c, nTokens, batch, allLogits, sample ) );
+		// the device advances n_past only when it samples (advance_kernel): mirror exactly that
+		if( !devTokens ) c.nPastHost = nPast;
+		if( sample && !allLogits ) c.nPastHost += nTokens;
 		c.lastLogitRows = allLogits ? batch * nTokens : batch;
 		WSP_CUDA( cudaEventRecord( c.ev[ 1 ], s ) );
 		if( sampledHost && sample && !allLogits )
@@ -580,12 +585,13 @@ namespace wsp
 	int ctxProfileDecode( Context& c, int batch, int nSteps, float* msByKind, int* launchesByKind )
 	{
 		if( batch < 1 || batch > c.maxB || nSteps < 1 ) return fail( WSP_E_INVALIDARG, "batch / steps" );
+		if( c.nPastHost + nSteps > c.e->hp.n_text_ctx ) return fail( WSP_E_BOUNDS, "n_past + n_steps exceeds n_text_ctx" );
 		WSP_CUDA( cudaSetDevice( c.e->device ) );
 		c.prof.on = true;
 		c.prof.used = 0;
 		c.prof.kinds.clear();
 		int rc = WSP_OK;
-		for( int i = 0; i < nSteps && rc >= 0; i++ ) rc = decodeSubmit( c, 1, batch, false, true );
+		for( int i = 0; i < nSteps && rc >= 0; i++ ) { rc = decodeSubmit( c, 1, batch, false, true ); if( rc >= 0 ) c.nPastHost++; }
 		c.prof.on = false;
 		if( rc < 0 ) return rc;
 		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
@@ -651,6 +657,7 @@ namespace wsp
 		WSP_CHECK( decodeSubmit( c, nPrompt, batch, false, true ) );
 		for( int i = 1; i < nDecode; i++ )
 			WSP_CHECK( decodeSubmit( c, 1, batch, false, true ) );
+		c.nPastHost = nPrompt + nDecode - 1;
 		WSP_CUDA( cudaEventRecord( c.ev[ 3 ], s ) );
 		c.lastLogitRows = batch;
 		// one D2H of the token log at the end: [batch][n_decode] int32

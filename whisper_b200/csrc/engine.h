@@ -145,6 +145,7 @@ namespace wsp
 		int* history = nullptr;         // [maxB][histCap]
 		int histCap = 0;
 		int lastLogitRows = 0;
+		int nPastHost = 0;              // host mirror of the device-resident n_past (it advances on the device between graph replays)
 		int debugEncLayers = -1;
 		int refThreads = 4;             // reference CPU thread count whose V^T*P arithmetic the decoder reproduces (0 = exact)
 

@@ -29,12 +29,12 @@ namespace wsp
 			template<class T> T get()
 			{
 				T v{};
-				if( pos + sizeof( T ) > size ) { ok = false; return v; }
+				if( sizeof( T ) > size - pos ) { ok = false; return v; }   // (pos <= size always: overflow-safe form)
 				memcpy( &v, p + pos, sizeof( T ) );
 				pos += sizeof( T );
 				return v;
 			}
-			bool skip( uint64_t n ) { if( pos + n > size ) { ok = false; return false; } pos += n; return true; }
+			bool skip( uint64_t n ) { if( n > size - pos ) { ok = false; return false; } pos += n; return true; }
 		};
 
 		void finishVocab( Vocab& v, int32_t nWords )
@@ -109,7 +109,10 @@ namespace wsp
 			if( !r.ok ) break;   // trailing bytes shorter than a header: treat as EOF like the reference (whisper.cpp:1012)
 			if( t.n_dims < 1 || t.n_dims > 3 || nameLen <= 0 || nameLen > 256 ) { err = "corrupt tensor header"; return WSP_E_FORMAT; }
 			for( int i = 0; i < t.n_dims; i++ ) t.ne[ i ] = r.get<int32_t>();
-			if( !r.ok || r.pos + (uint64_t)nameLen > size ) { err = "truncated tensor header"; return WSP_E_FILE; }
+			if( !r.ok || (uint64_t)nameLen > size - r.pos ) { err = "truncated tensor header"; return WSP_E_FILE; }
+			for( int i = 0; i < t.n_dims; i++ )
+				if( t.ne[ i ] <= 0 ) { err = "corrupt tensor header: non-positive dimension"; return WSP_E_FORMAT; }
+			if( t.ftype != 0 && t.ftype != 1 ) { err = "unsupported tensor type (only f32 = 0 and f16 = 1 are defined, whisper.cpp:1003-1051)"; return WSP_E_FORMAT; }
 			t.name.assign( reinterpret_cast<const char*>( data + r.pos ), nameLen );
 			r.pos += nameLen;
 			t.nbytes = (uint64_t)t.elements() * ( t.ftype == 0 ? 4 : 2 );
@@ -229,6 +232,14 @@ namespace wsp
 		}
 		m->imageSize = r.get<uint64_t>();
 		if( !r.ok ) { delete m; err = "truncated meta"; return WSP_E_FORMAT; }
+		// the blob is trusted for nothing: every tensor must lie inside the image it describes, with the size its shape implies
+		for( const TensorInfo& t : m->tensors )
+		{
+			bool good = t.n_dims >= 1 && t.n_dims <= 3 && ( t.ftype == 0 || t.ftype == 1 );
+			for( int i = 0; good && i < t.n_dims; i++ ) good = t.ne[ i ] > 0;
+			good = good && t.nbytes == (uint64_t)t.elements() * ( t.ftype == 0 ? 4 : 2 ) && t.offset <= m->imageSize && t.nbytes <= m->imageSize - t.offset;
+			if( !good ) { err = "meta blob: tensor " + t.name + " is inconsistent"; delete m; return WSP_E_FORMAT; }
+		}
 		const int rc = validateTensors( *m, err );
 		if( rc != WSP_OK ) { delete m; return rc; }
 		*out = m;

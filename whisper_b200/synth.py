@@ -208,7 +208,10 @@ def script_tokens(n_vocab: int):
     ts_end = [beg + 100 * (k + 1) for k in range(8)]
     ts_start = [t + 1 for t in ts_end[:7]]
     init, init2 = beg, beg + 4
-    specials = [eot, sot, transcribe, translate, init, init2] + ts_end + ts_start
+    # multilingual models: two language tokens (en, de) are active so that the distribution after [sot] — what
+    # whisper_lang_auto_detect reads (whisper.cpp:2428-2495) — is a real, audio-dependent decision between them
+    langs = [sot + 1 + 0, sot + 1 + 2] if sh else []
+    specials = [eot, sot, transcribe, translate, init, init2] + ts_end + ts_start + langs
     for i, t in enumerate(specials):
         codes[t] = special_code(i)
     for k in range(8):
@@ -221,8 +224,10 @@ def script_tokens(n_vocab: int):
         if SC_SPARSE and k not in (0, 3, 6):
             return [text_id(k, 0, k & 1)]
         return [text_id(k, 0, 0), text_id(k, 0, 1)]
-    for t in (sot, transcribe):
-        succ[t] = [init]
+    succ[sot] = langs if sh else [init]
+    succ[transcribe] = [init]
+    for t in langs:
+        succ[t] = [transcribe]
     succ[translate] = [init2]
     succ[init] = seg_first(0)
     succ[init2] = seg_first(4)
@@ -301,7 +306,7 @@ def _script_patch(name: str, ne, kind: str, data: np.ndarray, hp: "HParams") -> 
                     target = np.zeros(SC_NC)
                     for s_ in succ[t]:
                         target += codes[s_]
-                    if len(succ[t]) == 2:      # both branch candidates share the segment code: count it once
+                    if len(succ[t]) == 2:      # both text candidates share the segment code: count it once (specials have none)
                         target[0:16] *= 0.5
                     col = (ge * np.sqrt(2.0) / 3.0) * (target - codes[t])
                     w[:, u] = 0.0
@@ -443,8 +448,11 @@ def synth_pcm(chunk_id: int = 0, n_samples: int = 480000, seed: int = 12345) -> 
     """30 s of 16 kHz mono f32: 0.3*sin(2*pi*440*i/16000) + a slow chirp + 0.05*U(-0.5,0.5)  (SURVEY.md §8(d))."""
     i = np.arange(n_samples, dtype=np.float64)
     u = lcg_u32(seed + chunk_id, n_samples).astype(np.float64) / 4294967296.0 - 0.5
-    f2 = 180.0 + 40.0 * chunk_id
+    # the tone / envelope parameters cycle with period 16 (+ a small drift per cycle) so that every chunk id stays inside the family of
+    # clips the scripted models were calibrated on (tools/calibrate_script.py); the noise always differs
+    k, cyc = chunk_id % 16, chunk_id // 16
+    f2 = 180.0 + 40.0 * k + 7.0 * cyc
     x = 0.3 * np.sin(2 * np.pi * 440.0 * i / 16000.0) + 0.1 * np.sin(2 * np.pi * (f2 + i * (900.0 / n_samples)) * i / 16000.0) + 0.05 * u
     # amplitude envelope so frames differ (speech-like energy bursts)
-    env = 0.55 + 0.45 * np.sin(2 * np.pi * i / 16000.0 * (0.7 + 0.13 * chunk_id))
+    env = 0.55 + 0.45 * np.sin(2 * np.pi * i / 16000.0 * (0.7 + 0.13 * k + 0.011 * cyc))
     return (x * env).astype(np.float32)
