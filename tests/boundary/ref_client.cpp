@@ -5,7 +5,7 @@
 //   -> getSize / getSegments / getTokens -> Release
 // with its OWN iAudioBuffer implementation (a COM object defined by the client, consumed by the library), and prints the transcript in
 // a line format tests/test_boundary.py compares with the reference's whisper_full fixture.
-//   usage: ref_client <model.bin> <pcm.f32> <flags> <language> [second_call]
+//   usage: ref_client <model.bin> <pcm.f32> <flags> <language> [calls] [duration_ms]
 #include <string.h>   // the reference headers use strlen without including it (MSVC pulls it in transitively)
 #include "Whisper/API/whisperComLight.h"
 #include "Whisper/API/sFullParams.h"
@@ -73,6 +73,7 @@ int main( int argc, char** argv )
 	p.cpuThreads = 4;
 	p.new_segment_callback = &onNewSegment;
 	const int calls = argc > 5 ? atoi( argv[ 5 ] ) : 1;
+	if( argc > 6 ) p.duration_ms = atoi( argv[ 6 ] );
 	for( int i = 0; i < calls; i++ ) CHECK( ctx->runFull( p, buf ) );
 	iTranscribeResult* res = nullptr;
 	CHECK( ctx->getResults( eResultFlags::Tokens | eResultFlags::Timestamps, &res ) );

@@ -58,10 +58,10 @@ def test_client_built_against_reference_headers(name, tmp_path):
         pytest.skip("ref_client was not built (needs the reference headers at build time)")
     g = np.load(os.path.join(HERE, "golden", "full_runs.npz"))
     model, flags, max_tokens, off, dur, lang, calls = FULL_RUNS[name]
-    assert max_tokens == 0 and off == 0 and dur == 0
+    assert max_tokens == 0 and off == 0
     pcm_path = str(tmp_path / "clip.f32")
     full_pcm(int(g[name + "_pcm_base"])).astype("<f4").tofile(pcm_path)
-    out = _run(exe, synth.model_path(model), pcm_path, str(flags), lang, str(calls))
+    out = _run(exe, synth.model_path(model), pcm_path, str(flags), lang, str(calls), str(dur))
     segs = _client_segments(out)
     assert [[s[0], s[1]] for s in segs] == g[name + "_t"].tolist()
     assert [len(s[2]) for s in segs] == g[name + "_ntok"].tolist()

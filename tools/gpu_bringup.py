@@ -337,7 +337,8 @@ def stage_flow():
 
 
 def stage_steptiming(model_name="medium", batch=8):
-    """per-phase time of the dataflow decoder step as CTA 0 sees it (%globaltimer marks at every phase boundary)"""
+    """Where one decoder step goes, as CTA `WSP_TIMING_CTA` (default 0) of the dataflow kernel sees it: (id, %globaltimer) marks at every
+    phase boundary and at the sub-steps of a phase; printed as the mean time from the PREVIOUS mark, averaged over the layers."""
     from whisper_b200 import synth
     model_name = os.environ.get("STEP_MODEL", model_name)
     batch = int(os.environ.get("STEP_BATCH", batch))
@@ -345,16 +346,36 @@ def stage_steptiming(model_name="medium", batch=8):
     pcms = [synth.synth_pcm(i) for i in range(batch)]
     c.step_timing(True)
     c.run_chunks(pcms, m.prompt_init(), 40)
-    t = c.step_timing().astype(np.int64)
+    raw = c.step_timing().astype(np.int64).reshape(-1, 2)
+    raw = raw[: int(np.nonzero(raw[:, 1])[0].max()) + 1] if raw[:, 1].any() else raw[:0]
+    ids, t = raw[:, 0], raw[:, 1]
     L = m.n_text_layer
-    n = 1 + 8 * L + 1
-    t = t[:n]
-    d = np.diff(t) / 1e3
-    per = d[:8 * L].reshape(L, 8)
     names = ["LN1+QKV", "self-attn", "O+res", "LN+CQ", "cross-attn", "CO+res", "LN+FC1", "FC2+res"]
-    print("  %s B=%d: step %.1f us = layers %.1f + logits %.1f" % (model_name, batch, (t[-1] - t[0]) / 1e3, per.sum(), d[8 * L]), flush=True)
-    print("  per layer (mean over %d layers, us): " % L + " | ".join("%s %.2f" % (nm, v) for nm, v in zip(names, per.mean(0))) + " | layer %.2f" % per.sum(1).mean(), flush=True)
-    print("  layer 0: " + " ".join("%.2f" % v for v in per[0]) + "   last layer: " + " ".join("%.2f" % v for v in per[-1]), flush=True)
+    subn = {0: "phase done", 1: "inputs staged", 2: "1st weights landed" , 3: "MMAs done", 4: "stored"}
+    suba = {1: "q arrived", 2: "scores done", 3: "softmax done", 4: "chains done", 0: "phase done"}
+    acc = {}
+    for k in range(1, len(ids)):
+        acc.setdefault(int(ids[k]), []).append((t[k] - t[k - 1]) / 1e3)
+    print("  %s B=%d CTA %s: step %.1f us, %d marks" % (model_name, batch, os.environ.get("WSP_TIMING_CTA", "0"), (t[-1] - t[0]) / 1e3, len(ids)), flush=True)
+    phase_tot = {}
+    for key in sorted(acc):
+        ph, sb = key // 100 - 1, key % 100
+        lay, p8 = divmod(ph, 8)
+        phase_tot.setdefault(p8 if ph < 8 * L else 8, []).append(acc[key])
+    per_phase = {}
+    for key in sorted(acc):
+        ph, sb = key // 100 - 1, key % 100
+        p8 = ph % 8 if ph < 8 * L else 8
+        per_phase.setdefault((p8, sb), []).extend(acc[key])
+    for p8 in range(9):
+        items = sorted((sb if sb else 99, sb) for (pp, sb) in per_phase if pp == p8)
+        if not items:
+            continue
+        nm = names[p8] if p8 < 8 else "logits"
+        tot = sum(np.mean(per_phase[(p8, sb)]) for _, sb in items)
+        lab = suba if p8 in (1, 4) else subn
+        items = sorted(items, key=lambda it: (it[1] == 0, it[1]))
+        print("    %-10s %6.2f us | " % (nm, tot) + "  ".join("%s %.2f" % (lab.get(sb, "#%d" % sb), np.mean(per_phase[(p8, sb)])) for _, sb in items), flush=True)
 
 
 STAGES = {

@@ -162,6 +162,10 @@ namespace wsp
 			WSP_CHECK( devAlloc( c.flowCtrl, 8, true ) );
 			const char* env = getenv( "WSP_STEP_MODE" );
 			if( env && env[ 0 ] >= '0' && env[ 0 ] <= '2' ) c.stepMode = env[ 0 ] - '0';
+			env = getenv( "WSP_FLOW_L2" );
+			if( env ) c.flowL2Prefetch = env[ 0 ] != '0';
+			env = getenv( "WSP_TIMING_CTA" );
+			if( env ) c.stepTimingCta = atoi( env );
 		}
 		WSP_CUDA( kern::prepare( 4 * d ) );
 		WSP_CUDA( kern::megaPrepare( d ) );
@@ -388,6 +392,8 @@ namespace wsp
 			fa.tokens = c.tokensDev; fa.dNPast = c.dNPast;
 			fa.exch = c.flowExch; fa.ctrl = c.flowCtrl; fa.logits = c.logits; fa.timing = c.stepTiming ? c.megaTiming : nullptr;
 			fa.g = c.flowGeom;
+			fa.timingCta = c.stepTimingCta;
+			fa.l2Prefetch = c.flowL2Prefetch;
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepFlow( fa, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

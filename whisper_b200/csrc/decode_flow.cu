@@ -102,6 +102,12 @@ namespace kern
 			asm volatile( "ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( r.x ), "=r"( r.y ), "=r"( r.z ), "=r"( r.w ) : "l"( p ) : "memory" );
 			return r;
 		}
+		__device__ __forceinline__ uint32_t ldPoll32( const void* p )
+		{
+			uint32_t r;
+			asm volatile( "ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"( r ) : "l"( p ) : "memory" );
+			return r;
+		}
 		__device__ __forceinline__ bool hasSent32( const uint4& v ) { return v.x == SENT32 || v.y == SENT32 || v.z == SENT32 || v.w == SENT32; }
 		__device__ __forceinline__ bool hasSent16w( uint32_t w ) { return ( w & 0xFFFFu ) == 0xFFFFu || ( w >> 16 ) == 0xFFFFu; }
 		__device__ __forceinline__ bool hasSent16( const uint4& v ) { return hasSent16w( v.x ) || hasSent16w( v.y ) || hasSent16w( v.z ) || hasSent16w( v.w ); }
@@ -182,30 +188,41 @@ namespace kern
 			return y;
 		}
 
-		// scores of n K rows (128 bytes each, contiguous in shared memory) against the query held in registers: 8 lanes per row,
-		// 4 rows per warp instruction (512 contiguous bytes: conflict-free); returns the updated running maximum
+		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query.  Two lanes per row: lane half h owns bytes
+		// [64 h, 64 h + 64) of the row and the matching 32 query values (registers), four independent 16-byte loads and four independent
+		// accumulators, ONE shuffle per row.  (The first version used 8 lanes per row with a single 8-deep FMA chain and three dependent
+		// shuffles: 0.72 us per 128-row run, pure latency — 9 of the 22 us of a cross-attention phase.)  Returns the running maximum.
 		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const float* qf, float* sp, int warp, int lane, float lmax )
 		{
-			const int sub = lane & 7, rgrp = lane >> 3;
-			for( int r0 = warp * 4; r0 < n; r0 += FL_WARPS * 4 )
+			const int half = lane & 1, rw = lane >> 1;
+			for( int r0 = warp * 16; r0 < n; r0 += FL_WARPS * 16 )
 			{
-				const int r = r0 + rgrp;
-				uint4 u = make_uint4( 0, 0, 0, 0 );
-				if( r < n ) u = *reinterpret_cast<const uint4*>( kc + (size_t)r * 128 + sub * 16 );
-				const __half2* h2 = reinterpret_cast<const __half2*>( &u );
-				float s = 0.0f;
-#pragma unroll
-				for( int e = 0; e < 4; e++ )
-				{
-					const float2 f = __half22float2( h2[ e ] );
-					s += f.x * qf[ e * 2 ] + f.y * qf[ e * 2 + 1 ];
-				}
-				s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-				s += __shfl_xor_sync( 0xffffffffu, s, 2 );
-				s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+				const int r = r0 + rw;
+				float acc[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
 				if( r < n )
 				{
-					if( sub == 0 ) sp[ jBase + r ] = s;
+					const uint4* row = reinterpret_cast<const uint4*>( kc + (size_t)r * 128 + half * 64 );
+					uint4 u[ 4 ];
+#pragma unroll
+					for( int k = 0; k < 4; k++ ) u[ k ] = row[ k ];
+#pragma unroll
+					for( int k = 0; k < 4; k++ )
+					{
+						const __half2* h2 = reinterpret_cast<const __half2*>( &u[ k ] );
+#pragma unroll
+						for( int e = 0; e < 4; e++ )
+						{
+							const float2 f = __half22float2( h2[ e ] );
+							acc[ k ] = fmaf( f.x, qf[ k * 8 + e * 2 ], acc[ k ] );
+							acc[ k ] = fmaf( f.y, qf[ k * 8 + e * 2 + 1 ], acc[ k ] );
+						}
+					}
+				}
+				float s = ( acc[ 0 ] + acc[ 1 ] ) + ( acc[ 2 ] + acc[ 3 ] );
+				s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+				if( r < n )
+				{
+					if( half == 0 ) sp[ jBase + r ] = s;
 					lmax = fmaxf( lmax, s );
 				}
 			}
@@ -244,10 +261,23 @@ namespace kern
 		{
 			constexpr int N4 = Cfg<D>::N4;
 			const uint4* src = reinterpret_cast<const uint4*>( row );
+			SpinGuard guard;
+			// Probe before reading: four words at the quarter points of the row, polled with back-off, until they are written.  148
+			// CTAs re-reading whole 32 KB activation blocks while they wait would by themselves saturate the L2 (one round = 4.7 MB,
+			// ~10 TB/s when spinning) and starve the weight stream; the probes cost four sectors per round.
+			{
+				const uint32_t* w = reinterpret_cast<const uint32_t*>( row ) + ( lane & 3 ) * ( D / 4 ) + D / 8;
+				unsigned ns = 32;
+				while( !__all_sync( 0xffffffffu, ldPoll32( w ) != SENT32 ) )
+				{
+					__nanosleep( ns );
+					if( ns < 256 ) ns <<= 1;
+					guard.tick();
+				}
+			}
 			uint4 u[ N4 ];
 #pragma unroll
 			for( int i = 0; i < N4; i++ ) u[ i ] = ldPoll( src + i * 32 + lane );
-			SpinGuard guard;
 			while( true )
 			{
 				bool miss = false;
@@ -331,65 +361,62 @@ namespace kern
 				d2[ i * 32 + lane ] = u;
 			}
 		}
-		// B rows of D ready f16 activations (attention output, GELU output) from an exchange buffer -> shared memory
+		// B rows of D ready f16 activations (attention output, GELU output) from an exchange buffer -> shared memory, one warp per row
 		template<int D>
-		__device__ __forceinline__ void stageF16( const __half* src, size_t colStride, int B, uint8_t* act, int tid )
+		__device__ __forceinline__ void stageF16( const __half* src, size_t colStride, int B, uint8_t* act, int warp, int lane )
 		{
-			constexpr int V8 = D / 8;
+			constexpr int V8 = D / 8;                   // 16-byte pieces per row
+			constexpr int NI = ( V8 + 31 ) / 32;
 			constexpr int RS = Cfg<D>::RS;
-			constexpr int U = 4;
-			const int total = B * V8;
-			for( int base = 0; base < total; base += FL_CONSUMERS * U )
+			for( int c = warp; c < B; c += FL_WARPS )
 			{
-				uint4 u[ U ];
-				const __half* p[ U ];
-#pragma unroll
-				for( int k = 0; k < U; k++ )
-				{
-					const int i = base + k * FL_CONSUMERS + tid;
-					const int c = i / V8, kk = i - c * V8;
-					p[ k ] = i < total ? src + (size_t)c * colStride + kk * 8 : nullptr;
-					u[ k ] = make_uint4( 0, 0, 0, 0 );
-					if( p[ k ] ) u[ k ] = ldPoll( p[ k ] );
-				}
+				const __half* row = src + (size_t)c * colStride;
 				SpinGuard guard;
+				{
+					// probe four words of the row with back-off before reading it (see pollRowF32)
+					const uint32_t* w = reinterpret_cast<const uint32_t*>( row ) + ( lane & 3 ) * ( D / 8 ) + D / 16;
+					unsigned ns = 32;
+					while( !__all_sync( 0xffffffffu, !hasSent16w( ldPoll32( w ) ) ) )
+					{
+						__nanosleep( ns );
+						if( ns < 256 ) ns <<= 1;
+						guard.tick();
+					}
+				}
+				uint4 u[ NI ];
+#pragma unroll
+				for( int k = 0; k < NI; k++ )
+				{
+					const int i = k * 32 + lane;
+					u[ k ] = make_uint4( 0, 0, 0, 0 );
+					if( i < V8 ) u[ k ] = ldPoll( row + i * 8 );
+				}
 				while( true )
 				{
 					bool miss = false;
 #pragma unroll
-					for( int k = 0; k < U; k++ )
-						if( p[ k ] && hasSent16( u[ k ] ) )
+					for( int k = 0; k < NI; k++ )
+					{
+						const int i = k * 32 + lane;
+						if( i < V8 && hasSent16( u[ k ] ) )
 						{
-							u[ k ] = ldPoll( p[ k ] );
+							u[ k ] = ldPoll( row + i * 8 );
 							miss = true;
 						}
+					}
 					if( !miss ) break;
 					guard.tick();
 				}
 #pragma unroll
-				for( int k = 0; k < U; k++ )
+				for( int k = 0; k < NI; k++ )
 				{
-					const int i = base + k * FL_CONSUMERS + tid;
-					const int c = i / V8, kk = i - c * V8;
-					if( i < total ) *reinterpret_cast<uint4*>( act + (size_t)c * RS + kk * 16 ) = u[ k ];
+					const int i = k * 32 + lane;
+					if( i < V8 ) *reinterpret_cast<uint4*>( act + (size_t)c * RS + i * 16 ) = u[ k ];
 				}
 			}
 		}
 
 		enum { EP_QKV = 0, EP_RESID = 1, EP_QSCALE = 2, EP_GELU = 3, EP_LOGITS = 4 };
-		struct GemvOut
-		{
-			int epi;
-			int nOut, R;             // rows of the whole phase, rows per CTA
-			const float* bias;       // shared memory: this CTA's rows
-			float scale;
-			float* outF32;           // x (exchange) / logits
-			__half* outF16;          // q / cq / h (exchange)
-			__half* knew; __half* vnew;
-			__half* kCache; __half* vCache;
-			int ld;
-		};
-
 		// -----------------------------------------------------------------------------------------------------------
 		template<int D>
 		__global__ void __launch_bounds__( FL_THREADS, 1 )
@@ -440,6 +467,8 @@ namespace kern
 			const int r4 = cta * g.R4, n4 = max( 0, min( g.R4, 4 * D - r4 ) );
 			const int rv = cta * g.RV, nv = max( 0, min( g.RV, a.nVocab - rv ) );
 			const int nKcSelf = ( nkvOld + CR - 1 ) / CR;
+			const int dcSelf = ( nkvOld + 1 + parts - 1 ) / parts;
+			const int roundsSelf = ( dcSelf + CR - 1 ) / CR;
 			const int nKcCross = ( T + CR - 1 ) / CR;
 			const int dcCross = ( T + parts - 1 ) / parts;
 			const int roundsCross = ( dcCross + CR - 1 ) / CR;
@@ -491,20 +520,56 @@ namespace kern
 					uint8_t* dst = begin( (uint32_t)( n > 0 ? n * 128 : 0 ) );
 					if( lane == 0 && n > 0 ) ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, bar );
 				};
+				// HBM -> L2 ahead of the ring: the ring (~180 KB) is smaller than one (chunk, head)'s cross K/V (384 KB), so by itself it
+				// cannot run far enough ahead to hide DRAM latency after the cross-attention phase.  One bulk-prefetch instruction per
+				// contiguous range: this CTA's weight rows of the NEXT layer when this layer's cross-attention items are issued, and the
+				// cross K/V of its own (chunk, head) units at the START of the layer that will use them.
+				auto l2 = [ & ]( const void* p, size_t bytes ) {
+					if( lane == 0 && bytes >= 16 )
+						asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( p ), "r"( (uint32_t)( bytes & ~(size_t)15 ) ) : "memory" );
+				};
+				auto l2Weights = [ & ]( const FlowLayer& Ln ) {
+					l2( Ln.wqkv + (size_t)r3 * D, (size_t)n3 * D * 2 );
+					l2( Ln.wo + (size_t)r1 * D, (size_t)n1 * D * 2 );
+					l2( Ln.wcq + (size_t)r1 * D, (size_t)n1 * D * 2 );
+					l2( Ln.wco + (size_t)r1 * D, (size_t)n1 * D * 2 );
+					l2( Ln.w1 + (size_t)r4 * D, (size_t)n4 * D * 2 );
+					l2( Ln.w2 + (size_t)r1 * 4 * D, (size_t)n1 * 4 * D * 2 );
+				};
+				auto l2Cross = [ & ]( const FlowLayer& Ln ) {
+					for( int unit = cta; unit < B * H; unit += G )
+					{
+						l2( Ln.crossK + (size_t)unit * T * 64, (size_t)T * 128 );
+						l2( Ln.crossV + (size_t)unit * T * 64, (size_t)T * 128 );
+					}
+				};
+				const bool pf = a.l2Prefetch != 0;
 				for( int il = 0; il < L; il++ )
 				{
 					const FlowLayer& Lr = a.layers[ il ];
+					if( pf ) l2Cross( Lr );
 					sendParams( Lr.ln1g, Lr.ln1b, Lr.biasSlab + (size_t)cta * g.slabFloats, g.slabFloats );
 					sendWeights( Lr.wqkv, D, r3, n3, 1 );
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * a.nTextCtx * 64;   // unit = b * H + h
 						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
-						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.vCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
+						for( int i = 0; i < roundsSelf; i++ )
+							for( int p = 0; p < parts; p++ )
+							{
+								const int j0 = p * dcSelf + i * CR;
+								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcSelf, nkvOld ) );
+								sendKv( Lr.vCache + hb, j0, j1 - j0 );
+							}
 					}
 					sendWeights( Lr.wo, D, r1, n1, 1 );
 					sendParams( Lr.lncg, Lr.lncb, nullptr, 0 );
 					sendWeights( Lr.wcq, D, r1, n1, 1 );
+					if( pf )
+					{
+						if( il + 1 < L ) l2Weights( a.layers[ il + 1 ] );
+						else l2( a.tokEmb + (size_t)rv * D, (size_t)nv * D * 2 );
+					}
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * T * 64;
@@ -560,159 +625,38 @@ namespace kern
 				cSlot += n;
 				if( cSlot >= NS ) { cSlot -= NS; cPar ^= 1u; }
 			};
+			// debug: (id, %globaltimer) pairs of one CTA.  ids: 0 = kernel start, 100 * (phase + 1) + sub for the sub-steps of a phase
+			// (sub 0 = phase done; 1 = inputs arrived and staged; 2 = first weight slot landed; 3 = MMAs done; 4 = reduced + stored)
 			int markIdx = 0;
-			auto mark = [ & ]() {
-				if( a.timing && cta == 0 && tid == 0 && markIdx < 1024 )
+			const int markCta = a.timing ? a.timingCta : -1;
+			auto markId = [ & ]( int id ) {
+				if( cta == markCta && tid == 0 && markIdx < 2000 )
 				{
-					unsigned long long t;
-					asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t ) );
-					a.timing[ markIdx ] = t;
+					a.timing[ 2 * markIdx ] = (unsigned long long)id;
+					a.timing[ 2 * markIdx + 1 ] = globalNs();
 				}
 				markIdx++;
 			};
-			mark();
+			int curPhase = 0;
+			auto sub = [ & ]( int k ) { if( markCta >= 0 ) markId( 100 * ( curPhase + 1 ) + k ); };
+			auto mark = [ & ]() { markId( 100 * ( curPhase + 1 ) ); curPhase++; };
+			markId( 0 );
 
 			const int gq = lane >> 2, tq = lane & 3;
 			const bool twoTiles = B > 8;
 			const float qkScale = 0.35355339059327379f;   // 64^-1/4 (whisper.cpp:1588, 1595, 1700)
 
-			// LayerNorm staging of all B columns (one warp per column); src == nullptr: layer 0's input, embedded on the spot
-			auto stageLN = [ & ]( const float* src, const uint8_t* params ) {
-				const float* gamma = reinterpret_cast<const float*>( params );
-				const float* beta = gamma + D;
-				for( int c = warp; c < B; c += FL_WARPS )
-				{
-					float4 v[ C::N4 ];
-					if( src ) pollRowF32<D>( src + (size_t)c * D, v, lane );
-					else embedRow<D>( a.tokEmb + (size_t)a.tokens[ c ] * D, a.decPos + (size_t)nPast * D, v, lane );
-					normRow<D>( v, gamma, beta, reinterpret_cast<__half*>( act + (size_t)c * RS ), xres + c * 16, r1, n1, lane );
-				}
-			};
-
-			// weight-streaming GEMV of this CTA's rows: out[col][n] = sum_k W[n][k] * act[col][k].  KC = 1: the activations are staged
-			// already; KC = 4 (fc2): K = 4D is walked in four D-wide chunks, each staged from the exchange buffer `hsrc` first.
-			auto gemv = [ & ]( const GemvOut& o, int row0, int nRows, int KC, const __half* hsrc ) {
-				const int nUnits = ( nRows + 7 ) >> 3;
-				for( int u0 = 0; u0 < nUnits; u0 += 4 )
-				{
-					const int nb = min( 4, nUnits - u0 );
-					float acc0[ 4 ][ 4 ], acc1[ 4 ][ 4 ];
-#pragma unroll
-					for( int u = 0; u < 4; u++ )
-#pragma unroll
-						for( int i = 0; i < 4; i++ ) { acc0[ u ][ i ] = 0.0f; acc1[ u ][ i ] = 0.0f; }
-					for( int kc = 0; kc < KC; kc++ )
-					{
-						if( KC > 1 )
-						{
-							if( kc > 0 ) consumerSync();   // the previous chunk's MMAs have read `act`
-							stageF16<D>( hsrc + (size_t)kc * D, (size_t)4 * D, B, act, tid );
-							consumerSync();
-						}
-#pragma unroll
-						for( int u = 0; u < 4; u++ )
-						{
-							if( u < nb )
-							{
-								const uint8_t* w = waitSlot( 0 );
-								const uint8_t* wb = w + (size_t)gq * RS + tq * 16;
-								const uint8_t* xb0 = act + (size_t)gq * RS + tq * 16;
-								const uint8_t* xb1 = act + (size_t)( gq + 8 ) * RS + tq * 16;
-#pragma unroll
-								for( int s = 0; s < C::SPW; s++ )
-								{
-									const int st = warp + FL_WARPS * s;
-									if( st < C::STEPS )
-									{
-										const uint4 wv = *reinterpret_cast<const uint4*>( wb + st * 64 );
-										const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 64 );
-										mmaF( acc0[ u ], wv.x, wv.y, x0.x, x0.y );
-										mmaF( acc0[ u ], wv.z, wv.w, x0.z, x0.w );
-										if( twoTiles )
-										{
-											const uint4 x1 = *reinterpret_cast<const uint4*>( xb1 + st * 64 );
-											mmaF( acc1[ u ], wv.x, wv.y, x1.x, x1.y );
-											mmaF( acc1[ u ], wv.z, wv.w, x1.z, x1.w );
-										}
-									}
-								}
-								releaseSlots( 1 );
-							}
-						}
-					}
-					// cross-warp reduction: red[u][warp][row g][col]
-#pragma unroll
-					for( int u = 0; u < 4; u++ )
-					{
-						if( u < nb )
-						{
-							float* my = red + ( ( u * FL_WARPS + warp ) * 8 + gq ) * ncols;
-							my[ 2 * tq ] = acc0[ u ][ 0 ];
-							my[ 2 * tq + 1 ] = acc0[ u ][ 1 ];
-							if( twoTiles ) { my[ 8 + 2 * tq ] = acc1[ u ][ 0 ]; my[ 8 + 2 * tq + 1 ] = acc1[ u ][ 1 ]; }
-						}
-					}
-					consumerSync();
-					for( int idx = tid; idx < nb * B * 8; idx += FL_CONSUMERS )
-					{
-						const int u = idx / ( B * 8 );
-						const int rem = idx - u * B * 8;
-						const int c = rem >> 3, r = rem & 7;
-						const int rl = ( u0 + u ) * 8 + r;     // row within this CTA's range
-						if( rl >= nRows ) continue;
-						const int n = row0 + rl;
-						float v = 0.0f;
-#pragma unroll
-						for( int w = 0; w < FL_WARPS; w++ ) v += red[ ( ( u * FL_WARPS + w ) * 8 + r ) * ncols + c ];
-						const float bs = o.bias ? o.bias[ rl ] : 0.0f;
-						switch( o.epi )
-						{
-						case EP_QKV:
-						{
-							const int which = n / D;
-							const int nn = n - which * D;
-							if( which == 0 ) stX16( o.outF16 + (size_t)c * D + nn, __float2half_rn( ( v + bs ) * o.scale ) );
-							else
-							{
-								const int h = nn >> 6, e = nn & 63;
-								const size_t off = ( ( (size_t)c * H + h ) * a.nTextCtx + nPast ) * 64 + e;
-								if( which == 1 )
-								{
-									const __half kv = __float2half_rn( v * o.scale );
-									o.kCache[ off ] = kv;
-									stX16( o.knew + (size_t)c * D + nn, kv );
-								}
-								else
-								{
-									const __half vv = __float2half_rn( v + bs );
-									o.vCache[ off ] = vv;
-									stX16( o.vnew + (size_t)c * D + nn, vv );
-								}
-							}
-							break;
-						}
-						case EP_RESID:
-							stX32( o.outF32 + (size_t)c * D + n, v + bs + xres[ c * 16 + rl ] );
-							break;
-						case EP_QSCALE:
-							stX16( o.outF16 + (size_t)c * D + n, __float2half_rn( ( v + bs ) * o.scale ) );
-							break;
-						case EP_GELU:
-							stX16( o.outF16 + (size_t)c * o.ld + n, __float2half_rn( ptx::gelu_f16_semantics( v + bs ) ) );
-							break;
-						default:
-							o.outF32[ (size_t)c * o.ld + n ] = v;
-							break;
-						}
-					}
-					if( u0 + 4 < nUnits ) consumerSync();   // `red` is rewritten by the next batch
-				}
-			};
-
-			for( int il = 0; il < L; il++ )
+			// The step is ONE loop over (layer, phase) with a single copy of the weight-streaming GEMV code and a single copy of the
+			// attention code; a switch only fills in their operands.  (The first version of this kernel instantiated the GEMV seven
+			// times: 16 K SASS instructions = 256 KB, every phase started with a cold instruction cache — 1.2-1.5 us for the four
+			// MMA steps of an 8-row unit.  Round 1 measured the same effect on its barrier kernel: 12.4 K -> 7.0 K instructions.)
+			enum { PH_QKV = 0, PH_SELF = 1, PH_O = 2, PH_CQ = 3, PH_CROSS = 4, PH_CO = 5, PH_FC1 = 6, PH_FC2 = 7, PH_COUNT = 8 };
+#pragma unroll 1
+			for( int il = 0; il <= L; il++ )
 			{
-				const FlowLayer& Lr = a.layers[ il ];
-				uint8_t* const exb = a.exch + ( (size_t)set * L + il ) * exLayer;
+				const bool last = il == L;                // final LayerNorm + logits (a17)
+				const FlowLayer& Lr = a.layers[ last ? L - 1 : il ];
+				uint8_t* const exb = a.exch + ( (size_t)set * L + ( last ? L - 1 : il ) ) * exLayer;
 				float* const x1 = reinterpret_cast<float*>( exb );
 				float* const x2 = x1 + colsD;
 				float* const x3 = x2 + colsD;
@@ -724,191 +668,300 @@ namespace kern
 				__half* const cq = hbase + 4 * colsD;
 				__half* const attn2 = hbase + 5 * colsD;
 				__half* const hbuf = hbase + 6 * colsD;
-				const float* xin = nullptr;
-				if( il > 0 ) xin = reinterpret_cast<const float*>( a.exch + ( (size_t)set * L + il - 1 ) * exLayer ) + 2 * colsD;
+				const float* xprev = nullptr;             // the previous layer's output (nullptr: embed on the spot)
+				if( il > 0 && !last ) xprev = reinterpret_cast<const float*>( a.exch + ( (size_t)set * L + il - 1 ) * exLayer ) + 2 * colsD;
 
-				GemvOut o{};
-				o.scale = 1.0f; o.ld = D;
-
-				// ---- LN1 + (Q | K | V): K/V rows appended to the f16 cache (a14) ----
+#pragma unroll 1
+				for( int ph = 0; ph < PH_COUNT; ph++ )
 				{
-					const uint8_t* pr = waitSlot( 0 );
-					for( int i = tid; i < g.slabFloats; i += FL_CONSUMERS ) sbias[ i ] = reinterpret_cast<const float*>( pr + 2 * D * 4 )[ i ];
-					if( n3 > 0 ) stageLN( xin, pr );
-					consumerSync();
-					releaseSlots( 1 );
-					o.epi = EP_QKV; o.nOut = 3 * D; o.R = g.R3; o.bias = sbias + g.oQkv; o.scale = qkScale;
-					o.outF16 = qh; o.knew = knew; o.vnew = vnew; o.kCache = Lr.kCache; o.vCache = Lr.vCache;
-					gemv( o, r3, n3, 1, nullptr );
-					o.scale = 1.0f;
-				}
-				mark();
-				// ---- self attention over the cache (reference-exact f16 V^T*P chains), units = (chunk, head) ----
-				for( int unit = cta; unit < B * H; unit += G )
-				{
-					const int b = unit / H, h = unit - b * H;
-					const size_t vo = (size_t)b * D + h * 64;
-					if( tid < 24 )
+					if( ph == PH_SELF || ph == PH_CROSS )
 					{
-						const int arr = tid >> 3, piece = tid & 7;
-						const __half* src = ( arr == 0 ? qh : arr == 1 ? knew : vnew ) + vo + piece * 8;
-						uint4 u = ldPoll( src );
-						SpinGuard guard;
-						while( hasSent16( u ) ) { u = ldPoll( src ); guard.tick(); }
-						reinterpret_cast<uint4*>( sqkv )[ tid ] = u;
-					}
-					consumerSync();
-					float qf[ 8 ];
-					{
-						const __half* qs = reinterpret_cast<const __half*>( sqkv ) + ( lane & 7 ) * 8;
+						// =====================================================================================================
+						// attention of one new query per (chunk, head) over f16 K/V rows: the self-KV cache plus this step's own row
+						// (a14), or the encoder's cross memories (a15).  K rows stream through the ring in runs of CR rows and are
+						// scored as they land; V rows come in (round, part) order — part p of the reference's `parts` threads owns the
+						// key range [p*dc, (p+1)*dc) and accumulates it in an f16 chain (ggml.c:4680-4722).
+						// =====================================================================================================
+						const bool self = ph == PH_SELF;
+						const int nOld = self ? nkvOld : T;           // rows that come through the ring
+						const int n = nOld + ( self ? 1 : 0 );
+						const __half* qsrc = self ? qh : cq;
+						__half* dst = self ? attn1 : attn2;
+						const int nKc = ( nOld + CR - 1 ) / CR;
+						const int dc = ( n + parts - 1 ) / parts;
+						const int rounds = ( dc + CR - 1 ) / CR;
+#pragma unroll 1
+						for( int unit = cta; unit < B * H; unit += G )
+						{
+							const int b = unit / H, h = unit - b * H;
+							const size_t vo = (size_t)b * D + h * 64;
+							if( tid < ( self ? 24 : 8 ) )
+							{
+								const int arr = tid >> 3, piece = tid & 7;
+								const __half* src = ( arr == 0 ? qsrc : arr == 1 ? knew : vnew ) + vo + piece * 8;
+								uint4 u = ldPoll( src );
+								SpinGuard guard;
+								while( hasSent16( u ) ) { __nanosleep( 64 ); u = ldPoll( src ); guard.tick(); }
+								reinterpret_cast<uint4*>( sqkv )[ tid ] = u;
+							}
+							consumerSync();
+							sub( 1 );
+							float qf[ 32 ];   // this lane's half of the query (scoreRows)
+							{
+								const __half2* qs = reinterpret_cast<const __half2*>( sqkv ) + ( lane & 1 ) * 16;
 #pragma unroll
-						for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( qs[ e ] );
+								for( int e = 0; e < 16; e++ )
+								{
+									const float2 f = __half22float2( qs[ e ] );
+									qf[ 2 * e ] = f.x;
+									qf[ 2 * e + 1 ] = f.y;
+								}
+							}
+							float lmax = -INFINITY;
+#pragma unroll 1
+							for( int ci = 0; ci < nKc; ci++ )
+							{
+								const uint8_t* kc = waitSlot( 0 );
+								lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+								releaseSlots( 1 );
+							}
+							if( self ) lmax = scoreRows( sqkv + 128, 1, nOld, qf, sp, warp, lane, lmax );   // this step's own K row
+							sub( 2 );
+							softmaxRow( sp, n, lmax, sred, tid, warp, lane );
+							sub( 3 );
+							{
+								const int p = tid >> 6, e = tid & 63;
+								const int pEnd = min( ( p + 1 ) * dc, nOld );       // end of part p's rows that live in the ring
+								float y = 0.0f;
+#pragma unroll 1
+								for( int i = 0; i < rounds; i++ )
+								{
+									if( p < parts )
+									{
+										const int j0 = p * dc + i * CR;
+										const int j1 = min( j0 + CR, pEnd );
+										if( j1 > j0 )
+										{
+											const __half* vp = reinterpret_cast<const __half*>( waitSlot( p ) ) + e;
+											y = a.refThreads > 0 ? chainRows<true>( y, sp + j0, vp, j1 - j0 ) : chainRows<false>( y, sp + j0, vp, j1 - j0 );
+										}
+									}
+									releaseSlots( parts, true );
+								}
+								if( self && p < parts && nOld >= p * dc && nOld < ( p + 1 ) * dc )
+								{
+									// this step's own V row closes the chain of the part whose range it falls into
+									const __half* vp = reinterpret_cast<const __half*>( sqkv + 256 ) + e;
+									y = a.refThreads > 0 ? chainRows<true>( y, sp + nOld, vp, 1 ) : chainRows<false>( y, sp + nOld, vp, 1 );
+								}
+								if( p < parts ) so[ tid ] = y;
+							}
+							sub( 4 );
+							consumerSync();
+							if( tid < 64 )
+							{
+								float acc = so[ tid ];
+								for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
+								stX16( dst + vo + tid, __float2half_rn( acc ) );
+							}
+							consumerSync();
+						}
+						mark();
+						continue;
 					}
-					float lmax = -INFINITY;
-					for( int ci = 0; ci < nKcSelf; ci++ )
+
+					// =========================================================================================================
+					// weight-streaming GEMV of this CTA's rows: out[col][n] = sum_k W[n][k] * act[col][k]
+					// =========================================================================================================
+					int epi = EP_RESID, row0 = r1, nRows = n1, KC = 1, ld = D, biasOff = 0;
+					bool useLN = false;
+					const float* lnSrc = nullptr;
+					const __half* hSrc = nullptr;
+					size_t hStride = D;
+					float scale = 1.0f;
+					float* outF32 = nullptr;
+					__half* outF16 = nullptr;
+					if( last )
 					{
-						const uint8_t* kc = waitSlot( 0 );
-						lmax = scoreRows( kc, min( CR, nkvOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+						epi = EP_LOGITS; row0 = rv; nRows = nv; useLN = true; lnSrc = x3; outF32 = a.logits; ld = a.nVocab; biasOff = -1;
+					}
+					else switch( ph )
+					{
+					case PH_QKV:    // LN1 + (Q | K | V): K/V rows appended to the f16 cache (a14)
+						epi = EP_QKV; row0 = r3; nRows = n3; useLN = true; lnSrc = xprev; scale = qkScale; outF16 = qh; biasOff = g.oQkv;
+						break;
+					case PH_O:      // self-attention out projection + residual
+						hSrc = attn1; outF32 = x1; biasOff = g.oO;
+						break;
+					case PH_CQ:     // LN + cross-attention query (a15)
+						epi = EP_QSCALE; useLN = true; lnSrc = x1; scale = qkScale; outF16 = cq; biasOff = g.oCq;
+						break;
+					case PH_CO:     // cross-attention out projection + residual
+						hSrc = attn2; outF32 = x2; biasOff = g.oCo;
+						break;
+					case PH_FC1:    // LN + fc1 + GELU (a16)
+						epi = EP_GELU; row0 = r4; nRows = n4; useLN = true; lnSrc = x2; outF16 = hbuf; ld = 4 * D; biasOff = g.oFc1;
+						break;
+					default:        // PH_FC2: fc2 + residual, K = 4D walked in four D-wide chunks
+						hSrc = hbuf; hStride = (size_t)4 * D; KC = 4; outF32 = x3; biasOff = g.oFc2;
+						break;
+					}
+					const float* bias = biasOff >= 0 ? sbias + biasOff : nullptr;
+
+					if( useLN )
+					{
+						// LayerNorm gamma | beta (| this layer's bias slab) arrive through the ring
+						const uint8_t* pr = waitSlot( 0 );
+						if( ph == PH_QKV && !last )
+							for( int i = tid; i < g.slabFloats; i += FL_CONSUMERS ) sbias[ i ] = reinterpret_cast<const float*>( pr + 2 * D * 4 )[ i ];
+						if( nRows > 0 )
+						{
+							const float* gamma = reinterpret_cast<const float*>( pr );
+							const float* beta = gamma + D;
+							const bool embed = !last && ph == PH_QKV && il == 0;
+							for( int c = warp; c < B; c += FL_WARPS )
+							{
+								float4 v[ C::N4 ];
+								if( embed ) embedRow<D>( a.tokEmb + (size_t)a.tokens[ c ] * D, a.decPos + (size_t)nPast * D, v, lane );
+								else pollRowF32<D>( lnSrc + (size_t)c * D, v, lane );
+								normRow<D>( v, gamma, beta, reinterpret_cast<__half*>( act + (size_t)c * RS ), xres + c * 16, r1, n1, lane );
+							}
+						}
+						consumerSync();
+						sub( 1 );
 						releaseSlots( 1 );
 					}
-					lmax = scoreRows( sqkv + 128, 1, nkvOld, qf, sp, warp, lane, lmax );   // this step's own K row
-					const int nkv = nkvOld + 1;
-					softmaxRow( sp, nkv, lmax, sred, tid, warp, lane );
+					else if( KC == 1 && nRows > 0 )
 					{
-						const int dc = ( nkv + parts - 1 ) / parts;
-						const int p = tid >> 6, e = tid & 63;
-						if( p < parts )
+						stageF16<D>( hSrc, hStride, B, act, warp, lane );
+						consumerSync();
+						sub( 1 );
+					}
+
+					const int nUnits = ( nRows + 7 ) >> 3;
+#pragma unroll 1
+					for( int u0 = 0; u0 < nUnits; u0 += 4 )
+					{
+						const int nb = min( 4, nUnits - u0 );
+						float acc0[ 4 ][ 4 ], acc1[ 4 ][ 4 ];
+#pragma unroll
+						for( int u = 0; u < 4; u++ )
+#pragma unroll
+							for( int i = 0; i < 4; i++ ) { acc0[ u ][ i ] = 0.0f; acc1[ u ][ i ] = 0.0f; }
+#pragma unroll 1
+						for( int kc = 0; kc < KC; kc++ )
 						{
-							const int j0 = min( p * dc, nkv ), j1 = min( ( p + 1 ) * dc, nkv );
-							float y = 0.0f;
-							int j = j0;
-							while( j < j1 )
+							if( KC > 1 )
 							{
-								int n;
-								const __half* vp;
-								if( j < nkvOld )
+								if( kc > 0 ) consumerSync();   // the previous chunk's MMAs have read `act`
+								stageF16<D>( hSrc + (size_t)kc * D, hStride, B, act, warp, lane );
+								consumerSync();
+							}
+#pragma unroll
+							for( int u = 0; u < 4; u++ )
+							{
+								if( u < nb )
 								{
-									const int ci = j / CR;
-									n = min( j1, min( nkvOld, ( ci + 1 ) * CR ) ) - j;
-									vp = reinterpret_cast<const __half*>( waitSlot( ci ) ) + (size_t)( j - ci * CR ) * 64 + e;
+									const uint8_t* w = waitSlot( 0 );
+									if( u == 0 && kc == 0 && u0 == 0 ) sub( 2 );
+									const uint8_t* wb = w + (size_t)gq * RS + tq * 16;
+									const uint8_t* xb0 = act + (size_t)gq * RS + tq * 16;
+									const uint8_t* xb1 = act + (size_t)( gq + 8 ) * RS + tq * 16;
+#pragma unroll
+									for( int s = 0; s < C::SPW; s++ )
+									{
+										const int st = warp + FL_WARPS * s;
+										if( st < C::STEPS )
+										{
+											const uint4 wv = *reinterpret_cast<const uint4*>( wb + st * 64 );
+											const uint4 x0 = *reinterpret_cast<const uint4*>( xb0 + st * 64 );
+											mmaF( acc0[ u ], wv.x, wv.y, x0.x, x0.y );
+											mmaF( acc0[ u ], wv.z, wv.w, x0.z, x0.w );
+											if( twoTiles )
+											{
+												const uint4 x1v = *reinterpret_cast<const uint4*>( xb1 + st * 64 );
+												mmaF( acc1[ u ], wv.x, wv.y, x1v.x, x1v.y );
+												mmaF( acc1[ u ], wv.z, wv.w, x1v.z, x1v.w );
+											}
+										}
+									}
+									releaseSlots( 1 );
 								}
+							}
+						}
+						if( u0 == 0 ) sub( 3 );
+						// cross-warp reduction: red[u][warp][row g][col]
+#pragma unroll
+						for( int u = 0; u < 4; u++ )
+						{
+							if( u < nb )
+							{
+								float* my = red + ( ( u * FL_WARPS + warp ) * 8 + gq ) * ncols;
+								my[ 2 * tq ] = acc0[ u ][ 0 ];
+								my[ 2 * tq + 1 ] = acc0[ u ][ 1 ];
+								if( twoTiles ) { my[ 8 + 2 * tq ] = acc1[ u ][ 0 ]; my[ 8 + 2 * tq + 1 ] = acc1[ u ][ 1 ]; }
+							}
+						}
+						consumerSync();
+						for( int idx = tid; idx < nb * B * 8; idx += FL_CONSUMERS )
+						{
+							const int u = idx / ( B * 8 );
+							const int rem = idx - u * B * 8;
+							const int c = rem >> 3, r = rem & 7;
+							const int rl = ( u0 + u ) * 8 + r;     // row within this CTA's range
+							if( rl >= nRows ) continue;
+							const int nn0 = row0 + rl;
+							float v = 0.0f;
+#pragma unroll
+							for( int w = 0; w < FL_WARPS; w++ ) v += red[ ( ( u * FL_WARPS + w ) * 8 + r ) * ncols + c ];
+							const float bs = bias ? bias[ rl ] : 0.0f;
+							switch( epi )
+							{
+							case EP_QKV:
+							{
+								const int which = nn0 / D;
+								const int nn = nn0 - which * D;
+								if( which == 0 ) stX16( outF16 + (size_t)c * D + nn, __float2half_rn( ( v + bs ) * scale ) );
 								else
 								{
-									n = 1;
-									vp = reinterpret_cast<const __half*>( sqkv + 256 ) + e;   // this step's own V row
+									const int hh = nn >> 6, e = nn & 63;
+									const size_t off = ( ( (size_t)c * H + hh ) * a.nTextCtx + nPast ) * 64 + e;
+									if( which == 1 )
+									{
+										const __half kv = __float2half_rn( v * scale );
+										Lr.kCache[ off ] = kv;
+										stX16( knew + (size_t)c * D + nn, kv );
+									}
+									else
+									{
+										const __half vv = __float2half_rn( v + bs );
+										Lr.vCache[ off ] = vv;
+										stX16( vnew + (size_t)c * D + nn, vv );
+									}
 								}
-								y = a.refThreads > 0 ? chainRows<true>( y, sp + j, vp, n ) : chainRows<false>( y, sp + j, vp, n );
-								j += n;
+								break;
 							}
-							so[ tid ] = y;
-						}
-						releaseSlots( nKcSelf, true );
-					}
-					consumerSync();
-					if( tid < 64 )
-					{
-						float acc = so[ tid ];
-						for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
-						stX16( attn1 + vo + tid, __float2half_rn( acc ) );
-					}
-					consumerSync();
-				}
-				mark();
-				// ---- self-attention out projection + residual ----
-				o.epi = EP_RESID; o.nOut = D; o.R = g.R1; o.bias = sbias + g.oO; o.outF32 = x1;
-				if( n1 > 0 )
-				{
-					stageF16<D>( attn1, D, B, act, tid );
-					consumerSync();
-					gemv( o, r1, n1, 1, nullptr );
-				}
-				mark();
-				// ---- LN + cross-attention query (a15) ----
-				{
-					const uint8_t* pr = waitSlot( 0 );
-					if( n1 > 0 ) stageLN( x1, pr );
-					consumerSync();
-					releaseSlots( 1 );
-					o.epi = EP_QSCALE; o.bias = sbias + g.oCq; o.scale = qkScale; o.outF16 = cq;
-					gemv( o, r1, n1, 1, nullptr );
-					o.scale = 1.0f;
-				}
-				mark();
-				// ---- cross attention over the encoder's f16 K/V memories, units = (chunk, head) ----
-				for( int unit = cta; unit < B * H; unit += G )
-				{
-					const int b = unit / H, h = unit - b * H;
-					const size_t vo = (size_t)b * D + h * 64;
-					float qf[ 8 ];
-					{
-						const __half* src = cq + vo + ( lane & 7 ) * 8;
-						uint4 u = ldPoll( src );
-						SpinGuard guard;
-						while( hasSent16( u ) ) { u = ldPoll( src ); guard.tick(); }
-						const __half* qs = reinterpret_cast<const __half*>( &u );
-#pragma unroll
-						for( int e = 0; e < 8; e++ ) qf[ e ] = __half2float( qs[ e ] );
-					}
-					float lmax = -INFINITY;
-					for( int ci = 0; ci < nKcCross; ci++ )
-					{
-						const uint8_t* kc = waitSlot( 0 );
-						lmax = scoreRows( kc, min( CR, T - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
-						releaseSlots( 1 );
-					}
-					softmaxRow( sp, T, lmax, sred, tid, warp, lane );
-					{
-						const int p = tid >> 6, e = tid & 63;
-						float y = 0.0f;
-						for( int i = 0; i < roundsCross; i++ )
-						{
-							if( p < parts )
-							{
-								const int j0 = p * dcCross + i * CR;
-								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcCross, T ) );
-								if( j1 > j0 )
-								{
-									const __half* vp = reinterpret_cast<const __half*>( waitSlot( p ) ) + e;
-									y = a.refThreads > 0 ? chainRows<true>( y, sp + j0, vp, j1 - j0 ) : chainRows<false>( y, sp + j0, vp, j1 - j0 );
-								}
+							case EP_RESID:
+								stX32( outF32 + (size_t)c * D + nn0, v + bs + xres[ c * 16 + rl ] );
+								break;
+							case EP_QSCALE:
+								stX16( outF16 + (size_t)c * D + nn0, __float2half_rn( ( v + bs ) * scale ) );
+								break;
+							case EP_GELU:
+								stX16( outF16 + (size_t)c * ld + nn0, __float2half_rn( ptx::gelu_f16_semantics( v + bs ) ) );
+								break;
+							default:
+								outF32[ (size_t)c * ld + nn0 ] = v;
+								break;
 							}
-							releaseSlots( parts, true );
 						}
-						if( p < parts ) so[ tid ] = y;
+						if( u0 == 0 ) sub( 4 );
+						if( u0 + 4 < nUnits ) consumerSync();   // `red` is rewritten by the next batch
 					}
-					consumerSync();
-					if( tid < 64 )
-					{
-						float acc = so[ tid ];
-						for( int k = 1; k < parts; k++ ) acc += so[ k * 64 + tid ];
-						stX16( attn2 + vo + tid, __float2half_rn( acc ) );
-					}
-					consumerSync();
+					mark();
+					if( last ) break;
 				}
-				mark();
-				// ---- cross-attention out projection + residual ----
-				o.epi = EP_RESID; o.bias = sbias + g.oCo; o.outF32 = x2;
-				if( n1 > 0 )
-				{
-					stageF16<D>( attn2, D, B, act, tid );
-					consumerSync();
-					gemv( o, r1, n1, 1, nullptr );
-				}
-				mark();
-				// ---- LN + fc1 + GELU (a16) ----
-				{
-					const uint8_t* pr = waitSlot( 0 );
-					if( n4 > 0 ) stageLN( x2, pr );
-					consumerSync();
-					releaseSlots( 1 );
-					o.epi = EP_GELU; o.nOut = 4 * D; o.R = g.R4; o.bias = sbias + g.oFc1; o.outF16 = hbuf; o.ld = 4 * D;
-					gemv( o, r4, n4, 1, nullptr );
-				}
-				mark();
-				// ---- fc2 + residual ----
-				o.epi = EP_RESID; o.nOut = D; o.R = g.R1; o.bias = sbias + g.oFc2; o.outF32 = x3; o.ld = D;
-				gemv( o, r1, n1, 4, hbuf );
-				mark();
+				if( last ) break;
 				// ---- re-arm this layer's buffers of the idle set (their readers finished with the previous launch) ----
 				{
 					uint4* dst = reinterpret_cast<uint4*>( a.exch + ( (size_t)( set ^ 1 ) * L + il ) * exLayer );
@@ -918,18 +971,6 @@ namespace kern
 					for( size_t i = tid; i < per && lo + i < n16; i += FL_CONSUMERS ) dst[ lo + i ] = make_uint4( SENT32, SENT32, SENT32, SENT32 );
 				}
 			}
-			// ---- final LayerNorm + logits = tok_emb^T x (a17) ----
-			{
-				const float* xin = reinterpret_cast<const float*>( a.exch + ( (size_t)set * L + L - 1 ) * exLayer ) + 2 * colsD;
-				const uint8_t* pr = waitSlot( 0 );
-				if( nv > 0 ) stageLN( xin, pr );
-				consumerSync();
-				releaseSlots( 1 );
-				GemvOut o{};
-				o.epi = EP_LOGITS; o.nOut = a.nVocab; o.R = g.RV; o.bias = nullptr; o.scale = 1.0f; o.outF32 = a.logits; o.ld = a.nVocab;
-				gemv( o, rv, nv, 1, nullptr );
-			}
-			mark();
 			// the last CTA to finish flips the exchange set for the next launch
 			consumerSync();
 			if( tid == 0 )

@@ -37,7 +37,9 @@ namespace kern
 		uint8_t* exch = nullptr;            // exchange buffers: 2 sets x L layers x (maxB * d * 32) bytes, all 0xFF when idle
 		unsigned* ctrl = nullptr;           // [0] CTAs finished, [1] launch epoch (selects the exchange set)
 		float* logits = nullptr;            // [B][nVocab]
-		unsigned long long* timing = nullptr;   // optional: %globaltimer marks of CTA 0 (debug)
+		unsigned long long* timing = nullptr;   // optional: (id, %globaltimer) marks of CTA `timingCta` (debug)
+		int timingCta = 0;
+		int l2Prefetch = 0;                 // producer warp issues bulk L2 prefetches one layer ahead (WSP_FLOW_L2=1; measured slower, off by default)
 		FlowGeom g;
 		int NS = 0;                         // ring slots
 		int ncols = 8;                      // activation columns staged: 8 (B <= 8) or 16

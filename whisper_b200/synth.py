@@ -168,7 +168,7 @@ SC_GAIN = 1.0
 SC_ENC_CENTER = None            # mean of the encoder's ln_post output at unit gain, [d]
 SC_ENC_GAIN = 1.0
 SC_NOISE_LOGIT_RMS = 0.9
-SC_ENC_GAIN_CALIBRATED = 10.0
+SC_ENC_GAIN_CALIBRATED = 3.0
 
 
 def _hadamard(n):
