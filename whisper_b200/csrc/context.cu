@@ -163,7 +163,9 @@ namespace wsp
 			const char* env = getenv( "WSP_STEP_MODE" );
 			if( env && env[ 0 ] >= '0' && env[ 0 ] <= '2' ) c.stepMode = env[ 0 ] - '0';
 			env = getenv( "WSP_FLOW_L2" );
-			if( env ) c.flowL2Prefetch = env[ 0 ] != '0';
+			if( env ) c.flowL2Prefetch = atoi( env );
+			env = getenv( "WSP_FLOW_NK" );
+			if( env ) c.flowKRing = atoi( env );
 			env = getenv( "WSP_TIMING_CTA" );
 			if( env ) c.stepTimingCta = atoi( env );
 		}
@@ -394,6 +396,7 @@ namespace wsp
 			fa.g = c.flowGeom;
 			fa.timingCta = c.stepTimingCta;
 			fa.l2Prefetch = c.flowL2Prefetch;
+			fa.NK = c.flowKRing;
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepFlow( fa, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

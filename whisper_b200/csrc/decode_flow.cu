@@ -29,7 +29,8 @@ namespace kern
 	{
 		constexpr int FL_WARPS = 8;                    // consumer warps
 		constexpr int FL_CONSUMERS = FL_WARPS * 32;
-		constexpr int FL_THREADS = FL_CONSUMERS + 32;  // + the producer warp
+		constexpr int FL_THREADS = FL_CONSUMERS + 64;  // + the two producer warps (main ring, K ring)
+		constexpr int FL_NK = 4;                       // slots of the K ring (at most; FlowArgs::NK says how many a launch uses)
 		constexpr int FL_NSMAX = 32;
 		constexpr int FL_MAXT = 1536;
 		constexpr int FL_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA on sm_100
@@ -50,10 +51,10 @@ namespace kern
 		{
 			int act, red, sp, bias, xres, so, sred, qkv, bars, total;
 		};
-		__host__ __device__ inline SmemLayout smemLayout( int slot, int rs, int NS, int ncols )
+		__host__ __device__ inline SmemLayout smemLayout( int slot, int rs, int NS, int NK, int ncols )
 		{
 			SmemLayout l;
-			int o = NS * slot;
+			int o = ( NS + NK ) * slot;   // main ring, then the K ring
 			l.act = o; o += ncols * rs;
 			l.red = o; o += 4 * FL_WARPS * 8 * ncols * 4;
 			l.sp = o; o += FL_MAXT * 4;
@@ -62,15 +63,18 @@ namespace kern
 			l.so = o; o += 256 * 4;
 			l.sred = o; o += 64;
 			l.qkv = o; o += 3 * 128;
-			l.bars = o; o += 2 * FL_NSMAX * 8;
+			l.bars = o; o += ( 2 * FL_NSMAX + 2 * FL_NK ) * 8;
 			l.total = o;
 			return l;
 		}
-		inline int ringSlots( int slot, int rs, int ncols )
+		// how the slots that fit next to the fixed buffers are split: 4 for the K ring when the main ring keeps >= 6, else 2
+		inline void ringSlots( int slot, int rs, int ncols, int wantK, int& nsMain, int& nK )
 		{
-			const int fixed = smemLayout( slot, rs, 0, ncols ).total;
-			int ns = ( FL_SMEM_MAX - fixed ) / slot;
-			return ns > FL_NSMAX ? FL_NSMAX : ns;
+			const int fixed = smemLayout( slot, rs, 0, 0, ncols ).total;
+			const int total = ( FL_SMEM_MAX - fixed ) / slot;
+			nK = wantK <= 0 ? 0 : ( total - wantK >= 6 ? ( wantK > FL_NK ? FL_NK : wantK ) : 2 );
+			nsMain = total - nK;
+			if( nsMain > FL_NSMAX ) nsMain = FL_NSMAX;
 		}
 
 		// ---- small device helpers ------------------------------------------------------------------------------------
@@ -153,30 +157,28 @@ namespace kern
 
 		__device__ __forceinline__ float expTabF( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
 
-		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key
+		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key.
+		// One step is three dependent ALU instructions (FFMA -> F2FP.F16.F32 -> HADD2.F32); the operands of eight steps are loaded
+		// up front so that no shared-memory latency sits inside the dependency chain (unrolled by 4 with the loads inline it ran at
+		// 31 cycles per key: 5.8 us for the 375 keys of a cross-attention part).
 		template<bool F16>
 		__device__ __forceinline__ float chainRows( float y, const float* __restrict__ sp, const __half* __restrict__ v, int n )
 		{
 			int j = 0;
-			for( ; j + 4 <= n; j += 4 )
+			for( ; j + 8 <= n; j += 8 )
 			{
-				const float x0 = __half2float( v[ j * 64 ] );
-				const float x1 = __half2float( v[ ( j + 1 ) * 64 ] );
-				const float x2 = __half2float( v[ ( j + 2 ) * 64 ] );
-				const float x3 = __half2float( v[ ( j + 3 ) * 64 ] );
-				if( F16 )
+				float x[ 8 ], p[ 8 ];
+#pragma unroll
+				for( int k = 0; k < 8; k++ )
 				{
-					y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
+					x[ k ] = __half2float( v[ ( j + k ) * 64 ] );
+					p[ k ] = sp[ j + k ];
 				}
-				else
+#pragma unroll
+				for( int k = 0; k < 8; k++ )
 				{
-					y = __fmaf_rn( sp[ j ], x0, y );
-					y = __fmaf_rn( sp[ j + 1 ], x1, y );
-					y = __fmaf_rn( sp[ j + 2 ], x2, y );
-					y = __fmaf_rn( sp[ j + 3 ], x3, y );
+					if( F16 ) y = __half2float( __float2half_rn( __fmaf_rn( x[ k ], p[ k ], y ) ) );
+					else y = __fmaf_rn( p[ k ], x[ k ], y );
 				}
 			}
 			for( ; j < n; j++ )
@@ -264,7 +266,8 @@ namespace kern
 			SpinGuard guard;
 			// Probe before reading: four words at the quarter points of the row, polled with back-off, until they are written.  148
 			// CTAs re-reading whole 32 KB activation blocks while they wait would by themselves saturate the L2 (one round = 4.7 MB,
-			// ~10 TB/s when spinning) and starve the weight stream; the probes cost four sectors per round.
+			// ~10 TB/s when spinning) and starve the weight stream; the probes cost four sectors per round.  (Measured alternative:
+			// an optimistic full read first, probes only after a miss — every phase 0.3-0.9 us slower: CTAs arrive early as a rule.)
 			{
 				const uint32_t* w = reinterpret_cast<const uint32_t*>( row ) + ( lane & 3 ) * ( D / 4 ) + D / 8;
 				unsigned ns = 32;
@@ -362,56 +365,106 @@ namespace kern
 			}
 		}
 		// B rows of D ready f16 activations (attention output, GELU output) from an exchange buffer -> shared memory, one warp per row
+		// (two for B > 8).  Split in three so that fc2 can issue the loads of its next K chunk before the MMAs of the current one:
+		//   f16Issue: optimistic loads into registers;  f16Verify: wait (probe + back-off, see pollRowF32) until no sentinel is left;
+		//   f16Put: registers -> the activation rows in shared memory.
 		template<int D>
-		__device__ __forceinline__ void stageF16( const __half* src, size_t colStride, int B, uint8_t* act, int warp, int lane )
+		struct F16Rows
 		{
-			constexpr int V8 = D / 8;                   // 16-byte pieces per row
-			constexpr int NI = ( V8 + 31 ) / 32;
-			constexpr int RS = Cfg<D>::RS;
+			static constexpr int V8 = D / 8;                   // 16-byte pieces per row
+			static constexpr int NI = ( V8 + 31 ) / 32;
+			uint4 u[ 2 ][ NI ];
+		};
+		template<int D>
+		__device__ __forceinline__ void f16Probe( const __half* src, size_t colStride, int B, int warp, int lane )
+		{
 			for( int c = warp; c < B; c += FL_WARPS )
 			{
-				const __half* row = src + (size_t)c * colStride;
+				const uint32_t* w = reinterpret_cast<const uint32_t*>( src + (size_t)c * colStride ) + ( lane & 3 ) * ( D / 8 ) + D / 16;
 				SpinGuard guard;
+				unsigned ns = 32;
+				while( !__all_sync( 0xffffffffu, !hasSent16w( ldPoll32( w ) ) ) )
 				{
-					// probe four words of the row with back-off before reading it (see pollRowF32)
-					const uint32_t* w = reinterpret_cast<const uint32_t*>( row ) + ( lane & 3 ) * ( D / 8 ) + D / 16;
-					unsigned ns = 32;
-					while( !__all_sync( 0xffffffffu, !hasSent16w( ldPoll32( w ) ) ) )
-					{
-						__nanosleep( ns );
-						if( ns < 256 ) ns <<= 1;
-						guard.tick();
-					}
+					__nanosleep( ns );
+					if( ns < 256 ) ns <<= 1;
+					guard.tick();
 				}
-				uint4 u[ NI ];
+			}
+		}
+		template<int D>
+		__device__ __forceinline__ void f16Issue( F16Rows<D>& rg, const __half* src, size_t colStride, int B, int warp, int lane )
+		{
+			using R = F16Rows<D>;
 #pragma unroll
-				for( int k = 0; k < NI; k++ )
+			for( int q = 0; q < 2; q++ )
+			{
+				const int c = warp + q * FL_WARPS;
+				if( c >= B ) continue;
+				const __half* row = src + (size_t)c * colStride;
+#pragma unroll
+				for( int k = 0; k < R::NI; k++ )
 				{
 					const int i = k * 32 + lane;
-					u[ k ] = make_uint4( 0, 0, 0, 0 );
-					if( i < V8 ) u[ k ] = ldPoll( row + i * 8 );
+					rg.u[ q ][ k ] = make_uint4( 0, 0, 0, 0 );
+					if( i < R::V8 ) rg.u[ q ][ k ] = ldPoll( row + i * 8 );
 				}
+			}
+		}
+		template<int D>
+		__device__ __forceinline__ void f16Verify( F16Rows<D>& rg, const __half* src, size_t colStride, int B, int warp, int lane )
+		{
+			using R = F16Rows<D>;
+#pragma unroll
+			for( int q = 0; q < 2; q++ )
+			{
+				const int c = warp + q * FL_WARPS;
+				if( c >= B ) continue;
+				const __half* row = src + (size_t)c * colStride;
+				SpinGuard guard;
+				bool first = true;
 				while( true )
 				{
 					bool miss = false;
 #pragma unroll
-					for( int k = 0; k < NI; k++ )
+					for( int k = 0; k < R::NI; k++ ) miss |= ( k * 32 + lane < R::V8 ) && hasSent16( rg.u[ q ][ k ] );
+					if( !__any_sync( 0xffffffffu, miss ) ) break;
+					if( first )
 					{
-						const int i = k * 32 + lane;
-						if( i < V8 && hasSent16( u[ k ] ) )
+						first = false;
+						const uint32_t* w = reinterpret_cast<const uint32_t*>( row ) + ( lane & 3 ) * ( D / 8 ) + D / 16;
+						unsigned ns = 32;
+						while( !__all_sync( 0xffffffffu, !hasSent16w( ldPoll32( w ) ) ) )
 						{
-							u[ k ] = ldPoll( row + i * 8 );
-							miss = true;
+							__nanosleep( ns );
+							if( ns < 256 ) ns <<= 1;
+							guard.tick();
 						}
 					}
-					if( !miss ) break;
+#pragma unroll
+					for( int k = 0; k < R::NI; k++ )
+					{
+						const int i = k * 32 + lane;
+						if( i < R::V8 && hasSent16( rg.u[ q ][ k ] ) ) rg.u[ q ][ k ] = ldPoll( row + i * 8 );
+					}
 					guard.tick();
 				}
+			}
+		}
+		template<int D>
+		__device__ __forceinline__ void f16Put( const F16Rows<D>& rg, int B, uint8_t* act, int warp, int lane )
+		{
+			using R = F16Rows<D>;
+			constexpr int RS = Cfg<D>::RS;
 #pragma unroll
-				for( int k = 0; k < NI; k++ )
+			for( int q = 0; q < 2; q++ )
+			{
+				const int c = warp + q * FL_WARPS;
+				if( c >= B ) continue;
+#pragma unroll
+				for( int k = 0; k < R::NI; k++ )
 				{
 					const int i = k * 32 + lane;
-					if( i < V8 ) *reinterpret_cast<uint4*>( act + (size_t)c * RS + i * 16 ) = u[ k ];
+					if( i < R::V8 ) *reinterpret_cast<uint4*>( act + (size_t)c * RS + i * 16 ) = rg.u[ q ][ k ];
 				}
 			}
 		}
@@ -426,7 +479,8 @@ namespace kern
 			constexpr int RS = C::RS, SLOT = C::SLOT, CR = C::CR;
 			extern __shared__ __align__( 128 ) uint8_t fl_smem[];
 			const int NS = a.NS, ncols = a.ncols;
-			const SmemLayout lay = smemLayout( SLOT, RS, NS, ncols );
+			const int NK = a.NK;
+			const SmemLayout lay = smemLayout( SLOT, RS, NS, NK, ncols );
 			uint8_t* const ring = fl_smem;
 			uint8_t* const act = fl_smem + lay.act;
 			float* const red = reinterpret_cast<float*>( fl_smem + lay.red );
@@ -438,6 +492,9 @@ namespace kern
 			uint8_t* const sqkv = fl_smem + lay.qkv;
 			uint64_t* const full = reinterpret_cast<uint64_t*>( fl_smem + lay.bars );
 			uint64_t* const empty = full + FL_NSMAX;
+			uint64_t* const kFull = empty + FL_NSMAX;
+			uint64_t* const kEmpty = kFull + FL_NK;
+			uint8_t* const kring = ring + (size_t)NS * SLOT;   // the K ring's FL_NK slots follow the main ring's NS
 
 			const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 			const int cta = blockIdx.x, G = gridDim.x;
@@ -447,6 +504,11 @@ namespace kern
 				{
 					ptx::mbar_init( full + i, 1 );
 					ptx::mbar_init( empty + i, FL_WARPS );
+				}
+				for( int i = 0; i < FL_NK; i++ )
+				{
+					ptx::mbar_init( kFull + i, 1 );
+					ptx::mbar_init( kEmpty + i, FL_WARPS );
 				}
 				ptx::fence_barrier_init();
 			}
@@ -543,17 +605,17 @@ namespace kern
 						l2( Ln.crossV + (size_t)unit * T * 64, (size_t)T * 128 );
 					}
 				};
-				const bool pf = a.l2Prefetch != 0;
+				const bool pf = a.l2Prefetch >= 2;   // (mode 1: the K producer prefetches the cross K/V only)
 				for( int il = 0; il < L; il++ )
 				{
 					const FlowLayer& Lr = a.layers[ il ];
-					if( pf ) l2Cross( Lr );
 					sendParams( Lr.ln1g, Lr.ln1b, Lr.biasSlab + (size_t)cta * g.slabFloats, g.slabFloats );
 					sendWeights( Lr.wqkv, D, r3, n3, 1 );
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * a.nTextCtx * 64;   // unit = b * H + h
-						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
+						if( NK == 0 )
+							for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
 						for( int i = 0; i < roundsSelf; i++ )
 							for( int p = 0; p < parts; p++ )
 							{
@@ -573,7 +635,8 @@ namespace kern
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * T * 64;
-						for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
+						if( NK == 0 )
+							for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
 						for( int i = 0; i < roundsCross; i++ )
 							for( int p = 0; p < parts; p++ )
 							{
@@ -589,6 +652,50 @@ namespace kern
 				}
 				sendParams( a.lnfg, a.lnfb, nullptr, 0 );
 				sendWeights( a.tokEmb, D, rv, nv, 1 );
+				return;
+			}
+
+			// =========================================================================================================
+			// K producer warp: the key rows of every attention unit stream through their own small ring, in use order.  Keeping them
+			// out of the main ring lets that one hold the V rows of the cross-attention BEFORE the query exists (they used to queue
+			// behind 192 KB of keys and arrived in the middle of the f16 chains), while the keys — needed the moment the query lands,
+			// consumed in a microsecond — are prefetched FL_NK runs deep and otherwise stream at HBM rate into the scoring loop.
+			// =========================================================================================================
+			if( warp == FL_WARPS + 1 )
+			{
+				int kSlot = 0;
+				uint32_t kPar = 0;
+				bool kWrapped = false;
+				auto sendK = [ & ]( const __half* base, int j0, int n ) {
+					uint8_t* dst = kring + (size_t)kSlot * SLOT;
+					uint64_t* kb = kFull + kSlot;
+					if( lane == 0 )
+					{
+						if( kWrapped ) mbarWaitLong( kEmpty + kSlot, kPar ^ 1u );
+						ptx::mbar_expect_tx( kb, (uint32_t)n * 128 );
+						ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, kb );
+					}
+					__syncwarp();
+					if( ++kSlot == NK ) { kSlot = 0; kPar ^= 1u; kWrapped = true; }
+				};
+				for( int il = 0; il < L; il++ )
+				{
+					const FlowLayer& Lr = a.layers[ il ];
+					// HBM -> L2 for this layer's cross K/V of my units, ~15 us before the cross-attention phase needs them: the 49 MB per
+					// layer then stream during the latency-bound projection phases instead of in one HBM-bound burst behind the query
+					if( a.l2Prefetch >= 1 && lane == 0 )
+						for( int unit = cta; unit < B * H; unit += G )
+						{
+							const uint32_t bytes = (uint32_t)T * 128;
+							asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( Lr.crossK + (size_t)unit * T * 64 ), "r"( bytes ) : "memory" );
+							asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( Lr.crossV + (size_t)unit * T * 64 ), "r"( bytes ) : "memory" );
+						}
+					if( NK == 0 ) continue;
+					for( int unit = cta; unit < B * H; unit += G )
+						for( int ci = 0; ci < nKcSelf; ci++ ) sendK( Lr.kCache + (size_t)unit * a.nTextCtx * 64, ci * CR, min( CR, nkvOld - ci * CR ) );
+					for( int unit = cta; unit < B * H; unit += G )
+						for( int ci = 0; ci < nKcCross; ci++ ) sendK( Lr.crossK + (size_t)unit * T * 64, ci * CR, min( CR, T - ci * CR ) );
+				}
 				return;
 			}
 
@@ -627,6 +734,8 @@ namespace kern
 			};
 			// debug: (id, %globaltimer) pairs of one CTA.  ids: 0 = kernel start, 100 * (phase + 1) + sub for the sub-steps of a phase
 			// (sub 0 = phase done; 1 = inputs arrived and staged; 2 = first weight slot landed; 3 = MMAs done; 4 = reduced + stored)
+			int kcSlot = 0;
+			uint32_t kcPar = 0;
 			int markIdx = 0;
 			const int markCta = a.timing ? a.timingCta : -1;
 			auto markId = [ & ]( int id ) {
@@ -721,9 +830,18 @@ namespace kern
 #pragma unroll 1
 							for( int ci = 0; ci < nKc; ci++ )
 							{
-								const uint8_t* kc = waitSlot( 0 );
-								lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
-								releaseSlots( 1 );
+								if( NK == 0 )
+								{
+									const uint8_t* kc = waitSlot( 0 );
+									lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+									releaseSlots( 1 );
+									continue;
+								}
+								mbarWaitLong( kFull + kcSlot, kcPar );
+								lmax = scoreRows( kring + (size_t)kcSlot * SLOT, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+								__syncwarp();
+								if( lane == 0 ) ptx::mbar_arrive( kEmpty + kcSlot );
+								if( ++kcSlot == NK ) { kcSlot = 0; kcPar ^= 1u; }
 							}
 							if( self ) lmax = scoreRows( sqkv + 128, 1, nOld, qf, sp, warp, lane, lmax );   // this step's own K row
 							sub( 2 );
@@ -831,9 +949,14 @@ namespace kern
 						sub( 1 );
 						releaseSlots( 1 );
 					}
-					else if( KC == 1 && nRows > 0 )
+					F16Rows<D> hr;
+					if( !useLN && nRows > 0 )
 					{
-						stageF16<D>( hSrc, hStride, B, act, warp, lane );
+						// (fc2: the first of its four K chunks; the others are fetched behind the MMAs below)
+						f16Probe<D>( hSrc, hStride, B, warp, lane );
+						f16Issue<D>( hr, hSrc, hStride, B, warp, lane );
+						f16Verify<D>( hr, hSrc, hStride, B, warp, lane );
+						f16Put<D>( hr, B, act, warp, lane );
 						consumerSync();
 						sub( 1 );
 					}
@@ -851,12 +974,15 @@ namespace kern
 #pragma unroll 1
 						for( int kc = 0; kc < KC; kc++ )
 						{
-							if( KC > 1 )
+							if( kc > 0 )
 							{
-								if( kc > 0 ) consumerSync();   // the previous chunk's MMAs have read `act`
-								stageF16<D>( hSrc + (size_t)kc * D, hStride, B, act, warp, lane );
+								// this chunk's rows were requested before the previous chunk's MMAs
+								f16Verify<D>( hr, hSrc + (size_t)kc * D, hStride, B, warp, lane );
+								consumerSync();   // the previous chunk's MMAs have read `act`
+								f16Put<D>( hr, B, act, warp, lane );
 								consumerSync();
 							}
+							if( kc + 1 < KC ) f16Issue<D>( hr, hSrc + (size_t)( kc + 1 ) * D, hStride, B, warp, lane );
 #pragma unroll
 							for( int u = 0; u < 4; u++ )
 							{
@@ -1004,12 +1130,11 @@ namespace kern
 		}
 
 		template<int D>
-		int smemBytes( int ncols, int* nsOut )
+		int smemBytes( int ncols, int wantK, int& ns, int& nk )
 		{
 			using C = Cfg<D>;
-			const int ns = ringSlots( C::SLOT, C::RS, ncols );
-			if( nsOut ) *nsOut = ns;
-			return smemLayout( C::SLOT, C::RS, ns, ncols ).total;
+			ringSlots( C::SLOT, C::RS, ncols, wantK, ns, nk );
+			return smemLayout( C::SLOT, C::RS, ns, nk, ncols ).total;
 		}
 		template<int D>
 		cudaError_t prepareD()
@@ -1021,9 +1146,10 @@ namespace kern
 		cudaError_t launchD( FlowArgs& a, int numSMs, cudaStream_t s )
 		{
 			a.ncols = a.B > 8 ? 16 : 8;
-			int ns = 0;
-			const int smem = smemBytes<D>( a.ncols, &ns );
+			int ns = 0, nk = 0;
+			const int smem = smemBytes<D>( a.ncols, a.NK, ns, nk );   // a.NK in: requested K-ring depth (0 = keys through the main ring)
 			a.NS = ns;
+			a.NK = nk;
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3( (unsigned)numSMs );
 			cfg.blockDim = dim3( FL_THREADS );
@@ -1064,12 +1190,13 @@ namespace kern
 		if( !( d == 128 || d == 384 || d == 512 || d == 768 || d == 1024 || d == 1280 ) ) return false;
 		const FlowGeom g = flowGeometry( d, 51865, grid );
 		if( g.R1 > 16 || g.slabFloats > 256 ) return false;
-		// the self-attention V rows of one head are held in the ring all at once
 		const int rs = 2 * d + 64;
 		const int slot = 8 * rs > 16384 ? 8 * rs : 16384;
 		const int cr = ( slot / 128 ) & ~7;
-		const int ns = ringSlots( slot, rs, B > 8 ? 16 : 8 );
-		if( ( nTextCtx + cr - 1 ) / cr + 1 > ns || 4 + 1 > ns ) return false;
+		int ns = 0, nk = 0;
+		ringSlots( slot, rs, B > 8 ? 16 : 8, 0, ns, nk );
+		(void)cr;
+		if( 4 + 1 > ns ) return false;   // a round of V slots (one per reference thread) is held at once
 		return true;
 	}
 

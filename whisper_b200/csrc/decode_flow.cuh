@@ -41,7 +41,8 @@ namespace kern
 		int timingCta = 0;
 		int l2Prefetch = 0;                 // producer warp issues bulk L2 prefetches one layer ahead (WSP_FLOW_L2=1; measured slower, off by default)
 		FlowGeom g;
-		int NS = 0;                         // ring slots
+		int NS = 0;                         // main ring slots
+		int NK = 0;                         // K ring slots
 		int ncols = 8;                      // activation columns staged: 8 (B <= 8) or 16
 	};
 	bool flowSupported( int d, int B, int T, int H, int nTextCtx, int refThreads, int grid );

@@ -614,8 +614,84 @@ namespace kern
 	//   if sum_ts > max_tx or force_timestamp: p(text) = -inf;  top-4 by p; skip sot/solm/not among the first three.
 	constexpr int SM_THREADS = 1024;
 
-	struct Top1 { float v; int i; };
-	__device__ __forceinline__ Top1 better( Top1 a, Top1 b ) { return ( b.v > a.v || ( b.v == a.v && b.i < a.i ) ) ? b : a; }
+	// arg-max candidate; `tie`: another token has exactly the same probability (then the reference's pick depends on how
+	// std::partial_sort happens to arrange equal keys, see emulatePartialSort)
+	struct Top1 { float v; int i; int tie; };
+	__device__ __forceinline__ Top1 better( Top1 a, Top1 b )
+	{
+		Top1 r = ( b.v > a.v || ( b.v == a.v && b.i < a.i ) ) ? b : a;
+		if( a.v == b.v && a.i != b.i && a.v > -INFINITY ) r.tie = 1;
+		return r;
+	}
+
+	// The reference ranks candidates with std::partial_sort( top 4 ) on (probability, id) pairs compared by probability only
+	// (whisper.cpp:1932-1941).  With distinct probabilities that is "the largest"; with EXACT ties — typically a whole range of
+	// probabilities that underflowed to 0 in the f16-table softmax — the winner is whatever libstdc++'s heap-select + sort-heap leaves
+	// first.  This is that algorithm, statement by statement (bits/stl_heap.h: __push_heap, __adjust_heap, __make_heap, __sort_heap;
+	// bits/stl_algo.h: __heap_select), run by ONE thread over the row: slow (~1 ms) and only entered when a tie decides the token.
+	struct ProbId { double v; int i; };
+	__device__ void heapPush( ProbId* f, int hole, int top, ProbId val )
+	{
+		int parent = ( hole - 1 ) / 2;
+		while( hole > top && f[ parent ].v > val.v )
+		{
+			f[ hole ] = f[ parent ];
+			hole = parent;
+			parent = ( hole - 1 ) / 2;
+		}
+		f[ hole ] = val;
+	}
+	__device__ void heapAdjust( ProbId* f, int hole, int len, ProbId val )
+	{
+		const int top = hole;
+		int second = hole;
+		while( second < ( len - 1 ) / 2 )
+		{
+			second = 2 * ( second + 1 );
+			if( f[ second ].v > f[ second - 1 ].v ) second--;
+			f[ hole ] = f[ second ];
+			hole = second;
+		}
+		if( ( len & 1 ) == 0 && second == ( len - 2 ) / 2 )
+		{
+			second = 2 * ( second + 1 );
+			f[ hole ] = f[ second - 1 ];
+			hole = second - 1;
+		}
+		heapPush( f, hole, top, val );
+	}
+	__device__ __noinline__ Top1 emulatePartialSort( const float* probs, int nv, int beg, bool maskText, bool isInitial, int sot, int solm, int nott )
+	{
+		auto val = [ & ]( int i, float p ) -> double {
+			if( ( maskText && i < beg ) || ( isInitial && i >= beg + 101 ) ) return -(double)INFINITY;
+			return (double)p;
+		};
+		ProbId f[ 4 ];
+		for( int k = 0; k < 4; k++ ) f[ k ] = ProbId{ val( k, __ldcg( probs + k ) ), k };
+		// __make_heap( first, first + 4 )
+		for( int parent = ( 4 - 2 ) / 2;; parent-- )
+		{
+			const ProbId v = f[ parent ];
+			heapAdjust( f, parent, 4, v );
+			if( parent == 0 ) break;
+		}
+		// __heap_select: every later element that compares before the root replaces it
+		for( int i = 4; i < nv; i++ )
+		{
+			const double v = val( i, __ldcg( probs + i ) );
+			if( v > f[ 0 ].v ) heapAdjust( f, 0, 4, ProbId{ v, i } );
+		}
+		// __sort_heap
+		for( int last = 3; last >= 1; last-- )
+		{
+			const ProbId v = f[ last ];
+			f[ last ] = f[ 0 ];
+			heapAdjust( f, 0, last, v );
+		}
+		int res = 0;
+		while( ( f[ res ].i == sot || f[ res ].i == solm || f[ res ].i == nott ) && res < 3 ) res++;
+		return Top1{ (float)f[ res ].v, f[ res ].i, 0 };
+	}
 
 	__device__ Top1 blockArgmax( Top1 x, Top1* sbuf )
 	{
@@ -624,6 +700,7 @@ namespace kern
 			Top1 y;
 			y.v = __shfl_xor_sync( 0xffffffffu, x.v, o );
 			y.i = __shfl_xor_sync( 0xffffffffu, x.i, o );
+			y.tie = __shfl_xor_sync( 0xffffffffu, x.tie, o );
 			x = better( x, y );
 		}
 		__syncthreads();
@@ -662,6 +739,22 @@ namespace kern
 		double r = 0.0;
 		for( int w = 0; w < SM_THREADS / 32; w++ ) r += sbuf[ w ];
 		return r;
+	}
+
+	// `pick` is the arg-max over the eligible, non-banned tokens (lowest id among equals).  If its probability is shared — by another
+	// eligible token or by one of the banned ones — the reference's choice depends on std::partial_sort's handling of equal keys:
+	// reproduce it exactly.  The whole probability row must be visible in global memory (it is: written before the last barrier).
+	__device__ __forceinline__ Top1 resolveTies( Top1 pick, const SampleArgs& a, const float* probsRow, bool maskText, bool isInitial )
+	{
+		bool tie = pick.tie != 0;
+		if( !tie && !maskText )
+		{
+			const int banned[ 3 ] = { a.tokenSot, a.tokenSolm, a.tokenNot };
+			for( int k = 0; k < 3; k++ )
+				if( banned[ k ] >= 0 && banned[ k ] < a.tokenBeg && __ldcg( probsRow + banned[ k ] ) == pick.v ) tie = true;
+		}
+		if( !tie ) return pick;
+		return emulatePartialSort( probsRow, a.nVocab, a.tokenBeg, maskText, isInitial, a.tokenSot, a.tokenSolm, a.tokenNot );
 	}
 
 	__global__ void __launch_bounds__( SM_THREADS )
@@ -708,8 +801,8 @@ namespace kern
 		// The reference ranks the top 4 and skips sot / solm / not at most 3 times (whisper.cpp:1945-1953); those are the only three
 		// banned ids, so the pick is simply the arg-max over every other eligible token.  Eligibility depends on the timestamp test
 		// below, hence two candidates from the same pass: the best text token and the best timestamp token.
-		Top1 bestTs = { -INFINITY, 0x7fffffff };
-		Top1 bestTx = { -INFINITY, 0x7fffffff };
+		Top1 bestTs = { -INFINITY, 0x7fffffff, 0 };
+		Top1 bestTx = { -INFINITY, 0x7fffffff, 0 };
 		for( int i = tid; i < nv; i += SM_THREADS )
 		{
 			const float p = pr[ i ] * inv;
@@ -717,12 +810,12 @@ namespace kern
 			if( i < beg )
 			{
 				maxTx = fmaxf( maxTx, p );
-				if( i != a.tokenSot && i != a.tokenSolm && i != a.tokenNot ) bestTx = better( bestTx, Top1{ p, i } );
+				if( i != a.tokenSot && i != a.tokenSolm && i != a.tokenNot ) bestTx = better( bestTx, Top1{ p, i, 0 } );
 			}
 			else if( i < tsEnd )
 			{
 				sumTs += (double)p;
-				bestTs = better( bestTs, Top1{ p, i } );
+				bestTs = better( bestTs, Top1{ p, i, 0 } );
 			}
 		}
 		maxTx = blockMaxF( maxTx, sf );
@@ -734,7 +827,8 @@ namespace kern
 		{
 			Top1 pick = bestTs;
 			if( !maskText ) pick = better( bestTx, bestTs );
-			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0 };
+			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
+			pick = resolveTies( pick, a, a.probs + (size_t)b * nv, maskText, isInitial );
 			TokenData td;
 			td.id = pick.i;
 			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
@@ -810,8 +904,8 @@ namespace kern
 		const int tsEnd = isInitial ? min( beg + 101, nv ) : nv;
 		float maxTx = -1.0f;
 		double sumTs = 0.0;
-		Top1 bestTs = { -INFINITY, 0x7fffffff };
-		Top1 bestTx = { -INFINITY, 0x7fffffff };
+		Top1 bestTs = { -INFINITY, 0x7fffffff, 0 };
+		Top1 bestTx = { -INFINITY, 0x7fffffff, 0 };
 		for( int i = tid; i < n; i += SM_THREADS )
 		{
 			const float p = pr[ i ] * inv;
@@ -820,12 +914,12 @@ namespace kern
 			if( gi < beg )
 			{
 				maxTx = fmaxf( maxTx, p );
-				if( gi != a.tokenSot && gi != a.tokenSolm && gi != a.tokenNot ) bestTx = better( bestTx, Top1{ p, gi } );
+				if( gi != a.tokenSot && gi != a.tokenSolm && gi != a.tokenNot ) bestTx = better( bestTx, Top1{ p, gi, 0 } );
 			}
 			else if( gi < tsEnd )
 			{
 				sumTs += (double)p;
-				bestTs = better( bestTs, Top1{ p, gi } );
+				bestTs = better( bestTs, Top1{ p, gi, 0 } );
 			}
 		}
 		maxTx = blockMaxF( maxTx, sf );
@@ -850,7 +944,8 @@ namespace kern
 			const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
 			Top1 pick = bestTs;
 			if( !maskText ) pick = better( bestTx, bestTs );
-			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0 };
+			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
+			pick = resolveTies( pick, a, a.probs + (size_t)b * nv, maskText, isInitial );
 			TokenData td;
 			td.id = pick.i;
 			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
