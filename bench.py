@@ -7,7 +7,8 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input per GPU: `batch` independent 30 s chunks of 16 kHz
 PCM -> log-mel -> encoder -> cross-KV -> prompt + n_decode greedy decoder steps (timestamp rules, tokens fed back on the device).
-Workload = BASELINE.json configs[2]: ggml-medium shapes (synthetic weights, seed 1234), batch 8 per GPU, beam 1, 100 tokens.
+Workload = BASELINE.json configs[2]: ggml-medium shapes (synthetic "scripted" weights, seed 1234: whisper_b200/synth.py), batch 8 per GPU, beam 1,
+100 tokens.  Rank 0's chunks are those of the committed parity fixture of this configuration, and the line says whether the tokens matched.
 
   value : whole-job audio-s/s with the PCM already resident in HBM (wsp_upload_pcm + wsp_run_chunks_resident) — the log-mel
           front end, encoder and decoder all run inside the timed region; device time from CUDA events on the launching stream.
@@ -47,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="medium")
+    ap.add_argument("--model", default="medium-sc", help="synthetic model (whisper_b200/synth.py); -sc = scripted weights, same shapes and arithmetic")
     ap.add_argument("--batch", type=int, default=8, help="chunks per GPU per step")
     ap.add_argument("--n-decode", type=int, default=100, help="greedy tokens per chunk (BASELINE.md §2)")
     ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: CPU threads (0 = min(cores, 16))")
@@ -259,7 +260,22 @@ def run_ours(a):
     B, K, W = a.batch, a.steps, a.warmup
 
     # ---- inputs: distinct synthetic chunks per rank, pinned host memory for the e2e leg ----
-    pcms = [synth.synth_pcm(rank * B + i) for i in range(B)]
+    # rank 0 runs the very chunks of the committed parity fixture of this configuration (tests/golden/real_shapes.npz: the reference's
+    # greedy tokens for 8 chunks x 32 steps of medium-sc), so the measured run is checked against the reference while it is measured
+    chunk_ids = [rank * B + i for i in range(B)]
+    fixture_tokens = None
+    try:
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "real_shapes.npz"))
+        key = a.model.replace(".", "_").replace("-", "_")
+        if key + "_chunks" in fx and len(fx[key + "_chunks"]) == B:
+            if rank == 0:
+                chunk_ids = [int(x) for x in fx[key + "_chunks"]]
+                fixture_tokens = fx[key + "_tokens"]
+            else:
+                chunk_ids = [64 + rank * B + i for i in range(B)]
+    except Exception:
+        pass
+    pcms = [synth.synth_pcm(cid) for cid in chunk_ids]
     n_samp = pcms[0].size
     pinned = []
     for p in pcms:
@@ -403,6 +419,8 @@ def run_ours(a):
             "stage_ms_per_step": {"mel": stage[0] / K, "encode": stage[1] / K, "decode": stage[2] / K},
             "load": {"seconds": load_s, "nccl_broadcast_ms": bcast_ms, "weight_bytes": engine.weight_bytes()},
             "tokens_equal_e2e_vs_resident": same_tokens,
+            "tokens_match_reference_fixture": (None if fixture_tokens is None else
+                                               bool((np.asarray(toks_r)[:, :fixture_tokens.shape[1]] == fixture_tokens[:, :a.n_decode]).all())),
         }
         print(json.dumps(_jsonable(line)), flush=True)
     for p in pinned:

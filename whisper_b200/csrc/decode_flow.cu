@@ -29,8 +29,7 @@ namespace kern
 	{
 		constexpr int FL_WARPS = 8;                    // consumer warps
 		constexpr int FL_CONSUMERS = FL_WARPS * 32;
-		constexpr int FL_THREADS = FL_CONSUMERS + 64;  // + the two producer warps (main ring, K ring)
-		constexpr int FL_NK = 4;                       // slots of the K ring (at most; FlowArgs::NK says how many a launch uses)
+		constexpr int FL_THREADS = FL_CONSUMERS + 32;  // + the producer warp
 		constexpr int FL_NSMAX = 32;
 		constexpr int FL_MAXT = 1536;
 		constexpr int FL_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA on sm_100
@@ -51,10 +50,10 @@ namespace kern
 		{
 			int act, red, sp, bias, xres, so, sred, qkv, bars, total;
 		};
-		__host__ __device__ inline SmemLayout smemLayout( int slot, int rs, int NS, int NK, int ncols )
+		__host__ __device__ inline SmemLayout smemLayout( int slot, int rs, int NS, int ncols )
 		{
 			SmemLayout l;
-			int o = ( NS + NK ) * slot;   // main ring, then the K ring
+			int o = NS * slot;
 			l.act = o; o += ncols * rs;
 			l.red = o; o += 4 * FL_WARPS * 8 * ncols * 4;
 			l.sp = o; o += FL_MAXT * 4;
@@ -63,18 +62,15 @@ namespace kern
 			l.so = o; o += 256 * 4;
 			l.sred = o; o += 64;
 			l.qkv = o; o += 3 * 128;
-			l.bars = o; o += ( 2 * FL_NSMAX + 2 * FL_NK ) * 8;
+			l.bars = o; o += 2 * FL_NSMAX * 8;
 			l.total = o;
 			return l;
 		}
-		// how the slots that fit next to the fixed buffers are split: 4 for the K ring when the main ring keeps >= 6, else 2
-		inline void ringSlots( int slot, int rs, int ncols, int wantK, int& nsMain, int& nK )
+		inline int ringSlots( int slot, int rs, int ncols )
 		{
-			const int fixed = smemLayout( slot, rs, 0, 0, ncols ).total;
-			const int total = ( FL_SMEM_MAX - fixed ) / slot;
-			nK = wantK <= 0 ? 0 : ( total - wantK >= 6 ? ( wantK > FL_NK ? FL_NK : wantK ) : 2 );
-			nsMain = total - nK;
-			if( nsMain > FL_NSMAX ) nsMain = FL_NSMAX;
+			const int fixed = smemLayout( slot, rs, 0, ncols ).total;
+			int ns = ( FL_SMEM_MAX - fixed ) / slot;
+			return ns > FL_NSMAX ? FL_NSMAX : ns;
 		}
 
 		// ---- small device helpers ------------------------------------------------------------------------------------
@@ -157,28 +153,32 @@ namespace kern
 
 		__device__ __forceinline__ float expTabF( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
 
-		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key.
-		// One step is three dependent ALU instructions (FFMA -> F2FP.F16.F32 -> HADD2.F32); the operands of eight steps are loaded
-		// up front so that no shared-memory latency sits inside the dependency chain (unrolled by 4 with the loads inline it ran at
-		// 31 cycles per key: 5.8 us for the 375 keys of a cross-attention part).
+		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key: three
+		// dependent ALU instructions per key (FFMA -> F2FP.F16.F32 -> HADD2.F32), ~30 cycles — inherent to the reference's arithmetic
+		// (staging the operands of eight keys ahead of the chain changed nothing: it is not load-bound)
 		template<bool F16>
 		__device__ __forceinline__ float chainRows( float y, const float* __restrict__ sp, const __half* __restrict__ v, int n )
 		{
 			int j = 0;
-			for( ; j + 8 <= n; j += 8 )
+			for( ; j + 4 <= n; j += 4 )
 			{
-				float x[ 8 ], p[ 8 ];
-#pragma unroll
-				for( int k = 0; k < 8; k++ )
+				const float x0 = __half2float( v[ j * 64 ] );
+				const float x1 = __half2float( v[ ( j + 1 ) * 64 ] );
+				const float x2 = __half2float( v[ ( j + 2 ) * 64 ] );
+				const float x3 = __half2float( v[ ( j + 3 ) * 64 ] );
+				if( F16 )
 				{
-					x[ k ] = __half2float( v[ ( j + k ) * 64 ] );
-					p[ k ] = sp[ j + k ];
+					y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
+					y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
 				}
-#pragma unroll
-				for( int k = 0; k < 8; k++ )
+				else
 				{
-					if( F16 ) y = __half2float( __float2half_rn( __fmaf_rn( x[ k ], p[ k ], y ) ) );
-					else y = __fmaf_rn( p[ k ], x[ k ], y );
+					y = __fmaf_rn( sp[ j ], x0, y );
+					y = __fmaf_rn( sp[ j + 1 ], x1, y );
+					y = __fmaf_rn( sp[ j + 2 ], x2, y );
+					y = __fmaf_rn( sp[ j + 3 ], x3, y );
 				}
 			}
 			for( ; j < n; j++ )
@@ -479,8 +479,7 @@ namespace kern
 			constexpr int RS = C::RS, SLOT = C::SLOT, CR = C::CR;
 			extern __shared__ __align__( 128 ) uint8_t fl_smem[];
 			const int NS = a.NS, ncols = a.ncols;
-			const int NK = a.NK;
-			const SmemLayout lay = smemLayout( SLOT, RS, NS, NK, ncols );
+			const SmemLayout lay = smemLayout( SLOT, RS, NS, ncols );
 			uint8_t* const ring = fl_smem;
 			uint8_t* const act = fl_smem + lay.act;
 			float* const red = reinterpret_cast<float*>( fl_smem + lay.red );
@@ -492,9 +491,6 @@ namespace kern
 			uint8_t* const sqkv = fl_smem + lay.qkv;
 			uint64_t* const full = reinterpret_cast<uint64_t*>( fl_smem + lay.bars );
 			uint64_t* const empty = full + FL_NSMAX;
-			uint64_t* const kFull = empty + FL_NSMAX;
-			uint64_t* const kEmpty = kFull + FL_NK;
-			uint8_t* const kring = ring + (size_t)NS * SLOT;   // the K ring's FL_NK slots follow the main ring's NS
 
 			const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 			const int cta = blockIdx.x, G = gridDim.x;
@@ -505,11 +501,7 @@ namespace kern
 					ptx::mbar_init( full + i, 1 );
 					ptx::mbar_init( empty + i, FL_WARPS );
 				}
-				for( int i = 0; i < FL_NK; i++ )
-				{
-					ptx::mbar_init( kFull + i, 1 );
-					ptx::mbar_init( kEmpty + i, FL_WARPS );
-				}
+
 				ptx::fence_barrier_init();
 			}
 			__syncthreads();
@@ -582,30 +574,6 @@ namespace kern
 					uint8_t* dst = begin( (uint32_t)( n > 0 ? n * 128 : 0 ) );
 					if( lane == 0 && n > 0 ) ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, bar );
 				};
-				// HBM -> L2 ahead of the ring: the ring (~180 KB) is smaller than one (chunk, head)'s cross K/V (384 KB), so by itself it
-				// cannot run far enough ahead to hide DRAM latency after the cross-attention phase.  One bulk-prefetch instruction per
-				// contiguous range: this CTA's weight rows of the NEXT layer when this layer's cross-attention items are issued, and the
-				// cross K/V of its own (chunk, head) units at the START of the layer that will use them.
-				auto l2 = [ & ]( const void* p, size_t bytes ) {
-					if( lane == 0 && bytes >= 16 )
-						asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( p ), "r"( (uint32_t)( bytes & ~(size_t)15 ) ) : "memory" );
-				};
-				auto l2Weights = [ & ]( const FlowLayer& Ln ) {
-					l2( Ln.wqkv + (size_t)r3 * D, (size_t)n3 * D * 2 );
-					l2( Ln.wo + (size_t)r1 * D, (size_t)n1 * D * 2 );
-					l2( Ln.wcq + (size_t)r1 * D, (size_t)n1 * D * 2 );
-					l2( Ln.wco + (size_t)r1 * D, (size_t)n1 * D * 2 );
-					l2( Ln.w1 + (size_t)r4 * D, (size_t)n4 * D * 2 );
-					l2( Ln.w2 + (size_t)r1 * 4 * D, (size_t)n1 * 4 * D * 2 );
-				};
-				auto l2Cross = [ & ]( const FlowLayer& Ln ) {
-					for( int unit = cta; unit < B * H; unit += G )
-					{
-						l2( Ln.crossK + (size_t)unit * T * 64, (size_t)T * 128 );
-						l2( Ln.crossV + (size_t)unit * T * 64, (size_t)T * 128 );
-					}
-				};
-				const bool pf = a.l2Prefetch >= 2;   // (mode 1: the K producer prefetches the cross K/V only)
 				for( int il = 0; il < L; il++ )
 				{
 					const FlowLayer& Lr = a.layers[ il ];
@@ -614,8 +582,7 @@ namespace kern
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * a.nTextCtx * 64;   // unit = b * H + h
-						if( NK == 0 )
-							for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
+						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
 						for( int i = 0; i < roundsSelf; i++ )
 							for( int p = 0; p < parts; p++ )
 							{
@@ -627,16 +594,10 @@ namespace kern
 					sendWeights( Lr.wo, D, r1, n1, 1 );
 					sendParams( Lr.lncg, Lr.lncb, nullptr, 0 );
 					sendWeights( Lr.wcq, D, r1, n1, 1 );
-					if( pf )
-					{
-						if( il + 1 < L ) l2Weights( a.layers[ il + 1 ] );
-						else l2( a.tokEmb + (size_t)rv * D, (size_t)nv * D * 2 );
-					}
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * T * 64;
-						if( NK == 0 )
-							for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
+						for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
 						for( int i = 0; i < roundsCross; i++ )
 							for( int p = 0; p < parts; p++ )
 							{
@@ -652,50 +613,6 @@ namespace kern
 				}
 				sendParams( a.lnfg, a.lnfb, nullptr, 0 );
 				sendWeights( a.tokEmb, D, rv, nv, 1 );
-				return;
-			}
-
-			// =========================================================================================================
-			// K producer warp: the key rows of every attention unit stream through their own small ring, in use order.  Keeping them
-			// out of the main ring lets that one hold the V rows of the cross-attention BEFORE the query exists (they used to queue
-			// behind 192 KB of keys and arrived in the middle of the f16 chains), while the keys — needed the moment the query lands,
-			// consumed in a microsecond — are prefetched FL_NK runs deep and otherwise stream at HBM rate into the scoring loop.
-			// =========================================================================================================
-			if( warp == FL_WARPS + 1 )
-			{
-				int kSlot = 0;
-				uint32_t kPar = 0;
-				bool kWrapped = false;
-				auto sendK = [ & ]( const __half* base, int j0, int n ) {
-					uint8_t* dst = kring + (size_t)kSlot * SLOT;
-					uint64_t* kb = kFull + kSlot;
-					if( lane == 0 )
-					{
-						if( kWrapped ) mbarWaitLong( kEmpty + kSlot, kPar ^ 1u );
-						ptx::mbar_expect_tx( kb, (uint32_t)n * 128 );
-						ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, kb );
-					}
-					__syncwarp();
-					if( ++kSlot == NK ) { kSlot = 0; kPar ^= 1u; kWrapped = true; }
-				};
-				for( int il = 0; il < L; il++ )
-				{
-					const FlowLayer& Lr = a.layers[ il ];
-					// HBM -> L2 for this layer's cross K/V of my units, ~15 us before the cross-attention phase needs them: the 49 MB per
-					// layer then stream during the latency-bound projection phases instead of in one HBM-bound burst behind the query
-					if( a.l2Prefetch >= 1 && lane == 0 )
-						for( int unit = cta; unit < B * H; unit += G )
-						{
-							const uint32_t bytes = (uint32_t)T * 128;
-							asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( Lr.crossK + (size_t)unit * T * 64 ), "r"( bytes ) : "memory" );
-							asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( Lr.crossV + (size_t)unit * T * 64 ), "r"( bytes ) : "memory" );
-						}
-					if( NK == 0 ) continue;
-					for( int unit = cta; unit < B * H; unit += G )
-						for( int ci = 0; ci < nKcSelf; ci++ ) sendK( Lr.kCache + (size_t)unit * a.nTextCtx * 64, ci * CR, min( CR, nkvOld - ci * CR ) );
-					for( int unit = cta; unit < B * H; unit += G )
-						for( int ci = 0; ci < nKcCross; ci++ ) sendK( Lr.crossK + (size_t)unit * T * 64, ci * CR, min( CR, T - ci * CR ) );
-				}
 				return;
 			}
 
@@ -734,8 +651,6 @@ namespace kern
 			};
 			// debug: (id, %globaltimer) pairs of one CTA.  ids: 0 = kernel start, 100 * (phase + 1) + sub for the sub-steps of a phase
 			// (sub 0 = phase done; 1 = inputs arrived and staged; 2 = first weight slot landed; 3 = MMAs done; 4 = reduced + stored)
-			int kcSlot = 0;
-			uint32_t kcPar = 0;
 			int markIdx = 0;
 			const int markCta = a.timing ? a.timingCta : -1;
 			auto markId = [ & ]( int id ) {
@@ -830,18 +745,9 @@ namespace kern
 #pragma unroll 1
 							for( int ci = 0; ci < nKc; ci++ )
 							{
-								if( NK == 0 )
-								{
-									const uint8_t* kc = waitSlot( 0 );
-									lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
-									releaseSlots( 1 );
-									continue;
-								}
-								mbarWaitLong( kFull + kcSlot, kcPar );
-								lmax = scoreRows( kring + (size_t)kcSlot * SLOT, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
-								__syncwarp();
-								if( lane == 0 ) ptx::mbar_arrive( kEmpty + kcSlot );
-								if( ++kcSlot == NK ) { kcSlot = 0; kcPar ^= 1u; }
+								const uint8_t* kc = waitSlot( 0 );
+								lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
+								releaseSlots( 1 );
 							}
 							if( self ) lmax = scoreRows( sqkv + 128, 1, nOld, qf, sp, warp, lane, lmax );   // this step's own K row
 							sub( 2 );
@@ -925,6 +831,30 @@ namespace kern
 						break;
 					}
 					const float* bias = biasOff >= 0 ? sbias + biasOff : nullptr;
+
+					// Paced L2 prefetch of the NEXT cross-attention's K/V (49 MB per layer, 384 KB per unit — more than the ring holds,
+					// so without this it streams from HBM in one burst behind the query).  One sixth per projection phase, spread over the
+					// ~25 us in which the HBM pipe only carries 29 MB of weights: CO / FC1 / FC2 of the previous layer fetch K, QKV / O / CQ
+					// of this layer fetch V.  (All of it at once at the layer start was measured SLOWER: the burst delays the weights.)
+					if( a.l2Pace && tid == 0 && !last )
+					{
+						const int piece = ph == PH_CO ? 0 : ph == PH_FC1 ? 1 : ph == PH_FC2 ? 2 : ph == PH_QKV ? 3 : ph == PH_O ? 4 : 5;
+						const int target = piece < 3 ? il + 1 : il;          // whose cross-attention the piece belongs to
+						if( target < L )
+						{
+							const FlowLayer& Lt = a.layers[ target ];
+							const uint32_t third = ( ( (uint32_t)T * 128 / 3 ) + 15 ) & ~15u;
+							for( int unit = cta; unit < B * H; unit += G )
+							{
+								const uint8_t* base = reinterpret_cast<const uint8_t*>( ( piece < 3 ? Lt.crossK : Lt.crossV ) + (size_t)unit * T * 64 );
+								const uint32_t off = (uint32_t)( piece % 3 ) * third;
+								const uint32_t len = min( third, (uint32_t)T * 128 - off );
+								asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( base + off ), "r"( len ) : "memory" );
+								if( il == 0 && piece >= 3 )   // layer 0 has no previous layer to fetch its keys
+									asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( reinterpret_cast<const uint8_t*>( Lt.crossK + (size_t)unit * T * 64 ) + off ), "r"( len ) : "memory" );
+							}
+						}
+					}
 
 					if( useLN )
 					{
@@ -1130,11 +1060,11 @@ namespace kern
 		}
 
 		template<int D>
-		int smemBytes( int ncols, int wantK, int& ns, int& nk )
+		int smemBytes( int ncols, int& ns )
 		{
 			using C = Cfg<D>;
-			ringSlots( C::SLOT, C::RS, ncols, wantK, ns, nk );
-			return smemLayout( C::SLOT, C::RS, ns, nk, ncols ).total;
+			ns = ringSlots( C::SLOT, C::RS, ncols );
+			return smemLayout( C::SLOT, C::RS, ns, ncols ).total;
 		}
 		template<int D>
 		cudaError_t prepareD()
@@ -1146,10 +1076,9 @@ namespace kern
 		cudaError_t launchD( FlowArgs& a, int numSMs, cudaStream_t s )
 		{
 			a.ncols = a.B > 8 ? 16 : 8;
-			int ns = 0, nk = 0;
-			const int smem = smemBytes<D>( a.ncols, a.NK, ns, nk );   // a.NK in: requested K-ring depth (0 = keys through the main ring)
+			int ns = 0;
+			const int smem = smemBytes<D>( a.ncols, ns );
 			a.NS = ns;
-			a.NK = nk;
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3( (unsigned)numSMs );
 			cfg.blockDim = dim3( FL_THREADS );
@@ -1193,8 +1122,7 @@ namespace kern
 		const int rs = 2 * d + 64;
 		const int slot = 8 * rs > 16384 ? 8 * rs : 16384;
 		const int cr = ( slot / 128 ) & ~7;
-		int ns = 0, nk = 0;
-		ringSlots( slot, rs, B > 8 ? 16 : 8, 0, ns, nk );
+		const int ns = ringSlots( slot, rs, B > 8 ? 16 : 8 );
 		(void)cr;
 		if( 4 + 1 > ns ) return false;   // a round of V slots (one per reference thread) is held at once
 		return true;

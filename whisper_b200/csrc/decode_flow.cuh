@@ -39,10 +39,9 @@ namespace kern
 		float* logits = nullptr;            // [B][nVocab]
 		unsigned long long* timing = nullptr;   // optional: (id, %globaltimer) marks of CTA `timingCta` (debug)
 		int timingCta = 0;
-		int l2Prefetch = 0;                 // producer warp issues bulk L2 prefetches one layer ahead (WSP_FLOW_L2=1; measured slower, off by default)
+		int l2Pace = 0;                     // paced L2 prefetch of the next cross-attention's K/V (WSP_FLOW_L2PACE)
 		FlowGeom g;
-		int NS = 0;                         // main ring slots
-		int NK = 0;                         // K ring slots
+		int NS = 0;                         // ring slots
 		int ncols = 8;                      // activation columns staged: 8 (B <= 8) or 16
 	};
 	bool flowSupported( int d, int B, int T, int H, int nTextCtx, int refThreads, int grid );

@@ -169,8 +169,7 @@ namespace wsp
 		// N = 1 decoder step: 2 = dataflow kernel (default), 1 = round 1's barrier kernel, 0 = one kernel per op
 		int stepMode = 2;
 		int stepTimingCta = 0;
-		int flowKRing = 0;                // K-ring depth of the dataflow kernel (0 = keys through the main ring)
-		int flowL2Prefetch = 0;           // measured: 1898 vs 1678 us per step with the producer's L2 bulk prefetches on (medium, B = 8)
+		int flowL2Pace = 0;
 		bool stepTiming = false;        // record %globaltimer marks of CTA 0 into megaTiming (wsp_debug_step_timing)
 
 		// decode CUDA graph (N = 1 steady state)
