@@ -69,9 +69,11 @@ def greedy(o, prompt, n_steps, keep_logits=False):
                 step_logits=np.stack(step_logits) if keep_logits else None, last_logits=lg[0], prompt_logits=prompt_logits)
 
 
-def make(model_name: str, chunk0: int, n_samples: int, offset: int, threads_list=(1, 4)):
-    """Encoder trace points, cross-KV, teacher-forced logits and greedy tokens at 1 and 4 reference threads; the PCM chunk id is the
-    first one >= chunk0 whose greedy sequences are clear of near-ties at both thread counts."""
+def make(model_name: str, chunk0: int, n_samples: int, offset: int, threads_list=(1, 4, 6, 16)):
+    """Encoder trace points, cross-KV, teacher-forced logits and greedy tokens at 1, 4, 6 and 16 reference threads (the reference's
+    V^T*P arithmetic depends on its thread count, ggml.c:4680-4722; 4 is its default, 6 and 16 exercise two and four key ranges per
+    64-thread group of the decoder-step kernel); the PCM chunk id is the first one >= chunk0 whose greedy sequences are clear of
+    near-ties at every thread count."""
     path = synth.model_path(model_name)
     for chunk in range(chunk0, chunk0 + 40):
         pcm = synth.synth_pcm(chunk, n_samples)
@@ -230,6 +232,8 @@ def make_lang():
 # top-2 margins.  "medium-sc" is the BENCH CONFIGURATION itself (8 chunks, one batch); base.en runs 12 chunks (the two-tile path of the
 # decoder step, B in 9..16); large is configs[4]'s shape (a few steps: its encoder alone takes the CPU a minute).
 REAL_SHAPES = {"tiny.en-sc": (2, 24), "base.en-sc": (12, 16), "medium-sc": (8, 32), "large-sc": (1, 4)}
+# the bench configuration is also pinned at 16 reference threads — the thread count the reference arm of bench.py is timed with
+REAL_THREADS = {"medium-sc": (4, 16)}
 
 
 def make_real_shapes(models=None):
@@ -237,27 +241,38 @@ def make_real_shapes(models=None):
     for model, (n_chunks, steps) in REAL_SHAPES.items():
         if models and model not in models:
             continue
-        o = RefOracle(synth.model_path(model), threads=4)
+        ths = REAL_THREADS.get(model, (4,))
+        os_ = {th: RefOracle(synth.model_path(model), threads=th) for th in ths}
+        o = os_[ths[0]]
         prompt = prompt_of(o)
         key = model.replace(".", "_").replace("-", "_")
-        chosen, toks, logits, gaps = [], [], [], []
+        chosen = []
+        toks, logits, gaps = ({th: [] for th in ths} for _ in range(3))
         ch = 0
         while len(chosen) < n_chunks:
             assert ch < 200, "no clean chunks for " + model
-            o.pcm_to_mel(synth.synth_pcm(ch))
-            o.encode(0)
-            r = greedy(o, prompt, steps)
-            ok = r["gap"].min() >= GAP_SAFE and len(set(r["tokens"].tolist())) >= min(MIN_DISTINCT, steps)
-            print("  real/%s chunk %d: min gap %.3f %s tokens %s..." % (model, ch, r["gap"].min(), "keep" if ok else "skip", r["tokens"][:6].tolist()), flush=True)
+            mel = o.pcm_to_mel(synth.synth_pcm(ch))
+            rs = {}
+            for th in ths:
+                os_[th].set_mel(mel)
+                os_[th].encode(0)
+                rs[th] = greedy(os_[th], prompt, steps)
+            gap = min(float(r["gap"].min()) for r in rs.values())
+            ok = gap >= GAP_SAFE and min(len(set(r["tokens"].tolist())) for r in rs.values()) >= min(MIN_DISTINCT, steps)
+            print("  real/%s chunk %d: min gap %.3f %s tokens %s..." % (model, ch, gap, "keep" if ok else "skip", rs[ths[0]]["tokens"][:6].tolist()), flush=True)
             if ok:
-                chosen.append(ch); toks.append(r["tokens"]); logits.append(r["last_logits"][::LOGIT_STEP].astype(np.float32)); gaps.append(r["gap"])
+                chosen.append(ch)
+                for th in ths:
+                    toks[th].append(rs[th]["tokens"]); logits[th].append(rs[th]["last_logits"][::LOGIT_STEP].astype(np.float32)); gaps[th].append(rs[th]["gap"])
             ch += 1
         out[key + "_chunks"] = np.array(chosen, np.int32)
         out[key + "_prompt"] = np.array(prompt, np.int32)
-        out[key + "_tokens"] = np.stack(toks)
-        out[key + "_last_logits_sub"] = np.stack(logits)
-        out[key + "_gap"] = np.stack(gaps)
-        del o
+        for th in ths:
+            pre = key + ("" if th == 4 else "_t%d" % th)     # the keys without a thread suffix are the reference's default, 4 threads
+            out[pre + "_tokens"] = np.stack(toks[th])
+            out[pre + "_last_logits_sub"] = np.stack(logits[th])
+            out[pre + "_gap"] = np.stack(gaps[th])
+        del os_, o
     return out
 
 

@@ -63,7 +63,7 @@ def test_encoder_restatement_vs_golden(name, golden_dir, np_runs):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("threads", [1, 4, 6, 16])
 def test_decoder_restatement_vs_golden(name, threads, golden_dir, np_runs):
     """Teacher-forced on the reference's tokens: logits within TOL_LOGIT; greedy choice identical wherever the reference's own
     top-2 gap exceeds the tolerance.  The thread count matters: the reference accumulates V^T*P in f16 per thread."""

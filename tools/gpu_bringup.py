@@ -305,16 +305,18 @@ def stage_flow():
     """The dataflow decoder-step kernel against round 1's barrier kernel and the kernel-per-op path: same tokens, same logits (the GEMV
     and cross-attention arithmetic is bit-identical; self-attention scores are summed in a different order), and the decode time of each."""
     from whisper_b200 import capi, synth
-    cases = [("micro.en", 1, 20), ("micro.en", 4, 20), ("tiny.en", 8, 40), ("base.en", 3, 40), ("medium", 8, 100), ("large", 2, 20), ("medium", 12, 24)]
+    cases = [("micro.en", 1, 20), ("micro.en", 4, 20), ("tiny.en", 8, 40), ("base.en", 3, 40), ("medium", 8, 100), ("large", 2, 20), ("medium", 12, 24), ("medium-sc", 8, 60)]
     only = os.environ.get("FLOW_CASES")
     if only:
         cases = [cs for cs in cases if cs[0] in only.split(",")]
+    ref_threads = int(os.environ.get("FLOW_REFTHREADS", "4"))
     for (name, batch, n) in cases:
         path, m, e, c = _open(name, batch=batch)
+        c.set_reference_threads(ref_threads)
         pcms = [synth.synth_pcm(i) for i in range(batch)]
         prompt = m.prompt_init()
         res = {}
-        for mode in (2, 1, 0):
+        for mode in [int(x) for x in os.environ.get("FLOW_MODES", "2,1,0").split(",")]:
             c.set_step_mode(mode)
             try:
                 toks, st = c.run_chunks(pcms, prompt, n)
@@ -329,8 +331,12 @@ def stage_flow():
                     continue
                 same = (res[2][0] == res[mode][0]).all()
                 dl = np.abs(res[2][1] - res[mode][1]).max()
-                print("  %-9s B=%-2d n=%-3d flow vs mode %d: tokens %s, max|dlogit| %.3e | decode ms flow %.2f  mode%d %.2f" % (
-                    name, batch, n, mode, "same" if same else "DIFFER", dl, res[2][2], mode, res[mode][2]), flush=True)
+                first = ""
+                if not same:
+                    d = np.argwhere(res[2][0] != res[mode][0])
+                    first = " (first difference: chunk %d step %d; %d of %d chunks differ)" % (d[0][0], d[:, 1].min(), len(set(d[:, 0].tolist())), batch)
+                print("  %-9s B=%-2d n=%-3d flow vs mode %d: tokens %s%s, max|dlogit| %.3e | decode ms flow %.2f  mode%d %.2f" % (
+                    name, batch, n, mode, "same" if same else "DIFFER", first, dl, res[2][2], mode, res[mode][2]), flush=True)
             print("     tokens[0][:12]", res[2][0][0][:12].tolist(), flush=True)
         c.set_step_mode(2)
         c.close(); e.close(); m.close()
@@ -344,6 +350,7 @@ def stage_steptiming(model_name="medium", batch=8):
     batch = int(os.environ.get("STEP_BATCH", batch))
     path, m, e, c = _open(model_name, batch=batch)
     pcms = [synth.synth_pcm(i) for i in range(batch)]
+    c.set_reference_threads(int(os.environ.get("FLOW_REFTHREADS", "4")))
     c.step_timing(True)
     c.run_chunks(pcms, m.prompt_init(), 40)
     raw = c.step_timing().astype(np.int64).reshape(-1, 2)
@@ -353,6 +360,8 @@ def stage_steptiming(model_name="medium", batch=8):
     names = ["LN1+QKV", "self-attn", "O+res", "LN+CQ", "cross-attn", "CO+res", "LN+FC1", "FC2+res"]
     subn = {0: "phase done", 1: "inputs staged", 2: "1st weights landed" , 3: "MMAs done", 4: "stored"}
     suba = {1: "q arrived", 2: "scores done", 3: "softmax done", 4: "chains done", 0: "phase done"}
+    suba.update({10 + k: "K%d" % k for k in range(24)})
+    suba.update({40 + k: "V%d" % k for k in range(24)})
     acc = {}
     for k in range(1, len(ids)):
         acc.setdefault(int(ids[k]), []).append((t[k] - t[k - 1]) / 1e3)

@@ -162,8 +162,6 @@ namespace wsp
 			WSP_CHECK( devAlloc( c.flowCtrl, 8, true ) );
 			const char* env = getenv( "WSP_STEP_MODE" );
 			if( env && env[ 0 ] >= '0' && env[ 0 ] <= '2' ) c.stepMode = env[ 0 ] - '0';
-			env = getenv( "WSP_FLOW_L2PACE" );
-			if( env ) c.flowL2Pace = atoi( env );
 			env = getenv( "WSP_TIMING_CTA" );
 			if( env ) c.stepTimingCta = atoi( env );
 		}
@@ -393,7 +391,6 @@ namespace wsp
 			fa.exch = c.flowExch; fa.ctrl = c.flowCtrl; fa.logits = c.logits; fa.timing = c.stepTiming ? c.megaTiming : nullptr;
 			fa.g = c.flowGeom;
 			fa.timingCta = c.stepTimingCta;
-			fa.l2Pace = c.flowL2Pace;
 			WSP_KERNEL( KK_SKINNY, kern::decodeStepFlow( fa, d, e.numSMs, s ) ); n++;
 			if( sample )
 			{

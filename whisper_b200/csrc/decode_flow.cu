@@ -32,6 +32,7 @@ namespace kern
 		constexpr int FL_THREADS = FL_CONSUMERS + 32;  // + the producer warp
 		constexpr int FL_NSMAX = 32;
 		constexpr int FL_MAXT = 1536;
+		constexpr int FL_MAXPARTS = 16;                // reference thread counts whose V^T*P split the kernel reproduces
 		constexpr int FL_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA on sm_100
 		constexpr uint32_t SENT32 = 0xFFFFFFFFu;
 
@@ -59,7 +60,7 @@ namespace kern
 			l.sp = o; o += FL_MAXT * 4;
 			l.bias = o; o += 256 * 4;
 			l.xres = o; o += 16 * 16 * 4;
-			l.so = o; o += 256 * 4;
+			l.so = o; o += FL_MAXPARTS * 64 * 4;
 			l.sred = o; o += 64;
 			l.qkv = o; o += 3 * 128;
 			l.bars = o; o += 2 * FL_NSMAX * 8;
@@ -153,41 +154,25 @@ namespace kern
 
 		__device__ __forceinline__ float expTabF( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
 
-		// the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key: three
-		// dependent ALU instructions per key (FFMA -> F2FP.F16.F32 -> HADD2.F32), ~30 cycles — inherent to the reference's arithmetic
-		// (staging the operands of eight keys ahead of the chain changed nothing: it is not load-bound)
-		template<bool F16>
-		__device__ __forceinline__ float chainRows( float y, const float* __restrict__ sp, const __half* __restrict__ v, int n )
+		// The reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key — three dependent
+		// ALU instructions per key (FFMA -> F2FP.F16.F32 -> HADD2.F32), ~30 cycles, inherent to the reference's arithmetic (staging the
+		// operands of eight keys ahead of the chain changed nothing: it is not load-bound).  A thread runs up to four such chains side by
+		// side (reference thread counts above 4: 64 dims x `parts` chains over 256 threads); they are independent, so their steps overlap.
+		// Chain k reads rows [0, n[k]) at v + k * rr * 64 and the probabilities sp[j0[k] ...].  f16 = false: plain f32 accumulation.
+		__device__ __forceinline__ void chainMulti( float ( &y )[ 4 ], const float* __restrict__ sp, const __half* __restrict__ v, const int ( &j0 )[ 4 ], const int ( &n )[ 4 ], int nmax, int rr, bool f16 )
 		{
-			int j = 0;
-			for( ; j + 4 <= n; j += 4 )
+#pragma unroll 2
+			for( int j = 0; j < nmax; j++ )
 			{
-				const float x0 = __half2float( v[ j * 64 ] );
-				const float x1 = __half2float( v[ ( j + 1 ) * 64 ] );
-				const float x2 = __half2float( v[ ( j + 2 ) * 64 ] );
-				const float x3 = __half2float( v[ ( j + 3 ) * 64 ] );
-				if( F16 )
-				{
-					y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
-					y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
-				}
-				else
-				{
-					y = __fmaf_rn( sp[ j ], x0, y );
-					y = __fmaf_rn( sp[ j + 1 ], x1, y );
-					y = __fmaf_rn( sp[ j + 2 ], x2, y );
-					y = __fmaf_rn( sp[ j + 3 ], x3, y );
-				}
+#pragma unroll
+				for( int k = 0; k < 4; k++ )
+					if( j < n[ k ] )
+					{
+						const float x = __half2float( v[ ( k * rr + j ) * 64 ] );
+						const float t = __fmaf_rn( x, sp[ j0[ k ] + j ], y[ k ] );
+						y[ k ] = f16 ? __half2float( __float2half_rn( t ) ) : t;
+					}
 			}
-			for( ; j < n; j++ )
-			{
-				const float x = __half2float( v[ j * 64 ] );
-				if( F16 ) y = __half2float( __float2half_rn( __fmaf_rn( x, sp[ j ], y ) ) );
-				else y = __fmaf_rn( sp[ j ], x, y );
-			}
-			return y;
 		}
 
 		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query.  Two lanes per row: lane half h owns bytes
@@ -196,17 +181,21 @@ namespace kern
 		// shuffles: 0.72 us per 128-row run, pure latency — 9 of the 22 us of a cross-attention phase.)  Returns the running maximum.
 		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const float* qf, float* sp, int warp, int lane, float lmax )
 		{
-			const int half = lane & 1, rw = lane >> 1;
+			const int half = lane & 1, rw = lane >> 1, rot = rw & 3;
 			for( int r0 = warp * 16; r0 < n; r0 += FL_WARPS * 16 )
 			{
 				const int r = r0 + rw;
 				float acc[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
 				if( r < n )
 				{
-					const uint4* row = reinterpret_cast<const uint4*>( kc + (size_t)r * 128 + half * 64 );
+					// rows are 128 bytes apart — every row starts in bank 0 — so the eight lanes of a quarter warp (four rows x two halves)
+					// must each read a DIFFERENT 16-byte column in one LDS.128: lane (row, half) takes its four pieces in the order
+					// rot, rot+1, ... (mod 4), rot = row & 3, and holds its query values in the same rotated order.  (Reading piece k in
+					// every lane was a 4-way bank conflict: 512 instead of 128 shared-memory wavefronts per 128-row slot.)
+					const uint8_t* rowb = kc + (size_t)r * 128 + half * 64;
 					uint4 u[ 4 ];
 #pragma unroll
-					for( int k = 0; k < 4; k++ ) u[ k ] = row[ k ];
+					for( int k = 0; k < 4; k++ ) u[ k ] = *reinterpret_cast<const uint4*>( rowb + ( ( ( k + rot ) & 3 ) << 4 ) );
 #pragma unroll
 					for( int k = 0; k < 4; k++ )
 					{
@@ -471,7 +460,9 @@ namespace kern
 
 		enum { EP_QKV = 0, EP_RESID = 1, EP_QSCALE = 2, EP_GELU = 3, EP_LOGITS = 4 };
 		// -----------------------------------------------------------------------------------------------------------
-		template<int D>
+		// TIMED = the debug instantiation with the (id, %globaltimer) marks; the production instantiation carries none of that code
+		// (about 700 SASS instructions: with them the kernel outgrows the 128 KB instruction cache and every phase slows down)
+		template<int D, bool TIMED>
 		__global__ void __launch_bounds__( FL_THREADS, 1 )
 			decode_flow_kernel( const FlowArgs a )
 		{
@@ -520,12 +511,17 @@ namespace kern
 			const int r3 = cta * g.R3, n3 = max( 0, min( g.R3, 3 * D - r3 ) );
 			const int r4 = cta * g.R4, n4 = max( 0, min( g.R4, 4 * D - r4 ) );
 			const int rv = cta * g.RV, nv = max( 0, min( g.RV, a.nVocab - rv ) );
+			// V rows travel in (round, group) order: the four 64-thread groups of the consumers each own PG consecutive parts (one part
+			// each up to 4 reference threads), and one slot carries RR rows of each of a group's parts
+			const int NG = min( parts, 4 );
+			const int PG = ( parts + NG - 1 ) / NG;
+			const int RR = CR / PG;
 			const int nKcSelf = ( nkvOld + CR - 1 ) / CR;
 			const int dcSelf = ( nkvOld + 1 + parts - 1 ) / parts;
-			const int roundsSelf = ( dcSelf + CR - 1 ) / CR;
+			const int roundsSelf = ( dcSelf + RR - 1 ) / RR;
 			const int nKcCross = ( T + CR - 1 ) / CR;
 			const int dcCross = ( T + parts - 1 ) / parts;
-			const int roundsCross = ( dcCross + CR - 1 ) / CR;
+			const int roundsCross = ( dcCross + RR - 1 ) / RR;
 
 			// =========================================================================================================
 			// producer warp: everything that does not depend on this step, in consumption order, as far ahead as the ring allows
@@ -574,6 +570,21 @@ namespace kern
 					uint8_t* dst = begin( (uint32_t)( n > 0 ? n * 128 : 0 ) );
 					if( lane == 0 && n > 0 ) ptx::bulk_load_1d( dst, base + (size_t)j0 * 64, (uint32_t)n * 128, bar );
 				};
+				// one slot of V rows for group q in round i: rows [pp*dc + i*RR, ...) of each of the group's parts pp, clipped to the part and to nOld
+				auto sendV = [ & ]( const __half* base, int q, int i, int dc, int nOld ) {
+					int myJ0 = 0, myN = 0, total = 0;
+					for( int k = 0; k < PG; k++ )
+					{
+						const int pp = q * PG + k;
+						const int j0 = pp * dc + i * RR;
+						const int j1 = min( j0 + RR, min( ( pp + 1 ) * dc, nOld ) );
+						const int n = ( pp < parts && j1 > j0 ) ? j1 - j0 : 0;
+						total += n;
+						if( k == lane ) { myJ0 = j0; myN = n; }
+					}
+					uint8_t* dst = begin( (uint32_t)total * 128 );
+					if( myN > 0 ) ptx::bulk_load_1d( dst + (size_t)lane * RR * 128, base + (size_t)myJ0 * 64, (uint32_t)myN * 128, bar );
+				};
 				for( int il = 0; il < L; il++ )
 				{
 					const FlowLayer& Lr = a.layers[ il ];
@@ -584,12 +595,7 @@ namespace kern
 						const size_t hb = (size_t)unit * a.nTextCtx * 64;   // unit = b * H + h
 						for( int ci = 0; ci < nKcSelf; ci++ ) sendKv( Lr.kCache + hb, ci * CR, min( CR, nkvOld - ci * CR ) );
 						for( int i = 0; i < roundsSelf; i++ )
-							for( int p = 0; p < parts; p++ )
-							{
-								const int j0 = p * dcSelf + i * CR;
-								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcSelf, nkvOld ) );
-								sendKv( Lr.vCache + hb, j0, j1 - j0 );
-							}
+							for( int q = 0; q < NG; q++ ) sendV( Lr.vCache + hb, q, i, dcSelf, nkvOld );
 					}
 					sendWeights( Lr.wo, D, r1, n1, 1 );
 					sendParams( Lr.lncg, Lr.lncb, nullptr, 0 );
@@ -599,12 +605,7 @@ namespace kern
 						const size_t hb = (size_t)unit * T * 64;
 						for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
 						for( int i = 0; i < roundsCross; i++ )
-							for( int p = 0; p < parts; p++ )
-							{
-								const int j0 = p * dcCross + i * CR;
-								const int j1 = min( j0 + CR, min( ( p + 1 ) * dcCross, T ) );
-								sendKv( Lr.crossV + hb, j0, j1 - j0 );
-							}
+							for( int q = 0; q < NG; q++ ) sendV( Lr.crossV + hb, q, i, dcCross, T );
 					}
 					sendWeights( Lr.wco, D, r1, n1, 1 );
 					sendParams( Lr.ln3g, Lr.ln3b, nullptr, 0 );
@@ -652,8 +653,9 @@ namespace kern
 			// debug: (id, %globaltimer) pairs of one CTA.  ids: 0 = kernel start, 100 * (phase + 1) + sub for the sub-steps of a phase
 			// (sub 0 = phase done; 1 = inputs arrived and staged; 2 = first weight slot landed; 3 = MMAs done; 4 = reduced + stored)
 			int markIdx = 0;
-			const int markCta = a.timing ? a.timingCta : -1;
+			const int markCta = ( TIMED && a.timing ) ? a.timingCta : -1;
 			auto markId = [ & ]( int id ) {
+				if( !TIMED ) return;
 				if( cta == markCta && tid == 0 && markIdx < 2000 )
 				{
 					a.timing[ 2 * markIdx ] = (unsigned long long)id;
@@ -662,8 +664,8 @@ namespace kern
 				markIdx++;
 			};
 			int curPhase = 0;
-			auto sub = [ & ]( int k ) { if( markCta >= 0 ) markId( 100 * ( curPhase + 1 ) + k ); };
-			auto mark = [ & ]() { markId( 100 * ( curPhase + 1 ) ); curPhase++; };
+			auto sub = [ & ]( int k ) { if( TIMED && markCta >= 0 ) markId( 100 * ( curPhase + 1 ) + k ); };
+			auto mark = [ & ]() { if( TIMED ) { markId( 100 * ( curPhase + 1 ) ); curPhase++; } };
 			markId( 0 );
 
 			const int gq = lane >> 2, tq = lane & 3;
@@ -713,7 +715,7 @@ namespace kern
 						__half* dst = self ? attn1 : attn2;
 						const int nKc = ( nOld + CR - 1 ) / CR;
 						const int dc = ( n + parts - 1 ) / parts;
-						const int rounds = ( dc + CR - 1 ) / CR;
+						const int rounds = ( dc + RR - 1 ) / RR;
 #pragma unroll 1
 						for( int unit = cta; unit < B * H; unit += G )
 						{
@@ -730,15 +732,21 @@ namespace kern
 							}
 							consumerSync();
 							sub( 1 );
-							float qf[ 32 ];   // this lane's half of the query (scoreRows)
+							float qf[ 32 ];   // this lane's half of the query, its four 8-value pieces rotated by (row & 3) (scoreRows)
 							{
 								const __half2* qs = reinterpret_cast<const __half2*>( sqkv ) + ( lane & 1 ) * 16;
+								const int rot = ( lane >> 1 ) & 3;
 #pragma unroll
-								for( int e = 0; e < 16; e++ )
+								for( int k = 0; k < 4; k++ )
 								{
-									const float2 f = __half22float2( qs[ e ] );
-									qf[ 2 * e ] = f.x;
-									qf[ 2 * e + 1 ] = f.y;
+									const __half2* qp = qs + ( ( k + rot ) & 3 ) * 4;
+#pragma unroll
+									for( int e = 0; e < 4; e++ )
+									{
+										const float2 f = __half22float2( qp[ e ] );
+										qf[ k * 8 + 2 * e ] = f.x;
+										qf[ k * 8 + 2 * e + 1 ] = f.y;
+									}
 								}
 							}
 							float lmax = -INFINITY;
@@ -748,37 +756,60 @@ namespace kern
 								const uint8_t* kc = waitSlot( 0 );
 								lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
 								releaseSlots( 1 );
+								if( TIMED && !self ) sub( 10 + ci );
 							}
 							if( self ) lmax = scoreRows( sqkv + 128, 1, nOld, qf, sp, warp, lane, lmax );   // this step's own K row
 							sub( 2 );
 							softmaxRow( sp, n, lmax, sred, tid, warp, lane );
 							sub( 3 );
 							{
-								const int p = tid >> 6, e = tid & 63;
-								const int pEnd = min( ( p + 1 ) * dc, nOld );       // end of part p's rows that live in the ring
-								float y = 0.0f;
+								const int q = tid >> 6, e = tid & 63;
+								float y[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
 #pragma unroll 1
 								for( int i = 0; i < rounds; i++ )
 								{
-									if( p < parts )
+									if( q < NG )
 									{
-										const int j0 = p * dc + i * CR;
-										const int j1 = min( j0 + CR, pEnd );
-										if( j1 > j0 )
+										int j0[ 4 ], nk[ 4 ], nmax = 0;
+#pragma unroll
+										for( int k = 0; k < 4; k++ )
 										{
-											const __half* vp = reinterpret_cast<const __half*>( waitSlot( p ) ) + e;
-											y = a.refThreads > 0 ? chainRows<true>( y, sp + j0, vp, j1 - j0 ) : chainRows<false>( y, sp + j0, vp, j1 - j0 );
+											const int pp = q * PG + k;
+											j0[ k ] = pp * dc + i * RR;
+											const int j1 = min( j0[ k ] + RR, min( ( pp + 1 ) * dc, nOld ) );
+											nk[ k ] = ( k < PG && pp < parts && j1 > j0[ k ] ) ? j1 - j0[ k ] : 0;
+											nmax = max( nmax, nk[ k ] );
+										}
+										if( nmax > 0 )
+										{
+											const __half* vp = reinterpret_cast<const __half*>( waitSlot( q ) ) + e;
+											chainMulti( y, sp, vp, j0, nk, nmax, RR, a.refThreads > 0 );
 										}
 									}
-									releaseSlots( parts, true );
+									releaseSlots( NG, true );
+									if( TIMED && !self ) sub( 40 + i );
 								}
-								if( self && p < parts && nOld >= p * dc && nOld < ( p + 1 ) * dc )
+								if( self )
 								{
-									// this step's own V row closes the chain of the part whose range it falls into
-									const __half* vp = reinterpret_cast<const __half*>( sqkv + 256 ) + e;
-									y = a.refThreads > 0 ? chainRows<true>( y, sp + nOld, vp, 1 ) : chainRows<false>( y, sp + nOld, vp, 1 );
+									// this step's own V row closes the chain of the part whose key range it falls into
+									const int pOwn = nOld / dc;
+									if( pOwn < parts && q == pOwn / PG )
+									{
+										const float x = __half2float( reinterpret_cast<const __half*>( sqkv + 256 )[ e ] );
+										const float pj = sp[ nOld ];
+										const int ko = pOwn - q * PG;
+#pragma unroll
+										for( int k = 0; k < 4; k++ )
+											if( k == ko )
+												y[ k ] = a.refThreads > 0 ? __half2float( __float2half_rn( __fmaf_rn( x, pj, y[ k ] ) ) ) : __fmaf_rn( pj, x, y[ k ] );
+									}
 								}
-								if( p < parts ) so[ tid ] = y;
+#pragma unroll
+								for( int k = 0; k < 4; k++ )
+								{
+									const int pp = q * PG + k;
+									if( q < NG && k < PG && pp < parts ) so[ pp * 64 + e ] = y[ k ];
+								}
 							}
 							sub( 4 );
 							consumerSync();
@@ -832,29 +863,6 @@ namespace kern
 					}
 					const float* bias = biasOff >= 0 ? sbias + biasOff : nullptr;
 
-					// Paced L2 prefetch of the NEXT cross-attention's K/V (49 MB per layer, 384 KB per unit — more than the ring holds,
-					// so without this it streams from HBM in one burst behind the query).  One sixth per projection phase, spread over the
-					// ~25 us in which the HBM pipe only carries 29 MB of weights: CO / FC1 / FC2 of the previous layer fetch K, QKV / O / CQ
-					// of this layer fetch V.  (All of it at once at the layer start was measured SLOWER: the burst delays the weights.)
-					if( a.l2Pace && tid == 0 && !last )
-					{
-						const int piece = ph == PH_CO ? 0 : ph == PH_FC1 ? 1 : ph == PH_FC2 ? 2 : ph == PH_QKV ? 3 : ph == PH_O ? 4 : 5;
-						const int target = piece < 3 ? il + 1 : il;          // whose cross-attention the piece belongs to
-						if( target < L )
-						{
-							const FlowLayer& Lt = a.layers[ target ];
-							const uint32_t third = ( ( (uint32_t)T * 128 / 3 ) + 15 ) & ~15u;
-							for( int unit = cta; unit < B * H; unit += G )
-							{
-								const uint8_t* base = reinterpret_cast<const uint8_t*>( ( piece < 3 ? Lt.crossK : Lt.crossV ) + (size_t)unit * T * 64 );
-								const uint32_t off = (uint32_t)( piece % 3 ) * third;
-								const uint32_t len = min( third, (uint32_t)T * 128 - off );
-								asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( base + off ), "r"( len ) : "memory" );
-								if( il == 0 && piece >= 3 )   // layer 0 has no previous layer to fetch its keys
-									asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"( reinterpret_cast<const uint8_t*>( Lt.crossK + (size_t)unit * T * 64 ) + off ), "r"( len ) : "memory" );
-							}
-						}
-					}
 
 					if( useLN )
 					{
@@ -1070,7 +1078,11 @@ namespace kern
 		cudaError_t prepareD()
 		{
 			static PerDeviceMax attr;
-			return attr.raise( FL_SMEM_MAX, []( size_t n ) { return cudaFuncSetAttribute( decode_flow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n ); } );
+			return attr.raise( FL_SMEM_MAX, []( size_t n ) {
+				cudaError_t e = cudaFuncSetAttribute( decode_flow_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n );
+				if( e != cudaSuccess ) return e;
+				return cudaFuncSetAttribute( decode_flow_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n );
+			} );
 		}
 		template<int D>
 		cudaError_t launchD( FlowArgs& a, int numSMs, cudaStream_t s )
@@ -1089,7 +1101,8 @@ namespace kern
 			at[ 0 ].val.cooperative = 1;
 			cfg.attrs = at;
 			cfg.numAttrs = 1;
-			return cudaLaunchKernelEx( &cfg, decode_flow_kernel<D>, (const FlowArgs)a );
+			if( a.timing ) return cudaLaunchKernelEx( &cfg, decode_flow_kernel<D, true>, (const FlowArgs)a );
+			return cudaLaunchKernelEx( &cfg, decode_flow_kernel<D, false>, (const FlowArgs)a );
 		}
 		inline int pad4( int x ) { return ( x + 3 ) & ~3; }
 	}
@@ -1115,7 +1128,7 @@ namespace kern
 	bool flowSupported( int d, int B, int T, int H, int nTextCtx, int refThreads, int grid )
 	{
 		if( B < 1 || B > 16 || T > FL_MAXT || T < 1 || H * 64 != d || nTextCtx > FL_MAXT ) return false;
-		if( refThreads < 0 || refThreads > 4 ) return false;
+		if( refThreads < 0 || refThreads > FL_MAXPARTS ) return false;
 		if( !( d == 128 || d == 384 || d == 512 || d == 768 || d == 1024 || d == 1280 ) ) return false;
 		const FlowGeom g = flowGeometry( d, 51865, grid );
 		if( g.R1 > 16 || g.slabFloats > 256 ) return false;

@@ -39,7 +39,6 @@ namespace kern
 		float* logits = nullptr;            // [B][nVocab]
 		unsigned long long* timing = nullptr;   // optional: (id, %globaltimer) marks of CTA `timingCta` (debug)
 		int timingCta = 0;
-		int l2Pace = 0;                     // paced L2 prefetch of the next cross-attention's K/V (WSP_FLOW_L2PACE)
 		FlowGeom g;
 		int NS = 0;                         // ring slots
 		int ncols = 8;                      // activation columns staged: 8 (B <= 8) or 16

@@ -169,7 +169,6 @@ namespace wsp
 		// N = 1 decoder step: 2 = dataflow kernel (default), 1 = round 1's barrier kernel, 0 = one kernel per op
 		int stepMode = 2;
 		int stepTimingCta = 0;
-		int flowL2Pace = 0;
 		bool stepTiming = false;        // record %globaltimer marks of CTA 0 into megaTiming (wsp_debug_step_timing)
 
 		// decode CUDA graph (N = 1 steady state)
