@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="chunks per GPU per step")
     ap.add_argument("--n-decode", type=int, default=100, help="greedy tokens per chunk (BASELINE.md §2)")
     ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: CPU threads (0 = min(cores, 16))")
+    ap.add_argument("--arith-threads", type=int, default=0,
+                    help="reference thread count whose V^T*P arithmetic the decoder reproduces (the reference's result depends on its thread count, "
+                         "ggml.c:4680-4722).  0 = 16 — what the reference arm and the cpu_baseline leg run with on this box — when the parity "
+                         "fixture of the configuration is pinned at 16 threads, else 4 (the reference's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference CPU leg (model sweeps; the default run keeps it)")
     ap.add_argument("--ref-tokens", type=int, default=12, help="reference arm: decoder tokens actually run per sample")
     return ap.parse_args()
@@ -264,17 +268,22 @@ def run_ours(a):
     # greedy tokens for 8 chunks x 32 steps of medium-sc), so the measured run is checked against the reference while it is measured
     chunk_ids = [rank * B + i for i in range(B)]
     fixture_tokens = None
+    arith = a.arith_threads or 4
     try:
         fx = np.load(os.path.join(ROOT, "tests", "golden", "real_shapes.npz"))
         key = a.model.replace(".", "_").replace("-", "_")
         if key + "_chunks" in fx and len(fx[key + "_chunks"]) == B:
+            if not a.arith_threads and key + "_t16_tokens" in fx:
+                arith = 16
+            pre = key + ("" if arith == 4 else "_t%d" % arith)
             if rank == 0:
                 chunk_ids = [int(x) for x in fx[key + "_chunks"]]
-                fixture_tokens = fx[key + "_tokens"]
+                fixture_tokens = fx[pre + "_tokens"] if pre + "_tokens" in fx else None
             else:
                 chunk_ids = [64 + rank * B + i for i in range(B)]
     except Exception:
         pass
+    ctx.set_reference_threads(arith)
     pcms = [synth.synth_pcm(cid) for cid in chunk_ids]
     n_samp = pcms[0].size
     pinned = []
@@ -409,7 +418,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": "replicas x%d (independent chunks, no step-loop collective)" % world,
                        "chunks_per_step": B * world, "l2": "inputs larger than L2: every step streams 0.81 GB of decoder weights per token x %d tokens + 0.71 GB encoder weights" % a.n_decode,
-                       "reference_threads_arithmetic": 4},
+                       "reference_threads_arithmetic": arith},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * n_samp * 4 + B * len(prompt) * 4), "d2h_bytes_per_step": int(B * model.n_text_ctx * 4),
                     "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K},
             "gpu_launches": launches,

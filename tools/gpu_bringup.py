@@ -353,7 +353,10 @@ def stage_steptiming(model_name="medium", batch=8):
     c.set_reference_threads(int(os.environ.get("FLOW_REFTHREADS", "4")))
     c.step_timing(True)
     c.run_chunks(pcms, m.prompt_init(), 40)
-    raw = c.step_timing().astype(np.int64).reshape(-1, 2)
+    rawall = c.step_timing().astype(np.int64).reshape(-1, 2)
+    prod = rawall[2000:]
+    prod = prod[prod[:, 1] != 0]
+    raw = rawall[:2000]
     raw = raw[: int(np.nonzero(raw[:, 1])[0].max()) + 1] if raw[:, 1].any() else raw[:0]
     ids, t = raw[:, 0], raw[:, 1]
     L = m.n_text_layer
@@ -385,6 +388,29 @@ def stage_steptiming(model_name="medium", batch=8):
         lab = suba if p8 in (1, 4) else subn
         items = sorted(items, key=lambda it: (it[1] == 0, it[1]))
         print("    %-10s %6.2f us | " % (nm, tot) + "  ".join("%s %.2f" % (lab.get(sb, "#%d" % sb), np.mean(per_phase[(p8, sb)])) for _, sb in items), flush=True)
+    _producer_report(prod, ids, t, L)
+
+
+def _producer_report(prod, ids, t, L):
+    """When the producer warp ISSUED selected loads of a layer, relative to the consumers' phase boundaries of the same layer."""
+    if not len(prod):
+        return
+    cons = {int(i): int(tt) for i, tt in zip(ids, t)}
+    names = {1: "Wo", 2: "Pc", 3: "crossK0", 4: "crossK4", 5: "crossK8", 6: "crossV0", 7: "after crossV", 8: "after Wco"}
+    # consumer marks: phase p of layer l ends at id 100 * (8 l + p + 1); cross-attention starts when CQ (p = 3) ends
+    rel = {}
+    for pid, pt in prod:
+        il, code = divmod(int(pid) - 100000, 100)
+        if il < 1 or il >= L - 1:
+            continue
+        for nm, ph in (("self-attn end", 1), ("cross-attn start", 3), ("cross-attn end", 4)):
+            key = 100 * (8 * il + ph + 1)
+            if key in cons:
+                rel.setdefault((code, nm), []).append((pt - cons[key]) / 1e3)
+    for code in sorted(names):
+        parts = ["%s %+.2f" % (nm, np.mean(rel[(code, nm)])) for nm in ("self-attn end", "cross-attn start", "cross-attn end") if (code, nm) in rel]
+        if parts:
+            print("    producer issues %-13s at (us relative to the consumers'): %s" % (names[code], "  ".join(parts)), flush=True)
 
 
 STAGES = {

@@ -156,65 +156,111 @@ namespace kern
 
 		// The reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key — three dependent
 		// ALU instructions per key (FFMA -> F2FP.F16.F32 -> HADD2.F32), ~30 cycles, inherent to the reference's arithmetic (staging the
-		// operands of eight keys ahead of the chain changed nothing: it is not load-bound).  A thread runs up to four such chains side by
-		// side (reference thread counts above 4: 64 dims x `parts` chains over 256 threads); they are independent, so their steps overlap.
-		// Chain k reads rows [0, n[k]) at v + k * rr * 64 and the probabilities sp[j0[k] ...].  f16 = false: plain f32 accumulation.
-		__device__ __forceinline__ void chainMulti( float ( &y )[ 4 ], const float* __restrict__ sp, const __half* __restrict__ v, const int ( &j0 )[ 4 ], const int ( &n )[ 4 ], int nmax, int rr, bool f16 )
+		// operands of eight keys ahead of the chain changed nothing: it is not load-bound).
+		__device__ __forceinline__ float chainStep( float y, float x, float p ) { return __half2float( __float2half_rn( __fmaf_rn( x, p, y ) ) ); }
+		__device__ __forceinline__ float chainRows( float y, const float* __restrict__ sp, const __half* __restrict__ v, int n )
 		{
-#pragma unroll 2
-			for( int j = 0; j < nmax; j++ )
+			int j = 0;
+			for( ; j + 4 <= n; j += 4 )
 			{
+				const float x0 = __half2float( v[ j * 64 ] );
+				const float x1 = __half2float( v[ ( j + 1 ) * 64 ] );
+				const float x2 = __half2float( v[ ( j + 2 ) * 64 ] );
+				const float x3 = __half2float( v[ ( j + 3 ) * 64 ] );
+				y = chainStep( y, x0, sp[ j ] );
+				y = chainStep( y, x1, sp[ j + 1 ] );
+				y = chainStep( y, x2, sp[ j + 2 ] );
+				y = chainStep( y, x3, sp[ j + 3 ] );
+			}
+			for( ; j < n; j++ ) y = chainStep( y, __half2float( v[ j * 64 ] ), sp[ j ] );
+			return y;
+		}
+		// Four chains of one thread side by side (reference thread counts above 4: 64 dims x `parts` chains over 256 threads).  The chains
+		// are independent, so their dependent steps overlap: four cost about what one does.  Chain k reads rows [0, n[k]) at
+		// v + k * rr * 64 and the probabilities sp[j0[k] ...]; n[] does not increase with k (a group's parts are consecutive key ranges
+		// clipped to the same end).  The rows every live chain has go through the interleaved loop — no predicates, every load hoisted
+		// above the arithmetic; a chain without rows rides along as a copy of chain 0 whose result is dropped — and what is left of the
+		// longer ones (the last part is the short one) follows.
+		__device__ __forceinline__ void chainSide( float ( &y )[ 4 ], const float* __restrict__ sp, const __half* __restrict__ v, const int ( &j0 )[ 4 ], const int ( &n )[ 4 ], int rr )
+		{
+			int nmin = n[ 0 ];
+			const __half* vb[ 4 ];
+			const float* pb[ 4 ];
+			float t[ 4 ];
+#pragma unroll
+			for( int k = 0; k < 4; k++ )
+			{
+				const bool on = n[ k ] > 0;
+				if( on ) nmin = min( nmin, n[ k ] );
+				vb[ k ] = v + ( on ? k * rr * 64 : 0 );
+				pb[ k ] = sp + ( on ? j0[ k ] : j0[ 0 ] );
+				t[ k ] = y[ k ];
+			}
+			int j = 0;
+			for( ; j + 2 <= nmin; j += 2 )
+			{
+				float x[ 4 ][ 2 ], pj[ 4 ][ 2 ];
 #pragma unroll
 				for( int k = 0; k < 4; k++ )
-					if( j < n[ k ] )
+#pragma unroll
+					for( int i = 0; i < 2; i++ )
 					{
-						const float x = __half2float( v[ ( k * rr + j ) * 64 ] );
-						const float t = __fmaf_rn( x, sp[ j0[ k ] + j ], y[ k ] );
-						y[ k ] = f16 ? __half2float( __float2half_rn( t ) ) : t;
+						x[ k ][ i ] = __half2float( vb[ k ][ ( j + i ) * 64 ] );
+						pj[ k ][ i ] = pb[ k ][ j + i ];
 					}
+#pragma unroll
+				for( int i = 0; i < 2; i++ )
+#pragma unroll
+					for( int k = 0; k < 4; k++ ) t[ k ] = chainStep( t[ k ], x[ k ][ i ], pj[ k ][ i ] );
+			}
+#pragma unroll
+			for( int k = 0; k < 4; k++ )
+			{
+				if( n[ k ] > 0 ) y[ k ] = t[ k ];
+#pragma unroll 1
+				for( int i = j; i < n[ k ]; i++ ) y[ k ] = chainStep( y[ k ], __half2float( vb[ k ][ i * 64 ] ), pb[ k ][ i ] );
 			}
 		}
 
-		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query.  Two lanes per row: lane half h owns bytes
-		// [64 h, 64 h + 64) of the row and the matching 32 query values (registers), four independent 16-byte loads and four independent
-		// accumulators, ONE shuffle per row.  (The first version used 8 lanes per row with a single 8-deep FMA chain and three dependent
-		// shuffles: 0.72 us per 128-row run, pure latency — 9 of the 22 us of a cross-attention phase.)  Returns the running maximum.
-		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const float* qf, float* sp, int warp, int lane, float lmax )
+		__device__ __forceinline__ void mmaFull( float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1 )
 		{
-			const int half = lane & 1, rw = lane >> 1, rot = rw & 3;
+			asm volatile(
+				"mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+				: "+f"( c[ 0 ] ), "+f"( c[ 1 ] ), "+f"( c[ 2 ] ), "+f"( c[ 3 ] )
+				: "r"( a0 ), "r"( a1 ), "r"( a2 ), "r"( a3 ), "r"( b0 ), "r"( b1 ) );
+		}
+		// The 16-byte pieces of a 128-byte K row (or of the query) that lane (g, t) of an MMA holds: pieces t and t + 4, the two swapped
+		// for odd g.  Rows are 128 bytes apart — every row starts in bank 0 — so the eight lanes of a quarter warp (g = 2i, 2i + 1; t = 0..3)
+		// read eight DIFFERENT 16-byte columns in one LDS.128.  A dot product does not care in which order k is walked as long as both
+		// operands agree: B column n carries the query in the order of parity n & 1, and row m's score is C[m][m & 1].
+		__device__ __forceinline__ int scorePiece( int lane, int i ) { return ( ( ( lane & 3 ) + 4 * ( ( lane >> 2 ) & 1 ) + 4 * i ) & 7 ) * 16; }
+
+		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query: q . K[r] on the tensor cores, one m16n8k16
+		// tile of 16 rows per warp and pass, f16 products accumulated in f32 like the reference's ggml_vec_dot_f16 (in another order).
+		// (The first versions did this on the FMA pipe — 8 lanes per row, then 2 lanes per row with four accumulators: 130 instructions
+		// per lane and slot, 0.41-0.47 us per 128-row slot, 5.6 of the 17.5 us of a cross-attention phase.)  qB = the query pieces of this
+		// lane (scorePiece).  Returns the running maximum.
+		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const uint4 ( &qB )[ 2 ], float* sp, int warp, int lane, float lmax )
+		{
+			const int g = lane >> 2, odd = g & 1;
+			const int p0 = scorePiece( lane, 0 ), p1 = scorePiece( lane, 1 );
 			for( int r0 = warp * 16; r0 < n; r0 += FL_WARPS * 16 )
 			{
-				const int r = r0 + rw;
-				float acc[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
-				if( r < n )
+				// rows past n are read from row n - 1 (inside the slot) and their results dropped
+				const uint8_t* ra = kc + (size_t)min( r0 + g, n - 1 ) * 128;
+				const uint8_t* rb = kc + (size_t)min( r0 + g + 8, n - 1 ) * 128;
+				const uint4 a0 = *reinterpret_cast<const uint4*>( ra + p0 ), a1 = *reinterpret_cast<const uint4*>( ra + p1 );
+				const uint4 b0 = *reinterpret_cast<const uint4*>( rb + p0 ), b1 = *reinterpret_cast<const uint4*>( rb + p1 );
+				float c[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
+				mmaFull( c, a0.x, b0.x, a0.y, b0.y, qB[ 0 ].x, qB[ 0 ].y );
+				mmaFull( c, a0.z, b0.z, a0.w, b0.w, qB[ 0 ].z, qB[ 0 ].w );
+				mmaFull( c, a1.x, b1.x, a1.y, b1.y, qB[ 1 ].x, qB[ 1 ].y );
+				mmaFull( c, a1.z, b1.z, a1.w, b1.w, qB[ 1 ].z, qB[ 1 ].w );
+				if( ( lane & 3 ) == 0 )
 				{
-					// rows are 128 bytes apart — every row starts in bank 0 — so the eight lanes of a quarter warp (four rows x two halves)
-					// must each read a DIFFERENT 16-byte column in one LDS.128: lane (row, half) takes its four pieces in the order
-					// rot, rot+1, ... (mod 4), rot = row & 3, and holds its query values in the same rotated order.  (Reading piece k in
-					// every lane was a 4-way bank conflict: 512 instead of 128 shared-memory wavefronts per 128-row slot.)
-					const uint8_t* rowb = kc + (size_t)r * 128 + half * 64;
-					uint4 u[ 4 ];
-#pragma unroll
-					for( int k = 0; k < 4; k++ ) u[ k ] = *reinterpret_cast<const uint4*>( rowb + ( ( ( k + rot ) & 3 ) << 4 ) );
-#pragma unroll
-					for( int k = 0; k < 4; k++ )
-					{
-						const __half2* h2 = reinterpret_cast<const __half2*>( &u[ k ] );
-#pragma unroll
-						for( int e = 0; e < 4; e++ )
-						{
-							const float2 f = __half22float2( h2[ e ] );
-							acc[ k ] = fmaf( f.x, qf[ k * 8 + e * 2 ], acc[ k ] );
-							acc[ k ] = fmaf( f.y, qf[ k * 8 + e * 2 + 1 ], acc[ k ] );
-						}
-					}
-				}
-				float s = ( acc[ 0 ] + acc[ 1 ] ) + ( acc[ 2 ] + acc[ 3 ] );
-				s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-				if( r < n )
-				{
-					if( half == 0 ) sp[ jBase + r ] = s;
-					lmax = fmaxf( lmax, s );
+					const float sa = odd ? c[ 1 ] : c[ 0 ], sb = odd ? c[ 3 ] : c[ 2 ];
+					if( r0 + g < n ) { sp[ jBase + r0 + g ] = sa; lmax = fmaxf( lmax, sa ); }
+					if( r0 + g + 8 < n ) { sp[ jBase + r0 + g + 8 ] = sb; lmax = fmaxf( lmax, sb ); }
 				}
 			}
 			return lmax;
@@ -380,14 +426,17 @@ namespace kern
 				}
 			}
 		}
-		template<int D>
+		// PL = -1: both register planes, plane q = column warp + 8 q (B > 8).  PL = 0 / 1: ONE plane for column `warp` (B <= 8) — the
+		// other plane is then free to hold the NEXT chunk, so that fc2 keeps two of its four K chunks in flight.
+		template<int D, int PL>
 		__device__ __forceinline__ void f16Issue( F16Rows<D>& rg, const __half* src, size_t colStride, int B, int warp, int lane )
 		{
 			using R = F16Rows<D>;
 #pragma unroll
 			for( int q = 0; q < 2; q++ )
 			{
-				const int c = warp + q * FL_WARPS;
+				if( PL >= 0 && q != PL ) continue;
+				const int c = PL >= 0 ? warp : warp + q * FL_WARPS;
 				if( c >= B ) continue;
 				const __half* row = src + (size_t)c * colStride;
 #pragma unroll
@@ -399,14 +448,15 @@ namespace kern
 				}
 			}
 		}
-		template<int D>
+		template<int D, int PL>
 		__device__ __forceinline__ void f16Verify( F16Rows<D>& rg, const __half* src, size_t colStride, int B, int warp, int lane )
 		{
 			using R = F16Rows<D>;
 #pragma unroll
 			for( int q = 0; q < 2; q++ )
 			{
-				const int c = warp + q * FL_WARPS;
+				if( PL >= 0 && q != PL ) continue;
+				const int c = PL >= 0 ? warp : warp + q * FL_WARPS;
 				if( c >= B ) continue;
 				const __half* row = src + (size_t)c * colStride;
 				SpinGuard guard;
@@ -439,7 +489,7 @@ namespace kern
 				}
 			}
 		}
-		template<int D>
+		template<int D, int PL>
 		__device__ __forceinline__ void f16Put( const F16Rows<D>& rg, int B, uint8_t* act, int warp, int lane )
 		{
 			using R = F16Rows<D>;
@@ -447,7 +497,8 @@ namespace kern
 #pragma unroll
 			for( int q = 0; q < 2; q++ )
 			{
-				const int c = warp + q * FL_WARPS;
+				if( PL >= 0 && q != PL ) continue;
+				const int c = PL >= 0 ? warp : warp + q * FL_WARPS;
 				if( c >= B ) continue;
 #pragma unroll
 				for( int k = 0; k < R::NI; k++ )
@@ -545,6 +596,17 @@ namespace kern
 					if( ++pSlot == NS ) { pSlot = 0; pPar ^= 1u; wrapped = true; }
 					return dst;
 				};
+				// debug (TIMED): when the producer ISSUES selected loads, pairs 2000.. of the timing buffer, id = 100000 + 100 * layer + code
+				int pMark = 0;
+				auto pmark = [ & ]( int il, int code ) {
+					if( !TIMED || !a.timing || cta != a.timingCta ) return;
+					if( lane == 0 && pMark < 300 )
+					{
+						a.timing[ 2 * ( 2000 + pMark ) ] = (unsigned long long)( 100000 + 100 * il + code );
+						a.timing[ 2 * ( 2000 + pMark ) + 1 ] = globalNs();
+					}
+					pMark++;
+				};
 				auto sendParams = [ & ]( const float* gm, const float* bt, const float* slab, int slabFloats ) {
 					uint8_t* dst = begin( (uint32_t)( 2 * D * 4 + slabFloats * 4 ) );
 					if( lane == 0 ) ptx::bulk_load_1d( dst, gm, D * 4, bar );
@@ -597,17 +659,26 @@ namespace kern
 						for( int i = 0; i < roundsSelf; i++ )
 							for( int q = 0; q < NG; q++ ) sendV( Lr.vCache + hb, q, i, dcSelf, nkvOld );
 					}
+					pmark( il, 1 );
 					sendWeights( Lr.wo, D, r1, n1, 1 );
+					pmark( il, 2 );
 					sendParams( Lr.lncg, Lr.lncb, nullptr, 0 );
 					sendWeights( Lr.wcq, D, r1, n1, 1 );
 					for( int unit = cta; unit < B * H; unit += G )
 					{
 						const size_t hb = (size_t)unit * T * 64;
-						for( int ci = 0; ci < nKcCross; ci++ ) sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
+						for( int ci = 0; ci < nKcCross; ci++ )
+						{
+							if( ci == 0 || ci == 4 || ci == 8 ) pmark( il, 3 + ci / 4 );
+							sendKv( Lr.crossK + hb, ci * CR, min( CR, T - ci * CR ) );
+						}
+						pmark( il, 6 );
 						for( int i = 0; i < roundsCross; i++ )
 							for( int q = 0; q < NG; q++ ) sendV( Lr.crossV + hb, q, i, dcCross, T );
+						pmark( il, 7 );
 					}
 					sendWeights( Lr.wco, D, r1, n1, 1 );
+					pmark( il, 8 );
 					sendParams( Lr.ln3g, Lr.ln3b, nullptr, 0 );
 					sendWeights( Lr.w1, D, r4, n4, 1 );
 					sendWeights( Lr.w2, 4 * D, r1, n1, 4 );
@@ -639,14 +710,13 @@ namespace kern
 			// every phase of every `full` barrier complete and a later parity wait can never match a phase it skipped.
 			auto releaseSlots = [ & ]( int n, bool observe = false ) {
 				__syncwarp();
-				if( lane == 0 )
-					for( int k = 0; k < n; k++ )
-					{
-						uint32_t par;
-						const int idx = slotAt( k, par );
-						if( observe ) mbarWaitLong( full + idx, par );
-						ptx::mbar_arrive( empty + idx );
-					}
+				if( lane < n )   // lane k takes slot k (n <= 4): the waits and arrives of a V round overlap instead of queueing behind lane 0
+				{
+					uint32_t par;
+					const int idx = slotAt( lane, par );
+					if( observe ) mbarWaitLong( full + idx, par );
+					ptx::mbar_arrive( empty + idx );
+				}
 				cSlot += n;
 				if( cSlot >= NS ) { cSlot -= NS; cPar ^= 1u; }
 			};
@@ -732,23 +802,9 @@ namespace kern
 							}
 							consumerSync();
 							sub( 1 );
-							float qf[ 32 ];   // this lane's half of the query, its four 8-value pieces rotated by (row & 3) (scoreRows)
-							{
-								const __half2* qs = reinterpret_cast<const __half2*>( sqkv ) + ( lane & 1 ) * 16;
-								const int rot = ( lane >> 1 ) & 3;
-#pragma unroll
-								for( int k = 0; k < 4; k++ )
-								{
-									const __half2* qp = qs + ( ( k + rot ) & 3 ) * 4;
-#pragma unroll
-									for( int e = 0; e < 4; e++ )
-									{
-										const float2 f = __half22float2( qp[ e ] );
-										qf[ k * 8 + 2 * e ] = f.x;
-										qf[ k * 8 + 2 * e + 1 ] = f.y;
-									}
-								}
-							}
+							uint4 qf[ 2 ];    // this lane's two pieces of the (f16) query, in the order its K pieces come in (scorePiece)
+							qf[ 0 ] = *reinterpret_cast<const uint4*>( sqkv + scorePiece( lane, 0 ) );
+							qf[ 1 ] = *reinterpret_cast<const uint4*>( sqkv + scorePiece( lane, 1 ) );
 							float lmax = -INFINITY;
 #pragma unroll 1
 							for( int ci = 0; ci < nKc; ci++ )
@@ -783,7 +839,8 @@ namespace kern
 										if( nmax > 0 )
 										{
 											const __half* vp = reinterpret_cast<const __half*>( waitSlot( q ) ) + e;
-											chainMulti( y, sp, vp, j0, nk, nmax, RR, a.refThreads > 0 );
+											if( PG == 1 ) y[ 0 ] = chainRows( y[ 0 ], sp + j0[ 0 ], vp, nk[ 0 ] );
+											else chainSide( y, sp, vp, j0, nk, RR );
 										}
 									}
 									releaseSlots( NG, true );
@@ -801,7 +858,7 @@ namespace kern
 #pragma unroll
 										for( int k = 0; k < 4; k++ )
 											if( k == ko )
-												y[ k ] = a.refThreads > 0 ? __half2float( __float2half_rn( __fmaf_rn( x, pj, y[ k ] ) ) ) : __fmaf_rn( pj, x, y[ k ] );
+												y[ k ] = chainStep( y[ k ], x, pj );
 									}
 								}
 #pragma unroll
@@ -892,9 +949,9 @@ namespace kern
 					{
 						// (fc2: the first of its four K chunks; the others are fetched behind the MMAs below)
 						f16Probe<D>( hSrc, hStride, B, warp, lane );
-						f16Issue<D>( hr, hSrc, hStride, B, warp, lane );
-						f16Verify<D>( hr, hSrc, hStride, B, warp, lane );
-						f16Put<D>( hr, B, act, warp, lane );
+						f16Issue<D, -1>( hr, hSrc, hStride, B, warp, lane );
+						f16Verify<D, -1>( hr, hSrc, hStride, B, warp, lane );
+						f16Put<D, -1>( hr, B, act, warp, lane );
 						consumerSync();
 						sub( 1 );
 					}
@@ -915,12 +972,12 @@ namespace kern
 							if( kc > 0 )
 							{
 								// this chunk's rows were requested before the previous chunk's MMAs
-								f16Verify<D>( hr, hSrc + (size_t)kc * D, hStride, B, warp, lane );
+								f16Verify<D, -1>( hr, hSrc + (size_t)kc * D, hStride, B, warp, lane );
 								consumerSync();   // the previous chunk's MMAs have read `act`
-								f16Put<D>( hr, B, act, warp, lane );
+								f16Put<D, -1>( hr, B, act, warp, lane );
 								consumerSync();
 							}
-							if( kc + 1 < KC ) f16Issue<D>( hr, hSrc + (size_t)( kc + 1 ) * D, hStride, B, warp, lane );
+							if( kc + 1 < KC ) f16Issue<D, -1>( hr, hSrc + (size_t)( kc + 1 ) * D, hStride, B, warp, lane );
 #pragma unroll
 							for( int u = 0; u < 4; u++ )
 							{
@@ -1128,7 +1185,7 @@ namespace kern
 	bool flowSupported( int d, int B, int T, int H, int nTextCtx, int refThreads, int grid )
 	{
 		if( B < 1 || B > 16 || T > FL_MAXT || T < 1 || H * 64 != d || nTextCtx > FL_MAXT ) return false;
-		if( refThreads < 0 || refThreads > FL_MAXPARTS ) return false;
+		if( refThreads < 1 || refThreads > FL_MAXPARTS ) return false;   // 0 (plain f32 accumulation, not the reference's arithmetic) runs on the per-op path
 		if( !( d == 128 || d == 384 || d == 512 || d == 768 || d == 1024 || d == 1280 ) ) return false;
 		const FlowGeom g = flowGeometry( d, 51865, grid );
 		if( g.R1 > 16 || g.slabFloats > 256 ) return false;
