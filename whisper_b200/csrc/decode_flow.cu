@@ -235,32 +235,54 @@ namespace kern
 		// operands agree: B column n carries the query in the order of parity n & 1, and row m's score is C[m][m & 1].
 		__device__ __forceinline__ int scorePiece( int lane, int i ) { return ( ( ( lane & 3 ) + 4 * ( ( lane >> 2 ) & 1 ) + 4 * i ) & 7 ) * 16; }
 
-		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query: q . K[r] on the tensor cores, one m16n8k16
-		// tile of 16 rows per warp and pass, f16 products accumulated in f32 like the reference's ggml_vec_dot_f16 (in another order).
-		// (The first versions did this on the FMA pipe — 8 lanes per row, then 2 lanes per row with four accumulators: 130 instructions
-		// per lane and slot, 0.41-0.47 us per 128-row slot, 5.6 of the 17.5 us of a cross-attention phase.)  qB = the query pieces of this
-		// lane (scorePiece).  Returns the running maximum.
-		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const uint4 ( &qB )[ 2 ], float* sp, int warp, int lane, float lmax )
+		// Scores of n K rows (128 bytes each, contiguous in shared memory) against the query: q . K[r] on the tensor cores, m16n8k16 tiles
+		// of 16 rows, f16 products accumulated in f32 like the reference's ggml_vec_dot_f16 (in another order).  (The first versions did
+		// this on the FMA pipe — 8 lanes per row, then 2 lanes per row with four accumulators: 130 instructions per lane and slot,
+		// 0.41-0.47 us per 128-row slot, 5.6 of the 17.5 us of a cross-attention phase.)  qB = the query pieces of this lane (scorePiece).
+		// The calling warp takes the tiles tile0, tile0 + tileStep, ..., TI of them at a time: their loads are issued together and their
+		// four-HMMA chains interleaved.  <1>( warp, 8 ) spreads one slot over the eight warps (self-attention: one short slot);
+		// <4>( 0, 1 ) gives a whole 128-row slot to one warp — the way a long run of slots is scored: whatever a warp computes on a slot,
+		// the slot costs it a fixed ~300 cycles of dependent latency (barrier wait -> LDS -> chained HMMAs -> STS -> release), so eight
+		// warps on eight DIFFERENT slots score a resident key memory about twice as fast as eight warps sharing every slot
+		// (cross-attention, 12 slots: 4.6 -> 2.5 us).  Returns the running maximum.
+		template<int TI>
+		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const uint4 ( &qB )[ 2 ], float* sp, int tile0, int tileStep, int lane, float lmax )
 		{
 			const int g = lane >> 2, odd = g & 1;
 			const int p0 = scorePiece( lane, 0 ), p1 = scorePiece( lane, 1 );
-			for( int r0 = warp * 16; r0 < n; r0 += FL_WARPS * 16 )
+			for( int tb = tile0; tb * 16 < n; tb += tileStep * TI )
 			{
-				// rows past n are read from row n - 1 (inside the slot) and their results dropped
-				const uint8_t* ra = kc + (size_t)min( r0 + g, n - 1 ) * 128;
-				const uint8_t* rb = kc + (size_t)min( r0 + g + 8, n - 1 ) * 128;
-				const uint4 a0 = *reinterpret_cast<const uint4*>( ra + p0 ), a1 = *reinterpret_cast<const uint4*>( ra + p1 );
-				const uint4 b0 = *reinterpret_cast<const uint4*>( rb + p0 ), b1 = *reinterpret_cast<const uint4*>( rb + p1 );
-				float c[ 4 ] = { 0.0f, 0.0f, 0.0f, 0.0f };
-				mmaFull( c, a0.x, b0.x, a0.y, b0.y, qB[ 0 ].x, qB[ 0 ].y );
-				mmaFull( c, a0.z, b0.z, a0.w, b0.w, qB[ 0 ].z, qB[ 0 ].w );
-				mmaFull( c, a1.x, b1.x, a1.y, b1.y, qB[ 1 ].x, qB[ 1 ].y );
-				mmaFull( c, a1.z, b1.z, a1.w, b1.w, qB[ 1 ].z, qB[ 1 ].w );
+				uint4 a0[ TI ], a1[ TI ], b0[ TI ], b1[ TI ];
+				float c[ TI ][ 4 ];
+#pragma unroll
+				for( int i = 0; i < TI; i++ )
+				{
+					// rows past n are read from row n - 1 (inside the slot) and their results dropped
+					const int r0 = ( tb + i * tileStep ) * 16;
+					const uint8_t* ra = kc + (size_t)min( r0 + g, n - 1 ) * 128;
+					const uint8_t* rb = kc + (size_t)min( r0 + g + 8, n - 1 ) * 128;
+					a0[ i ] = *reinterpret_cast<const uint4*>( ra + p0 ); a1[ i ] = *reinterpret_cast<const uint4*>( ra + p1 );
+					b0[ i ] = *reinterpret_cast<const uint4*>( rb + p0 ); b1[ i ] = *reinterpret_cast<const uint4*>( rb + p1 );
+					c[ i ][ 0 ] = c[ i ][ 1 ] = c[ i ][ 2 ] = c[ i ][ 3 ] = 0.0f;
+				}
+#pragma unroll
+				for( int i = 0; i < TI; i++ ) mmaFull( c[ i ], a0[ i ].x, b0[ i ].x, a0[ i ].y, b0[ i ].y, qB[ 0 ].x, qB[ 0 ].y );
+#pragma unroll
+				for( int i = 0; i < TI; i++ ) mmaFull( c[ i ], a0[ i ].z, b0[ i ].z, a0[ i ].w, b0[ i ].w, qB[ 0 ].z, qB[ 0 ].w );
+#pragma unroll
+				for( int i = 0; i < TI; i++ ) mmaFull( c[ i ], a1[ i ].x, b1[ i ].x, a1[ i ].y, b1[ i ].y, qB[ 1 ].x, qB[ 1 ].y );
+#pragma unroll
+				for( int i = 0; i < TI; i++ ) mmaFull( c[ i ], a1[ i ].z, b1[ i ].z, a1[ i ].w, b1[ i ].w, qB[ 1 ].z, qB[ 1 ].w );
 				if( ( lane & 3 ) == 0 )
 				{
-					const float sa = odd ? c[ 1 ] : c[ 0 ], sb = odd ? c[ 3 ] : c[ 2 ];
-					if( r0 + g < n ) { sp[ jBase + r0 + g ] = sa; lmax = fmaxf( lmax, sa ); }
-					if( r0 + g + 8 < n ) { sp[ jBase + r0 + g + 8 ] = sb; lmax = fmaxf( lmax, sb ); }
+#pragma unroll
+					for( int i = 0; i < TI; i++ )
+					{
+						const int r0 = ( tb + i * tileStep ) * 16;
+						const float sa = odd ? c[ i ][ 1 ] : c[ i ][ 0 ], sb = odd ? c[ i ][ 3 ] : c[ i ][ 2 ];
+						if( r0 + g < n ) { sp[ jBase + r0 + g ] = sa; lmax = fmaxf( lmax, sa ); }
+						if( r0 + g + 8 < n ) { sp[ jBase + r0 + g + 8 ] = sb; lmax = fmaxf( lmax, sb ); }
+					}
 				}
 			}
 			return lmax;
@@ -806,15 +828,34 @@ namespace kern
 							qf[ 0 ] = *reinterpret_cast<const uint4*>( sqkv + scorePiece( lane, 0 ) );
 							qf[ 1 ] = *reinterpret_cast<const uint4*>( sqkv + scorePiece( lane, 1 ) );
 							float lmax = -INFINITY;
-#pragma unroll 1
-							for( int ci = 0; ci < nKc; ci++ )
+							if( nKc <= 1 )
 							{
-								const uint8_t* kc = waitSlot( 0 );
-								lmax = scoreRows( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, lane, lmax );
-								releaseSlots( 1 );
-								if( TIMED && !self ) sub( 10 + ci );
+								// one short slot (self-attention): its tiles spread over the warps
+								for( int ci = 0; ci < nKc; ci++ )
+								{
+									const uint8_t* kc = waitSlot( 0 );
+									lmax = scoreRows<1>( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, FL_WARPS, lane, lmax );
+									releaseSlots( 1 );
+								}
 							}
-							if( self ) lmax = scoreRows( sqkv + 128, 1, nOld, qf, sp, warp, lane, lmax );   // this step's own K row
+							else
+							{
+								// a run of slots, eight at a time: warp w scores slot w of the group alone, then every warp releases all of them
+								const int GS = min( FL_WARPS, NS );   // a group's slots are all in the ring at once
+#pragma unroll 1
+								for( int c0 = 0; c0 < nKc; c0 += GS )
+								{
+									const int ng = min( GS, nKc - c0 );
+									if( warp < ng )
+									{
+										const uint8_t* kc = waitSlot( warp );
+										lmax = scoreRows<4>( kc, min( CR, nOld - ( c0 + warp ) * CR ), ( c0 + warp ) * CR, qf, sp, 0, 1, lane, lmax );
+									}
+									releaseSlots( ng, true );
+									if( TIMED && !self ) sub( 10 + c0 / GS );
+								}
+							}
+							if( self ) lmax = scoreRows<1>( sqkv + 128, 1, nOld, qf, sp, warp, FL_WARPS, lane, lmax );   // this step's own K row
 							sub( 2 );
 							softmaxRow( sp, n, lmax, sred, tid, warp, lane );
 							sub( 3 );
