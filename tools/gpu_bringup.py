@@ -296,6 +296,8 @@ def stage_profile(model_name="medium", batch=8, n_decode=3):
     from whisper_b200 import synth
     path, m, e, c = _open(model_name, batch=batch)
     c.set_graph(os.environ.get("WSP_GRAPH", "0") == "1")
+    c.set_reference_threads(int(os.environ.get("FLOW_REFTHREADS", "4")))
+    n_decode = int(os.environ.get("PROFILE_NDECODE", n_decode))
     pcms = [synth.synth_pcm(i) for i in range(batch)]
     toks, st = c.run_chunks(pcms, m.prompt_init(), n_decode)
     print("  profile run stages", st.tolist(), flush=True)
