@@ -234,6 +234,20 @@ def run_reference(a):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(a):
+    # stdout carries ONE JSON line: whatever libraries print to file descriptor 1 meanwhile (NCCL prints its version banner there)
+    # is sent to stderr, and the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _run_ours(a, real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+
+
+def _run_ours(a, real_stdout):
     import torch
     import torch.distributed as dist
     from whisper_b200 import capi, synth
@@ -333,10 +347,9 @@ def run_ours(a):
     e2e_wall = max_over_ranks(e2e_wall)
 
     # ---- value leg: PCM resident in HBM; clocks sampled during this region ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
+    sampler = ClockSampler(local)     # every rank watches its own GPU; rank 0's sample goes into "clocks", the others into "per_rank"
+    sampler.start()
+    time.sleep(0.15)
     launches0 = L.wsp_launch_count()
     stage = np.zeros(3)
     barrier()
@@ -347,8 +360,15 @@ def run_ours(a):
     val_ms_dev = ctx.timer_stop()
     barrier()
     launches = int(L.wsp_launch_count() - launches0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     val_ms = max_over_ranks(val_ms_dev)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([val_ms_dev / K, stage[0] / K, stage[1] / K, stage[2] / K, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": i, "ms_per_step": float(t[0]), "mel_ms": float(t[1]), "encode_ms": float(t[2]), "decode_ms": float(t[3]), "sm_mhz": float(t[4])}
+                    for i, t in enumerate(allr)]
     same_tokens = bool((toks_r == toks).all())
 
     # ---- roofline of the dominant kernel: instrumented decoder pass (event pair around every launch) ----
@@ -424,14 +444,14 @@ def run_ours(a):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "clocks": clocks,
+            "clocks": clocks, "per_rank": per_rank,
             "stage_ms_per_step": {"mel": stage[0] / K, "encode": stage[1] / K, "decode": stage[2] / K},
             "load": {"seconds": load_s, "nccl_broadcast_ms": bcast_ms, "weight_bytes": engine.weight_bytes()},
             "tokens_equal_e2e_vs_resident": same_tokens,
             "tokens_match_reference_fixture": (None if fixture_tokens is None else
                                                bool((np.asarray(toks_r)[:, :fixture_tokens.shape[1]] == fixture_tokens[:, :a.n_decode]).all())),
         }
-        print(json.dumps(_jsonable(line)), flush=True)
+        os.write(real_stdout, (json.dumps(_jsonable(line)) + "\n").encode())
     for p in pinned:
         L.wsp_host_free(p)
     if world > 1:
