@@ -246,11 +246,11 @@ namespace kern
 		// warps on eight DIFFERENT slots score a resident key memory about twice as fast as eight warps sharing every slot
 		// (cross-attention, 12 slots: 4.6 -> 2.5 us).  Returns the running maximum.
 		template<int TI>
-		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const uint4 ( &qB )[ 2 ], float* sp, int tile0, int tileStep, int tileEnd, int lane, float lmax )
+		__device__ __forceinline__ float scoreRows( const uint8_t* kc, int n, int jBase, const uint4 ( &qB )[ 2 ], float* sp, int tile0, int tileStep, int lane, float lmax )
 		{
 			const int g = lane >> 2, odd = g & 1;
 			const int p0 = scorePiece( lane, 0 ), p1 = scorePiece( lane, 1 );
-			for( int tb = tile0; tb < tileEnd && tb * 16 < n; tb += tileStep * TI )
+			for( int tb = tile0; tb * 16 < n; tb += tileStep * TI )
 			{
 				uint4 a0[ TI ], a1[ TI ], b0[ TI ], b1[ TI ];
 				float c[ TI ][ 4 ];
@@ -833,31 +833,28 @@ namespace kern
 								for( int ci = 0; ci < nKc; ci++ )
 								{
 									const uint8_t* kc = waitSlot( 0 );
-									lmax = scoreRows<1>( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, FL_WARPS, CR / 16, lane, lmax );
+									lmax = scoreRows<1>( kc, min( CR, nOld - ci * CR ), ci * CR, qf, sp, warp, FL_WARPS, lane, lmax );
 									releaseSlots( 1 );
 								}
 							}
 							else
 							{
-								// a run of slots, four at a time: warps w and w + 4 score the two halves (four 16-row tiles each) of slot w of the
-								// group, then every warp releases the group.  (Eight slots at a time, a slot per warp: the first slots are
-								// released — and the V stream behind them can start — after 1.4 us instead of 0.5.)
-								const int GS = min( FL_WARPS / 2, NS );   // a group's slots are all in the ring at once
+								// a run of slots, eight at a time: warp w scores slot w of the group alone, then every warp releases all of them
+								const int GS = min( FL_WARPS, NS );   // a group's slots are all in the ring at once
 #pragma unroll 1
 								for( int c0 = 0; c0 < nKc; c0 += GS )
 								{
 									const int ng = min( GS, nKc - c0 );
-									const int sl = warp % GS, hf = warp / GS;
-									if( sl < ng && hf < 2 )
+									if( warp < ng )
 									{
-										const uint8_t* kc = waitSlot( sl );
-										lmax = scoreRows<4>( kc, min( CR, nOld - ( c0 + sl ) * CR ), ( c0 + sl ) * CR, qf, sp, 4 * hf, 1, 4 * hf + 4, lane, lmax );
+										const uint8_t* kc = waitSlot( warp );
+										lmax = scoreRows<4>( kc, min( CR, nOld - ( c0 + warp ) * CR ), ( c0 + warp ) * CR, qf, sp, 0, 1, lane, lmax );
 									}
 									releaseSlots( ng, true );
 									if( TIMED && !self ) sub( 10 + c0 / GS );
 								}
 							}
-							if( self ) lmax = scoreRows<1>( sqkv + 128, 1, nOld, qf, sp, warp, FL_WARPS, 1, lane, lmax );   // this step's own K row
+							if( self ) lmax = scoreRows<1>( sqkv + 128, 1, nOld, qf, sp, warp, FL_WARPS, lane, lmax );   // this step's own K row
 							sub( 2 );
 							softmaxRow( sp, n, lmax, sred, tid, warp, lane );
 							sub( 3 );
