@@ -168,6 +168,30 @@ def test_batch_equals_single():
     assert t2.tolist() == t4[:2].tolist()
 
 
+@pytest.mark.parametrize("threads", [2, 3, 5, 8, 9, 12, 13, 16])
+def test_step_kernels_agree_for_every_thread_count(threads):
+    """The dataflow step kernel (mode 2), round 1's barrier kernel (mode 1) and the kernel-per-op path (mode 0) reproduce the same
+    reference arithmetic: same greedy tokens, logits within the summation-order noise, at reference thread counts that put one,
+    two, three and four key ranges on a 64-thread group of the step kernel (the fixtures pin 1, 4, 6, 16 against the reference)."""
+    m, e, c = open_model("micro.en-sc", 2)
+    g = golden("micro_en_30s")
+    pcms = [synth.synth_pcm(int(g["chunk"])), synth.synth_pcm(int(g["chunk"]), 400000)]
+    prompt = g["prompt"].tolist()
+    c.set_reference_threads(threads)
+    res = {}
+    try:
+        for mode in (2, 1, 0):
+            c.set_step_mode(mode)
+            toks, _ = c.run_chunks(pcms, prompt, N_STEPS)
+            res[mode] = (toks.copy(), c.logits(2).copy())
+    finally:
+        c.set_step_mode(2)
+        c.set_reference_threads(4)
+    for mode in (1, 0):
+        assert res[2][0].tolist() == res[mode][0].tolist(), (threads, mode)
+        assert np.abs(res[2][1] - res[mode][1]).max() < TOL_LOGIT, (threads, mode)
+
+
 def test_live_reference_when_prebuilt():
     """If oracle/_ref travelled to this box, compare against the reference live on a case that has no committed fixture."""
     from oracle import ref
