@@ -5,10 +5,13 @@
 //   S = (K q) / sqrt(64)  (f16 x f16 -> f32),  P = softmax(S),  P rounded to f16,  O = V^T P  (f16 x f16 -> f32).
 // Here: one CTA = 128 queries of one (chunk, head); K/V^T tiles of 128 keys arrive by TMA; S = Q K^T and O_tile = P V are
 // tcgen05.mma with accumulators in TMEM; the online softmax runs one query row per thread (no shuffles): the whole 128-wide score row
-// is pulled into registers with four TMEM loads in flight and handled in ONE pass; the running output lives in registers (rescaled
-// per tile), so TMEM is never stored to.  The scores of tile j+1 are issued right behind P*V of tile j, so they are ready before the
-// threads come back from reading O.  Two CTAs co-reside per SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax also
-// overlaps the other's MMAs.
+// is pulled into registers with four TMEM loads in flight and handled in ONE pass.  The running output stays IN TMEM: P*V of every
+// tile accumulates onto it, relative to a per-row reference maximum that is only moved when a tile's maximum exceeds it by more than
+// 2^8 (then the thread rescales its own TMEM lane: tcgen05.ld / multiply / tcgen05.st — a handful of times per row, in the first
+// tiles).  So a tile no longer waits for its own P*V, reads O back and rescales 64 values: P*V of tile j runs behind the score load
+// and the row maximum of tile j+1, and only the writes of the next P wait for it.  The scores of tile j+1 are issued right behind
+// P*V of tile j; V^T tiles are double-buffered.  Two CTAs co-reside per SM (97 KB smem, 256 TMEM columns each) so one CTA's
+// softmax also overlaps the other's MMAs.
 //
 // Rounding points kept from the oracle: Q, K, V and P are f16, all accumulation is f32.  Deliberate difference: exp is
 // exp2f (not the oracle's f16 exp LUT, ggml.c:6065-6067) and P is rounded before the 1/sum normalisation (the oracle rounds after, :6082).
@@ -25,7 +28,8 @@ namespace attn
 	constexpr int SK_BYTES = TK * HD * 2;         // 16 KB
 	constexpr int SV_BYTES = HD * TK * 2;         // 16 KB, two [64][64] sub-tiles
 	constexpr int SP_BYTES = TQ * TK * 2;         // 32 KB, two [128][64] sub-tiles
-	constexpr int SMEM_BYTES = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + 128 + 1024;
+	constexpr int SMEM_BYTES = SQ_BYTES + SK_BYTES + 2 * SV_BYTES + SP_BYTES + 128 + 1024;
+	constexpr float REF_SLACK = 8.0f;             // a row's reference may lag its running maximum by this much (log2 units): P <= 256
 	constexpr uint32_t TMEM_COLS = 256;           // S: [0,128)  O tile: [128,192)
 
 	// 2^x on the MUFU pipe without exp2f's range-reduction wrapper (x <= 0 here; results below 2^-126 may flush to zero, far below
@@ -51,14 +55,14 @@ namespace attn
 		uint8_t* sQ = smem;
 		uint8_t* sK = sQ + SQ_BYTES;
 		uint8_t* sV = sK + SK_BYTES;
-		uint8_t* sP = sV + SV_BYTES;
+		uint8_t* sP = sV + 2 * SV_BYTES;              // (two V^T buffers)
 		uint64_t* bars = reinterpret_cast<uint64_t*>( sP + SP_BYTES );
 		uint64_t* bar_q = bars + 0;
 		uint64_t* bar_k = bars + 1;
-		uint64_t* bar_v = bars + 2;
-		uint64_t* bar_s = bars + 3;
-		uint64_t* bar_o = bars + 4;
-		uint32_t* tmem_slot = reinterpret_cast<uint32_t*>( bars + 5 );
+		uint64_t* bar_v = bars + 2;                   // [2]: one per V^T buffer
+		uint64_t* bar_s = bars + 4;
+		uint64_t* bar_o = bars + 5;
+		uint32_t* tmem_slot = reinterpret_cast<uint32_t*>( bars + 6 );
 
 		const int tid = threadIdx.x;
 		const int warp = tid >> 5;
@@ -71,7 +75,7 @@ namespace attn
 			ptx::prefetch_tensormap( &mapQ );
 			ptx::prefetch_tensormap( &mapK );
 			ptx::prefetch_tensormap( &mapVt );
-			for( int i = 0; i < 5; i++ )
+			for( int i = 0; i < 6; i++ )
 				ptx::mbar_init( &bars[ i ], 1 );
 			ptx::fence_barrier_init();
 		}
@@ -97,15 +101,18 @@ namespace attn
 			ptx::mbar_expect_tx( bar_v, SV_BYTES );
 			ptx::tma_load_2d( sV, &mapVt, bar_v, 0, bh * HD );
 			ptx::tma_load_2d( sV + SV_BYTES / 2, &mapVt, bar_v, 64, bh * HD );
+			if( nkv > 1 )
+			{
+				ptx::mbar_expect_tx( bar_v + 1, SV_BYTES );
+				ptx::tma_load_2d( sV + SV_BYTES, &mapVt, bar_v + 1, TK, bh * HD );
+				ptx::tma_load_2d( sV + SV_BYTES + SV_BYTES / 2, &mapVt, bar_v + 1, TK + 64, bh * HD );
+			}
 		}
 
 		constexpr uint32_t idescS = ptx::umma_idesc_f16( TQ, TK );
 		constexpr uint32_t idescO = ptx::umma_idesc_f16( TQ, HD );
 
-		float o_acc[ HD ];
-#pragma unroll
-		for( int i = 0; i < HD; i++ ) o_acc[ i ] = 0.0f;
-		float m_run = -INFINITY;
+		float m_ref = -INFINITY;     // reference maximum of this row's O (in TMEM) and l: P = 2^((s - m_ref) * c)
 		float l_run = 0.0f;
 		const uint32_t lane_base = (uint32_t)( warp * 32 ) << 16;   // this warp's TMEM lane quadrant
 		const int r = tid;                                          // my query row inside the tile
@@ -149,7 +156,7 @@ namespace attn
 #pragma unroll
 			for( int ch = 0; ch < TK / 32; ch++ ) ptx::tmem_ld_32x32( tmem_S + lane_base + (uint32_t)( ch * 32 ), sc + ch * 32 );
 			ptx::tmem_ld_wait();
-			float mx = m_run;
+			float mx = -INFINITY;
 			if( fullTile )
 			{
 #pragma unroll
@@ -161,9 +168,47 @@ namespace attn
 				for( int i = 0; i < TK; i++ )
 					if( i < nvalid ) mx = fmaxf( mx, __uint_as_float( sc[ i ] ) );
 			}
-			const float alpha = m_run == -INFINITY ? 0.0f : ex2Approx( ( m_run - mx ) * c );   // first tile: nothing to rescale
-			m_run = mx;
-			const float nmc = -mx * c;
+
+			// P*V of the previous tile has to be done before its P is overwritten (and before O is touched); it ran behind the loads and
+			// the row maximum above
+			if( j > 0 )
+			{
+				ptx::mbar_wait( bar_o, ph ^ 1u );
+				ptx::tc_fence_after();
+				if( tid == 0 && j + 1 < nkv )
+				{
+					// the V^T buffer of tile j-1 is free: fetch tile j+1 into it
+					uint64_t* bv = bar_v + ( ( j + 1 ) & 1 );
+					uint8_t* dv = sV + ( ( j + 1 ) & 1 ) * SV_BYTES;
+					ptx::mbar_expect_tx( bv, SV_BYTES );
+					ptx::tma_load_2d( dv, &mapVt, bv, ( j + 1 ) * TK, bh * HD );
+					ptx::tma_load_2d( dv + SV_BYTES / 2, &mapVt, bv, ( j + 1 ) * TK + 64, bh * HD );
+				}
+				__syncwarp();
+				// move the reference of a row whose maximum ran away from it: O (this thread's TMEM lane) and l shrink by 2^(old - new).
+				// Warp-uniform (the TMEM accesses are collective); rows that stay get the factor 1.
+				const bool move = ( mx - m_ref ) * c > REF_SLACK;
+				if( __any_sync( 0xffffffffu, move ) )
+				{
+					const float f = move ? ex2Approx( ( m_ref - mx ) * c ) : 1.0f;
+#pragma unroll
+					for( int hh = 0; hh < HD / 32; hh++ )
+					{
+						uint32_t rg[ 32 ];
+						ptx::tmem_ld_32x32( tmem_O + lane_base + (uint32_t)( hh * 32 ), rg );
+						ptx::tmem_ld_wait();
+#pragma unroll
+						for( int i = 0; i < 32; i++ ) rg[ i ] = __float_as_uint( __uint_as_float( rg[ i ] ) * f );
+						ptx::tmem_st_32x32( tmem_O + lane_base + (uint32_t)( hh * 32 ), rg );
+					}
+					ptx::tmem_st_wait();
+					l_run *= f;
+					if( move ) m_ref = mx;
+				}
+			}
+			else
+				m_ref = mx;
+			const float nmc = -m_ref * c;
 
 			// probabilities -> f16 -> swizzled smem (A operand of P*V)
 			float lsum = 0.0f;
@@ -196,29 +241,29 @@ namespace attn
 					*reinterpret_cast<uint4*>( sub + chunk16 * 16 ) = u;
 				}
 			}
-			l_run = l_run * alpha + lsum;
+			l_run += lsum;
 
 			ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
 			ptx::tc_fence_before();
-			__syncthreads();            // P complete, and every thread has its S row in registers: the S columns are free again
+			__syncthreads();            // P complete, every thread has its S row in registers (the S columns are free again), O lanes settled
 
 			if( tid == 0 )
 			{
 				ptx::tc_fence_after();
-				ptx::mbar_wait( bar_v, ph );
+				ptx::mbar_wait( bar_v + ( j & 1 ), (uint32_t)( ( j >> 1 ) & 1 ) );
 				ptx::tc_fence_after();
+				const uint8_t* sVj = sV + ( j & 1 ) * SV_BYTES;
 #pragma unroll
 				for( int k = 0; k < TK / 16; k++ )
 				{
 					const uint64_t da = ptx::umma_desc_sw128( ptx::smem_u32( sP + ( k >> 2 ) * ( SP_BYTES / 2 ) ) ) + (uint64_t)( ( k & 3 ) * 2 );
-					const uint64_t db = ptx::umma_desc_sw128( ptx::smem_u32( sV + ( k >> 2 ) * ( SV_BYTES / 2 ) ) ) + (uint64_t)( ( k & 3 ) * 2 );
-					ptx::umma_f16( tmem_O, da, db, idescO, k != 0 ? 1u : 0u );
+					const uint64_t db = ptx::umma_desc_sw128( ptx::smem_u32( sVj + ( k >> 2 ) * ( SV_BYTES / 2 ) ) ) + (uint64_t)( ( k & 3 ) * 2 );
+					ptx::umma_f16( tmem_O, da, db, idescO, ( k != 0 || j != 0 ) ? 1u : 0u );   // O accumulates over the tiles
 				}
 				ptx::umma_commit( bar_o );
 				if( j + 1 < nkv )
 				{
-					// the NEXT tile's scores right behind this P*V: the tensor core computes them while the threads read O back and
-					// rescale, so no tile waits for its own Q*K^T any more
+					// the NEXT tile's scores right behind this P*V
 					ptx::mbar_wait( bar_k, ph ^ 1u );
 					ptx::tc_fence_after();
 					const uint64_t dq = ptx::umma_desc_sw128( ptx::smem_u32( sQ ) );
@@ -230,26 +275,21 @@ namespace attn
 				}
 			}
 			__syncwarp();
-			ptx::mbar_wait( bar_o, ph );
-			ptx::tc_fence_after();
-			if( tid == 0 && j + 1 < nkv )
-			{
-				ptx::mbar_expect_tx( bar_v, SV_BYTES );
-				ptx::tma_load_2d( sV, &mapVt, bar_v, ( j + 1 ) * TK, bh * HD );
-				ptx::tma_load_2d( sV + SV_BYTES / 2, &mapVt, bar_v, ( j + 1 ) * TK + 64, bh * HD );
-			}
-			__syncwarp();
-
-			{
-				uint32_t rg[ HD ];
-				ptx::tmem_ld_32x32( tmem_O + lane_base, rg );
-				ptx::tmem_ld_32x32( tmem_O + lane_base + 32u, rg + 32 );
-				ptx::tmem_ld_wait();
-#pragma unroll
-				for( int i = 0; i < HD; i++ ) o_acc[ i ] = o_acc[ i ] * alpha + __uint_as_float( rg[ i ] );
-			}
-			ptx::tc_fence_before();
 		}
+
+		// the last P*V, then O / l as f16
+		ptx::mbar_wait( bar_o, (uint32_t)( ( nkv - 1 ) & 1 ) );
+		ptx::tc_fence_after();
+		float o_acc[ HD ];
+		{
+			uint32_t rg[ HD ];
+			ptx::tmem_ld_32x32( tmem_O + lane_base, rg );
+			ptx::tmem_ld_32x32( tmem_O + lane_base + 32u, rg + 32 );
+			ptx::tmem_ld_wait();
+#pragma unroll
+			for( int i = 0; i < HD; i++ ) o_acc[ i ] = __uint_as_float( rg[ i ] );
+		}
+		ptx::tc_fence_before();
 
 		// write O / l as f16, merged-heads layout [chunk][t][h*64 + e]
 		const int t = q0 + r;

@@ -588,7 +588,7 @@ wsp_status wsp_test_sample( int32_t device, int32_t rows, int32_t n_vocab, const
 	WSP_CHECK( requireSm100( device ) );
 	static_assert( sizeof( wsp_token_data ) == sizeof( kern::TokenData ), "token data layout" );
 	DevTmp<float> dl, dp;
-	DevTmp<int> dflags;
+	DevTmp<int> dflags, dscratch;
 	DevTmp<kern::TokenData> dout;
 	WSP_CUDA( dl.alloc( (size_t)rows * n_vocab ) ); WSP_CUDA( dp.alloc( (size_t)rows * n_vocab ) ); WSP_CUDA( dflags.alloc( 2 ) ); WSP_CUDA( dout.alloc( rows ) );
 	WSP_CUDA( cudaMemcpy( dl.p, logits, (size_t)rows * n_vocab * 4, cudaMemcpyHostToDevice ) );
@@ -598,6 +598,8 @@ wsp_status wsp_test_sample( int32_t device, int32_t rows, int32_t n_vocab, const
 	sa.logits = dl.p; sa.probs = dp.p; sa.B = rows; sa.nVocab = n_vocab;
 	sa.tokenBeg = special4[ 0 ]; sa.tokenSot = special4[ 1 ]; sa.tokenSolm = special4[ 2 ]; sa.tokenNot = special4[ 3 ];
 	sa.dForceTs = dflags.p; sa.out = dout.p; sa.N = 1;
+	WSP_CUDA( dscratch.alloc( (size_t)rows * ( (size_t)n_vocab + 1024 ) ) );
+	sa.tieScratch = dscratch.p;
 	WSP_CUDA( kern::sampleGreedy( sa, 0 ) );
 	WSP_CUDA( cudaDeviceSynchronize() );
 	g_launchCount.fetch_add( 2 );

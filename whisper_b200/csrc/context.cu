@@ -34,7 +34,7 @@ namespace wsp
 		for( auto& s : slots ) { if( s.mel ) cudaFree( s.mel ); if( s.pcm ) cudaFree( s.pcm ); }
 		for( auto& v : prof.pool ) cudaEventDestroy( v );
 		for( auto& v : timerEv ) if( v ) cudaEventDestroy( v );
-		void* bufs[] = { flowLayers, flowBias, flowExch, flowCtrl, megaLayers, megaBarrier, megaTiming, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs,
+		void* bufs[] = { flowLayers, flowBias, flowExch, flowCtrl, megaLayers, megaBarrier, megaTiming, melMax, pcmDev, melF16, conv1, x, xn, q, k, vt, attn, h, crossK, crossV, selfK, selfV, xd, qd, attnD, hD, logits, probs, tieScratch,
 			tokensDev, dNPast, sampled, history };
 		for( void* b : bufs ) if( b ) cudaFree( b );
 		for( auto& v : ev ) if( v ) cudaEventDestroy( v );
@@ -78,6 +78,7 @@ namespace wsp
 		WSP_CHECK( devAlloc( c.hD, B * kMaxDecodeTokens * 4 * d ) );
 		WSP_CHECK( devAlloc( c.logits, B * kAllLogitsTokens * hp.n_vocab ) );
 		WSP_CHECK( devAlloc( c.probs, B * kAllLogitsTokens * hp.n_vocab ) );
+		WSP_CHECK( devAlloc( c.tieScratch, B * ( (size_t)hp.n_vocab + 1024 ) ) );
 		WSP_CHECK( devAlloc( c.tokensDev, B * kMaxDecodeTokens, true ) );
 		WSP_CHECK( devAlloc( c.dNPast, 8, true ) );
 		c.dFlags = c.dNPast + 2;
@@ -395,7 +396,7 @@ namespace wsp
 			if( sample )
 			{
 				kern::SampleArgs sa;
-				sa.logits = c.logits; sa.probs = c.probs; sa.B = batch; sa.nVocab = hp.n_vocab;
+				sa.logits = c.logits; sa.probs = c.probs; sa.tieScratch = c.tieScratch; sa.B = batch; sa.nVocab = hp.n_vocab;
 				sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
 				sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
 				sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;
@@ -417,7 +418,7 @@ namespace wsp
 			if( sample )
 			{
 				kern::SampleArgs sa;
-				sa.logits = c.logits; sa.probs = c.probs; sa.B = batch; sa.nVocab = hp.n_vocab;
+				sa.logits = c.logits; sa.probs = c.probs; sa.tieScratch = c.tieScratch; sa.B = batch; sa.nVocab = hp.n_vocab;
 				sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
 				sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
 				sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;
@@ -478,7 +479,7 @@ namespace wsp
 		if( sample && !allLogits )
 		{
 			kern::SampleArgs sa;
-			sa.logits = c.logits; sa.probs = c.probs; sa.B = batch; sa.nVocab = hp.n_vocab;
+			sa.logits = c.logits; sa.probs = c.probs; sa.tieScratch = c.tieScratch; sa.B = batch; sa.nVocab = hp.n_vocab;
 			sa.tokenBeg = e.tokBeg; sa.tokenSot = e.tokSot; sa.tokenSolm = e.tokSolm; sa.tokenNot = e.tokNot;
 			sa.dForceTs = c.dFlags; sa.out = c.sampled; sa.nextTokens = c.tokensDev; sa.dNPast = c.dNPast; sa.N = N;
 			sa.history = c.history; sa.histCap = c.histCap; sa.dStep = c.dStep;

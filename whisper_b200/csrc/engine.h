@@ -137,6 +137,7 @@ namespace wsp
 		__half* hD = nullptr;           // [maxB*kMaxDecodeTokens][4d]
 		float* logits = nullptr;        // [maxB*kAllLogitsTokens][n_vocab]
 		float* probs = nullptr;
+		int* tieScratch = nullptr;      // [maxB][n_vocab + 1024]: survivor lists of the sampler's exact tie emulation
 		int* tokensDev = nullptr;       // [maxB*kMaxDecodeTokens]
 		int* dNPast = nullptr;          // device scalars: n_past | flags[2] | step
 		int* dFlags = nullptr;

@@ -108,6 +108,7 @@ namespace kern
 		int histCap = 0;
 		int* dStep = nullptr;
 		int rowInSmem = 0;              // set by sampleGreedy: the row fits the 227 KB shared memory
+		int* tieScratch = nullptr;      // [B][nVocab + 1024] ints: survivor lists of the exact tie emulation (null: one-thread emulation)
 	};
 	cudaError_t sampleGreedy( const SampleArgs& a, cudaStream_t s );
 

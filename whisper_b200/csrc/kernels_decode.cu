@@ -693,6 +693,96 @@ namespace kern
 		return Top1{ (float)f[ res ].v, f[ res ].i, 0 };
 	}
 
+	// The same result with the whole CTA at work.  std::__heap_select only ever moves an element into the heap that compares
+	// strictly above the heap's root, and the root — the 4th largest value of the prefix processed so far — never decreases.  So
+	// after thread 0 has run the exact algorithm over the first TIE_PRE elements, every later element that is not above the root
+	// reached there (T1) can be dropped without changing a single heap operation: all warps filter their contiguous region of the row
+	// against T1 (coalesced loads, ballot, survivors appended in index order to `scratch`), and thread 0 replays the exact algorithm
+	// over the survivors only.  A row whose top probability is shared costs ~10 us this way instead of ~110 us on one thread
+	// (degenerate rows tie at every step: that was 11 % of a decoder step).  Called by every thread of the CTA; the result is valid
+	// in thread 0.  scratch: nv + 32 * warps ints.
+	constexpr int TIE_PRE = 1024;
+	struct TieShared
+	{
+		float t1;
+		int tie, maskText;
+		int cnt[ 32 ];
+	};
+	__device__ Top1 emulatePartialSortCta( const float* probs, int nv, int beg, bool maskText, bool isInitial, int sot, int solm, int nott, int* scratch, TieShared& sh, int nThreads )
+	{
+		auto val = [ & ]( int i, float p ) -> double {
+			if( ( maskText && i < beg ) || ( isInitial && i >= beg + 101 ) ) return -(double)INFINITY;
+			return (double)p;
+		};
+		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nWarps = nThreads >> 5;
+		const int pre = nv < TIE_PRE ? nv : TIE_PRE;
+		ProbId f[ 4 ];
+		if( tid == 0 )
+		{
+			for( int k = 0; k < 4; k++ ) f[ k ] = ProbId{ val( k, __ldcg( probs + k ) ), k };
+			for( int parent = ( 4 - 2 ) / 2;; parent-- )
+			{
+				const ProbId v = f[ parent ];
+				heapAdjust( f, parent, 4, v );
+				if( parent == 0 ) break;
+			}
+			for( int i = 4; i < pre; i++ )
+			{
+				const double v = val( i, __ldcg( probs + i ) );
+				if( v > f[ 0 ].v ) heapAdjust( f, 0, 4, ProbId{ v, i } );
+			}
+			sh.t1 = (float)f[ 0 ].v;    // (the values are floats or -inf: exact)
+		}
+		__syncthreads();
+		const float t1 = sh.t1;
+		const int region = ( ( ( nv - pre + nWarps - 1 ) / nWarps + 31 ) / 32 ) * 32;
+		{
+			const int i0 = pre + warp * region, i1 = min( nv, i0 + region );
+			int cnt = 0;
+			for( int base = i0; base < i1; base += 512 )
+			{
+				float v[ 16 ];   // sixteen independent loads in flight per lane: the filter is bound by L2 latency, not by work
+#pragma unroll
+				for( int u = 0; u < 16; u++ )
+				{
+					const int i = base + u * 32 + lane;
+					v[ u ] = i < i1 ? (float)val( i, __ldcg( probs + i ) ) : -INFINITY;
+				}
+#pragma unroll
+				for( int u = 0; u < 16; u++ )
+				{
+					const bool keep = v[ u ] > t1;
+					const unsigned m = __ballot_sync( 0xffffffffu, keep );
+					if( keep ) scratch[ warp * region + cnt + __popc( m & ( ( 1u << lane ) - 1u ) ) ] = base + u * 32 + lane;
+					cnt += __popc( m );
+				}
+			}
+			if( lane == 0 ) sh.cnt[ warp ] = cnt;
+		}
+		__syncthreads();
+		if( tid != 0 ) return Top1{ 0.0f, 0, 0 };
+		for( int w = 0; w < nWarps; w++ )
+		{
+			const int* list = scratch + w * region;
+			const int n = sh.cnt[ w ];
+			for( int k = 0; k < n; k++ )
+			{
+				const int i = list[ k ];
+				const double v = val( i, __ldcg( probs + i ) );
+				if( v > f[ 0 ].v ) heapAdjust( f, 0, 4, ProbId{ v, i } );
+			}
+		}
+		for( int last = 3; last >= 1; last-- )
+		{
+			const ProbId v = f[ last ];
+			f[ last ] = f[ 0 ];
+			heapAdjust( f, 0, last, v );
+		}
+		int res = 0;
+		while( ( f[ res ].i == sot || f[ res ].i == solm || f[ res ].i == nott ) && res < 3 ) res++;
+		return Top1{ (float)f[ res ].v, f[ res ].i, 0 };
+	}
+
 	__device__ Top1 blockArgmax( Top1 x, Top1* sbuf )
 	{
 		for( int o = 16; o > 0; o >>= 1 )
@@ -744,7 +834,7 @@ namespace kern
 	// `pick` is the arg-max over the eligible, non-banned tokens (lowest id among equals).  If its probability is shared — by another
 	// eligible token or by one of the banned ones — the reference's choice depends on std::partial_sort's handling of equal keys:
 	// reproduce it exactly.  The whole probability row must be visible in global memory (it is: written before the last barrier).
-	__device__ __forceinline__ Top1 resolveTies( Top1 pick, const SampleArgs& a, const float* probsRow, bool maskText, bool isInitial )
+	__device__ __forceinline__ bool needsTieEmulation( Top1 pick, const SampleArgs& a, const float* probsRow, bool maskText )
 	{
 		bool tie = pick.tie != 0;
 		if( !tie && !maskText )
@@ -753,8 +843,23 @@ namespace kern
 			for( int k = 0; k < 3; k++ )
 				if( banned[ k ] >= 0 && banned[ k ] < a.tokenBeg && __ldcg( probsRow + banned[ k ] ) == pick.v ) tie = true;
 		}
-		if( !tie ) return pick;
-		return emulatePartialSort( probsRow, a.nVocab, a.tokenBeg, maskText, isInitial, a.tokenSot, a.tokenSolm, a.tokenNot );
+		return tie;
+	}
+	// called by every thread of the CTA that finishes a row; `pick` and the result are thread 0's
+	__device__ __forceinline__ Top1 resolveTies( Top1 pick, const SampleArgs& a, int b, bool maskText, bool isInitial, TieShared& sh )
+	{
+		const float* probsRow = a.probs + (size_t)b * a.nVocab;
+		if( threadIdx.x == 0 ) sh.tie = needsTieEmulation( pick, a, probsRow, maskText ) ? 1 : 0;
+		__syncthreads();
+		if( !sh.tie ) return pick;
+		if( !a.tieScratch )
+		{
+			if( threadIdx.x == 0 ) pick = emulatePartialSort( probsRow, a.nVocab, a.tokenBeg, maskText, isInitial, a.tokenSot, a.tokenSolm, a.tokenNot );
+			return pick;
+		}
+		const Top1 r = emulatePartialSortCta( probsRow, a.nVocab, a.tokenBeg, maskText, isInitial, a.tokenSot, a.tokenSolm, a.tokenNot,
+			a.tieScratch + (size_t)b * ( a.nVocab + 32 * ( SM_THREADS / 32 ) ), sh, SM_THREADS );
+		return threadIdx.x == 0 ? r : pick;
 	}
 
 	__global__ void __launch_bounds__( SM_THREADS )
@@ -823,12 +928,14 @@ namespace kern
 		bestTs = blockArgmax( bestTs, st );
 		bestTx = blockArgmax( bestTx, st );
 		const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
+		__shared__ TieShared tieSh;
+		Top1 pick = bestTs;
+		if( !maskText ) pick = better( bestTx, bestTs );
+		if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
+		__syncthreads();     // the whole probability row is in global memory
+		pick = resolveTies( pick, a, b, maskText, isInitial, tieSh );
 		if( tid == 0 )
 		{
-			Top1 pick = bestTs;
-			if( !maskText ) pick = better( bestTx, bestTs );
-			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
-			pick = resolveTies( pick, a, a.probs + (size_t)b * nv, maskText, isInitial );
 			TokenData td;
 			td.id = pick.i;
 			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
@@ -931,21 +1038,33 @@ namespace kern
 			part.maxTx = maxTx; part.sumTs = sumTs; part.bestTs = bestTs; part.bestTx = bestTx;
 		}
 		cluster.sync();
-		if( rank == 0 && tid == 0 )
+		__shared__ TieShared tieSh;
+		if( rank == 0 )
 		{
-			for( unsigned r = 1; r < SC_CL; r++ )
-			{
-				const ClusterPart* q = cluster.map_shared_rank( &part, r );
-				maxTx = fmaxf( maxTx, q->maxTx );
-				sumTs += q->sumTs;
-				bestTs = better( bestTs, q->bestTs );
-				bestTx = better( bestTx, q->bestTx );
-			}
-			const bool maskText = ( sumTs > (double)maxTx ) || forceTs;
+			// the row is finished by the first CTA of its cluster: thread 0 combines the partials, all threads help if the top
+			// probability is shared (resolveTies)
 			Top1 pick = bestTs;
-			if( !maskText ) pick = better( bestTx, bestTs );
-			if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
-			pick = resolveTies( pick, a, a.probs + (size_t)b * nv, maskText, isInitial );
+			if( tid == 0 )
+			{
+				for( unsigned r = 1; r < SC_CL; r++ )
+				{
+					const ClusterPart* q = cluster.map_shared_rank( &part, r );
+					maxTx = fmaxf( maxTx, q->maxTx );
+					sumTs += q->sumTs;
+					bestTs = better( bestTs, q->bestTs );
+					bestTx = better( bestTx, q->bestTx );
+				}
+				const bool mt = ( sumTs > (double)maxTx ) || forceTs;
+				pick = bestTs;
+				if( !mt ) pick = better( bestTx, bestTs );
+				if( pick.i == 0x7fffffff ) pick = Top1{ 0.0f, 0, 1 };
+				tieSh.maskText = mt ? 1 : 0;
+			}
+			__syncthreads();
+			const bool maskText = tieSh.maskText != 0;
+			pick = resolveTies( pick, a, b, maskText, isInitial, tieSh );
+		if( tid == 0 )
+		{
 			TokenData td;
 			td.id = pick.i;
 			td.tid = bestTs.i == 0x7fffffff ? 0 : bestTs.i;
@@ -955,6 +1074,7 @@ namespace kern
 			a.out[ b ] = td;
 			if( a.nextTokens ) a.nextTokens[ b ] = td.id;
 			if( a.history && a.dStep && *a.dStep < a.histCap ) a.history[ (size_t)b * a.histCap + *a.dStep ] = td.id;
+		}
 		}
 		cluster.sync();   // nobody leaves while a peer may still read its partials
 	}
