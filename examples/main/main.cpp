@@ -21,7 +21,7 @@ namespace
 	{
 		int nThreads = 4, offsetMs = 0, durationMs = 0, maxContext = -1, maxLen = 0, device = 0;
 		float wordThold = 0.01f;
-		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false;
+		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false, stream = false, verifyStream = false;
 		std::string language = "en", model = "models/ggml-base.en.bin", prompt;
 		std::vector<std::string> inputs;
 	};
@@ -47,6 +47,7 @@ namespace
 		fprintf( stderr, "  -l LANG,  --language LANG [%-7s] spoken language (\"auto\" = detect)\n", p.language.c_str() );
 		fprintf( stderr, "  -m FNAME, --model FNAME   [%-7s] model path\n", p.model.c_str() );
 		fprintf( stderr, "  -f FNAME, --file FNAME    path of the input audio file (16-bit or float WAV)\n" );
+		fprintf( stderr, "  -st,      --stream        read the file while transcribing it (iContext::runStreamed; 16 kHz files, no -ml)\n" );
 		fprintf( stderr, "  --prompt TEXT             initial prompt for the model\n\n" );
 	}
 
@@ -79,6 +80,8 @@ namespace
 			else if( a == "-f" || a == "--file" ) p.inputs.push_back( next() );
 			else if( a == "-gpu" || a == "--use-gpu" ) p.device = atoi( next() );
 			else if( a == "--prompt" ) p.prompt = next();
+			else if( a == "-st" || a == "--stream" ) p.stream = true;
+			else if( a == "--verify-stream" ) p.verifyStream = true;
 			else if( a == "-p" || a == "--processors" || a == "-on" || a == "--offset-n" ) next();
 			else { fprintf( stderr, "error: unknown or unsupported argument: %s\n", a.c_str() ); usage( argv[ 0 ], p ); return false; }
 		}
@@ -141,6 +144,86 @@ namespace
 		}
 		return true;
 	}
+
+	// ---- the same file as a pull source for iContext::runStreamed: the header is parsed up front, the samples are read and converted
+	// block by block when the library asks for them (the counterpart of iMediaFoundation::openAudioFile, Examples/main/main.cpp:306-310)
+	class WavStream
+	{
+		FILE* f = nullptr;
+		uint32_t channels = 0, bits = 0;
+		uint64_t framesLeft = 0;
+		std::vector<uint8_t> raw;
+
+	public:
+		uint32_t rate = 0;
+		uint64_t frames = 0;
+		~WavStream() { if( f ) fclose( f ); }
+		bool open( const std::string& path )
+		{
+			f = fopen( path.c_str(), "rb" );
+			if( !f ) { fprintf( stderr, "error: cannot open %s\n", path.c_str() ); return false; }
+			uint8_t h[ 12 ];
+			if( fread( h, 1, 12, f ) != 12 || memcmp( h, "RIFF", 4 ) != 0 || memcmp( h + 8, "WAVE", 4 ) != 0 ) { fprintf( stderr, "error: %s is not a RIFF/WAVE file\n", path.c_str() ); return false; }
+			uint32_t format = 0;
+			while( true )
+			{
+				uint8_t ch[ 8 ];
+				if( fread( ch, 1, 8, f ) != 8 ) break;
+				const uint32_t len = (uint32_t)ch[ 4 ] | ( (uint32_t)ch[ 5 ] << 8 ) | ( (uint32_t)ch[ 6 ] << 16 ) | ( (uint32_t)ch[ 7 ] << 24 );
+				if( memcmp( ch, "fmt ", 4 ) == 0 && len >= 16 && len <= 256 )
+				{
+					uint8_t fm[ 256 ];
+					if( fread( fm, 1, len, f ) != len ) break;
+					auto u16 = [ & ]( size_t o ) { return (uint32_t)fm[ o ] | ( (uint32_t)fm[ o + 1 ] << 8 ); };
+					format = u16( 0 ); channels = u16( 2 ); rate = u16( 4 ) | ( u16( 6 ) << 16 ); bits = u16( 14 );
+					if( format == 0xFFFE && len >= 26 ) format = u16( 24 );
+					if( len & 1 ) fseek( f, 1, SEEK_CUR );
+				}
+				else if( memcmp( ch, "data", 4 ) == 0 )
+				{
+					if( !channels || !rate || !( ( format == 1 && bits == 16 ) || ( format == 3 && bits == 32 ) ) )
+					{
+						fprintf( stderr, "error: %s: only 16-bit PCM and 32-bit float WAV files are supported\n", path.c_str() );
+						return false;
+					}
+					const long pos = ftell( f );
+					fseek( f, 0, SEEK_END );
+					const long end = ftell( f );
+					fseek( f, pos, SEEK_SET );
+					const uint64_t avail = end > pos ? (uint64_t)( end - pos ) : 0;
+					frames = framesLeft = std::min<uint64_t>( len, avail ) / ( (uint64_t)channels * bits / 8 );
+					return true;
+				}
+				else if( fseek( f, (long)len + ( len & 1 ), SEEK_CUR ) != 0 ) break;
+			}
+			fprintf( stderr, "error: %s: no audio data found\n", path.c_str() );
+			return false;
+		}
+		static HRESULT WSPCALL read( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept
+		{
+			WavStream& w = *static_cast<WavStream*>( pv );
+			const size_t frame = (size_t)w.channels * w.bits / 8;
+			const uint32_t n = (uint32_t)std::min<uint64_t>( capacity, w.framesLeft );
+			*written = 0;
+			if( n == 0 ) return S_OK;
+			try { w.raw.resize( (size_t)n * frame ); } catch( ... ) { return E_OUTOFMEMORY; }
+			const size_t got = fread( w.raw.data(), frame, n, w.f );
+			for( size_t i = 0; i < got; i++ )
+			{
+				float acc = 0;
+				for( uint32_t c = 0; c < w.channels; c++ )
+				{
+					const uint8_t* p = w.raw.data() + i * frame + (size_t)c * w.bits / 8;
+					if( w.bits == 16 ) acc += (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
+					else { float v; memcpy( &v, p, 4 ); acc += v; }
+				}
+				mono[ i ] = acc / (float)w.channels;
+			}
+			w.framesLeft = got < n ? 0 : w.framesLeft - got;
+			*written = (uint32_t)got;
+			return S_OK;
+		}
+	};
 
 	// ---- writers: txt / srt / vtt as Examples/main/textWriter.cpp produces them (UTF-8 BOM, CRLF, leading blanks of a segment dropped)
 	std::string fmtTime( uint64_t ticks, bool comma )
@@ -220,6 +303,32 @@ int main( int argc, char** argv )
 	if( params.inputs.empty() ) { fprintf( stderr, "error: no input files specified\n" ); usage( argv[ 0 ], params ); return 2; }
 	if( params.language != "auto" && findLanguageKeyA( params.language.c_str() ) == UINT32_MAX ) { fprintf( stderr, "error: unknown language '%s'\n", params.language.c_str() ); return 3; }
 
+	if( params.verifyStream )
+	{
+		// self-check of the streaming WAV reader against the buffered one (no model, no GPU): same samples whatever the block sizes asked for
+		for( const std::string& fname : params.inputs )
+		{
+			std::vector<float> whole, pulled;
+			WavStream ws;
+			if( !readWav( fname, whole ) || !ws.open( fname ) ) return 8;
+			if( ws.rate != 16000 ) { fprintf( stderr, "%s: not a 16 kHz file\n", fname.c_str() ); return 8; }
+			uint32_t lcg = 7;
+			while( true )
+			{
+				lcg = lcg * 1664525u + 1013904223u;
+				std::vector<float> blk( 1 + ( lcg >> 8 ) % 40000 );
+				uint32_t got = 0;
+				if( FAILED( WavStream::read( blk.data(), (uint32_t)blk.size(), &got, &ws ) ) ) return 9;
+				if( got == 0 ) break;
+				pulled.insert( pulled.end(), blk.begin(), blk.begin() + got );
+			}
+			const bool same = pulled.size() == whole.size() && ws.frames == whole.size() && 0 == memcmp( pulled.data(), whole.data(), whole.size() * 4 );
+			printf( "%s: %zu samples, streamed reader %s\n", fname.c_str(), whole.size(), same ? "identical" : "DIFFERS" );
+			if( !same ) return 10;
+		}
+		return 0;
+	}
+
 	std::wstring wmodel( params.model.begin(), params.model.end() );
 	const std::wstring adapter = std::to_wstring( params.device );
 	sModelSetup setup;
@@ -242,10 +351,32 @@ int main( int argc, char** argv )
 			params.translate = false;
 			fprintf( stderr, "main: WARNING: model is not multilingual, ignoring language and translation options\n" );
 		}
+		// like the reference's CLI (STREAM_AUDIO, main.cpp:304-319): stream unless token-level timestamps are wanted; here streaming
+		// is opt-in (-st) and limited to files that need no resampling
+		WavStream wavStream;
+		bool streamed = params.stream && params.maxLen <= 0;
+		if( params.stream && !streamed ) fprintf( stderr, "main: WARNING: --max-len needs the whole clip, falling back to buffered mode\n" );
+		if( streamed )
+		{
+			if( !wavStream.open( fname ) ) return 8;
+			if( wavStream.rate != 16000 )
+			{
+				fprintf( stderr, "main: WARNING: %s is not a 16 kHz file, falling back to buffered mode\n", fname.c_str() );
+				streamed = false;
+			}
+		}
 		std::vector<float> pcm;
-		if( !readWav( fname, pcm ) ) return 8;
 		iAudioBuffer* buffer = nullptr;
-		if( FAILED( createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer ) ) ) return 9;
+		iAudioReader* reader = nullptr;
+		if( streamed )
+		{
+			if( FAILED( createAudioReader( &WavStream::read, &wavStream, (int64_t)( wavStream.frames / 160 ) * 100000, &reader ) ) ) return 9;
+		}
+		else
+		{
+			if( !readWav( fname, pcm ) ) return 8;
+			if( FAILED( createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer ) ) ) return 9;
+		}
 
 		sFullParams wp;
 		context->fullDefaultParams( eSamplingStrategy::Greedy, &wp );
@@ -266,8 +397,16 @@ int main( int argc, char** argv )
 		SegmentPrinter printer{ params.noTimestamps };
 		wp.new_segment_callback = &onNewSegment;
 		wp.new_segment_callback_user_data = &printer;
-		hr = context->runFull( wp, buffer );
-		buffer->Release();
+		if( streamed )
+		{
+			hr = context->runStreamed( wp, sProgressSink{ nullptr, nullptr }, reader );
+			reader->Release();
+		}
+		else
+		{
+			hr = context->runFull( wp, buffer );
+			buffer->Release();
+		}
 		if( FAILED( hr ) ) { fprintf( stderr, "Unable to process audio: 0x%08x\n", (unsigned)hr ); return 10; }
 		if( params.noTimestamps ) printf( "\n" );
 		if( params.outTxt && !writeResult( context, fname, Fmt::Txt, !params.noTimestamps ) ) fprintf( stderr, "Unable to produce the text file\n" );

@@ -9,6 +9,7 @@
  *   wsp_engine_create         Whisper/Whisper/WhisperModel.cpp:257-340 (loadGpu: tensors -> VRAM)
  *   wsp_context_create        Whisper/Whisper/ModelImpl.cpp:14 (createContext), KV sizing Whisper/Whisper/WhisperContext.cpp:291-308
  *   wsp_pcm_to_mel            Whisper/source/whisper.h:97 whisper_pcm_to_mel      (Whisper/Whisper/Spectrogram.cpp:64-121)
+ *   wsp_pcm_to_mel_window     Whisper/Whisper/MelStreamer.cpp:128-236 (MelStreamer::makeTransposedBuffer / makeBuffer: one window of a streamed clip)
  *   wsp_set_mel               Whisper/source/whisper.h:107 whisper_set_mel
  *   wsp_encode                Whisper/source/whisper.h:117 whisper_encode          (Whisper/Whisper/WhisperContext.cpp:310 encode)
  *   wsp_decode                Whisper/source/whisper.h:128 whisper_decode + :140-150 whisper_sample_best/timestamp
@@ -106,9 +107,15 @@ uint64_t wsp_engine_weight_bytes( const wsp_engine* e );
 wsp_status wsp_context_create( wsp_engine* e, int32_t max_batch, wsp_context** out );
 void wsp_context_destroy( wsp_context* c );
 wsp_status wsp_synchronize( wsp_context* c );
+/* device memory held by the context: workspaces, KV caches, mel slots (ContextImpl::getMemoryUse, Whisper/Whisper/ContextImpl.misc.cpp:170-182) */
+uint64_t wsp_context_device_bytes( const wsp_context* c );
 
 /* a1: 16 kHz mono f32 PCM (host) -> log-mel of chunk slot `slot`, kept on the device.  n_len = n_samples / 160 frames. */
 wsp_status wsp_pcm_to_mel( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples );
+/* a1, streamed flavour (iContext::runStreamed): log-mel of frames [0, n_frames) of `pcm` — which should extend 240 samples past the
+ * last frame unless the stream ends there — normalised by the maximum over these frames only, floored at 1e-20; `forced_max` (may be
+ * NULL) replaces that maximum, `max_out` (may be NULL) receives the maximum found.  The slot then holds n_frames frames. */
+wsp_status wsp_pcm_to_mel_window( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples, int32_t n_frames, const float* forced_max, float* max_out );
 wsp_status wsp_set_mel( wsp_context* c, int32_t slot, const float* mel, int32_t n_len );     /* [80][n_len] */
 int32_t wsp_mel_len( wsp_context* c, int32_t slot );
 wsp_status wsp_get_mel( wsp_context* c, int32_t slot, float* dst, size_t cap_floats );

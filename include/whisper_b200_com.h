@@ -9,6 +9,7 @@
 //   iModel                   Whisper/API/iContext.cl.h:46-60       {abefb4c9-e8d8-46a3-8747-5afbadef1adb}
 //   iTranscribeResult        Whisper/API/iTranscribeResult.cl.h:7-14  {2871a73f-5ce3-48f8-8779-6582ee11935e}
 //   iAudioBuffer             Whisper/API/iMediaFoundation.cl.h:9-17   {013583aa-c9eb-42bc-83db-633c2c317051}
+//   iAudioReader             Whisper/API/iMediaFoundation.cl.h:19-26  {35b988da-04a6-476a-a193-d8891d5dc390}  (input of iContext::runStreamed)
 //   sFullParams, flags       Whisper/API/sFullParams.h:5-130
 //   sSegment, sToken, ...    Whisper/API/TranscribeStructs.h:8-137
 //   sModelSetup, callbacks   Whisper/API/sModelSetup.h:6-41, sLoadModelCallbacks.h:5-14, loggerApi.h:7-34, SpecialTokens.h, sLanguageList.h
@@ -58,6 +59,18 @@ namespace ComLight
 		virtual uint32_t WSPCALL Release() = 0;
 	};
 }
+
+// The reference's iAudioReader hands out the Media Foundation source reader it wraps; its header only forward-declares the type
+// (`struct IMFSourceReader;`, Whisper/API/iMediaFoundation.cl.h:5).  There is no Media Foundation here, so this library DEFINES that
+// type for Linux clients: a pull source of 16 kHz mono f32 PCM in stream order (what Whisper/MF/PcmReader.cpp turns the MF samples
+// into before anything else looks at them).
+struct IMFSourceReader : public ComLight::IUnknown
+{
+	static constexpr GUID iid() { return GUID{ 0x6f1d2c3a, 0x52b7, 0x4e0c, { 0x9a, 0x41, 0x7b, 0x20, 0x0b, 0x2b, 0x20, 0x01 } }; }   // this library's own
+	// Up to `capacity` samples into `mono`; *written == 0 with S_OK means the stream has ended.  Called from one thread at a time,
+	// possibly not the thread that called runStreamed (MelStreamerThread reads ahead on a background thread).
+	virtual HRESULT WSPCALL readPcm( float* mono, uint32_t capacity, uint32_t* written ) = 0;
+};
 
 namespace Whisper
 {
@@ -163,7 +176,13 @@ namespace Whisper
 		virtual const float* WSPCALL getPcmStereo() const = 0;
 		virtual HRESULT WSPCALL getTime( int64_t& rdi ) const = 0;
 	};
-	struct iAudioReader;
+	struct iAudioReader : public ComLight::IUnknown
+	{
+		static constexpr GUID iid() { return GUID{ 0x35b988da, 0x04a6, 0x476a, { 0xa1, 0x93, 0xd8, 0x89, 0x1d, 0x5d, 0xc3, 0x90 } }; }
+		virtual HRESULT WSPCALL getDuration( int64_t& rdi ) const = 0;          // 100 ns ticks; the stream is floor( ticks / 100000 ) mel frames long (PcmReader.cpp:247-272)
+		virtual HRESULT WSPCALL getReader( IMFSourceReader** pp ) const = 0;    // AddRef'ed
+		virtual HRESULT WSPCALL requestedStereo() const = 0;                    // S_OK / S_FALSE; stereo (diarisation) is not delivered here
+	};
 	struct iAudioCapture;
 	struct sCaptureCallbacks;
 	struct iMediaFoundation;
@@ -212,5 +231,9 @@ namespace Whisper
 	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp );   // E_NOTIMPL: audio decoding is the host application's business here
 	// not in the reference: an iAudioBuffer over caller-owned 16 kHz mono f32 PCM (replaces the Media Foundation loader, Whisper/MF/)
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp );
+	// not in the reference either: an iAudioReader over a caller-supplied pull callback (replaces iMediaFoundation::openAudioFile /
+	// loadAudioFileData, Whisper/API/iMediaFoundation.cl.h:38-39).  `durationTicks` announces the stream length (100 ns units).
+	using pfnReadPcm = HRESULT( WSPCALL* )( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept;
+	HRESULT WSPCALL createAudioReader( pfnReadPcm pfn, void* pv, int64_t durationTicks, iAudioReader** pp );
 	}
 }

@@ -87,6 +87,65 @@ int32_t wspc_run_full( void* h, const float* pcm, int32_t nSamples, uint32_t fla
 	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
 	return FAILED( hr2 ) ? hr2 : hr;
 }
+// iContext::runStreamed over an iAudioReader made with createAudioReader: the PCM is handed out in ragged blocks (1..maxBlock samples,
+// never more than asked for), the way a decoder delivers it.  progressOut[0] = number of progress calls, [1] = 1 if they never
+// decreased and ended at exactly 1.0, [2] = number of read calls.
+int32_t wspc_run_streamed( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t maxTokens, int32_t cpuThreads,
+	int32_t offsetMs, int32_t durationMs, int32_t maxBlock, int32_t* progressOut )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return E_POINTER;
+	sFullParams p;
+	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
+	if( FAILED( hr ) ) return hr;
+	p.flags = (eFullParamsFlags)flags;
+	p.language = ( language && strcmp( language, "auto" ) != 0 ) ? findLanguageKeyA( language ) : makeLanguageKey( "auto" );
+	p.max_tokens = maxTokens;
+	p.cpuThreads = cpuThreads;
+	p.offset_ms = offsetMs;
+	p.duration_ms = durationMs;
+	p.new_segment_callback = &segCallback;
+	p.new_segment_callback_user_data = s;
+	s->segCallbackCounts.clear();
+	struct Source { const float* pcm; uint32_t n, pos, maxBlock, calls, lcg; } src{ pcm, (uint32_t)nSamples, 0, (uint32_t)( maxBlock > 0 ? maxBlock : 1 ), 0, 12345u };
+	auto readFn = []( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept -> HRESULT {
+		Source* k = static_cast<Source*>( pv );
+		k->calls++;
+		k->lcg = k->lcg * 1664525u + 1013904223u;
+		uint32_t want = 1 + ( k->lcg >> 8 ) % k->maxBlock;
+		if( want > capacity ) want = capacity;
+		if( want > k->n - k->pos ) want = k->n - k->pos;
+		if( want ) memcpy( mono, k->pcm + k->pos, (size_t)want * 4 );
+		k->pos += want;
+		*written = want;
+		return S_OK;
+	};
+	struct Progress { int calls = 0; double last = -1.0; bool monotonic = true; } prog;
+	sProgressSink sink;
+	sink.pfn = []( double val, iContext*, void* pv ) noexcept -> HRESULT {
+		Progress* g = static_cast<Progress*>( pv );
+		if( val < g->last ) g->monotonic = false;
+		g->last = val;
+		g->calls++;
+		return S_OK;
+	};
+	sink.pv = &prog;
+	iAudioReader* reader = nullptr;
+	hr = createAudioReader( readFn, &src, (int64_t)( (uint32_t)nSamples / 160 ) * 100000, &reader );
+	if( FAILED( hr ) ) return hr;
+	hr = s->context->runStreamed( p, sink, reader );
+	reader->Release();
+	if( progressOut )
+	{
+		progressOut[ 0 ] = prog.calls;
+		progressOut[ 1 ] = ( prog.monotonic && prog.last == 1.0 ) ? 1 : 0;
+		progressOut[ 2 ] = (int32_t)src.calls;
+	}
+	if( FAILED( hr ) ) return hr;
+	if( s->result ) { s->result->Release(); s->result = nullptr; }
+	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
+	return FAILED( hr2 ) ? hr2 : hr;
+}
 void wspc_set_max_len( void* h, int32_t maxLen ) { static_cast<Session*>( h )->maxLen = maxLen; }
 int64_t wspc_token_t0( void* h, int32_t i, int32_t j )
 {
@@ -176,7 +235,7 @@ int32_t wspc_query_interfaces( void* h )
 	sProgressSink sink{ nullptr, nullptr };
 	sFullParams fp;
 	s->context->fullDefaultParams( eSamplingStrategy::Greedy, &fp );
-	if( s->context->runStreamed( fp, sink, nullptr ) != E_NOTIMPL ) return 6;
+	if( s->context->runStreamed( fp, sink, nullptr ) != E_POINTER ) return 6;
 	return 0;
 }
 uint32_t wspc_find_language_key( const char* lang ) { return findLanguageKeyA( lang ); }

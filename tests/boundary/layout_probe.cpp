@@ -64,12 +64,13 @@ int main()
 	ENUMV( eModelImplementation::GPU ); ENUMV( eModelImplementation::Hybrid ); ENUMV( eModelImplementation::Reference );
 	ENUMV( eTokenFlags::Special ); ENUMV( eLogLevel::Error ); ENUMV( eLogLevel::Debug ); ENUMV( eSpeakerChannel::NoStereoData );
 	guid( "IUnknown", ComLight::IUnknown::iid() ); guid( "iContext", iContext::iid() ); guid( "iModel", iModel::iid() );
-	guid( "iTranscribeResult", iTranscribeResult::iid() ); guid( "iAudioBuffer", iAudioBuffer::iid() );
+	guid( "iTranscribeResult", iTranscribeResult::iid() ); guid( "iAudioBuffer", iAudioBuffer::iid() ); guid( "iAudioReader", iAudioReader::iid() );
 	SLOT( iContext, QueryInterface ); SLOT( iContext, AddRef ); SLOT( iContext, Release );
 	SLOT( iContext, runFull ); SLOT( iContext, runStreamed ); SLOT( iContext, runCapture ); SLOT( iContext, getResults ); SLOT( iContext, detectSpeaker );
 	SLOT( iContext, getModel ); SLOT( iContext, fullDefaultParams ); SLOT( iContext, timingsPrint ); SLOT( iContext, timingsReset );
 	SLOT( iModel, createContext ); SLOT( iModel, tokenize ); SLOT( iModel, isMultilingual ); SLOT( iModel, getSpecialTokens ); SLOT( iModel, stringFromToken ); SLOT( iModel, clone );
 	SLOT( iTranscribeResult, getSize ); SLOT( iTranscribeResult, getSegments ); SLOT( iTranscribeResult, getTokens );
 	SLOT( iAudioBuffer, countSamples ); SLOT( iAudioBuffer, getPcmMono ); SLOT( iAudioBuffer, getPcmStereo ); SLOT( iAudioBuffer, getTime );
+	SLOT( iAudioReader, getDuration ); SLOT( iAudioReader, getReader ); SLOT( iAudioReader, requestedStereo );
 	return 0;
 }

@@ -38,6 +38,52 @@ def test_layout_matches_reference_headers():
         assert _run(ref) == want, "layout_reference.txt is stale: regenerate it with tests/boundary/_build/probe_ref"
 
 
+def test_pcm_streamer_unit():
+    """The PCM queue behind iContext::runStreamed (whisper_b200/csrc/pcm_streamer.h, host-only): windows at increasing offsets are the
+    source's samples for any block sizes, with and without the background reader; backward seeks and source failures are reported."""
+    exe = os.path.join(BUILD, "streamer_test")
+    if not os.path.exists(exe):
+        pytest.fail("tests/boundary/_build/streamer_test is missing: run __graft_entry__.build()")
+    assert "streamer_test: ok" in _run(exe)
+
+
+def test_cli_streaming_wav_reader(tmp_path):
+    """The CLI's block-wise WAV reader (the pull source it hands to iContext::runStreamed) delivers exactly the samples of its buffered
+    reader: 16-bit mono, 16-bit stereo (down-mixed), 32-bit float with a foreign chunk of odd length in front of the data.  No GPU: the
+    CLI's --verify-stream self-check loads no model."""
+    import struct
+    import wave
+    exe = os.path.join(os.path.dirname(HERE), "examples", "main", "whisper_b200_main")
+    if not os.path.exists(exe):
+        pytest.fail("examples/main/whisper_b200_main is missing: run __graft_entry__.build()")
+    rng = np.random.default_rng(5)
+    paths = []
+    for name, ch, n in (("mono.wav", 1, 16000 * 7 + 13), ("stereo.wav", 2, 16000 * 3 + 1)):
+        p = str(tmp_path / name)
+        with wave.open(p, "wb") as w:
+            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(rng.integers(-30000, 30000, size=n * ch).astype("<i2").tobytes())
+        paths.append(p)
+    data = rng.standard_normal(50001).astype("<f4").tobytes()
+    body = (b"WAVE" + b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 3, 1, 16000, 64000, 4, 32)
+            + b"LIST" + struct.pack("<I", 5) + b"abcde\0" + b"data" + struct.pack("<I", len(data)) + data)
+    p = str(tmp_path / "float.wav")
+    open(p, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    paths.append(p)
+    out = _run(exe, "--verify-stream", *sum((["-f", q] for q in paths), []))
+    assert out.count("streamed reader identical") == 3
+
+
+def test_com_exports_include_the_streaming_factory():
+    """whisper.def's exports plus the two Linux factories (createAudioBuffer, createAudioReader) are in the product library."""
+    from whisper_b200 import capi
+    so = capi.lib()._name
+    syms = subprocess.run(["nm", "-DC", so], stdout=subprocess.PIPE, text=True, check=True).stdout
+    for f in ("setupLogger", "loadModel", "findLanguageKeyW", "findLanguageKeyA", "getSupportedLanguages", "listGPUs", "initMediaFoundation",
+              "createAudioBuffer", "createAudioReader"):
+        assert "Whisper::%s(" % f in syms, f
+
+
 def _client_segments(out):
     segs = []
     for line in out.splitlines():

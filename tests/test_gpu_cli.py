@@ -47,6 +47,22 @@ def test_cli_writes_the_library_transcript(tmp_path):
     assert vtt == "WEBVTT\r\n\r\n" + "".join("%s --> %s\r\n%s\r\n\r\n" % (fmt(s["t0"]), fmt(s["t1"]), s["text"].lstrip(" \t")) for s in segs)
 
 
+def test_cli_streamed_equals_buffered(tmp_path):
+    """-st: the file is read while it is transcribed (iContext::runStreamed over the CLI's block-wise WAV reader) — same console transcript
+    as the buffered run of the same file (per-window mel normalisation cannot flip a decision on this clip, see test_gpu_com.py)."""
+    pcm16 = np.clip(np.round(full_pcm(10)[:16000 * 50] * 32768.0), -32768, 32767).astype("<i2")
+    wav = str(tmp_path / "clip.wav")
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm16.tobytes())
+    outs = []
+    for extra in ([], ["-st"]):
+        r = subprocess.run([EXE, "-m", synth.model_path(FULL_MODEL), "-f", wav, "-d", "40000"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([ln for ln in r.stdout.splitlines() if ln.startswith("[")])
+        assert "Memory Usage" in r.stderr and "Encode" in r.stderr          # timingsPrint's table (ContextImpl.misc.cpp:170-182)
+    assert len(outs[0]) >= 8 and outs[0] == outs[1]
+
+
 def test_cli_rejects_bad_input(tmp_path):
     if not os.path.exists(EXE):
         pytest.skip("CLI not built")

@@ -39,6 +39,8 @@ def _lib():
     L.wspc_tokenize.restype = i32; L.wspc_tokenize.argtypes = [vp, C.c_char_p, C.POINTER(i32), i32]
     L.wspc_string_from_token.restype = C.c_char_p; L.wspc_string_from_token.argtypes = [vp, i32]
     L.wspc_special_tokens.restype = i32; L.wspc_special_tokens.argtypes = [vp, C.POINTER(i32)]
+    L.wspc_run_streamed.restype = i32
+    L.wspc_run_streamed.argtypes = [vp, C.POINTER(C.c_float), i32, C.c_uint32, C.c_char_p, i32, i32, i32, i32, i32, C.POINTER(i32)]
     L.wspc_set_max_len.argtypes = [vp, i32]
     for f in ("wspc_token_t0", "wspc_token_t1"):
         getattr(L, f).restype = C.c_int64; getattr(L, f).argtypes = [vp, i32, i32]
@@ -83,6 +85,63 @@ def run_full(L, h, pcm, flags=0, language=b"en", max_tokens=0, threads=4, off=0,
                          tokens=[L.wspc_token_id(h, i, j) for j in range(n)], flags=[L.wspc_token_flags(h, i, j) for j in range(n)],
                          token_t=[[L.wspc_token_t0(h, i, j), L.wspc_token_t1(h, i, j)] for j in range(n)]))
     return hr, segs
+
+
+def _segments(L, h):
+    segs = []
+    for i in range(L.wspc_n_segments(h)):
+        n = L.wspc_segment_n_tokens(h, i)
+        segs.append(dict(t0=L.wspc_segment_t0(h, i), t1=L.wspc_segment_t1(h, i), text=L.wspc_segment_text(h, i).decode(errors="replace"),
+                         tokens=[L.wspc_token_id(h, i, j) for j in range(n)]))
+    return segs
+
+
+def run_streamed(L, h, pcm, flags=0, language=b"en", max_tokens=0, threads=4, off=0, dur=0, max_block=4096):
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    info = (C.c_int32 * 3)()
+    hr = L.wspc_run_streamed(h, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size, flags, language, max_tokens, threads, off, dur, max_block, info)
+    return hr, (_segments(L, h) if hr >= 0 else []), list(info)
+
+
+# iContext::runStreamed (ContextImpl.misc.cpp:391-419) runs the loop of runFull over a spectrogram that is produced window by window from a
+# pull source and normalised per window (MelStreamer.cpp:128-170).  The reference has no CPU implementation of it to generate fixtures
+# from; but on these clips a window's own maximum and the clip's differ by < 0.003 and only the ~10 of 240 000 values per window that sit
+# more than 8 below the maximum see the difference (checked on the CPU: test_oracle-side numbers in DESIGN.md §7), four orders of magnitude
+# below the fixtures' decision margins — so the streamed transcript must be the whisper_full fixture's.
+@pytest.mark.parametrize("name", ["plain", "special_offset_duration", "ml_german", "special_nocontext_max40"])
+def test_run_streamed_matches_reference_driver(name):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "full_runs.npz"))
+    model, flags, max_tokens, off, dur, lang, calls = FULL_RUNS[name]
+    assert calls == 1
+    L, h = open_session(model)
+    pcm = full_pcm(int(g[name + "_pcm_base"]))
+    hr, segs, info = run_streamed(L, h, pcm, flags=flags | 2, language=lang.encode(), max_tokens=max_tokens, off=off, dur=dur,
+                                  max_block={"plain": 4096, "special_offset_duration": 977, "ml_german": 16000, "special_nocontext_max40": 50000}[name])
+    assert hr == 0
+    assert [[s["t0"], s["t1"]] for s in segs] == g[name + "_t"].tolist()
+    assert [t for s in segs for t in s["tokens"]] == g[name + "_tokens"].tolist()
+    assert [s["text"] for s in segs] == g[name + "_text"].tolist()
+    assert L.wspc_segment_callback_total(h) == len(segs)
+    # progress sink: called at the top of every window and once with 1.0 at the end (ContextImpl.cpp:533-540, 788-792), never decreasing
+    assert info[0] >= 3 and info[1] == 1
+    # the source was read sequentially to (about) where the last window ended, not slurped: every read returned <= max_block samples
+    assert info[2] > 10
+
+
+def test_run_streamed_without_reader_thread_and_rules(session):
+    """cpuThreads = 1 selects the on-demand reader (MelStreamerSimple) — and the 1-thread reference arithmetic — so the comparison is
+    runStreamed against runFull on this GPU; TokenTimestamps is refused in streaming mode, a clip under one second is a no-op."""
+    L, h = session
+    pcm = full_pcm(10)[:16000 * 47]
+    hr, want = run_full(L, h, pcm, flags=2, threads=1)
+    assert hr == 0 and len(want) > 5
+    hr, segs, info = run_streamed(L, h, pcm, flags=2, threads=1, max_block=12345)
+    assert hr == 0 and info[1] == 1
+    assert [(s["t0"], s["t1"], s["text"], s["tokens"]) for s in segs] == [(s["t0"], s["t1"], s["text"], s["tokens"]) for s in want]
+    hr, _, _ = run_streamed(L, h, pcm, flags=2 | 0x100)
+    assert (hr & 0xFFFFFFFF) == 0x80004001                     # E_NOTIMPL (ContextImpl.misc.cpp:393-397)
+    hr, segs, _ = run_streamed(L, h, pcm[:8000], flags=2)
+    assert hr == 0 and segs == []
 
 
 @pytest.mark.parametrize("name", list(FULL_RUNS))

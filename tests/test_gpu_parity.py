@@ -61,6 +61,38 @@ def test_mel_edge_cases():
     assert np.allclose(c.get_mel(0), (-10.0 + 4.0) / 4.0)
 
 
+def test_mel_streamed_window():
+    """wsp_pcm_to_mel_window, the log-mel of iContext::runStreamed: one window normalised by its own maximum (floor 1e-20), or by a
+    forced one (MelStreamer.cpp:128-183), against the numpy restatement oracle/whisper_np.py::log_mel_window."""
+    from oracle import whisper_np as wn
+    m, e, c = open_model("micro.en-sc")
+    filters = wn.NpModel(synth.model_path("micro.en-sc")).filters
+    pcm = np.concatenate([synth.synth_pcm(11), 0.05 * synth.synth_pcm(12)])          # 60 s, the second half 26 dB quieter
+    for i0, n_frames, samples in ((0, 3000, 480240), (2500, 3000, 480240), (3100, 2900, 2900 * 160), (5990, 10, 1600), (0, 1, 100)):
+        seg = pcm[i0 * 160:i0 * 160 + samples]
+        want, found_want = wn.log_mel_window(seg, filters, n_frames)
+        found = c.pcm_to_mel_window(0, seg, n_frames)
+        got = c.get_mel(0)
+        assert got.shape == (80, n_frames)
+        assert abs(found - found_want) < 4 * TOL_MEL          # raw log10 units = 4 x the normalised ones
+        assert np.abs(got - want).max() < TOL_MEL
+    # a forced maximum (the streamer re-using the previous window's at the tail of a stream) moves the clamp level
+    seg = pcm[3100 * 160:]
+    want, _ = wn.log_mel_window(seg, filters, 2900, forced_max=3.5)
+    found = c.pcm_to_mel_window(0, seg, 2900, forced_max=3.5)
+    assert found < 3.0 and np.abs(c.get_mel(0) - want).max() < TOL_MEL and c.get_mel(0).min() >= (3.5 - 8 + 4) / 4 - 1e-6
+    # silence: every band at log10(1e-10) = -10, maximum floored at 1e-20 -> clamp at -8 -> -1.0 everywhere
+    found = c.pcm_to_mel_window(0, np.zeros(16000, np.float32), 100)
+    assert found == float(np.float32(1e-20)) and np.all(c.get_mel(0) == -1.0)
+    # no frames at all
+    c.pcm_to_mel_window(0, np.zeros(0, np.float32), 0)
+    assert c.get_mel(0).shape == (80, 0)
+    # the whole-clip entry point is unaffected by what the window calls left behind
+    g = golden("micro_en_30s")
+    c.pcm_to_mel(0, synth.synth_pcm(int(g["chunk"])))
+    assert np.abs(c.get_mel(0)[:, ::MEL_STEP] - g["mel"]).max() < TOL_MEL
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_encoder_trace_points(name):
     """Same named intermediates the reference traces (whisper.cpp:1121-1432), layer by layer."""

@@ -46,6 +46,26 @@ def test_mel_restatement_vs_golden(name, golden_dir, np_runs):
     assert np.abs(mel[:, ::MEL_STEP] - g["mel"]).max() < TOL_MEL
 
 
+def test_streamed_window_mel_restatement(golden_dir):
+    """log_mel_window (the streamed normalisation of MelStreamer.cpp:128-183, which cannot be run here) shares its per-frame transform with
+    the pinned log_mel: on a whole clip whose maximum exceeds the 1e-20 floor the two must agree bit for bit, a window cut out of a longer
+    clip must equal the same columns renormalised, a forced maximum replaces the found one, silence sits at the floor."""
+    m = wn.NpModel(synth.model_path("micro.en-sc"))
+    pcm = synth.synth_pcm(int(load(golden_dir, "micro_en_30s")["chunk"]))
+    whole = wn.log_mel(pcm, m.filters)
+    win, found = wn.log_mel_window(pcm, m.filters, pcm.size // 160)
+    assert np.array_equal(whole, win) and found > 1.0
+    # frames [500, 1500) of the clip: the window's last frames read on into the following samples, exactly like the same frames of the clip
+    sub, f2 = wn.log_mel_window(pcm[500 * 160:1500 * 160 + 240], m.filters, 1000)
+    raw = wn.log_mel_raw(pcm, m.filters)[:, 500:1500]
+    assert f2 == float(raw.max())
+    assert np.array_equal(sub, ((np.maximum(raw, np.float32(np.float32(f2) - np.float32(8))) + np.float32(4)) * np.float32(0.25)).astype(np.float32))
+    forced, f3 = wn.log_mel_window(pcm[500 * 160:1500 * 160 + 240], m.filters, 1000, forced_max=found)
+    assert f3 == f2 and np.array_equal(forced, np.maximum(whole[:, 500:1500], forced)) and forced.min() >= (found - 8 + 4) / 4 - 1e-6
+    silent, f4 = wn.log_mel_window(np.zeros(16000, np.float32), m.filters, 100)
+    assert f4 == float(np.float32(1e-20)) and np.all(silent == -1.0)      # max(-10, 1e-20 - 8) = -8 -> (-8 + 4) / 4
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_encoder_restatement_vs_golden(name, golden_dir, np_runs):
     g = load(golden_dir, name)

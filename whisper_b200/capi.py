@@ -36,7 +36,7 @@ EXPORTS = [
     "wsp_model_is_multilingual", "wsp_model_file_data", "wsp_model_meta_serialize", "wsp_model_from_meta",
     "wsp_engine_create", "wsp_engine_create_from_image", "wsp_engine_destroy", "wsp_engine_weight_bytes",
     "wsp_context_create", "wsp_context_destroy", "wsp_synchronize",
-    "wsp_pcm_to_mel", "wsp_set_mel", "wsp_mel_len", "wsp_get_mel", "wsp_encode", "wsp_decode", "wsp_get_logits", "wsp_get_probs",
+    "wsp_context_device_bytes", "wsp_pcm_to_mel", "wsp_pcm_to_mel_window", "wsp_set_mel", "wsp_mel_len", "wsp_get_mel", "wsp_encode", "wsp_decode", "wsp_get_logits", "wsp_get_probs",
     "wsp_detect_language", "wsp_run_chunks", "wsp_run_chunks_resident", "wsp_upload_pcm", "wsp_timer_start", "wsp_timer_stop", "wsp_profile_decode", "wsp_get_tensor", "wsp_debug_set_encoder_layers", "wsp_debug_set_graph", "wsp_debug_set_step_mode", "wsp_debug_enable_step_timing", "wsp_debug_step_timing", "wsp_set_reference_threads",
     "wsp_host_alloc", "wsp_host_free", "wsp_timings",
     "wsp_replicas_create", "wsp_replicas_count", "wsp_replicas_run_chunks", "wsp_replicas_debug_fail_next", "wsp_replicas_destroy",
@@ -88,7 +88,9 @@ def lib():
     sig("wsp_context_create", i32, [vp, i32, C.POINTER(vp)])
     sig("wsp_context_destroy", None, [vp])
     sig("wsp_synchronize", i32, [vp])
+    sig("wsp_context_device_bytes", u64, [vp])
     sig("wsp_pcm_to_mel", i32, [vp, i32, fp, i32])
+    sig("wsp_pcm_to_mel_window", i32, [vp, i32, fp, i32, i32, fp, fp])
     sig("wsp_set_mel", i32, [vp, i32, fp, i32])
     sig("wsp_mel_len", i32, [vp, i32])
     sig("wsp_get_mel", i32, [vp, i32, fp, sz])
@@ -245,6 +247,14 @@ class Context:
     def pcm_to_mel(self, slot: int, pcm: np.ndarray):
         pcm = np.ascontiguousarray(pcm, np.float32)
         check(self.L.wsp_pcm_to_mel(self.h, slot, _f(pcm), pcm.size))
+
+    def pcm_to_mel_window(self, slot: int, pcm: np.ndarray, n_frames: int, forced_max: float | None = None) -> float:
+        """Streamed flavour of the log-mel (one window, normalised by its own maximum); returns that maximum."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        fm = None if forced_max is None else C.c_float(forced_max)
+        out = C.c_float(0)
+        check(self.L.wsp_pcm_to_mel_window(self.h, slot, _f(pcm), pcm.size, n_frames, None if fm is None else C.byref(fm), C.byref(out)))
+        return float(out.value)
 
     def set_mel(self, slot: int, mel: np.ndarray):
         mel = np.ascontiguousarray(mel, np.float32)

@@ -154,6 +154,8 @@ void wsp_engine_destroy( wsp_engine* e )
 }
 uint64_t wsp_engine_weight_bytes( const wsp_engine* e ) { return e ? e->e->arenaUsed : 0; }
 
+uint64_t wsp_context_device_bytes( const wsp_context* c ) { return c ? c->c->devBytes : 0; }
+
 // ---- context ----
 wsp_status wsp_context_create( wsp_engine* e, int32_t max_batch, wsp_context** out )
 {
@@ -181,6 +183,11 @@ wsp_status wsp_pcm_to_mel( wsp_context* c, int32_t slot, const float* pcm, int32
 {
 	if( !c ) return fail( WSP_E_POINTER, "context" );
 	return guarded( [ & ]() -> wsp_status { return ctxPcmToMel( *c->c, slot, pcm, n_samples ); } );
+}
+wsp_status wsp_pcm_to_mel_window( wsp_context* c, int32_t slot, const float* pcm, int32_t n_samples, int32_t n_frames, const float* forced_max, float* max_out )
+{
+	if( !c ) return fail( WSP_E_POINTER, "context" );
+	return guarded( [ & ]() -> wsp_status { return ctxPcmToMelWindow( *c->c, slot, pcm, n_samples, n_frames, forced_max, max_out ); } );
 }
 wsp_status wsp_set_mel( wsp_context* c, int32_t slot, const float* mel, int32_t n_len )
 {

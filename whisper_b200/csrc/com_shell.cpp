@@ -8,8 +8,11 @@
 // The D3D back-end's driver (Whisper/Whisper/ContextImpl.cpp:452-794) differs slightly (it always skips 1 s on failure); the oracle wins.
 #include "../../include/whisper_b200.h"
 #include "../../include/whisper_b200_com.h"
+#include "pcm_streamer.h"
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <functional>
 #include <math.h>
 #include <map>
 
@@ -206,6 +209,40 @@ namespace
 		HRESULT WSPCALL getTime( int64_t& rdi ) const override { rdi = 0; return S_OK; }
 	};
 
+	// iAudioReader over a pull callback (createAudioReader): the Linux replacement of iMediaFoundation::openAudioFile
+	class CallbackSourceReader : public Object<IMFSourceReader>
+	{
+		pfnReadPcm pfn;
+		void* pv;
+
+	public:
+		CallbackSourceReader( pfnReadPcm f, void* p ) : pfn( f ), pv( p ) {}
+		HRESULT WSPCALL readPcm( float* mono, uint32_t capacity, uint32_t* written ) override
+		{
+			if( !mono || !written ) return E_POINTER;
+			*written = 0;
+			return pfn( mono, capacity, written, pv );
+		}
+	};
+	class AudioReaderObj : public Object<iAudioReader>
+	{
+		CallbackSourceReader* source;
+		int64_t duration;
+		~AudioReaderObj() override { source->Release(); }
+
+	public:
+		AudioReaderObj( pfnReadPcm f, void* p, int64_t ticks ) : source( new CallbackSourceReader( f, p ) ), duration( ticks ) {}
+		HRESULT WSPCALL getDuration( int64_t& rdi ) const override { rdi = duration; return S_OK; }
+		HRESULT WSPCALL getReader( IMFSourceReader** pp ) const override
+		{
+			if( !pp ) return E_POINTER;
+			source->AddRef();
+			*pp = source;
+			return S_OK;
+		}
+		HRESULT WSPCALL requestedStereo() const override { return S_FALSE; }
+	};
+
 	struct ResultData
 	{
 		// whisper_token_data (whisper.h:71-85): t0 / t1 stay -1 unless token-level timestamps were requested
@@ -283,6 +320,16 @@ namespace
 		int tidLast = 0;
 		void computeTokenTimestamps( size_t iSegment, float tholdPt, float tholdPtsum );
 		int wrapSegment( int maxLen );
+		// host-timed blocks of timingsPrint: [0] whole run calls (eCpuBlock::RunComplete), [1] client callbacks (eCpuBlock::Callbacks)
+		double hostMs[ 2 ] = { 0.0, 0.0 };
+		int64_t hostCalls[ 2 ] = { 0, 0 };
+		struct HostTimer
+		{
+			double& ms; int64_t& calls;
+			std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+			HostTimer( ContextObj& c, int i ) : ms( c.hostMs[ i ] ), calls( c.hostCalls[ i ] ) {}
+			~HostTimer() { ms += std::chrono::duration<double, std::milli>( std::chrono::steady_clock::now() - t0 ).count(); calls++; }
+		};
 
 		~ContextObj() override;
 
@@ -292,17 +339,22 @@ namespace
 			return check( wsp_decode( ctx, tokens.data(), (int32_t)tokens.size(), nPast, 1, flags, &out ), "wsp_decode" );
 		}
 		HRESULT detectLanguage( int& langId );
+		// where the loop's mel comes from: `prepare( seek )` makes the window that starts at frame `seek` available in slot 0 and returns
+		// the frame offset to encode at (the iSpectrogram of Whisper/Whisper/iSpectrogram.h:11-23, with makeBuffer + upload folded into one)
+		struct MelSource
+		{
+			int nLen = 0;
+			std::function<HRESULT( int seek, int32_t& encodeAt )> prepare;
+		};
+		HRESULT checkParams( const sFullParams& params );
+		HRESULT runImpl( const sFullParams& params, const sProgressSink& progress, const MelSource& mel, bool tokenTimestamps );
 
 	public:
 		ContextObj( ModelObj* m, const std::shared_ptr<SharedEngine>& e );
 		HRESULT init() { return check( wsp_context_create( eng->engine, 1, &ctx ), "wsp_context_create" ); }
 
 		HRESULT WSPCALL runFull( const sFullParams& params, const iAudioBuffer* buffer ) override;
-		HRESULT WSPCALL runStreamed( const sFullParams&, const sProgressSink&, const iAudioReader* ) override
-		{
-			logMessage( eLogLevel::Error, "whisper_b200: runStreamed is not implemented (same as the Reference back-end, whisperCom.cpp:139-143)" );
-			return E_NOTIMPL;
-		}
+		HRESULT WSPCALL runStreamed( const sFullParams& params, const sProgressSink& progress, const iAudioReader* reader ) override;
 		HRESULT WSPCALL runCapture( const sFullParams&, const sCaptureCallbacks&, const iAudioCapture* ) override
 		{
 			logMessage( eLogLevel::Error, "whisper_b200: runCapture is not implemented (same as the Reference back-end, whisperCom.cpp:144-148)" );
@@ -350,16 +402,48 @@ namespace
 		}
 		HRESULT WSPCALL timingsPrint() override
 		{
+			// the per-block table of ContextImpl::timingsPrint (ContextImpl.misc.cpp:170-182, ProfileCollection::print): host-timed blocks,
+			// device-timed blocks (CUDA events on the context's stream), then the memory table
 			float ms[ 4 ]; int32_t calls[ 4 ];
 			HR( check( wsp_timings( ctx, ms, calls, 0 ), "wsp_timings" ) );
-			logMessage( eLogLevel::Info, "whisper_b200 timings (device):      mel = %8.2f ms / %d calls", ms[ 0 ], calls[ 0 ] );
-			logMessage( eLogLevel::Info, "whisper_b200 timings (device):   encode = %8.2f ms / %d calls", ms[ 1 ], calls[ 1 ] );
-			logMessage( eLogLevel::Info, "whisper_b200 timings (device):   decode = %8.2f ms / %d calls (sampling included)", ms[ 2 ], calls[ 2 ] );
+			auto line = []( const char* name, double msTotal, int64_t count ) {
+				if( count <= 0 ) return;
+				auto scaled = []( double v, const char*& unit ) { if( v >= 1000.0 ) { unit = "seconds"; return v / 1000.0; } if( v >= 1.0 ) { unit = "milliseconds"; return v; } unit = "microseconds"; return v * 1000.0; };
+				const char* u1; const char* u2;
+				const double total = scaled( msTotal, u1 );
+				if( count == 1 ) logMessage( eLogLevel::Info, "%s\t%g %s", name, total, u1 );
+				else
+				{
+					const double avg = scaled( msTotal / (double)count, u2 );
+					logMessage( eLogLevel::Info, "%s\t%g %s, %lld calls, %g %s average", name, total, u1, (long long)count, avg, u2 );
+				}
+			};
+			logMessage( eLogLevel::Info, "    CPU Tasks" );
+			line( "RunComplete", hostMs[ 0 ], hostCalls[ 0 ] );
+			line( "Callbacks", hostMs[ 1 ], hostCalls[ 1 ] );
+			logMessage( eLogLevel::Info, "    GPU Tasks" );
+			line( "Spectrogram", ms[ 0 ], calls[ 0 ] );
+			line( "Encode", ms[ 1 ], calls[ 1 ] );
+			line( "Decode", ms[ 2 ], calls[ 2 ] );
+			line( "Sample", ms[ 3 ], calls[ 3 ] );
+			auto mem = []( const char* what, uint64_t vram ) {
+				const char* unit = "bytes"; double v = (double)vram;
+				if( vram >= ( 1ull << 30 ) ) { v /= (double)( 1ull << 30 ); unit = "GB"; }
+				else if( vram >= ( 1ull << 20 ) ) { v /= (double)( 1ull << 20 ); unit = "MB"; }
+				else if( vram >= ( 1ull << 10 ) ) { v /= 1024.0; unit = "KB"; }
+				logMessage( eLogLevel::Info, "%s\t0 bytes RAM, %g %s VRAM", what, v, unit );
+			};
+			logMessage( eLogLevel::Info, "    Memory Usage" );
+			const uint64_t mModel = wsp_engine_weight_bytes( eng->engine ), mCtx = wsp_context_device_bytes( ctx );
+			mem( "Model", mModel );
+			mem( "Context", mCtx );
+			mem( "Total", mModel + mCtx );
 			return S_OK;
 		}
 		HRESULT WSPCALL timingsReset() override
 		{
 			float ms[ 4 ]; int32_t calls[ 4 ];
+			hostMs[ 0 ] = hostMs[ 1 ] = 0.0; hostCalls[ 0 ] = hostCalls[ 1 ] = 0;
 			return check( wsp_timings( ctx, ms, calls, 1 ), "wsp_timings" );
 		}
 		// not part of the COM surface: used by the flat test helpers below
@@ -682,12 +766,12 @@ namespace
 		return S_OK;
 	}
 
-	HRESULT WSPCALL ContextObj::runFull( const sFullParams& params, const iAudioBuffer* buffer )
+	HRESULT ContextObj::checkParams( const sFullParams& params )
 	{
-		if( !buffer ) return E_POINTER;
 		if( params.flag( eFullParamsFlags::SpeedupAudio ) )
 		{
-			logMessage( eLogLevel::Error, "whisper_b200: SpeedupAudio (phase vocoder) is not implemented" );
+			// the reference's GPU back-end answers the same (ContextImpl.cpp:459-463); only its CPU back-end has the phase vocoder
+			logMessage( eLogLevel::Error, "whisper_b200: the SpeedupAudio flag is not implemented (nor is it by the reference's GPU model)" );
 			return E_NOTIMPL;
 		}
 		const int nAudioCtx = eng->hp[ 1 ];
@@ -698,8 +782,13 @@ namespace
 		}
 		// the reference's decoder arithmetic depends on its thread count; follow the caller's cpuThreads
 		const int threads = params.cpuThreads < 1 ? 1 : ( params.cpuThreads > 16 ? 16 : params.cpuThreads );
-		HR( check( wsp_set_reference_threads( ctx, threads ), "wsp_set_reference_threads" ) );
+		return check( wsp_set_reference_threads( ctx, threads ), "wsp_set_reference_threads" );
+	}
 
+	HRESULT WSPCALL ContextObj::runFull( const sFullParams& params, const iAudioBuffer* buffer )
+	{
+		if( !buffer ) return E_POINTER;
+		HR( checkParams( params ) );
 		results.segs.clear();                                                                     // whisper.cpp:2771-2773
 		const float* pcm = buffer->getPcmMono();
 		const int nSamples = (int)buffer->countSamples();
@@ -711,7 +800,71 @@ namespace
 			tBeg = 0; tLast = 0; tidLast = 0;
 			energy = signalEnergy( pcm, nSamples, 32 );
 		}
-		const int nLen = wsp_mel_len( ctx, 0 );
+		MelSource mel;
+		mel.nLen = wsp_mel_len( ctx, 0 );
+		mel.prepare = []( int seek, int32_t& encodeAt ) -> HRESULT { encodeAt = seek; return S_OK; };   // the whole clip's mel is resident
+		return runImpl( params, sProgressSink{ nullptr, nullptr }, mel, tokenTimestamps );
+	}
+
+	// iContext::runStreamed (Whisper/Whisper/ContextImpl.misc.cpp:391-419): the same loop, fed window by window from a source that
+	// delivers PCM in stream order.  What differs from runFull, as in the reference: every window's log-mel is normalised by ITS OWN
+	// maximum (MelStreamer::makeTransposedBuffer, MelStreamer.cpp:128-170) — the clip's global maximum is not known while streaming —
+	// and token-level timestamps are refused (they need the whole signal's energy).
+	HRESULT WSPCALL ContextObj::runStreamed( const sFullParams& params, const sProgressSink& progress, const iAudioReader* reader )
+	{
+		if( !reader ) return E_POINTER;
+		if( params.flag( eFullParamsFlags::TokenTimestamps ) )
+		{
+			logMessage( eLogLevel::Error, "eFullParamsFlags.TokenTimestamps flag is not supported in streaming mode" );
+			return E_NOTIMPL;
+		}
+		HR( checkParams( params ) );
+		results.segs.clear();
+		int64_t ticks = 0;
+		HR( reader->getDuration( ticks ) );
+		if( ticks < 0 ) return E_INVALIDARG;
+		IMFSourceReader* src = nullptr;
+		HR( reader->getReader( &src ) );
+		if( !src ) return E_POINTER;
+		struct Releaser { IMFSourceReader* p; ~Releaser() { p->Release(); } } releaser{ src };
+		const int64_t frames = ticks / 100000;                                                     // PcmReader.cpp:265-270
+		if( frames > 0x7FFFFFFF - 3000 ) return E_INVALIDARG;
+		// cpuThreads >= 2 reads the source ahead on a background thread, like MelStreamerThread (ContextImpl.misc.cpp:404-413)
+		wsp::PcmStreamer streamer( [ src ]( float* dst, uint32_t cap, uint32_t* got ) -> int32_t { return src->readPcm( dst, cap, got ); },
+			(size_t)frames, params.cpuThreads > 1 );
+		size_t lastBufferEnd = ~(size_t)0;
+		float lastBufferMax = 0.0f;
+		MelSource mel;
+		mel.nLen = (int)frames;
+		mel.prepare = [ & ]( int seek, int32_t& encodeAt ) -> HRESULT {
+			// MelInputTensor.cpp:36-52: frames [ i0, i1 ) of the stream, the rest of the 3000-frame window stays zero
+			const size_t nLen = streamer.length();
+			const size_t i0 = std::min( (size_t)seek, nLen );
+			const size_t i1 = std::min( (size_t)seek + 3000, nLen );
+			const float* pcm = nullptr;
+			size_t nSamples = 0;
+			const int32_t hr = streamer.window( i0, i1 - i0, &pcm, &nSamples );
+			if( hr < 0 )
+			{
+				logMessage( eLogLevel::Error, hr == E_UNEXPECTED ? "MelStreamer doesn't support backwards seeks" : "runStreamed: the audio reader failed" );
+				return hr;
+			}
+			// MelStreamer.cpp:152-166: a window that ends where the previous one ended (the tail of the stream) keeps that window's maximum
+			const size_t bufferEnd = i1;
+			float found = 0.0f;
+			const bool reuse = lastBufferEnd == bufferEnd;
+			HR( check( wsp_pcm_to_mel_window( ctx, 0, pcm, (int32_t)nSamples, (int32_t)( i1 - i0 ), reuse ? &lastBufferMax : nullptr, &found ), "wsp_pcm_to_mel_window" ) );
+			if( !reuse ) { lastBufferEnd = bufferEnd; lastBufferMax = found; }
+			encodeAt = 0;
+			return S_OK;
+		};
+		return runImpl( params, progress, mel, false );
+	}
+
+	HRESULT ContextObj::runImpl( const sFullParams& params, const sProgressSink& progress, const MelSource& mel, const bool tokenTimestamps )
+	{
+		HostTimer runComplete( *this, 0 );
+		const int nLen = mel.nLen;
 
 		const int tokEot = eng->tokEot(), tokSot = eng->tokSot(), tokPrev = eng->tokPrev(), tokBeg = eng->tokBeg();
 		const int nTextCtx = eng->nTextCtx();
@@ -721,6 +874,8 @@ namespace
 		if( params.language == 0 || params.language == makeLanguageKey( "auto" ) )              // :2789-2801
 		{
 			if( nLen < 1 ) return S_OK;
+			int32_t at = 0;
+			HR( mel.prepare( 0, at ) );
 			HR( detectLanguage( langId ) );
 			logMessage( eLogLevel::Info, "whisper_b200: auto-detected language: %s", languages().codes[ langId ].c_str() );
 		}
@@ -754,6 +909,7 @@ namespace
 		const bool printSpecial = params.flag( eFullParamsFlags::PrintSpecial );
 
 		int seek = seekStart;
+		bool stoppedPrematurely = false;
 		while( true )                                                                              // :2861
 		{
 			const int progressCur = ( 100 * ( seek - seekStart ) ) / ( seekEnd - seekStart );
@@ -762,15 +918,23 @@ namespace
 				progressPrev += 5;
 				if( params.flag( eFullParamsFlags::PrintProgress ) ) logMessage( eLogLevel::Info, "runFull: progress = %3d%%", progressPrev );
 			}
+			if( progress.pfn )                                                                     // ContextImpl.cpp:533-540
+			{
+				HostTimer cb( *this, 1 );
+				const HRESULT hr = progress.pfn( (double)( seek - seekStart ) / (double)( seekEnd - seekStart ), this, progress.pv );
+				if( FAILED( hr ) ) return hr;
+			}
 			if( seek + 100 >= seekEnd ) break;                                                    // :2871
 			if( seek > seekStart && seek + 500 >= seekEnd ) promptPast.clear();                    // :2877
 			if( params.encoder_begin_callback )                                                    // :2881-2886 (HRESULT flavour: sFullParams.h:18-19)
 			{
+				HostTimer cb( *this, 1 );
 				const HRESULT hr = params.encoder_begin_callback( this, params.encoder_begin_callback_user_data );
 				if( FAILED( hr ) ) return hr;
-				if( hr != S_OK ) break;
+				if( hr != S_OK ) { stoppedPrematurely = true; break; }
 			}
-			const int32_t seek32 = seek;
+			int32_t seek32 = seek;
+			HR( mel.prepare( seek, seek32 ) );
 			HR( check( wsp_encode( ctx, &seek32, 1 ), "wsp_encode" ) );                            // :2889
 
 			int nPast = 0;
@@ -847,6 +1011,7 @@ namespace
 				}
 				if( params.new_segment_callback )
 				{
+					HostTimer cb( *this, 1 );
 					const HRESULT hr = params.new_segment_callback( this, (uint32_t)nNew, params.new_segment_callback_user_data );
 					if( FAILED( hr ) ) return hr;
 				}
@@ -880,6 +1045,11 @@ namespace
 				if( !text.empty() ) HR( emit( t0, (int64_t)seek + seekDelta, text, i0, (int)tokensCur.size() ) );
 			}
 			seek += seekDelta;                                                                     // :3121
+		}
+		if( progress.pfn && !stoppedPrematurely )                                                  // ContextImpl.cpp:788-792
+		{
+			const HRESULT hr = progress.pfn( 1.0, this, progress.pv );
+			if( FAILED( hr ) ) return hr;
 		}
 		return S_OK;
 	}
@@ -999,6 +1169,13 @@ namespace Whisper
 	{
 		if( pp ) *pp = nullptr;
 		return E_NOTIMPL;
+	}
+	HRESULT WSPCALL createAudioReader( pfnReadPcm pfn, void* pv, int64_t durationTicks, iAudioReader** pp )
+	{
+		if( !pp || !pfn ) return E_POINTER;
+		if( durationTicks < 0 ) return E_INVALIDARG;
+		*pp = new AudioReaderObj( pfn, pv, durationTicks );
+		return S_OK;
 	}
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp )
 	{

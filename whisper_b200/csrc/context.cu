@@ -10,6 +10,7 @@ namespace wsp
 {
 	namespace
 	{
+		thread_local uint64_t t_allocated = 0;   // bytes handed out by devAlloc on this thread (read by its callers)
 		template<class T> int devAlloc( T*& p, size_t count, bool zero = false )
 		{
 			void* v = nullptr;
@@ -21,6 +22,7 @@ namespace wsp
 				if( e != cudaSuccess ) return cudaFail( e, "cudaMemset" );
 			}
 			p = static_cast<T*>( v );
+			t_allocated += count * sizeof( T );
 			return WSP_OK;
 		}
 		inline void launched( int n = 1 ) { g_launchCount.fetch_add( (uint64_t)n, std::memory_order_relaxed ); }
@@ -49,6 +51,8 @@ namespace wsp
 		Context& c = *cp;
 		c.e = e;
 		c.maxB = maxBatch;
+		t_allocated = 0;
+		struct Tally { Context& c; ~Tally() { c.devBytes += t_allocated; t_allocated = 0; } } tally{ c };
 		const HParams& hp = e->hp;
 		const int d = hp.n_audio_state, H = hp.n_audio_head, T = hp.n_audio_ctx, L = hp.n_text_layer;
 		if( T * 2 != kFrames ) return fail( WSP_E_FORMAT, "n_audio_ctx must be 1500" );
@@ -186,7 +190,9 @@ namespace wsp
 			if( s.mel ) cudaFree( s.mel );
 			s.mel = nullptr;
 			const int cap = nLen < kFrames ? kFrames : nLen;
+			c.devBytes -= (uint64_t)80 * s.cap * 4;
 			WSP_CHECK( devAlloc( s.mel, (size_t)80 * cap ) );
+			c.devBytes += (uint64_t)80 * cap * 4;
 			s.cap = cap;
 		}
 		s.nLen = nLen;
@@ -208,7 +214,9 @@ namespace wsp
 	{
 		if( floats <= c.pcmCap ) return WSP_OK;
 		if( c.pcmDev ) { WSP_CUDA( cudaStreamSynchronize( c.stream ) ); cudaFree( c.pcmDev ); c.pcmDev = nullptr; }
+		c.devBytes -= (uint64_t)c.pcmCap * 4;
 		WSP_CHECK( devAlloc( c.pcmDev, floats ) );
+		c.devBytes += (uint64_t)floats * 4;
 		c.pcmCap = floats;
 		return WSP_OK;
 	}
@@ -222,6 +230,44 @@ namespace wsp
 		if( nSamples > 0 )
 			WSP_CUDA( cudaMemcpyAsync( c.pcmDev, pcmHost, (size_t)nSamples * 4, cudaMemcpyHostToDevice, c.stream ) );
 		WSP_CHECK( melFromDevicePcm( c, slot, c.pcmDev, nSamples ) );
+		WSP_CUDA( cudaEventRecord( c.ev[ 1 ], c.stream ) );
+		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
+		float ms = 0;
+		cudaEventElapsedTime( &ms, c.ev[ 0 ], c.ev[ 1 ] );
+		c.ms[ 0 ] += ms; c.calls[ 0 ]++;
+		return WSP_OK;
+	}
+
+	// One window of a streamed clip (Whisper/Whisper/MelStreamer.cpp:128-236): frames [0, nFrames) of the PCM handed in — the PCM may
+	// (and, except at the end of a stream, does) extend past the last frame so that every frame sees its full 400 samples — normalised
+	// by the maximum over THESE frames only, floored at 1e-20 (:136), or by `forcedMax` when the streamer re-uses the maximum of the
+	// previous, longer window that ended at the same frame (:152-166).  Same kernels as the whole-clip path.
+	int ctxPcmToMelWindow( Context& c, int slot, const float* pcmHost, int nSamples, int nFrames, const float* forcedMax, float* maxOut )
+	{
+		if( ( !pcmHost && nSamples != 0 ) || nSamples < 0 || nFrames < 0 ) return fail( WSP_E_INVALIDARG, "pcm / frame count" );
+		WSP_CUDA( cudaSetDevice( c.e->device ) );
+		WSP_CHECK( ensurePcm( c, (size_t)( nSamples > 0 ? nSamples : 1 ) ) );
+		WSP_CHECK( ensureMelSlot( c, slot, nFrames ) );
+		MelSlot& s = c.slots[ slot ];
+		WSP_CUDA( cudaEventRecord( c.ev[ 0 ], c.stream ) );
+		if( nSamples > 0 )
+			WSP_CUDA( cudaMemcpyAsync( c.pcmDev, pcmHost, (size_t)nSamples * 4, cudaMemcpyHostToDevice, c.stream ) );
+		WSP_CUDA( kern::melPower( c.e->mel, c.pcmDev, nSamples, nFrames, s.mel, c.melMax + slot, c.stream ) );
+		int32_t ordered = 0;
+		WSP_CUDA( cudaMemcpyAsync( &ordered, c.melMax + slot, 4, cudaMemcpyDeviceToHost, c.stream ) );
+		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
+		// the device keeps the maximum as an order-preserving integer (kernels_frontend.cu: orderedFromFloat)
+		auto toFloat = []( int32_t i ) { const int32_t b = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy( &f, &b, 4 ); return f; };
+		auto toOrdered = []( float f ) { int32_t b; memcpy( &b, &f, 4 ); return b >= 0 ? b : b ^ 0x7FFFFFFF; };
+		float mmax = toFloat( ordered );
+		if( !( mmax > 1e-20f ) ) mmax = 1e-20f;
+		if( maxOut ) *maxOut = mmax;
+		if( forcedMax ) mmax = *forcedMax;
+		const int32_t wanted = toOrdered( mmax );
+		if( wanted != ordered )
+			WSP_CUDA( cudaMemcpyAsync( c.melMax + slot, &wanted, 4, cudaMemcpyHostToDevice, c.stream ) );
+		WSP_CUDA( kern::melNormalize( s.mel, 80 * nFrames, c.melMax + slot, c.stream ) );
+		launched( 3 );
 		WSP_CUDA( cudaEventRecord( c.ev[ 1 ], c.stream ) );
 		WSP_CUDA( cudaStreamSynchronize( c.stream ) );
 		float ms = 0;

@@ -113,6 +113,7 @@ namespace wsp
 		std::vector<MelSlot> slots;
 		int* melMax = nullptr;          // [maxB] ordered-int maxima
 		float* pcmDev = nullptr; size_t pcmCap = 0;
+		uint64_t devBytes = 0;          // device memory this context holds (timingsPrint's memory table)
 
 		// encoder workspaces
 		__half* melF16 = nullptr;       // [maxB][3002][80]
@@ -191,6 +192,7 @@ namespace wsp
 
 	int createContext( Engine* e, int maxBatch, Context** out );
 	int ctxPcmToMel( Context& c, int slot, const float* pcmHost, int nSamples );
+	int ctxPcmToMelWindow( Context& c, int slot, const float* pcmHost, int nSamples, int nFrames, const float* forcedMax, float* maxOut );
 	int ctxSetMel( Context& c, int slot, const float* melHost, int nLen );
 	int ctxEncode( Context& c, const int32_t* offsets, int batch );
 	int ctxDecode( Context& c, const int32_t* tokensHost, int nTokens, int nPast, int batch, uint32_t flags, wsp_token_data* sampledHost );
