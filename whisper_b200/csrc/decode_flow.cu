@@ -21,6 +21,7 @@
 #include "decode_flow.cuh"
 #include "per_device.h"
 #include "ptx.cuh"
+#include "ref_arith.cuh"
 #include <math.h>
 
 namespace kern
@@ -152,7 +153,6 @@ namespace kern
 			while( !ptx::mbar_try_wait( bar, parity ) ) g.tick();
 		}
 
-		__device__ __forceinline__ float expTabF( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
 
 		// The reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893): y = f16( fma( V[j][e], P[j], y ) ) key by key — three dependent
 		// ALU instructions per key (FFMA -> F2FP.F16.F32 -> HADD2.F32), ~30 cycles, inherent to the reference's arithmetic (staging the
@@ -299,7 +299,7 @@ namespace kern
 			float lsum = 0.0f;
 			for( int j = tid; j < n; j += FL_CONSUMERS )
 			{
-				const float e = expTabF( sp[ j ] - mx );
+				const float e = expF16Table( sp[ j ] - mx );
 				sp[ j ] = e;
 				lsum += e;
 			}

@@ -12,6 +12,7 @@
 #include "decode_mega.cuh"
 #include "per_device.h"
 #include "ptx.cuh"
+#include "ref_arith.cuh"
 #include <math.h>
 
 namespace kern
@@ -65,29 +66,6 @@ namespace kern
 		}
 		__device__ __forceinline__ void cpAsyncCommit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
 		__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile( "cp.async.wait_group 0;" ::: "memory" ); }
-
-		__device__ __forceinline__ float expTab( float x ) { return __half2float( __float2half_rn( expf( __half2float( __float2half_rn( x ) ) ) ) ); }
-
-		// see kernels_decode.cu: the reference's f16-accumulated V^T*P (ggml.c:4680-4722, 871-893)
-		__device__ __forceinline__ float pvChain( const float* __restrict__ sp, const __half* __restrict__ v, size_t vStride, int j0, int j1 )
-		{
-			float y = 0.0f;
-			int j = j0;
-			for( ; j + 4 <= j1; j += 4 )
-			{
-				const float x0 = __half2float( v[ (size_t)j * vStride ] );
-				const float x1 = __half2float( v[ (size_t)( j + 1 ) * vStride ] );
-				const float x2 = __half2float( v[ (size_t)( j + 2 ) * vStride ] );
-				const float x3 = __half2float( v[ (size_t)( j + 3 ) * vStride ] );
-				y = __half2float( __float2half_rn( __fmaf_rn( x0, sp[ j ], y ) ) );
-				y = __half2float( __float2half_rn( __fmaf_rn( x1, sp[ j + 1 ], y ) ) );
-				y = __half2float( __float2half_rn( __fmaf_rn( x2, sp[ j + 2 ], y ) ) );
-				y = __half2float( __float2half_rn( __fmaf_rn( x3, sp[ j + 3 ], y ) ) );
-			}
-			for( ; j < j1; j++ )
-				y = __half2float( __float2half_rn( __fmaf_rn( __half2float( v[ (size_t)j * vStride ] ), sp[ j ], y ) ) );
-			return y;
-		}
 
 		// debug: CTA 0 / thread 0 writes %globaltimer into a fixed slot (last layer wins); tm == nullptr in normal runs
 		__device__ __forceinline__ void subMark( unsigned long long* tm, int k )
@@ -520,7 +498,7 @@ namespace kern
 				float lsum = 0.0f;
 				for( int j = tid; j < nkv; j += MG_THREADS )
 				{
-					const float e = expTab( sm.sp[ j ] - mx );
+					const float e = expF16Table( sm.sp[ j ] - mx );
 					sm.sp[ j ] = e;
 					lsum += e;
 				}
@@ -539,7 +517,7 @@ namespace kern
 					const int part = idx >> 6, e = idx & 63;
 					const int j0 = min( part * dc, nkv ), j1 = min( ( part + 1 ) * dc, nkv );
 					float y;
-					if( a.refThreads > 0 ) y = pvChain( sm.sp, sV + e, 64, j0, j1 );
+					if( a.refThreads > 0 ) y = pvChainF16( sm.sp, sV + e, 64, j0, j1 );
 					else
 					{
 						y = 0.0f;
@@ -651,7 +629,7 @@ namespace kern
 				float lsum = 0.0f;
 				for( int j = tid; j < T; j += MG_THREADS )
 				{
-					const float e = expTab( sm.sp[ j ] - mx );
+					const float e = expF16Table( sm.sp[ j ] - mx );
 					sm.sp[ j ] = e;
 					lsum += e;
 				}
@@ -672,7 +650,7 @@ namespace kern
 					const int part = idx >> 6, e = idx & 63;
 					const int j0 = min( part * dc, T ), j1 = min( ( part + 1 ) * dc, T );
 					float y;
-					if( a.refThreads > 0 ) y = pvChain( sm.sp, sv + e, 64, j0, j1 );
+					if( a.refThreads > 0 ) y = pvChainF16( sm.sp, sv + e, 64, j0, j1 );
 					else
 					{
 						y = 0.0f;
