@@ -10,6 +10,8 @@
 //   iTranscribeResult        Whisper/API/iTranscribeResult.cl.h:7-14  {2871a73f-5ce3-48f8-8779-6582ee11935e}
 //   iAudioBuffer             Whisper/API/iMediaFoundation.cl.h:9-17   {013583aa-c9eb-42bc-83db-633c2c317051}
 //   iAudioReader             Whisper/API/iMediaFoundation.cl.h:19-26  {35b988da-04a6-476a-a193-d8891d5dc390}  (input of iContext::runStreamed)
+//   iAudioCapture            Whisper/API/iMediaFoundation.cl.h:28-34  {747752c2-d9fd-40df-8847-583c781bf013}  (input of iContext::runCapture)
+//   sCaptureParams, eCaptureStatus, sCaptureCallbacks   Whisper/API/MfStructs.h:16-52
 //   sFullParams, flags       Whisper/API/sFullParams.h:5-130
 //   sSegment, sToken, ...    Whisper/API/TranscribeStructs.h:8-137
 //   sModelSetup, callbacks   Whisper/API/sModelSetup.h:6-41, sLoadModelCallbacks.h:5-14, loggerApi.h:7-34, SpecialTokens.h, sLanguageList.h
@@ -183,8 +185,31 @@ namespace Whisper
 		virtual HRESULT WSPCALL getReader( IMFSourceReader** pp ) const = 0;    // AddRef'ed
 		virtual HRESULT WSPCALL requestedStereo() const = 0;                    // S_OK / S_FALSE; stereo (diarisation) is not delivered here
 	};
-	struct iAudioCapture;
-	struct sCaptureCallbacks;
+	// ---- MfStructs.h: live capture ----
+	enum struct eCaptureFlags : uint32_t { Stereo = 1 };
+	struct sCaptureParams
+	{
+		float minDuration = 2.0f;
+		float maxDuration = 3.0f;
+		float dropStartSilence = 0.25f;
+		float pauseDuration = 0.333f;
+		uint32_t flags = 0;
+	};
+	enum struct eCaptureStatus : uint8_t { Listening = 1, Voice = 2, Transcribing = 4, Stalled = 0x80 };
+	using pfnShouldCancel = HRESULT( WSPCALL* )( void* pv ) noexcept;                            // S_OK to continue, S_FALSE to stop the capture session
+	using pfnCaptureStatus = HRESULT( WSPCALL* )( void* pv, eCaptureStatus status ) noexcept;
+	struct sCaptureCallbacks
+	{
+		pfnShouldCancel shouldCancel;
+		pfnCaptureStatus captureStatus;
+		void* pv;
+	};
+	struct iAudioCapture : public ComLight::IUnknown
+	{
+		static constexpr GUID iid() { return GUID{ 0x747752c2, 0xd9fd, 0x40df, { 0x88, 0x47, 0x58, 0x3c, 0x78, 0x1b, 0xf0, 0x13 } }; }
+		virtual HRESULT WSPCALL getReader( IMFSourceReader** pp ) const = 0;
+		virtual const sCaptureParams& WSPCALL getParams() const = 0;
+	};
 	struct iMediaFoundation;
 
 	struct iTranscribeResult : public ComLight::IUnknown
@@ -235,5 +260,8 @@ namespace Whisper
 	// loadAudioFileData, Whisper/API/iMediaFoundation.cl.h:38-39).  `durationTicks` announces the stream length (100 ns units).
 	using pfnReadPcm = HRESULT( WSPCALL* )( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept;
 	HRESULT WSPCALL createAudioReader( pfnReadPcm pfn, void* pv, int64_t durationTicks, iAudioReader** pp );
+	// ... and an iAudioCapture over the same kind of callback, for a live source (replaces iMediaFoundation::openCaptureDevice, :42).
+	// The callback blocks until audio is available; returning *written == 0 ends the session with E_EOF like a device that went away.
+	HRESULT WSPCALL createAudioCapture( pfnReadPcm pfn, void* pv, const sCaptureParams& captureParams, iAudioCapture** pp );
 	}
 }

@@ -2,7 +2,11 @@
 // through ctypes.  Built into tests/boundary/_build/libwspc_test.so and linked against libwhisper_b200.so: it uses nothing but the
 // public header, exactly like a client application would (Examples/main/main.cpp:210-318 of the reference).
 #include "whisper_b200_com.h"
+#include "../../whisper_b200/csrc/capture_loop.h"   // host-only header: used to predict where the capture loop cuts (wspc_capture_cuts)
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 using namespace Whisper;
 
@@ -16,6 +20,56 @@ namespace
 		iTranscribeResult* result = nullptr;
 		std::vector<int> segCallbackCounts;
 		int maxLen = 0;
+		// runCapture: segments collected from inside new_segment_callback (on the library's transcriber thread)
+		struct CapturedSeg { uint64_t t0, t1; std::string text; std::vector<int> tokens; };
+		std::vector<CapturedSeg> captured;
+	};
+	HRESULT captureSegCallback( iContext* ctx, uint32_t nNew, void* pv ) noexcept
+	{
+		Session* s = static_cast<Session*>( pv );
+		iTranscribeResult* res = nullptr;
+		if( FAILED( ctx->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &res ) ) ) return E_FAIL;
+		sTranscribeLength len;
+		res->getSize( len );
+		for( uint32_t i = len.countSegments - nNew; i < len.countSegments; i++ )
+		{
+			const sSegment& seg = res->getSegments()[ i ];
+			Session::CapturedSeg c{ seg.time.begin.ticks, seg.time.end.ticks, seg.text, {} };
+			for( uint32_t j = 0; j < seg.countTokens; j++ ) c.tokens.push_back( res->getTokens()[ seg.firstToken + j ].id );
+			s->captured.push_back( std::move( c ) );
+		}
+		res->Release();
+		return S_OK;
+	}
+	// a live source played from an array: it delivers ragged blocks and — like a real-time device feeding a transcriber that is faster
+	// than real time — never runs ahead of a transcription in flight, which makes the utterance cuts deterministic
+	struct LiveSource
+	{
+		const float* pcm; uint32_t n, pos = 0, lcg = 4242u;
+		std::atomic<uint8_t> status{ 0 };
+		int transcriptions = 0, stalls = 0;
+		LiveSource( const float* p, uint32_t count ) : pcm( p ), n( count ) {}
+		HRESULT read( float* mono, uint32_t capacity, uint32_t* written )
+		{
+			for( int waited = 0; ( status.load() & (uint8_t)eCaptureStatus::Transcribing ) && waited < 300000; waited++ )   // at most ~30 s: a test must not hang
+				std::this_thread::sleep_for( std::chrono::microseconds( 100 ) );
+			lcg = lcg * 1664525u + 1013904223u;
+			uint32_t want = 100 + ( lcg >> 8 ) % 900;
+			if( want > capacity ) want = capacity;
+			if( want > n - pos ) want = n - pos;
+			if( want ) memcpy( mono, pcm + pos, (size_t)want * 4 );
+			pos += want;
+			*written = want;
+			return S_OK;
+		}
+		HRESULT onStatus( uint8_t bits )
+		{
+			const uint8_t old = status.exchange( bits );
+			if( ( bits & (uint8_t)eCaptureStatus::Transcribing ) && !( old & (uint8_t)eCaptureStatus::Transcribing ) ) transcriptions++;
+			if( ( bits & (uint8_t)eCaptureStatus::Stalled ) && !( old & (uint8_t)eCaptureStatus::Stalled ) ) stalls++;
+			return S_OK;
+		}
+		bool finished() const { return pos >= n && !( status.load() & (uint8_t)eCaptureStatus::Transcribing ); }
 	};
 	HRESULT segCallback( iContext*, uint32_t nNew, void* pv ) noexcept
 	{
@@ -88,8 +142,9 @@ int32_t wspc_run_full( void* h, const float* pcm, int32_t nSamples, uint32_t fla
 	return FAILED( hr2 ) ? hr2 : hr;
 }
 // iContext::runStreamed over an iAudioReader made with createAudioReader: the PCM is handed out in ragged blocks (1..maxBlock samples,
-// never more than asked for), the way a decoder delivers it.  progressOut[0] = number of progress calls, [1] = 1 if they never
-// decreased and ended at exactly 1.0, [2] = number of read calls.
+// never more than asked for), the way a decoder delivers it.  progressOut[0] = number of progress calls, [1] = 1 if the per-window
+// values never decreased (the last window may overshoot 1.0 when the final seek passes the end, as in the reference's formula) and
+// the closing call reported exactly 1.0, [2] = number of read calls.
 int32_t wspc_run_streamed( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t maxTokens, int32_t cpuThreads,
 	int32_t offsetMs, int32_t durationMs, int32_t maxBlock, int32_t* progressOut )
 {
@@ -120,11 +175,12 @@ int32_t wspc_run_streamed( void* h, const float* pcm, int32_t nSamples, uint32_t
 		*written = want;
 		return S_OK;
 	};
-	struct Progress { int calls = 0; double last = -1.0; bool monotonic = true; } prog;
+	struct Progress { int calls = 0; double last = -1.0, prev = -1.0; bool monotonic = true; } prog;
 	sProgressSink sink;
 	sink.pfn = []( double val, iContext*, void* pv ) noexcept -> HRESULT {
 		Progress* g = static_cast<Progress*>( pv );
-		if( val < g->last ) g->monotonic = false;
+		if( g->last < g->prev ) g->monotonic = false;   // judged one call late: the closing 1.0 is exempt
+		g->prev = g->last;
 		g->last = val;
 		g->calls++;
 		return S_OK;
@@ -145,6 +201,63 @@ int32_t wspc_run_streamed( void* h, const float* pcm, int32_t nSamples, uint32_t
 	if( s->result ) { s->result->Release(); s->result = nullptr; }
 	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
 	return FAILED( hr2 ) ? hr2 : hr;
+}
+// iContext::runCapture over an iAudioCapture made with createAudioCapture.  info[0] = segments collected, [1] = transcriptions started,
+// [2] = stalls, [3] = samples the source handed out.
+int32_t wspc_run_capture( void* h, const float* pcm, int32_t nSamples, uint32_t flags, const char* language, int32_t cpuThreads, float minDuration, float maxDuration, int32_t* info )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return E_POINTER;
+	sFullParams p;
+	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
+	if( FAILED( hr ) ) return hr;
+	p.flags = (eFullParamsFlags)flags;
+	p.language = findLanguageKeyA( language );
+	p.cpuThreads = cpuThreads;
+	p.new_segment_callback = &captureSegCallback;
+	p.new_segment_callback_user_data = s;
+	s->captured.clear();
+	LiveSource src( pcm, (uint32_t)nSamples );
+	sCaptureParams cp;
+	cp.minDuration = minDuration;
+	cp.maxDuration = maxDuration;
+	iAudioCapture* cap = nullptr;
+	hr = createAudioCapture( []( float* m, uint32_t c, uint32_t* w, void* pv ) noexcept -> HRESULT { return static_cast<LiveSource*>( pv )->read( m, c, w ); }, &src, cp, &cap );
+	if( FAILED( hr ) ) return hr;
+	sCaptureCallbacks cb;
+	cb.pv = &src;
+	cb.shouldCancel = []( void* pv ) noexcept -> HRESULT { return static_cast<LiveSource*>( pv )->finished() ? S_FALSE : S_OK; };
+	cb.captureStatus = []( void* pv, eCaptureStatus st ) noexcept -> HRESULT { return static_cast<LiveSource*>( pv )->onStatus( (uint8_t)st ); };
+	hr = s->context->runCapture( p, cb, cap );
+	cap->Release();
+	if( info )
+	{
+		info[ 0 ] = (int32_t)s->captured.size(); info[ 1 ] = src.transcriptions; info[ 2 ] = src.stalls; info[ 3 ] = (int32_t)src.pos;
+	}
+	return hr;
+}
+int64_t wspc_captured_t0( void* h, int32_t i ) { return (int64_t) static_cast<Session*>( h )->captured[ i ].t0; }   // 100 ns ticks
+int64_t wspc_captured_t1( void* h, int32_t i ) { return (int64_t) static_cast<Session*>( h )->captured[ i ].t1; }
+const char* wspc_captured_text( void* h, int32_t i ) { return static_cast<Session*>( h )->captured[ i ].text.c_str(); }
+int32_t wspc_captured_n_tokens( void* h, int32_t i ) { return (int32_t) static_cast<Session*>( h )->captured[ i ].tokens.size(); }
+int32_t wspc_captured_token( void* h, int32_t i, int32_t j ) { return static_cast<Session*>( h )->captured[ i ].tokens[ j ]; }
+// Where the capture loop cuts the same signal, predicted on the CPU with the same (host-only) loop and a transcriber that does nothing:
+// starts[i], sizes[i] in samples; returns the number of utterances.
+int32_t wspc_capture_cuts( const float* pcm, int32_t nSamples, float minDuration, float maxDuration, int64_t* starts, int32_t* sizes, int32_t cap )
+{
+	LiveSource src( pcm, (uint32_t)nSamples );
+	sCaptureParams cp;
+	int32_t n = 0;
+	{
+		wsp::CaptureLoop loop(
+			[ &src ]( float* d, uint32_t c, uint32_t* w ) -> int32_t { return src.read( d, c, w ); },
+			[ &src ]( uint8_t bits ) -> int32_t { return src.onStatus( bits ); },
+			[ & ]( const std::vector<float>& u, int64_t first ) -> int32_t { if( n < cap ) { starts[ n ] = first; sizes[ n ] = (int32_t)u.size(); } n++; return 0; },
+			wsp::CaptureLoop::settingsFromSeconds( minDuration, maxDuration, cp.dropStartSilence, cp.pauseDuration ) );
+		loop.startup();
+		while( !src.finished() && loop.step() >= 0 ) {}
+	}
+	return n;
 }
 void wspc_set_max_len( void* h, int32_t maxLen ) { static_cast<Session*>( h )->maxLen = maxLen; }
 int64_t wspc_token_t0( void* h, int32_t i, int32_t j )

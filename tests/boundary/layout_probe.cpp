@@ -72,5 +72,12 @@ int main()
 	SLOT( iTranscribeResult, getSize ); SLOT( iTranscribeResult, getSegments ); SLOT( iTranscribeResult, getTokens );
 	SLOT( iAudioBuffer, countSamples ); SLOT( iAudioBuffer, getPcmMono ); SLOT( iAudioBuffer, getPcmStereo ); SLOT( iAudioBuffer, getTime );
 	SLOT( iAudioReader, getDuration ); SLOT( iAudioReader, getReader ); SLOT( iAudioReader, requestedStereo );
+	// live capture (MfStructs.h, iMediaFoundation.cl.h:28-34)
+	SZ( sCaptureParams ); OFF( sCaptureParams, minDuration ); OFF( sCaptureParams, maxDuration ); OFF( sCaptureParams, dropStartSilence ); OFF( sCaptureParams, pauseDuration ); OFF( sCaptureParams, flags );
+	SZ( sCaptureCallbacks ); OFF( sCaptureCallbacks, shouldCancel ); OFF( sCaptureCallbacks, captureStatus ); OFF( sCaptureCallbacks, pv );
+	ENUMV( eCaptureStatus::Listening ); ENUMV( eCaptureStatus::Voice ); ENUMV( eCaptureStatus::Transcribing ); ENUMV( eCaptureStatus::Stalled ); ENUMV( eCaptureFlags::Stereo );
+	{ sCaptureParams d; printf( "  sCaptureParams defaults %g %g %g %g %u\n", d.minDuration, d.maxDuration, d.dropStartSilence, d.pauseDuration, d.flags ); }
+	guid( "iAudioCapture", iAudioCapture::iid() );
+	SLOT( iAudioCapture, getReader ); SLOT( iAudioCapture, getParams );
 	return 0;
 }

@@ -47,6 +47,16 @@ def test_pcm_streamer_unit():
     assert "streamer_test: ok" in _run(exe)
 
 
+def test_capture_loop_unit():
+    """The listening loop behind iContext::runCapture (whisper_b200/csrc/capture_loop.h + vad.h, host-only) with a fake transcriber:
+    utterance cutting by the reference's rules, intact samples at the claimed offsets, status reports, stall-and-drop under a slow
+    transcriber, error propagation, E_EOF at the end of the source."""
+    exe = os.path.join(BUILD, "capture_test")
+    if not os.path.exists(exe):
+        pytest.fail("tests/boundary/_build/capture_test is missing: run __graft_entry__.build()")
+    assert "capture_test: ok" in _run(exe)
+
+
 def test_cli_streaming_wav_reader(tmp_path):
     """The CLI's block-wise WAV reader (the pull source it hands to iContext::runStreamed) delivers exactly the samples of its buffered
     reader: 16-bit mono, 16-bit stereo (down-mixed), 32-bit float with a foreign chunk of odd length in front of the data.  No GPU: the
@@ -75,12 +85,12 @@ def test_cli_streaming_wav_reader(tmp_path):
 
 
 def test_com_exports_include_the_streaming_factory():
-    """whisper.def's exports plus the two Linux factories (createAudioBuffer, createAudioReader) are in the product library."""
+    """whisper.def's exports plus the three Linux factories (createAudioBuffer, createAudioReader, createAudioCapture) are in the product library."""
     from whisper_b200 import capi
     so = capi.lib()._name
     syms = subprocess.run(["nm", "-DC", so], stdout=subprocess.PIPE, text=True, check=True).stdout
     for f in ("setupLogger", "loadModel", "findLanguageKeyW", "findLanguageKeyA", "getSupportedLanguages", "listGPUs", "initMediaFoundation",
-              "createAudioBuffer", "createAudioReader"):
+              "createAudioBuffer", "createAudioReader", "createAudioCapture"):
         assert "Whisper::%s(" % f in syms, f
 
 

@@ -41,6 +41,15 @@ def _lib():
     L.wspc_special_tokens.restype = i32; L.wspc_special_tokens.argtypes = [vp, C.POINTER(i32)]
     L.wspc_run_streamed.restype = i32
     L.wspc_run_streamed.argtypes = [vp, C.POINTER(C.c_float), i32, C.c_uint32, C.c_char_p, i32, i32, i32, i32, i32, C.POINTER(i32)]
+    L.wspc_run_capture.restype = i32
+    L.wspc_run_capture.argtypes = [vp, C.POINTER(C.c_float), i32, C.c_uint32, C.c_char_p, i32, C.c_float, C.c_float, C.POINTER(i32)]
+    L.wspc_capture_cuts.restype = i32
+    L.wspc_capture_cuts.argtypes = [C.POINTER(C.c_float), i32, C.c_float, C.c_float, C.POINTER(C.c_int64), C.POINTER(i32), i32]
+    for f in ("wspc_captured_t0", "wspc_captured_t1"):
+        getattr(L, f).restype = C.c_int64; getattr(L, f).argtypes = [vp, i32]
+    L.wspc_captured_text.restype = C.c_char_p; L.wspc_captured_text.argtypes = [vp, i32]
+    L.wspc_captured_n_tokens.restype = i32; L.wspc_captured_n_tokens.argtypes = [vp, i32]
+    L.wspc_captured_token.restype = i32; L.wspc_captured_token.argtypes = [vp, i32, i32]
     L.wspc_set_max_len.argtypes = [vp, i32]
     for f in ("wspc_token_t0", "wspc_token_t1"):
         getattr(L, f).restype = C.c_int64; getattr(L, f).argtypes = [vp, i32, i32]
@@ -142,6 +151,46 @@ def test_run_streamed_without_reader_thread_and_rules(session):
     assert (hr & 0xFFFFFFFF) == 0x80004001                     # E_NOTIMPL (ContextImpl.misc.cpp:393-397)
     hr, segs, _ = run_streamed(L, h, pcm[:8000], flags=2)
     assert hr == 0 and segs == []
+
+
+def capture_signal():
+    """13 s of quiet noise with three voiced stretches (amplitude-modulated harmonic tone) — what the capture loop's voice detector keys on."""
+    n = 16000 * 13
+    t = np.arange(n) / 16000.0
+    x = 0.001 * np.random.default_rng(3).uniform(-1, 1, n)
+    voiced = ((t >= 1.0) & (t < 2.2)) | ((t >= 3.4) & (t < 8.4)) | ((t >= 10.0) & (t < 10.6))
+    tone = sum(np.sin(2 * np.pi * 140 * k * t) / k for k in range(1, 10))
+    return (x + voiced * 0.2 * tone * 0.5 * (1 + np.sin(2 * np.pi * 4 * t))).astype(np.float32)
+
+
+def test_run_capture_transcribes_the_detected_utterances(session):
+    """iContext::runCapture (ContextImpl.capture.cpp:392-429) on a live source played from an array: the listening loop cuts utterances
+    with the voice detector (both pinned on the CPU: tests/test_vad.py, tests/boundary/capture_test.cpp) and transcribes each on its
+    background thread; the segments delivered through new_segment_callback must be those of runFull on exactly those slices, shifted by
+    the utterance's position in the stream (iAudioBuffer::getTime -> mediaTimeOffset, ContextImpl.misc.cpp:264-286)."""
+    L, h = session
+    x = capture_signal()
+    xp = x.ctypes.data_as(C.POINTER(C.c_float))
+    starts, sizes = (C.c_int64 * 16)(), (C.c_int32 * 16)()
+    n_cuts = L.wspc_capture_cuts(xp, x.size, 2.0, 3.0, starts, sizes, 16)
+    assert 3 <= n_cuts <= 16
+    info = (C.c_int32 * 4)()
+    hr = L.wspc_run_capture(h, xp, x.size, 2, b"en", 4, 2.0, 3.0, info)          # NoContext: every utterance starts from a clean prompt
+    assert hr == 0
+    assert info[1] == n_cuts and info[2] == 0 and info[3] == x.size
+    got = [(L.wspc_captured_t0(h, i), L.wspc_captured_t1(h, i), L.wspc_captured_text(h, i).decode(errors="replace"),
+            [L.wspc_captured_token(h, i, j) for j in range(L.wspc_captured_n_tokens(h, i))]) for i in range(info[0])]
+    want = []
+    for k in range(n_cuts):
+        hr, segs = run_full(L, h, x[starts[k]:starts[k] + sizes[k]], flags=2)
+        assert hr == 0
+        offset = starts[k] * 10000000 // 16000
+        want += [(s["t0"] * 100000 + offset, s["t1"] * 100000 + offset, s["text"], s["tokens"]) for s in segs]
+    assert len(want) >= 1
+    assert got == want
+    # parameter validation (ContextImpl.capture.cpp:397-411) and a NULL capture object
+    assert (L.wspc_run_capture(h, xp, x.size, 2, b"en", 4, 0.05, 3.0, info) & 0xFFFFFFFF) == 0x80070057
+    assert (L.wspc_run_capture(h, xp, x.size, 2, b"en", 4, 2.0, 31.0, info) & 0xFFFFFFFF) == 0x80070057
 
 
 @pytest.mark.parametrize("name", list(FULL_RUNS))

@@ -9,6 +9,7 @@
 #include "../../include/whisper_b200.h"
 #include "../../include/whisper_b200_com.h"
 #include "pcm_streamer.h"
+#include "capture_loop.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -243,12 +244,31 @@ namespace
 		HRESULT WSPCALL requestedStereo() const override { return S_FALSE; }
 	};
 
+	class AudioCaptureObj : public Object<iAudioCapture>
+	{
+		CallbackSourceReader* source;
+		sCaptureParams params;
+		~AudioCaptureObj() override { source->Release(); }
+
+	public:
+		AudioCaptureObj( pfnReadPcm f, void* p, const sCaptureParams& cp ) : source( new CallbackSourceReader( f, p ) ), params( cp ) {}
+		HRESULT WSPCALL getReader( IMFSourceReader** pp ) const override
+		{
+			if( !pp ) return E_POINTER;
+			source->AddRef();
+			*pp = source;
+			return S_OK;
+		}
+		const sCaptureParams& WSPCALL getParams() const override { return params; }
+	};
+
 	struct ResultData
 	{
 		// whisper_token_data (whisper.h:71-85): t0 / t1 stay -1 unless token-level timestamps were requested
 		struct Tok { wsp_token_data d; int64_t t0 = -1, t1 = -1; float vlen = 0.0f; };
 		struct Seg { int64_t t0, t1; std::string text; std::vector<Tok> tokens; };
 		std::vector<Seg> segs;
+		int64_t timeOffset = 0;   // 100 ns ticks: iAudioBuffer::getTime of the clip (ContextImpl::mediaTimeOffset, ContextImpl.misc.cpp:264-286, 364)
 	};
 
 	class ResultObj : public Object<iTranscribeResult>
@@ -271,8 +291,8 @@ namespace
 				const auto& s = rd.segs[ i ];
 				sSegment seg;
 				seg.text = texts[ i ].c_str();
-				seg.time.begin.ticks = (uint64_t)( s.t0 * 100000 );
-				seg.time.end.ticks = (uint64_t)( s.t1 * 100000 );
+				seg.time.begin.ticks = (uint64_t)( s.t0 * 100000 + rd.timeOffset );
+				seg.time.end.ticks = (uint64_t)( s.t1 * 100000 + rd.timeOffset );
 				seg.firstToken = (uint32_t)tokens.size();
 				seg.countTokens = 0;
 				if( makeTokens )
@@ -283,8 +303,8 @@ namespace
 						const wsp_token_data& t = tok.d;
 						sToken tk;
 						tk.text = wsp_model_token_text( e->model, t.id );
-						tk.time.begin.ticks = (uint64_t)( tok.t0 * 100000 );   // -1 (not computed) converts like the reference's MFllMulDiv( -1, ... )
-						tk.time.end.ticks = (uint64_t)( tok.t1 * 100000 );
+						tk.time.begin.ticks = (uint64_t)( tok.t0 * 100000 + rd.timeOffset );   // -1 (not computed) converts like the reference's MFllMulDiv( -1, ... )
+						tk.time.end.ticks = (uint64_t)( tok.t1 * 100000 + rd.timeOffset );
 						tk.probability = t.p; tk.probabilityTimestamp = t.pt; tk.ptsum = t.ptsum; tk.vlen = tok.vlen;
 						tk.id = t.id;
 						tk.flags = t.id >= e->tokEot() ? eTokenFlags::Special : eTokenFlags::None;
@@ -355,11 +375,7 @@ namespace
 
 		HRESULT WSPCALL runFull( const sFullParams& params, const iAudioBuffer* buffer ) override;
 		HRESULT WSPCALL runStreamed( const sFullParams& params, const sProgressSink& progress, const iAudioReader* reader ) override;
-		HRESULT WSPCALL runCapture( const sFullParams&, const sCaptureCallbacks&, const iAudioCapture* ) override
-		{
-			logMessage( eLogLevel::Error, "whisper_b200: runCapture is not implemented (same as the Reference back-end, whisperCom.cpp:144-148)" );
-			return E_NOTIMPL;
-		}
+		HRESULT WSPCALL runCapture( const sFullParams& params, const sCaptureCallbacks& callbacks, const iAudioCapture* reader ) override;
 		HRESULT WSPCALL getResults( eResultFlags flags, iTranscribeResult** pp ) const override
 		{
 			if( !pp ) return E_POINTER;
@@ -790,6 +806,8 @@ namespace
 		if( !buffer ) return E_POINTER;
 		HR( checkParams( params ) );
 		results.segs.clear();                                                                     // whisper.cpp:2771-2773
+		results.timeOffset = 0;
+		HR( buffer->getTime( results.timeOffset ) );                                              // ContextImpl.misc.cpp:364
 		const float* pcm = buffer->getPcmMono();
 		const int nSamples = (int)buffer->countSamples();
 		if( !pcm && nSamples > 0 ) return E_POINTER;
@@ -820,6 +838,7 @@ namespace
 		}
 		HR( checkParams( params ) );
 		results.segs.clear();
+		results.timeOffset = 0;                                                                   // ContextImpl.misc.cpp:399
 		int64_t ticks = 0;
 		HR( reader->getDuration( ticks ) );
 		if( ticks < 0 ) return E_INVALIDARG;
@@ -859,6 +878,64 @@ namespace
 			return S_OK;
 		};
 		return runImpl( params, progress, mel, false );
+	}
+
+	// iContext::runCapture (Whisper/Whisper/ContextImpl.capture.cpp:392-429): listen to a live source until the client's shouldCancel
+	// says stop; the voice activity detector cuts the audio into utterances and each one goes through runFull on a background thread
+	// while listening continues (csrc/capture_loop.h).  Results reach the client through sFullParams::new_segment_callback — on that
+	// background thread, as in the reference — with times offset by the utterance's position in the stream (iAudioBuffer::getTime).
+	HRESULT WSPCALL ContextObj::runCapture( const sFullParams& params, const sCaptureCallbacks& callbacks, const iAudioCapture* reader )
+	{
+		if( !reader ) return E_POINTER;
+		const sCaptureParams& cp = reader->getParams();
+		if( !( cp.minDuration >= 0.125f && cp.minDuration <= 30.0f ) )
+		{
+			logMessage( eLogLevel::Error, "%s parameter %g is out of range", "minDuration", cp.minDuration );
+			return E_INVALIDARG;
+		}
+		if( !( cp.maxDuration >= 0.125f && cp.maxDuration <= 30.0f ) )
+		{
+			logMessage( eLogLevel::Error, "%s parameter %g is out of range", "maxDuration", cp.maxDuration );
+			return E_INVALIDARG;
+		}
+		IMFSourceReader* src = nullptr;
+		HR( reader->getReader( &src ) );
+		if( !src ) return E_POINTER;
+		struct Releaser { IMFSourceReader* p; ~Releaser() { p->Release(); } } releaser{ src };
+
+		// the utterance handed to runFull: a stack object, never reference-counted away (TranscribeBufferObj, ContextImpl.capture.cpp:15-53)
+		struct Utterance : public iAudioBuffer
+		{
+			const std::vector<float>& pcm;
+			int64_t firstSample;
+			Utterance( const std::vector<float>& p, int64_t f ) : pcm( p ), firstSample( f ) {}
+			HRESULT WSPCALL QueryInterface( REFIID, void** ) override { return E_NOINTERFACE; }
+			uint32_t WSPCALL AddRef() override { return 1; }
+			uint32_t WSPCALL Release() override { return 1; }
+			uint32_t WSPCALL countSamples() const override { return (uint32_t)pcm.size(); }
+			const float* WSPCALL getPcmMono() const override { return pcm.empty() ? nullptr : pcm.data(); }
+			const float* WSPCALL getPcmStereo() const override { return nullptr; }
+			HRESULT WSPCALL getTime( int64_t& rdi ) const override { rdi = firstSample * 10000000 / 16000; return S_OK; }
+		};
+		wsp::CaptureLoop::StatusFn status;
+		if( callbacks.captureStatus )
+			status = [ &callbacks ]( uint8_t bits ) -> int32_t { return callbacks.captureStatus( callbacks.pv, (eCaptureStatus)bits ); };
+		wsp::CaptureLoop loop(
+			[ src ]( float* dst, uint32_t cap, uint32_t* got ) -> int32_t { return src->readPcm( dst, cap, got ); },
+			status,
+			[ this, &params ]( const std::vector<float>& pcm, int64_t firstSample ) -> int32_t {
+				Utterance u( pcm, firstSample );
+				return runFull( params, &u );
+			},
+			wsp::CaptureLoop::settingsFromSeconds( cp.minDuration, cp.maxDuration, cp.dropStartSilence, cp.pauseDuration ) );
+		HR( loop.startup() );
+		while( true )
+		{
+			const HRESULT cancel = callbacks.shouldCancel ? callbacks.shouldCancel( callbacks.pv ) : S_OK;
+			if( FAILED( cancel ) ) return cancel;
+			if( cancel != S_OK ) return S_OK;      // the loop's destructor lets a transcription in flight finish
+			HR( loop.step() );
+		}
 	}
 
 	HRESULT ContextObj::runImpl( const sFullParams& params, const sProgressSink& progress, const MelSource& mel, const bool tokenTimestamps )
@@ -1175,6 +1252,12 @@ namespace Whisper
 		if( !pp || !pfn ) return E_POINTER;
 		if( durationTicks < 0 ) return E_INVALIDARG;
 		*pp = new AudioReaderObj( pfn, pv, durationTicks );
+		return S_OK;
+	}
+	HRESULT WSPCALL createAudioCapture( pfnReadPcm pfn, void* pv, const sCaptureParams& captureParams, iAudioCapture** pp )
+	{
+		if( !pp || !pfn ) return E_POINTER;
+		*pp = new AudioCaptureObj( pfn, pv, captureParams );
 		return S_OK;
 	}
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp )
