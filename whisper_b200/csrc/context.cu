@@ -210,6 +210,30 @@ namespace wsp
 		return WSP_OK;
 	}
 
+	// log-mel of chunks [0, batch) in one pair of launches per 16 chunks: pcmOf( b ) / samplesOf( b ) name chunk b's device PCM
+	template<class P, class N>
+	static int melBatchFromDevicePcm( Context& c, int batch, P pcmOf, N samplesOf )
+	{
+		for( int b0 = 0; b0 < batch; b0 += kern::MEL_BATCH )
+		{
+			kern::MelBatch mb{};
+			mb.count = batch - b0 < kern::MEL_BATCH ? batch - b0 : kern::MEL_BATCH;
+			mb.maxSlots = c.melMax + b0;
+			for( int i = 0; i < mb.count; i++ )
+			{
+				const int n = samplesOf( b0 + i );
+				WSP_CHECK( ensureMelSlot( c, b0 + i, n / 160 ) );   // whisper.cpp:2080
+				mb.pcm[ i ] = pcmOf( b0 + i );
+				mb.mel[ i ] = c.slots[ b0 + i ].mel;
+				mb.nSamples[ i ] = n;
+				mb.nLen[ i ] = n / 160;
+			}
+			WSP_CUDA( kern::melBatch( c.e->mel, mb, c.stream ) );
+			launched( 3 );
+		}
+		return WSP_OK;
+	}
+
 	static int ensurePcm( Context& c, size_t floats )
 	{
 		if( floats <= c.pcmCap ) return WSP_OK;
@@ -674,24 +698,24 @@ namespace wsp
 		{
 			// inputs already in HBM (wsp_upload_pcm): the log-mel front end still runs inside the timed region
 			for( int b = 0; b < batch; b++ )
-			{
-				const MelSlot& ms = c.slots[ b ];
-				if( !ms.pcm ) return fail( WSP_E_INVALIDARG, "no resident PCM in slot " + std::to_string( b ) + " (call wsp_upload_pcm)" );
-				WSP_CHECK( melFromDevicePcm( c, b, ms.pcm, ms.pcmSamples ) );
-			}
+				if( !c.slots[ b ].pcm ) return fail( WSP_E_INVALIDARG, "no resident PCM in slot " + std::to_string( b ) + " (call wsp_upload_pcm)" );
+			WSP_CHECK( melBatchFromDevicePcm( c, batch, [ & ]( int b ) { return (const float*)c.slots[ b ].pcm; }, [ & ]( int b ) { return c.slots[ b ].pcmSamples; } ) );
 		}
 		else
 		{
 			size_t total = 0;
 			for( int b = 0; b < batch; b++ ) { if( nSamples[ b ] < 0 ) return fail( WSP_E_INVALIDARG, "n_samples" ); total += (size_t)nSamples[ b ]; }
 			WSP_CHECK( ensurePcm( c, total ? total : 1 ) );
+			std::vector<size_t> offs( (size_t)batch );
 			size_t off = 0;
 			for( int b = 0; b < batch; b++ )
 			{
-				WSP_CUDA( cudaMemcpyAsync( c.pcmDev + off, pcm[ b ], (size_t)nSamples[ b ] * 4, cudaMemcpyHostToDevice, s ) );
-				WSP_CHECK( melFromDevicePcm( c, b, c.pcmDev + off, nSamples[ b ] ) );
+				if( nSamples[ b ] > 0 )
+					WSP_CUDA( cudaMemcpyAsync( c.pcmDev + off, pcm[ b ], (size_t)nSamples[ b ] * 4, cudaMemcpyHostToDevice, s ) );
+				offs[ (size_t)b ] = off;
 				off += (size_t)nSamples[ b ];
 			}
+			WSP_CHECK( melBatchFromDevicePcm( c, batch, [ & ]( int b ) { return (const float*)( c.pcmDev + offs[ (size_t)b ] ); }, [ & ]( int b ) { return (int)nSamples[ b ]; } ) );
 		}
 		WSP_CUDA( cudaEventRecord( c.ev[ 1 ], s ) );
 		WSP_CHECK( encodeAsync( c, nullptr, batch ) );

@@ -35,6 +35,18 @@ namespace kern
 		const float* filters = nullptr;  // [80][201] from the model file
 	};
 	// pcm [nSamples] -> raw log10 mel [80][nLen] (row = band) and the running maximum (ordered-int encoded float) in *maxSlot
+	// up to MEL_BATCH chunks transformed and normalised by one launch each (power, normalise); maxSlots[b] is chunk b's maximum
+	constexpr int MEL_BATCH = 16;
+	struct MelBatch
+	{
+		const float* pcm[ MEL_BATCH ];
+		float* mel[ MEL_BATCH ];       // [80][nLen[b]]
+		int nSamples[ MEL_BATCH ];
+		int nLen[ MEL_BATCH ];
+		int* maxSlots;                 // [count] consecutive
+		int count;
+	};
+	cudaError_t melBatch( const MelTables& tb, const MelBatch& mb, cudaStream_t s );
 	cudaError_t melPower( const MelTables& tb, const float* pcm, int nSamples, int nLen, float* melRaw, int* maxSlot, cudaStream_t s );
 	// in place: clamp to (max - 8), (x + 4) / 4
 	cudaError_t melNormalize( float* mel, int count, const int* maxSlot, cudaStream_t s );

@@ -31,8 +31,7 @@ namespace kern
 	constexpr int MEL_BINS = 201;
 	constexpr int MEL_BANDS = 80;
 
-	__global__ void __launch_bounds__( 256 )
-		mel_power_kernel( MelTables tb, const float* __restrict__ pcm, int nSamples, int nLen, float* __restrict__ melRaw, int* maxSlot )
+	__device__ __forceinline__ void melFrame( const MelTables& tb, const float* __restrict__ pcm, int nSamples, int nLen, float* __restrict__ melRaw, int* maxSlot, const int frame )
 	{
 		__shared__ float sx[ MEL_FFT ];
 		__shared__ double sc[ MEL_FFT ];
@@ -41,7 +40,6 @@ namespace kern
 		__shared__ double sB[ 2 ][ MEL_FFT / 4 ];   //                 sine-side combinations
 		__shared__ float sp[ MEL_BINS + 7 ];
 		__shared__ float smax[ 8 ];
-		const int frame = blockIdx.x;
 		const int tid = threadIdx.x;
 		const int offset = frame * MEL_HOP;
 		for( int n = tid; n < MEL_FFT; n += blockDim.x )
@@ -124,24 +122,62 @@ namespace kern
 		}
 	}
 
-	__global__ void mel_norm_kernel( float* mel, int count, const int* maxSlot )
+	__global__ void __launch_bounds__( 256 )
+		mel_power_kernel( MelTables tb, const float* __restrict__ pcm, int nSamples, int nLen, float* __restrict__ melRaw, int* maxSlot )
 	{
-		const int i = blockIdx.x * blockDim.x + threadIdx.x;
-		if( i >= count ) return;
+		melFrame( tb, pcm, nSamples, nLen, melRaw, maxSlot, blockIdx.x );
+	}
+	// the same for up to MEL_BATCH chunks in one launch: blockIdx.y = chunk (the driver loop of BASELINE.md §2 transforms B chunks per step)
+	__global__ void __launch_bounds__( 256 )
+		mel_power_batch_kernel( MelTables tb, MelBatch mb )
+	{
+		const int b = blockIdx.y;
+		if( (int)blockIdx.x >= mb.nLen[ b ] ) return;
+		melFrame( tb, mb.pcm[ b ], mb.nSamples[ b ], mb.nLen[ b ], mb.mel[ b ], mb.maxSlots + b, blockIdx.x );
+	}
+
+	__device__ __forceinline__ void melNormOne( float* mel, int i, const int* maxSlot )
+	{
 		// whisper.cpp:2161-2177: mmax (double) -= 8.0; clamp; (x + 4.0) / 4.0 in double, stored as float
 		const double mmax = (double)floatFromOrdered( *maxSlot ) - 8.0;
 		float v = mel[ i ];
 		if( (double)v < mmax ) v = (float)mmax;
 		mel[ i ] = (float)( ( (double)v + 4.0 ) / 4.0 );
 	}
+	__global__ void mel_norm_kernel( float* mel, int count, const int* maxSlot )
+	{
+		const int i = blockIdx.x * blockDim.x + threadIdx.x;
+		if( i >= count ) return;
+		melNormOne( mel, i, maxSlot );
+	}
+	__global__ void mel_norm_batch_kernel( MelBatch mb )
+	{
+		const int b = blockIdx.y;
+		const int i = blockIdx.x * blockDim.x + threadIdx.x;
+		if( i >= MEL_BANDS * mb.nLen[ b ] ) return;
+		melNormOne( mb.mel[ b ], i, mb.maxSlots + b );
+	}
 
-	__global__ void init_max_kernel( int* maxSlot ) { *maxSlot = orderedFromFloat( -1e20f ); }
+	__global__ void init_max_kernel( int* maxSlot ) { maxSlot[ threadIdx.x ] = orderedFromFloat( -1e20f ); }
 
 	cudaError_t melPower( const MelTables& tb, const float* pcm, int nSamples, int nLen, float* melRaw, int* maxSlot, cudaStream_t s )
 	{
 		init_max_kernel<<<1, 1, 0, s>>>( maxSlot );
 		if( nLen > 0 )
 			mel_power_kernel<<<nLen, 256, 0, s>>>( tb, pcm, nSamples, nLen, melRaw, maxSlot );
+		return cudaGetLastError();
+	}
+	cudaError_t melBatch( const MelTables& tb, const MelBatch& mb, cudaStream_t s )
+	{
+		if( mb.count < 1 || mb.count > MEL_BATCH ) return cudaErrorInvalidValue;
+		int maxLen = 0;
+		for( int b = 0; b < mb.count; b++ ) maxLen = mb.nLen[ b ] > maxLen ? mb.nLen[ b ] : maxLen;
+		init_max_kernel<<<1, mb.count, 0, s>>>( mb.maxSlots );
+		if( maxLen > 0 )
+		{
+			mel_power_batch_kernel<<<dim3( maxLen, mb.count ), 256, 0, s>>>( tb, mb );
+			mel_norm_batch_kernel<<<dim3( ( MEL_BANDS * maxLen + 255 ) / 256, mb.count ), 256, 0, s>>>( mb );
+		}
 		return cudaGetLastError();
 	}
 	cudaError_t melNormalize( float* mel, int count, const int* maxSlot, cudaStream_t s )
