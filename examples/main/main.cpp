@@ -21,7 +21,7 @@ namespace
 	{
 		int nThreads = 4, offsetMs = 0, durationMs = 0, maxContext = -1, maxLen = 0, device = 0;
 		float wordThold = 0.01f;
-		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false, stream = false, verifyStream = false;
+		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false, stream = false, verifyStream = false, diarize = false;
 		std::string language = "en", model = "models/ggml-base.en.bin", prompt;
 		std::vector<std::string> inputs;
 	};
@@ -39,6 +39,7 @@ namespace
 		fprintf( stderr, "  -ml N,    --max-len N     [%-7d] maximum segment length in characters\n", p.maxLen );
 		fprintf( stderr, "  -wt N,    --word-thold N  [%-7.2f] word timestamp probability threshold\n", p.wordThold );
 		fprintf( stderr, "  -tr,      --translate     translate from source language to english\n" );
+		fprintf( stderr, "  -di,      --diarize       stereo audio diarization: prefix every segment with (speaker 0 / 1 / ?)\n" );
 		fprintf( stderr, "  -otxt,    --output-txt    output result in a text file\n" );
 		fprintf( stderr, "  -ovtt,    --output-vtt    output result in a vtt file\n" );
 		fprintf( stderr, "  -osrt,    --output-srt    output result in a srt file\n" );
@@ -82,6 +83,7 @@ namespace
 			else if( a == "--prompt" ) p.prompt = next();
 			else if( a == "-st" || a == "--stream" ) p.stream = true;
 			else if( a == "--verify-stream" ) p.verifyStream = true;
+			else if( a == "-di" || a == "--diarize" ) p.diarize = true;
 			else if( a == "-p" || a == "--processors" || a == "-on" || a == "--offset-n" ) next();
 			else { fprintf( stderr, "error: unknown or unsupported argument: %s\n", a.c_str() ); usage( argv[ 0 ], p ); return false; }
 		}
@@ -89,7 +91,8 @@ namespace
 	}
 
 	// ---- RIFF/WAVE -> 16 kHz mono f32 -------------------------------------------------------------------------------
-	bool readWav( const std::string& path, std::vector<float>& mono16k )
+	// stereo16k (optional): interleaved left/right of a file with two or more channels, for --diarize; left empty for mono files
+	bool readWav( const std::string& path, std::vector<float>& mono16k, std::vector<float>* stereo16k = nullptr )
 	{
 		FILE* f = fopen( path.c_str(), "rb" );
 		if( !f ) { fprintf( stderr, "error: cannot open %s\n", path.c_str() ); return false; }
@@ -120,19 +123,42 @@ namespace
 			return false;
 		}
 		const size_t frame = (size_t)channels * bits / 8, n = dataLen / frame;
-		std::vector<float> mono( n );
+		std::vector<float> mono( n ), stereo;
+		const bool keepStereo = stereo16k && channels >= 2;
+		if( keepStereo ) stereo.resize( 2 * n );
 		for( size_t i = 0; i < n; i++ )
 		{
 			float acc = 0;
 			for( uint32_t c = 0; c < channels; c++ )
 			{
 				const uint8_t* p = buf.data() + dataOff + i * frame + (size_t)c * bits / 8;
-				if( bits == 16 ) acc += (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
-				else { float v; memcpy( &v, p, 4 ); acc += v; }
+				float v;
+				if( bits == 16 ) v = (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
+				else memcpy( &v, p, 4 );
+				acc += v;
+				if( keepStereo && c < 2 ) stereo[ 2 * i + c ] = v;
 			}
 			mono[ i ] = acc / (float)channels;
 		}
-		if( rate == 16000 ) { mono16k.swap( mono ); return true; }
+		if( stereo16k ) stereo16k->clear();
+		if( rate == 16000 )
+		{
+			mono16k.swap( mono );
+			if( keepStereo ) stereo16k->swap( stereo );
+			return true;
+		}
+		if( keepStereo )
+		{
+			const size_t ms = (size_t)( (double)n * 16000.0 / rate );
+			stereo16k->resize( 2 * ms );
+			for( size_t i = 0; i < ms; i++ )
+			{
+				const double x = (double)i * rate / 16000.0;
+				const size_t i0 = (size_t)x, i1 = std::min( i0 + 1, n - 1 );
+				const float t = (float)( x - (double)i0 );
+				for( int c = 0; c < 2; c++ ) ( *stereo16k )[ 2 * i + c ] = stereo[ 2 * i0 + c ] * ( 1.0f - t ) + stereo[ 2 * i1 + c ] * t;
+			}
+		}
 		const size_t m = (size_t)( (double)n * 16000.0 / rate );
 		mono16k.resize( m );
 		for( size_t i = 0; i < m; i++ )
@@ -272,7 +298,7 @@ namespace
 		return true;
 	}
 
-	struct SegmentPrinter { bool noTimestamps; uint32_t printed = 0; };
+	struct SegmentPrinter { bool noTimestamps; bool diarize = false; uint32_t printed = 0; };
 	HRESULT onNewSegment( iContext* ctx, uint32_t nNew, void* pv ) noexcept
 	{
 		SegmentPrinter* sp = static_cast<SegmentPrinter*>( pv );
@@ -283,8 +309,13 @@ namespace
 		const sSegment* segs = res->getSegments();
 		for( uint32_t i = len.countSegments - std::min( nNew, len.countSegments ); i < len.countSegments; i++ )
 		{
+			// --diarize (Examples/main/main.cpp:95-117): which stereo channel carried this segment
+			const char* speaker = "";
+			eSpeakerChannel channel;
+			if( sp->diarize && SUCCEEDED( ctx->detectSpeaker( segs[ i ].time, channel ) ) && channel != eSpeakerChannel::NoStereoData )
+				speaker = channel == eSpeakerChannel::Left ? "(speaker 0)" : ( channel == eSpeakerChannel::Right ? "(speaker 1)" : "(speaker ?)" );
 			if( sp->noTimestamps ) printf( "%s", segs[ i ].text );
-			else printf( "[%s --> %s]  %s\n", fmtTime( segs[ i ].time.begin.ticks, false ).c_str(), fmtTime( segs[ i ].time.end.ticks, false ).c_str(), segs[ i ].text );
+			else printf( "[%s --> %s]  %s%s\n", fmtTime( segs[ i ].time.begin.ticks, false ).c_str(), fmtTime( segs[ i ].time.end.ticks, false ).c_str(), speaker, segs[ i ].text );
 		}
 		fflush( stdout );
 		return S_OK;
@@ -354,8 +385,8 @@ int main( int argc, char** argv )
 		// like the reference's CLI (STREAM_AUDIO, main.cpp:304-319): stream unless token-level timestamps are wanted; here streaming
 		// is opt-in (-st) and limited to files that need no resampling
 		WavStream wavStream;
-		bool streamed = params.stream && params.maxLen <= 0;
-		if( params.stream && !streamed ) fprintf( stderr, "main: WARNING: --max-len needs the whole clip, falling back to buffered mode\n" );
+		bool streamed = params.stream && params.maxLen <= 0 && !params.diarize;
+		if( params.stream && !streamed ) fprintf( stderr, "main: WARNING: --max-len / --diarize need the whole clip, falling back to buffered mode\n" );
 		if( streamed )
 		{
 			if( !wavStream.open( fname ) ) return 8;
@@ -374,8 +405,12 @@ int main( int argc, char** argv )
 		}
 		else
 		{
-			if( !readWav( fname, pcm ) ) return 8;
-			if( FAILED( createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer ) ) ) return 9;
+			std::vector<float> stereo;
+			if( !readWav( fname, pcm, params.diarize ? &stereo : nullptr ) ) return 8;
+			if( params.diarize && stereo.empty() ) fprintf( stderr, "main: WARNING: %s has one channel, --diarize has nothing to compare\n", fname.c_str() );
+			const HRESULT hrBuf = stereo.empty() ? createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer )
+				: createAudioBufferStereo( pcm.data(), stereo.data(), (uint32_t)pcm.size(), &buffer );
+			if( FAILED( hrBuf ) ) return 9;
 		}
 
 		sFullParams wp;
@@ -394,7 +429,7 @@ int main( int argc, char** argv )
 		wp.thold_pt = params.wordThold;
 		wp.max_len = params.maxLen;
 		if( !prompt.empty() ) { wp.prompt_tokens = prompt.data(); wp.prompt_n_tokens = (int)prompt.size(); }
-		SegmentPrinter printer{ params.noTimestamps };
+		SegmentPrinter printer{ params.noTimestamps, params.diarize };
 		wp.new_segment_callback = &onNewSegment;
 		wp.new_segment_callback_user_data = &printer;
 		if( streamed )

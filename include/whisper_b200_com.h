@@ -256,6 +256,9 @@ namespace Whisper
 	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp );   // E_NOTIMPL: audio decoding is the host application's business here
 	// not in the reference: an iAudioBuffer over caller-owned 16 kHz mono f32 PCM (replaces the Media Foundation loader, Whisper/MF/)
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp );
+	// the same with the interleaved left/right samples kept next to the mono mix (loadAudioFile( path, stereo = true ), the --diarize
+	// option of the reference CLI): what iContext::detectSpeaker compares
+	HRESULT WSPCALL createAudioBufferStereo( const float* pcmMono, const float* pcmStereo, uint32_t countSamples, iAudioBuffer** pp );
 	// not in the reference either: an iAudioReader over a caller-supplied pull callback (replaces iMediaFoundation::openAudioFile /
 	// loadAudioFileData, Whisper/API/iMediaFoundation.cl.h:38-39).  `durationTicks` announces the stream length (100 ns units).
 	using pfnReadPcm = HRESULT( WSPCALL* )( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept;

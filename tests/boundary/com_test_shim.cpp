@@ -259,6 +259,55 @@ int32_t wspc_capture_cuts( const float* pcm, int32_t nSamples, float minDuration
 	}
 	return n;
 }
+// runFull on a buffer that keeps its interleaved stereo samples; iContext::detectSpeaker is asked about every new segment from inside
+// new_segment_callback (the only place it works, like in the reference).  speakers[i] = eSpeakerChannel of segment i; returns the
+// HRESULT of runFull, or of the first failing detectSpeaker.  pcmStereo == NULL uses a mono-only buffer.  *afterRun receives what
+// detectSpeaker answers once the run is over.
+int32_t wspc_run_full_stereo( void* h, const float* pcmMono, const float* pcmStereo, int32_t nSamples, uint32_t flags, int32_t durationMs, int32_t* speakers, int32_t cap, int32_t* afterRun )
+{
+	Session* s = static_cast<Session*>( h );
+	if( !s ) return E_POINTER;
+	sFullParams p;
+	HRESULT hr = s->context->fullDefaultParams( eSamplingStrategy::Greedy, &p );
+	if( FAILED( hr ) ) return hr;
+	p.flags = (eFullParamsFlags)flags;
+	p.duration_ms = durationMs;
+	struct Log { int32_t* out; int32_t cap, n; HRESULT failed; } log{ speakers, cap, 0, S_OK };
+	p.new_segment_callback = []( iContext* ctx, uint32_t nNew, void* pv ) noexcept -> HRESULT {
+		Log* g = static_cast<Log*>( pv );
+		iTranscribeResult* res = nullptr;
+		if( FAILED( ctx->getResults( eResultFlags::Timestamps, &res ) ) ) return E_FAIL;
+		sTranscribeLength len;
+		res->getSize( len );
+		for( uint32_t i = len.countSegments - nNew; i < len.countSegments; i++ )
+		{
+			eSpeakerChannel ch = eSpeakerChannel::Unsure;
+			const HRESULT hr = ctx->detectSpeaker( res->getSegments()[ i ].time, ch );
+			if( FAILED( hr ) ) g->failed = hr;
+			if( g->n < g->cap ) g->out[ g->n ] = (int32_t)(uint8_t)ch;
+			g->n++;
+		}
+		res->Release();
+		return S_OK;
+	};
+	p.new_segment_callback_user_data = &log;
+	iAudioBuffer* buf = nullptr;
+	hr = pcmStereo ? createAudioBufferStereo( pcmMono, pcmStereo, (uint32_t)nSamples, &buf ) : createAudioBuffer( pcmMono, (uint32_t)nSamples, &buf );
+	if( FAILED( hr ) ) return hr;
+	hr = s->context->runFull( p, buf );
+	buf->Release();
+	if( afterRun )
+	{
+		sTimeInterval t{ { 0 }, { 10000000 } };
+		eSpeakerChannel ch;
+		*afterRun = s->context->detectSpeaker( t, ch );
+	}
+	if( FAILED( hr ) ) return hr;
+	if( FAILED( log.failed ) ) return log.failed;
+	if( s->result ) { s->result->Release(); s->result = nullptr; }
+	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
+	return FAILED( hr2 ) ? hr2 : log.n;
+}
 void wspc_set_max_len( void* h, int32_t maxLen ) { static_cast<Session*>( h )->maxLen = maxLen; }
 int64_t wspc_token_t0( void* h, int32_t i, int32_t j )
 {

@@ -63,6 +63,27 @@ def test_cli_streamed_equals_buffered(tmp_path):
     assert len(outs[0]) >= 8 and outs[0] == outs[1]
 
 
+def test_cli_diarize_labels_the_louder_channel(tmp_path):
+    """-di: a stereo file keeps its channels (createAudioBufferStereo) and every printed segment carries iContext::detectSpeaker's answer in
+    the reference CLI's wording (Examples/main/main.cpp:95-117, 136); the transcript itself is that of the mono mix."""
+    mono = full_pcm(10)[:16000 * 40]
+    t = np.arange(mono.size) / 16000.0
+    g_left = np.where((t // 4).astype(np.int64) % 2 == 0, 1.6, 0.4)          # left louder for 4 s, right louder for 4 s, ...
+    st = np.empty(2 * mono.size, np.float64)
+    st[0::2] = mono * g_left
+    st[1::2] = mono * (2.0 - g_left)
+    wav = str(tmp_path / "stereo.wav")
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(np.clip(np.round(st * 16384.0), -32768, 32767).astype("<i2").tobytes())
+    r = subprocess.run([EXE, "-m", synth.model_path(FULL_MODEL), "-f", wav, "-d", "32000", "-di"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("[")]
+    assert len(lines) >= 8 and all("(speaker " in ln for ln in lines)
+    # segments inside the first 4 s are left-dominated, those inside the next 4 s right-dominated
+    assert "(speaker 0)" in lines[0] and any("(speaker 1)" in ln for ln in lines)
+
+
 def test_cli_rejects_bad_input(tmp_path):
     if not os.path.exists(EXE):
         pytest.skip("CLI not built")

@@ -50,6 +50,8 @@ def _lib():
     L.wspc_captured_text.restype = C.c_char_p; L.wspc_captured_text.argtypes = [vp, i32]
     L.wspc_captured_n_tokens.restype = i32; L.wspc_captured_n_tokens.argtypes = [vp, i32]
     L.wspc_captured_token.restype = i32; L.wspc_captured_token.argtypes = [vp, i32, i32]
+    L.wspc_run_full_stereo.restype = i32
+    L.wspc_run_full_stereo.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, C.c_uint32, i32, C.POINTER(i32), i32, C.POINTER(i32)]
     L.wspc_set_max_len.argtypes = [vp, i32]
     for f in ("wspc_token_t0", "wspc_token_t1"):
         getattr(L, f).restype = C.c_int64; getattr(L, f).argtypes = [vp, i32, i32]
@@ -151,6 +153,36 @@ def test_run_streamed_without_reader_thread_and_rules(session):
     assert (hr & 0xFFFFFFFF) == 0x80004001                     # E_NOTIMPL (ContextImpl.misc.cpp:393-397)
     hr, segs, _ = run_streamed(L, h, pcm[:8000], flags=2)
     assert hr == 0 and segs == []
+
+
+def test_detect_speaker_from_the_segment_callback(session):
+    """iContext::detectSpeaker (ContextImpl.diarize.cpp:75-112): per-channel sum of |sample| over a segment's interval of the stereo
+    samples that came with the clip, a channel wins when it exceeds 1.1 x the other; only answers while a run is in progress."""
+    L, h = session
+    mono = full_pcm(10)[:16000 * 40]
+    t = np.arange(mono.size) / 16000.0
+    # left loud for 2 s, right loud for 2 s, balanced for 2 s, ...; (left + right) / 2 stays the mono mix
+    phase = (t // 2).astype(np.int64) % 3
+    g_left = np.choose(phase, [1.6, 0.4, 1.0]).astype(np.float32)
+    stereo = np.empty(2 * mono.size, np.float32)
+    stereo[0::2] = mono * g_left
+    stereo[1::2] = mono * (2.0 - g_left)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    speakers, after = (C.c_int32 * 64)(), C.c_int32(0)
+    n = L.wspc_run_full_stereo(h, fp(mono), fp(stereo), mono.size, 2, 32000, speakers, 64, C.byref(after))
+    assert n >= 8
+    segs = _segments(L, h)
+    assert len(segs) == n
+    want = []
+    for s in segs:
+        a, b = s["t0"] * 160, s["t1"] * 160
+        left, right = np.abs(stereo[2 * a:2 * b:2]).sum(dtype=np.float64), np.abs(stereo[2 * a + 1:2 * b:2]).sum(dtype=np.float64)
+        want.append((1 if left > 1.1 * right else 0) | (2 if right > 1.1 * left else 0))
+    assert list(speakers)[:n] == want and {1, 2} <= set(want)          # Left = 1, Right = 2, Unsure = 0 (TranscribeStructs.h)
+    assert (after.value & 0xFFFFFFFF) == 0x80040007                    # OLE_E_BLANK outside the callbacks
+    # a mono-only buffer: NoStereoData
+    n2 = L.wspc_run_full_stereo(h, fp(mono), None, mono.size, 2, 32000, speakers, 64, None)
+    assert n2 == n and set(list(speakers)[:n2]) == {0xFF}
 
 
 def capture_signal():

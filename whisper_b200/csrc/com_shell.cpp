@@ -200,13 +200,14 @@ namespace
 
 	class AudioBufferObj : public Object<iAudioBuffer>
 	{
-		std::vector<float> pcm;
+		std::vector<float> pcm, stereo;
 
 	public:
 		AudioBufferObj( const float* p, uint32_t n ) : pcm( p, p + n ) {}
+		AudioBufferObj( const float* p, const float* interleaved, uint32_t n ) : pcm( p, p + n ), stereo( interleaved, interleaved + 2 * (size_t)n ) {}
 		uint32_t WSPCALL countSamples() const override { return (uint32_t)pcm.size(); }
 		const float* WSPCALL getPcmMono() const override { return pcm.data(); }
-		const float* WSPCALL getPcmStereo() const override { return nullptr; }
+		const float* WSPCALL getPcmStereo() const override { return stereo.empty() ? nullptr : stereo.data(); }
 		HRESULT WSPCALL getTime( int64_t& rdi ) const override { rdi = 0; return S_OK; }
 	};
 
@@ -340,6 +341,10 @@ namespace
 		int tidLast = 0;
 		void computeTokenTimestamps( size_t iSegment, float tholdPt, float tholdPtsum );
 		int wrapSegment( int maxLen );
+		// what detectSpeaker looks at: the stereo samples of the clip being transcribed (ContextImpl::currentSpectrogram, ContextImpl.cpp:441-450)
+		bool insideRun = false;
+		const float* curStereo = nullptr;
+		uint64_t curStereoFrames = 0;
 		// host-timed blocks of timingsPrint: [0] whole run calls (eCpuBlock::RunComplete), [1] client callbacks (eCpuBlock::Callbacks)
 		double hostMs[ 2 ] = { 0.0, 0.0 };
 		int64_t hostCalls[ 2 ] = { 0, 0 };
@@ -394,10 +399,39 @@ namespace
 			*pp = staticResult;
 			return S_OK;
 		}
-		HRESULT WSPCALL detectSpeaker( const sTimeInterval&, eSpeakerChannel& result ) const override
+		HRESULT WSPCALL detectSpeaker( const sTimeInterval& time, eSpeakerChannel& result ) const override
 		{
-			result = eSpeakerChannel::NoStereoData;
-			return E_NOTIMPL;
+			// ContextImpl::detectSpeaker (Whisper/Whisper/ContextImpl.diarize.cpp:75-112): sum of |sample| per channel over the interval,
+			// a channel wins when it is more than 1.1 x the other.  Only meaningful while a run is in progress, i.e. from the callbacks.
+			result = eSpeakerChannel::Unsure;
+			if( !insideRun )
+			{
+				logMessage( eLogLevel::Error, "iContext.detectSpeaker() method only works when called from the callbacks" );
+				return WSP_HR( 0x80040007 );   // OLE_E_BLANK
+			}
+			const int64_t begin = ( ( (int64_t)time.begin.ticks - results.timeOffset ) * 100 ) / 10000000;   // 10 ms chunks, :9-13
+			const int64_t end = ( ( (int64_t)time.end.ticks - results.timeOffset ) * 100 ) / 10000000;
+			if( end - begin <= 0 ) return S_OK;
+			if( !curStereo )
+			{
+				result = eSpeakerChannel::NoStereoData;
+				return S_OK;
+			}
+			const uint64_t first = (uint64_t)begin * 160, count = (uint64_t)( end - begin ) * 160;       // Spectrogram::copyStereoPcm, Spectrogram.cpp:142-168
+			if( begin < 0 || first >= curStereoFrames ) return E_BOUNDS;
+			const uint64_t n = std::min<uint64_t>( count, curStereoFrames - first );                     // the rest of the slice is zero: adds nothing
+			// the reference adds two stereo samples per step into four f32 lanes and folds them at the end (:26-50); same order here
+			float accL[ 2 ] = { 0, 0 }, accR[ 2 ] = { 0, 0 };
+			const float* p = curStereo + 2 * first;
+			for( uint64_t i = 0; i < n; i++ )
+			{
+				accL[ i & 1 ] += fabsf( p[ 2 * i ] );
+				accR[ i & 1 ] += fabsf( p[ 2 * i + 1 ] );
+			}
+			const float left = accL[ 0 ] + accL[ 1 ], right = accR[ 0 ] + accR[ 1 ];
+			const uint32_t mask = ( left > right * 1.1f ? 1u : 0u ) | ( right > left * 1.1f ? 2u : 0u );   // :53-71
+			result = (eSpeakerChannel)mask;
+			return S_OK;
 		}
 		HRESULT WSPCALL getModel( iModel** pp ) override;
 		HRESULT WSPCALL fullDefaultParams( eSamplingStrategy strategy, sFullParams* rdi ) override
@@ -821,6 +855,8 @@ namespace
 		MelSource mel;
 		mel.nLen = wsp_mel_len( ctx, 0 );
 		mel.prepare = []( int seek, int32_t& encodeAt ) -> HRESULT { encodeAt = seek; return S_OK; };   // the whole clip's mel is resident
+		curStereo = buffer->getPcmStereo();
+		curStereoFrames = curStereo ? (uint64_t)nSamples : 0;
 		return runImpl( params, sProgressSink{ nullptr, nullptr }, mel, tokenTimestamps );
 	}
 
@@ -941,6 +977,12 @@ namespace
 	HRESULT ContextObj::runImpl( const sFullParams& params, const sProgressSink& progress, const MelSource& mel, const bool tokenTimestamps )
 	{
 		HostTimer runComplete( *this, 0 );
+		struct RunScope
+		{
+			ContextObj& c;
+			RunScope( ContextObj& o ) : c( o ) { c.insideRun = true; }
+			~RunScope() { c.insideRun = false; c.curStereo = nullptr; c.curStereoFrames = 0; }
+		} runScope( *this );
 		const int nLen = mel.nLen;
 
 		const int tokEot = eng->tokEot(), tokSot = eng->tokSot(), tokPrev = eng->tokPrev(), tokBeg = eng->tokBeg();
@@ -1258,6 +1300,12 @@ namespace Whisper
 	{
 		if( !pp || !pfn ) return E_POINTER;
 		*pp = new AudioCaptureObj( pfn, pv, captureParams );
+		return S_OK;
+	}
+	HRESULT WSPCALL createAudioBufferStereo( const float* pcmMono, const float* pcmStereo, uint32_t countSamples, iAudioBuffer** pp )
+	{
+		if( !pp || ( ( !pcmMono || !pcmStereo ) && countSamples ) ) return E_POINTER;
+		*pp = new AudioBufferObj( pcmMono, pcmStereo, countSamples );
 		return S_OK;
 	}
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp )
