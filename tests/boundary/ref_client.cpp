@@ -5,7 +5,11 @@
 //   -> getSize / getSegments / getTokens -> Release
 // with its OWN iAudioBuffer implementation (a COM object defined by the client, consumed by the library), and prints the transcript in
 // a line format tests/test_boundary.py compares with the reference's whisper_full fixture.
-//   usage: ref_client <model.bin> <pcm.f32> <flags> <language> [calls] [duration_ms]
+// With a 7th argument "stream" the clip goes through iContext::runStreamed instead, from the client's OWN iAudioReader object.  The
+// reference's headers leave the type that reader hands out incomplete (`struct IMFSourceReader;`, iMediaFoundation.cl.h:5) because
+// on Windows it comes from <mfreadwrite.h>; on Linux the client completes it with the pull interface libwhisper_b200.so documents
+// (include/whisper_b200_com.h) — the only declaration in this file that does not come from the reference tree.
+//   usage: ref_client <model.bin> <pcm.f32> <flags> <language> [calls] [duration_ms] [stream]
 #include <string.h>   // the reference headers use strlen without including it (MSVC pulls it in transitively)
 #include "Whisper/API/whisperComLight.h"
 #include "Whisper/API/sFullParams.h"
@@ -31,6 +35,48 @@ struct PcmBuffer final : public iAudioBuffer
 	const float* COMLIGHTCALL getPcmMono() const override { return pcm.data(); }
 	const float* COMLIGHTCALL getPcmStereo() const override { return nullptr; }
 	HRESULT COMLIGHTCALL getTime( int64_t& rdi ) const override { rdi = 0; return S_OK; }
+};
+
+// the Linux completion of the reference's forward declaration (see the header comment)
+struct IMFSourceReader : public ComLight::IUnknown
+{
+	virtual HRESULT COMLIGHTCALL readPcm( float* mono, uint32_t capacity, uint32_t* written ) = 0;
+};
+struct PcmSource final : public IMFSourceReader
+{
+	const std::vector<float>& pcm;
+	size_t pos = 0;
+	uint32_t refs = 1;
+	explicit PcmSource( const std::vector<float>& p ) : pcm( p ) {}
+	HRESULT COMLIGHTCALL QueryInterface( REFIID, void** ) override { return E_NOINTERFACE; }
+	uint32_t COMLIGHTCALL AddRef() override { return ++refs; }
+	uint32_t COMLIGHTCALL Release() override { const uint32_t r = --refs; if( !r ) delete this; return r; }
+	HRESULT COMLIGHTCALL readPcm( float* mono, uint32_t capacity, uint32_t* written ) override
+	{
+		const size_t n = capacity < 3001 ? capacity : 3001;   // odd-sized blocks
+		const size_t take = n < pcm.size() - pos ? n : pcm.size() - pos;
+		if( take ) memcpy( mono, pcm.data() + pos, take * 4 );
+		pos += take;
+		*written = (uint32_t)take;
+		return S_OK;
+	}
+};
+struct PcmReaderObj final : public iAudioReader
+{
+	PcmSource* source;
+	uint32_t refs = 1;
+	explicit PcmReaderObj( const std::vector<float>& p ) : source( new PcmSource( p ) ) {}
+	HRESULT COMLIGHTCALL QueryInterface( REFIID riid, void** pp ) override
+	{
+		if( !pp ) return E_POINTER;
+		if( riid == iAudioReader::iid() || riid == ComLight::IUnknown::iid() ) { *pp = this; refs++; return S_OK; }
+		return E_NOINTERFACE;
+	}
+	uint32_t COMLIGHTCALL AddRef() override { return ++refs; }
+	uint32_t COMLIGHTCALL Release() override { const uint32_t r = --refs; if( !r ) { source->Release(); delete this; } return r; }
+	HRESULT COMLIGHTCALL getDuration( int64_t& rdi ) const override { rdi = (int64_t)( source->pcm.size() / 160 ) * 100000; return S_OK; }
+	HRESULT COMLIGHTCALL getReader( IMFSourceReader** pp ) const override { source->AddRef(); *pp = source; return S_OK; }
+	HRESULT COMLIGHTCALL requestedStereo() const override { return S_FALSE; }
 };
 
 static int g_segCallbacks = 0;
@@ -74,7 +120,19 @@ int main( int argc, char** argv )
 	p.new_segment_callback = &onNewSegment;
 	const int calls = argc > 5 ? atoi( argv[ 5 ] ) : 1;
 	if( argc > 6 ) p.duration_ms = atoi( argv[ 6 ] );
-	for( int i = 0; i < calls; i++ ) CHECK( ctx->runFull( p, buf ) );
+	if( argc > 7 && 0 == strcmp( argv[ 7 ], "stream" ) )
+	{
+		PcmReaderObj* reader = new PcmReaderObj( buf->pcm );
+		sProgressSink sink{ nullptr, nullptr };
+		for( int i = 0; i < calls; i++ )
+		{
+			reader->source->pos = 0;
+			CHECK( ctx->runStreamed( p, sink, reader ) );
+		}
+		reader->Release();
+	}
+	else
+		for( int i = 0; i < calls; i++ ) CHECK( ctx->runFull( p, buf ) );
 	iTranscribeResult* res = nullptr;
 	CHECK( ctx->getResults( eResultFlags::Tokens | eResultFlags::Timestamps, &res ) );
 	sTranscribeLength len{};

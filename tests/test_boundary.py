@@ -106,18 +106,19 @@ def _client_segments(out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["plain", "context_second_call", "ml_translate"])
+@pytest.mark.parametrize("name", ["plain", "context_second_call", "ml_translate", "plain/stream"])
 def test_client_built_against_reference_headers(name, tmp_path):
     from tests.golden.make_golden import FULL_RUNS, full_pcm
     exe = os.path.join(BUILD, "ref_client")
     if not os.path.exists(exe):
         pytest.skip("ref_client was not built (needs the reference headers at build time)")
     g = np.load(os.path.join(HERE, "golden", "full_runs.npz"))
+    name, _, mode = name.partition("/")          # "/stream": the same clip through iContext::runStreamed from the client's own iAudioReader
     model, flags, max_tokens, off, dur, lang, calls = FULL_RUNS[name]
     assert max_tokens == 0 and off == 0
     pcm_path = str(tmp_path / "clip.f32")
     full_pcm(int(g[name + "_pcm_base"])).astype("<f4").tofile(pcm_path)
-    out = _run(exe, synth.model_path(model), pcm_path, str(flags), lang, str(calls), str(dur))
+    out = _run(exe, synth.model_path(model), pcm_path, str(flags), lang, str(calls), str(dur), *([mode] if mode else []))
     segs = _client_segments(out)
     assert [[s[0], s[1]] for s in segs] == g[name + "_t"].tolist()
     assert [len(s[2]) for s in segs] == g[name + "_ntok"].tolist()
