@@ -153,6 +153,14 @@ def test_run_streamed_without_reader_thread_and_rules(session):
     assert (hr & 0xFFFFFFFF) == 0x80004001                     # E_NOTIMPL (ContextImpl.misc.cpp:393-397)
     hr, segs, _ = run_streamed(L, h, pcm[:8000], flags=2)
     assert hr == 0 and segs == []
+    # language = auto on the multilingual model: the first window is made for the detection pass, then again for the loop
+    from tests.golden.make_golden import FULL_MODEL_ML
+    Lm, hm = open_session(FULL_MODEL_ML)
+    hr, want = run_full(Lm, hm, pcm, flags=2, language=b"auto")
+    assert hr == 0 and len(want) > 5
+    hr, segs, _ = run_streamed(Lm, hm, pcm, flags=2, language=b"auto", max_block=3333)
+    assert hr == 0
+    assert [(s["t0"], s["t1"], s["text"], s["tokens"]) for s in segs] == [(s["t0"], s["t1"], s["text"], s["tokens"]) for s in want]
 
 
 def test_detect_speaker_from_the_segment_callback(session):

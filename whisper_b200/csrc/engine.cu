@@ -265,7 +265,24 @@ namespace wsp
 			double* dc = up.alloc<double>( 400 );
 			double* ds = up.alloc<double>( 400 );
 			float* df = up.alloc<float>( m.filters.size() );
-			if( !dh || !dc || !ds || !df ) return fail( WSP_E_OUTOFMEMORY, "weight arena" );
+			double2* dt = up.alloc<double2>( 400 );
+			short2* db = up.alloc<short2>( 80 );
+			if( !dh || !dc || !ds || !df || !dt || !db ) return fail( WSP_E_OUTOFMEMORY, "weight arena" );
+			std::vector<double2> tw( 400 );
+			for( int i = 0; i < 400; i++ ) tw[ i ] = make_double2( ct[ i ], st[ i ] );
+			// the bins a band actually weighs: skipping the exact zeros of a filter row leaves the double sum bit-identical (x + 0.0 == x)
+			std::vector<short2> bands( 80, make_short2( 0, 201 ) );
+			if( m.filters.size() == (size_t)80 * 201 )
+				for( int j = 0; j < 80; j++ )
+				{
+					int lo = 201, hi = 0;
+					for( int k = 0; k < 201; k++ )
+						if( m.filters[ (size_t)j * 201 + k ] != 0.0f ) { lo = k < lo ? k : lo; hi = k + 1; }
+					bands[ (size_t)j ] = lo < hi ? make_short2( (short)lo, (short)hi ) : make_short2( 0, 0 );
+				}
+			WSP_CUDA( cudaMemcpy( dt, tw.data(), 400 * sizeof( double2 ), cudaMemcpyHostToDevice ) );
+			WSP_CUDA( cudaMemcpy( db, bands.data(), 80 * sizeof( short2 ), cudaMemcpyHostToDevice ) );
+			e->mel.twiddle = dt; e->mel.band = db;
 			WSP_CUDA( cudaMemcpy( dh, hann.data(), 400 * 4, cudaMemcpyHostToDevice ) );
 			WSP_CUDA( cudaMemcpy( dc, ct.data(), 400 * 8, cudaMemcpyHostToDevice ) );
 			WSP_CUDA( cudaMemcpy( ds, st.data(), 400 * 8, cudaMemcpyHostToDevice ) );

@@ -33,6 +33,8 @@ namespace kern
 		const double* cosT = nullptr;    // [400]  cos(2*pi*m/400)
 		const double* sinT = nullptr;    // [400]
 		const float* filters = nullptr;  // [80][201] from the model file
+		const double2* twiddle = nullptr; // [400]  { cosT, sinT } interleaved: one 16-byte shared-memory read per DFT term
+		const short2* band = nullptr;     // [80]   [x, y) = the bins where the band's filter row is non-zero (real filter banks are triangular)
 	};
 	// pcm [nSamples] -> raw log10 mel [80][nLen] (row = band) and the running maximum (ordered-int encoded float) in *maxSlot
 	// up to MEL_BATCH chunks transformed and normalised by one launch each (power, normalise); maxSlots[b] is chunk b's maximum

@@ -34,8 +34,7 @@ namespace kern
 	__device__ __forceinline__ void melFrame( const MelTables& tb, const float* __restrict__ pcm, int nSamples, int nLen, float* __restrict__ melRaw, int* maxSlot, const int frame )
 	{
 		__shared__ float sx[ MEL_FFT ];
-		__shared__ double sc[ MEL_FFT ];
-		__shared__ double ss[ MEL_FFT ];
+		__shared__ double2 stw[ MEL_FFT ];          // { cos, sin }( 2 pi m / 400 )
 		__shared__ double sA[ 2 ][ MEL_FFT / 4 ];   // [k parity][n]: cosine-side combinations
 		__shared__ double sB[ 2 ][ MEL_FFT / 4 ];   //                 sine-side combinations
 		__shared__ float sp[ MEL_BINS + 7 ];
@@ -46,8 +45,7 @@ namespace kern
 		{
 			const int idx = offset + n;
 			sx[ n ] = idx < nSamples ? tb.hann[ n ] * pcm[ idx ] : 0.0f;
-			sc[ n ] = tb.cosT[ n ];
-			ss[ n ] = tb.sinT[ n ];
+			stw[ n ] = tb.twiddle[ n ];
 		}
 		__syncthreads();
 		// Real 400-point DFT in a quarter of the multiply-adds.  With w = exp(-2 pi i k / 400):
@@ -88,8 +86,9 @@ namespace kern
 #pragma unroll 4
 			for( int n = 1; n < Q; n++ )
 			{
-				re += A[ n ] * sc[ idx ];
-				im -= Bv[ n ] * ss[ idx ];
+				const double2 w = stw[ idx ];
+				re += A[ n ] * w.x;
+				im -= Bv[ n ] * w.y;
 				idx += k;
 				if( idx >= MEL_FFT ) idx -= MEL_FFT;
 			}
@@ -103,8 +102,9 @@ namespace kern
 		if( tid < MEL_BANDS )
 		{
 			const float* f = tb.filters + tid * MEL_BINS;
+			const short2 range = tb.band[ tid ];   // outside it the filter row is exactly zero: those terms add +0.0
 			double sum = 0.0;
-			for( int k = 0; k < MEL_BINS; k++ )
+			for( int k = range.x; k < range.y; k++ )
 				sum += (double)( sp[ k ] * f[ k ] );   // float product, double accumulate (whisper.cpp:2139-2143)
 			if( sum < 1e-10 ) sum = 1e-10;
 			v = (float)log10( sum );
