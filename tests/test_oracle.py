@@ -66,6 +66,31 @@ def test_streamed_window_mel_restatement(golden_dir):
     assert f4 == float(np.float32(1e-20)) and np.all(silent == -1.0)      # max(-10, 1e-20 - 8) = -8 -> (-8 + 4) / 4
 
 
+def test_streamed_and_whole_clip_normalisation_nearly_coincide_on_the_full_run_clips(golden_dir):
+    """The GPU tests require runStreamed's transcript to EQUAL the whisper_full fixtures although the streamed mel is normalised per window
+    (tests/test_gpu_com.py).  That is sound only if the two normalisations barely differ on those clips; measured here with the numpy
+    restatements: at every window position the per-window and the clip-wide log-mel differ in a few dozen of 240 000 values, by
+    less than 1e-3 — four orders of magnitude under the fixtures' smallest decision margin (GAP_SAFE = 0.1 in logit units)."""
+    from tests.golden.make_golden import FULL_MODEL, full_pcm
+    m = wn.NpModel(synth.model_path(FULL_MODEL))
+    g = load(golden_dir, "full_runs")
+    pcm = full_pcm(int(g["plain_pcm_base"]))
+    raw = wn.log_mel_raw(pcm, m.filters)
+    n_len = raw.shape[1]
+
+    def normalise(x, mx):
+        return ((np.maximum(x, np.float32(np.float32(mx) - np.float32(8))) + np.float32(4)) * np.float32(0.25)).astype(np.float32)
+
+    whole = normalise(raw, raw.max())
+    assert np.abs(whole - wn.log_mel(pcm, m.filters)).max() < 1e-6          # the f32 form of the pinned whole-clip normalisation
+    worst, most = 0.0, 0
+    for seek in range(0, 6400, 100):
+        w = raw[:, seek:min(seek + 3000, n_len)]
+        d = np.abs(normalise(w, max(float(w.max()), 1e-20)) - whole[:, seek:seek + w.shape[1]])
+        worst, most = max(worst, float(d.max())), max(most, int((d > 0).sum()))
+    assert worst < 1e-3 and most < 100, (worst, most)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_encoder_restatement_vs_golden(name, golden_dir, np_runs):
     g = load(golden_dir, name)
