@@ -21,7 +21,7 @@ namespace
 	{
 		int nThreads = 4, offsetMs = 0, durationMs = 0, maxContext = -1, maxLen = 0, device = 0;
 		float wordThold = 0.01f;
-		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false, stream = false, verifyStream = false, diarize = false;
+		bool translate = false, outTxt = false, outVtt = false, outSrt = false, printSpecial = false, noTimestamps = false, stream = false, diarize = false;
 		std::string language = "en", model = "models/ggml-base.en.bin", prompt;
 		std::vector<std::string> inputs;
 	};
@@ -48,7 +48,7 @@ namespace
 		fprintf( stderr, "  -l LANG,  --language LANG [%-7s] spoken language (\"auto\" = detect)\n", p.language.c_str() );
 		fprintf( stderr, "  -m FNAME, --model FNAME   [%-7s] model path\n", p.model.c_str() );
 		fprintf( stderr, "  -f FNAME, --file FNAME    path of the input audio file (16-bit or float WAV)\n" );
-		fprintf( stderr, "  -st,      --stream        read the file while transcribing it (iContext::runStreamed; 16 kHz files, no -ml)\n" );
+		fprintf( stderr, "  -st,      --stream        read the file while transcribing it (iContext::runStreamed; not with -ml / -di)\n" );
 		fprintf( stderr, "  --prompt TEXT             initial prompt for the model\n\n" );
 	}
 
@@ -82,174 +82,12 @@ namespace
 			else if( a == "-gpu" || a == "--use-gpu" ) p.device = atoi( next() );
 			else if( a == "--prompt" ) p.prompt = next();
 			else if( a == "-st" || a == "--stream" ) p.stream = true;
-			else if( a == "--verify-stream" ) p.verifyStream = true;
 			else if( a == "-di" || a == "--diarize" ) p.diarize = true;
 			else if( a == "-p" || a == "--processors" || a == "-on" || a == "--offset-n" ) next();
 			else { fprintf( stderr, "error: unknown or unsupported argument: %s\n", a.c_str() ); usage( argv[ 0 ], p ); return false; }
 		}
 		return true;
 	}
-
-	// ---- RIFF/WAVE -> 16 kHz mono f32 -------------------------------------------------------------------------------
-	// stereo16k (optional): interleaved left/right of a file with two or more channels, for --diarize; left empty for mono files
-	bool readWav( const std::string& path, std::vector<float>& mono16k, std::vector<float>* stereo16k = nullptr )
-	{
-		FILE* f = fopen( path.c_str(), "rb" );
-		if( !f ) { fprintf( stderr, "error: cannot open %s\n", path.c_str() ); return false; }
-		std::vector<uint8_t> buf;
-		fseek( f, 0, SEEK_END ); const long sz = ftell( f ); fseek( f, 0, SEEK_SET );
-		buf.resize( sz > 0 ? (size_t)sz : 0 );
-		const bool ok = sz > 12 && fread( buf.data(), 1, buf.size(), f ) == buf.size();
-		fclose( f );
-		if( !ok || memcmp( buf.data(), "RIFF", 4 ) != 0 || memcmp( buf.data() + 8, "WAVE", 4 ) != 0 ) { fprintf( stderr, "error: %s is not a RIFF/WAVE file\n", path.c_str() ); return false; }
-		auto u16 = [ & ]( size_t o ) { return (uint32_t)buf[ o ] | ( (uint32_t)buf[ o + 1 ] << 8 ); };
-		auto u32 = [ & ]( size_t o ) { return u16( o ) | ( u16( o + 2 ) << 16 ); };
-		uint32_t format = 0, channels = 0, rate = 0, bits = 0;
-		size_t dataOff = 0, dataLen = 0;
-		for( size_t o = 12; o + 8 <= buf.size(); )
-		{
-			const uint32_t len = u32( o + 4 );
-			if( memcmp( buf.data() + o, "fmt ", 4 ) == 0 && len >= 16 )
-			{
-				format = u16( o + 8 ); channels = u16( o + 10 ); rate = u32( o + 12 ); bits = u16( o + 22 );
-				if( format == 0xFFFE && len >= 26 ) format = u16( o + 32 );   // WAVE_FORMAT_EXTENSIBLE: the sub-format's first word
-			}
-			else if( memcmp( buf.data() + o, "data", 4 ) == 0 ) { dataOff = o + 8; dataLen = std::min<size_t>( len, buf.size() - dataOff ); break; }
-			o += 8 + (size_t)len + ( len & 1 );
-		}
-		if( !dataOff || !channels || !rate || !( ( format == 1 && bits == 16 ) || ( format == 3 && bits == 32 ) ) )
-		{
-			fprintf( stderr, "error: %s: only 16-bit PCM and 32-bit float WAV files are supported\n", path.c_str() );
-			return false;
-		}
-		const size_t frame = (size_t)channels * bits / 8, n = dataLen / frame;
-		std::vector<float> mono( n ), stereo;
-		const bool keepStereo = stereo16k && channels >= 2;
-		if( keepStereo ) stereo.resize( 2 * n );
-		for( size_t i = 0; i < n; i++ )
-		{
-			float acc = 0;
-			for( uint32_t c = 0; c < channels; c++ )
-			{
-				const uint8_t* p = buf.data() + dataOff + i * frame + (size_t)c * bits / 8;
-				float v;
-				if( bits == 16 ) v = (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
-				else memcpy( &v, p, 4 );
-				acc += v;
-				if( keepStereo && c < 2 ) stereo[ 2 * i + c ] = v;
-			}
-			mono[ i ] = acc / (float)channels;
-		}
-		if( stereo16k ) stereo16k->clear();
-		if( rate == 16000 )
-		{
-			mono16k.swap( mono );
-			if( keepStereo ) stereo16k->swap( stereo );
-			return true;
-		}
-		if( keepStereo )
-		{
-			const size_t ms = (size_t)( (double)n * 16000.0 / rate );
-			stereo16k->resize( 2 * ms );
-			for( size_t i = 0; i < ms; i++ )
-			{
-				const double x = (double)i * rate / 16000.0;
-				const size_t i0 = (size_t)x, i1 = std::min( i0 + 1, n - 1 );
-				const float t = (float)( x - (double)i0 );
-				for( int c = 0; c < 2; c++ ) ( *stereo16k )[ 2 * i + c ] = stereo[ 2 * i0 + c ] * ( 1.0f - t ) + stereo[ 2 * i1 + c ] * t;
-			}
-		}
-		const size_t m = (size_t)( (double)n * 16000.0 / rate );
-		mono16k.resize( m );
-		for( size_t i = 0; i < m; i++ )
-		{
-			const double x = (double)i * rate / 16000.0;
-			const size_t i0 = (size_t)x, i1 = std::min( i0 + 1, n - 1 );
-			const float t = (float)( x - (double)i0 );
-			mono16k[ i ] = mono[ i0 ] * ( 1.0f - t ) + mono[ i1 ] * t;
-		}
-		return true;
-	}
-
-	// ---- the same file as a pull source for iContext::runStreamed: the header is parsed up front, the samples are read and converted
-	// block by block when the library asks for them (the counterpart of iMediaFoundation::openAudioFile, Examples/main/main.cpp:306-310)
-	class WavStream
-	{
-		FILE* f = nullptr;
-		uint32_t channels = 0, bits = 0;
-		uint64_t framesLeft = 0;
-		std::vector<uint8_t> raw;
-
-	public:
-		uint32_t rate = 0;
-		uint64_t frames = 0;
-		~WavStream() { if( f ) fclose( f ); }
-		bool open( const std::string& path )
-		{
-			f = fopen( path.c_str(), "rb" );
-			if( !f ) { fprintf( stderr, "error: cannot open %s\n", path.c_str() ); return false; }
-			uint8_t h[ 12 ];
-			if( fread( h, 1, 12, f ) != 12 || memcmp( h, "RIFF", 4 ) != 0 || memcmp( h + 8, "WAVE", 4 ) != 0 ) { fprintf( stderr, "error: %s is not a RIFF/WAVE file\n", path.c_str() ); return false; }
-			uint32_t format = 0;
-			while( true )
-			{
-				uint8_t ch[ 8 ];
-				if( fread( ch, 1, 8, f ) != 8 ) break;
-				const uint32_t len = (uint32_t)ch[ 4 ] | ( (uint32_t)ch[ 5 ] << 8 ) | ( (uint32_t)ch[ 6 ] << 16 ) | ( (uint32_t)ch[ 7 ] << 24 );
-				if( memcmp( ch, "fmt ", 4 ) == 0 && len >= 16 && len <= 256 )
-				{
-					uint8_t fm[ 256 ];
-					if( fread( fm, 1, len, f ) != len ) break;
-					auto u16 = [ & ]( size_t o ) { return (uint32_t)fm[ o ] | ( (uint32_t)fm[ o + 1 ] << 8 ); };
-					format = u16( 0 ); channels = u16( 2 ); rate = u16( 4 ) | ( u16( 6 ) << 16 ); bits = u16( 14 );
-					if( format == 0xFFFE && len >= 26 ) format = u16( 24 );
-					if( len & 1 ) fseek( f, 1, SEEK_CUR );
-				}
-				else if( memcmp( ch, "data", 4 ) == 0 )
-				{
-					if( !channels || !rate || !( ( format == 1 && bits == 16 ) || ( format == 3 && bits == 32 ) ) )
-					{
-						fprintf( stderr, "error: %s: only 16-bit PCM and 32-bit float WAV files are supported\n", path.c_str() );
-						return false;
-					}
-					const long pos = ftell( f );
-					fseek( f, 0, SEEK_END );
-					const long end = ftell( f );
-					fseek( f, pos, SEEK_SET );
-					const uint64_t avail = end > pos ? (uint64_t)( end - pos ) : 0;
-					frames = framesLeft = std::min<uint64_t>( len, avail ) / ( (uint64_t)channels * bits / 8 );
-					return true;
-				}
-				else if( fseek( f, (long)len + ( len & 1 ), SEEK_CUR ) != 0 ) break;
-			}
-			fprintf( stderr, "error: %s: no audio data found\n", path.c_str() );
-			return false;
-		}
-		static HRESULT WSPCALL read( float* mono, uint32_t capacity, uint32_t* written, void* pv ) noexcept
-		{
-			WavStream& w = *static_cast<WavStream*>( pv );
-			const size_t frame = (size_t)w.channels * w.bits / 8;
-			const uint32_t n = (uint32_t)std::min<uint64_t>( capacity, w.framesLeft );
-			*written = 0;
-			if( n == 0 ) return S_OK;
-			try { w.raw.resize( (size_t)n * frame ); } catch( ... ) { return E_OUTOFMEMORY; }
-			const size_t got = fread( w.raw.data(), frame, n, w.f );
-			for( size_t i = 0; i < got; i++ )
-			{
-				float acc = 0;
-				for( uint32_t c = 0; c < w.channels; c++ )
-				{
-					const uint8_t* p = w.raw.data() + i * frame + (size_t)c * w.bits / 8;
-					if( w.bits == 16 ) acc += (float)(int16_t)( p[ 0 ] | ( p[ 1 ] << 8 ) ) / 32768.0f;
-					else { float v; memcpy( &v, p, 4 ); acc += v; }
-				}
-				mono[ i ] = acc / (float)w.channels;
-			}
-			w.framesLeft = got < n ? 0 : w.framesLeft - got;
-			*written = (uint32_t)got;
-			return S_OK;
-		}
-	};
 
 	// ---- writers: txt / srt / vtt as Examples/main/textWriter.cpp produces them (UTF-8 BOM, CRLF, leading blanks of a segment dropped)
 	std::string fmtTime( uint64_t ticks, bool comma )
@@ -334,32 +172,6 @@ int main( int argc, char** argv )
 	if( params.inputs.empty() ) { fprintf( stderr, "error: no input files specified\n" ); usage( argv[ 0 ], params ); return 2; }
 	if( params.language != "auto" && findLanguageKeyA( params.language.c_str() ) == UINT32_MAX ) { fprintf( stderr, "error: unknown language '%s'\n", params.language.c_str() ); return 3; }
 
-	if( params.verifyStream )
-	{
-		// self-check of the streaming WAV reader against the buffered one (no model, no GPU): same samples whatever the block sizes asked for
-		for( const std::string& fname : params.inputs )
-		{
-			std::vector<float> whole, pulled;
-			WavStream ws;
-			if( !readWav( fname, whole ) || !ws.open( fname ) ) return 8;
-			if( ws.rate != 16000 ) { fprintf( stderr, "%s: not a 16 kHz file\n", fname.c_str() ); return 8; }
-			uint32_t lcg = 7;
-			while( true )
-			{
-				lcg = lcg * 1664525u + 1013904223u;
-				std::vector<float> blk( 1 + ( lcg >> 8 ) % 40000 );
-				uint32_t got = 0;
-				if( FAILED( WavStream::read( blk.data(), (uint32_t)blk.size(), &got, &ws ) ) ) return 9;
-				if( got == 0 ) break;
-				pulled.insert( pulled.end(), blk.begin(), blk.begin() + got );
-			}
-			const bool same = pulled.size() == whole.size() && ws.frames == whole.size() && 0 == memcmp( pulled.data(), whole.data(), whole.size() * 4 );
-			printf( "%s: %zu samples, streamed reader %s\n", fname.c_str(), whole.size(), same ? "identical" : "DIFFERS" );
-			if( !same ) return 10;
-		}
-		return 0;
-	}
-
 	std::wstring wmodel( params.model.begin(), params.model.end() );
 	const std::wstring adapter = std::to_wstring( params.device );
 	sModelSetup setup;
@@ -370,6 +182,8 @@ int main( int argc, char** argv )
 	if( FAILED( hr ) ) { fprintf( stderr, "failed to load the model: 0x%08x\n", (unsigned)hr ); return 4; }
 	std::vector<int> prompt;
 	if( !params.prompt.empty() && FAILED( model->tokenize( params.prompt.c_str(), &collectPrompt, &prompt ) ) ) { fprintf( stderr, "failed to tokenize the initial prompt\n" ); return 5; }
+	iMediaFoundation* mf = nullptr;
+	if( FAILED( initMediaFoundation( &mf ) ) ) { fprintf( stderr, "failed to initialize the media layer\n" ); return 7; }
 	iContext* context = nullptr;
 	hr = model->createContext( &context );
 	if( FAILED( hr ) ) { fprintf( stderr, "failed to initialize whisper context: 0x%08x\n", (unsigned)hr ); return 6; }
@@ -382,36 +196,15 @@ int main( int argc, char** argv )
 			params.translate = false;
 			fprintf( stderr, "main: WARNING: model is not multilingual, ignoring language and translation options\n" );
 		}
-		// like the reference's CLI (STREAM_AUDIO, main.cpp:304-319): stream unless token-level timestamps are wanted; here streaming
-		// is opt-in (-st) and limited to files that need no resampling
-		WavStream wavStream;
-		bool streamed = params.stream && params.maxLen <= 0 && !params.diarize;
+		// like the reference's CLI (main.cpp:304-319): the media layer opens the file — streamed (its STREAM_AUDIO build; here opt-in
+		// with -st) unless token-level timestamps or diarisation need the whole clip, else loaded into a buffer
+		const bool streamed = params.stream && params.maxLen <= 0 && !params.diarize;
 		if( params.stream && !streamed ) fprintf( stderr, "main: WARNING: --max-len / --diarize need the whole clip, falling back to buffered mode\n" );
-		if( streamed )
-		{
-			if( !wavStream.open( fname ) ) return 8;
-			if( wavStream.rate != 16000 )
-			{
-				fprintf( stderr, "main: WARNING: %s is not a 16 kHz file, falling back to buffered mode\n", fname.c_str() );
-				streamed = false;
-			}
-		}
-		std::vector<float> pcm;
 		iAudioBuffer* buffer = nullptr;
 		iAudioReader* reader = nullptr;
-		if( streamed )
-		{
-			if( FAILED( createAudioReader( &WavStream::read, &wavStream, (int64_t)( wavStream.frames / 160 ) * 100000, &reader ) ) ) return 9;
-		}
-		else
-		{
-			std::vector<float> stereo;
-			if( !readWav( fname, pcm, params.diarize ? &stereo : nullptr ) ) return 8;
-			if( params.diarize && stereo.empty() ) fprintf( stderr, "main: WARNING: %s has one channel, --diarize has nothing to compare\n", fname.c_str() );
-			const HRESULT hrBuf = stereo.empty() ? createAudioBuffer( pcm.data(), (uint32_t)pcm.size(), &buffer )
-				: createAudioBufferStereo( pcm.data(), stereo.data(), (uint32_t)pcm.size(), &buffer );
-			if( FAILED( hrBuf ) ) return 9;
-		}
+		hr = streamed ? mf->openAudioFile( fname.c_str(), params.diarize, &reader ) : mf->loadAudioFile( fname.c_str(), params.diarize, &buffer );
+		if( FAILED( hr ) ) { fprintf( stderr, "error: cannot read %s (16-bit PCM or 32-bit float RIFF/WAVE expected): 0x%08x\n", fname.c_str(), (unsigned)hr ); return 8; }
+		if( params.diarize && buffer && !buffer->getPcmStereo() ) fprintf( stderr, "main: WARNING: %s has one channel, --diarize has nothing to compare\n", fname.c_str() );
 
 		sFullParams wp;
 		context->fullDefaultParams( eSamplingStrategy::Greedy, &wp );
@@ -449,6 +242,7 @@ int main( int argc, char** argv )
 		if( params.outVtt && !writeResult( context, fname, Fmt::Vtt, true ) ) fprintf( stderr, "Unable to produce the vtt file\n" );
 	}
 	context->timingsPrint();
+	mf->Release();
 	context->Release();
 	model->Release();
 	return 0;

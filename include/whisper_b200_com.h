@@ -210,7 +210,23 @@ namespace Whisper
 		virtual HRESULT WSPCALL getReader( IMFSourceReader** pp ) const = 0;
 		virtual const sCaptureParams& WSPCALL getParams() const = 0;
 	};
-	struct iMediaFoundation;
+	struct sCaptureDevice { const wchar_t* displayName; const wchar_t* endpoint; };                 // MfStructs.h:5-14
+	using pfnFoundCaptureDevices = HRESULT( WSPCALL* )( int len, const sCaptureDevice* buffer, void* pv );
+#ifndef _MSC_VER
+	using LPCTSTR = const char*;                                                                     // ComLightLib/comLightCommon.h:8
+#endif
+	// The reference's media layer (Whisper/API/iMediaFoundation.cl.h:36-49).  The Linux object behind initMediaFoundation decodes
+	// RIFF/WAVE (16-bit PCM or 32-bit float, any rate and channel count) instead of everything Media Foundation can open; it has no
+	// capture devices (listCaptureDevices reports none, openCaptureDevice answers E_NOTIMPL — use createAudioCapture).
+	struct iMediaFoundation : public ComLight::IUnknown
+	{
+		static constexpr GUID iid() { return GUID{ 0xfb9763a5, 0xd77d, 0x4b6e, { 0xaf, 0xf8, 0xf4, 0x94, 0x81, 0x3c, 0xeb, 0xd8 } }; }
+		virtual HRESULT WSPCALL loadAudioFile( LPCTSTR path, bool stereo, iAudioBuffer** pp ) const = 0;
+		virtual HRESULT WSPCALL openAudioFile( LPCTSTR path, bool stereo, iAudioReader** pp ) = 0;
+		virtual HRESULT WSPCALL loadAudioFileData( const void* data, uint64_t size, bool stereo, iAudioReader** pp ) = 0;
+		virtual HRESULT WSPCALL listCaptureDevices( pfnFoundCaptureDevices pfn, void* pv ) = 0;
+		virtual HRESULT WSPCALL openCaptureDevice( LPCTSTR endpoint, const sCaptureParams& captureParams, iAudioCapture** pp ) = 0;
+	};
 
 	struct iTranscribeResult : public ComLight::IUnknown
 	{
@@ -253,7 +269,7 @@ namespace Whisper
 	uint32_t WSPCALL findLanguageKeyA( const char* lang );
 	HRESULT WSPCALL getSupportedLanguages( sLanguageList& rdi );
 	HRESULT WSPCALL listGPUs( pfnListAdapters pfn, void* pv );
-	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp );   // E_NOTIMPL: audio decoding is the host application's business here
+	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp );   // the WAV-only media layer described at iMediaFoundation above
 	// not in the reference: an iAudioBuffer over caller-owned 16 kHz mono f32 PCM (replaces the Media Foundation loader, Whisper/MF/)
 	HRESULT WSPCALL createAudioBuffer( const float* pcmMono, uint32_t countSamples, iAudioBuffer** pp );
 	// the same with the interleaved left/right samples kept next to the mono mix (loadAudioFile( path, stereo = true ), the --diarize

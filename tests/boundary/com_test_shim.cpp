@@ -308,6 +308,76 @@ int32_t wspc_run_full_stereo( void* h, const float* pcmMono, const float* pcmSte
 	const HRESULT hr2 = s->context->getResults( (eResultFlags)( (uint32_t)eResultFlags::Tokens | (uint32_t)eResultFlags::Timestamps ), &s->result );
 	return FAILED( hr2 ) ? hr2 : log.n;
 }
+// ---- the media layer: initMediaFoundation -> loadAudioFile / openAudioFile / loadAudioFileData (no GPU involved) ----
+// mode 0: loadAudioFile (whole file -> iAudioBuffer); 1: openAudioFile, 2: loadAudioFileData on the file's bytes — both read to the end
+// through iAudioReader::getReader()->readPcm in blocks of `block` samples.  mono[cap] receives the samples, stereo[2*cap] (nullable) the
+// pairs (mode 0 only); info[0] = 1 if the object reports stereo, info[1..2] = getDuration ticks (low / high word).  Returns the sample
+// count or a negative HRESULT.
+int32_t wspc_media_decode( const char* path, int32_t mode, int32_t wantStereo, int32_t block, float* mono, float* stereo, int32_t cap, int32_t* info )
+{
+	iMediaFoundation* mf = nullptr;
+	HRESULT hr = initMediaFoundation( &mf );
+	if( FAILED( hr ) ) return hr;
+	int32_t n = 0;
+	if( mode == 0 )
+	{
+		iAudioBuffer* buf = nullptr;
+		hr = mf->loadAudioFile( path, wantStereo != 0, &buf );
+		if( SUCCEEDED( hr ) )
+		{
+			n = (int32_t)buf->countSamples();
+			if( n > cap ) n = cap;
+			memcpy( mono, buf->getPcmMono(), (size_t)n * 4 );
+			const float* st = buf->getPcmStereo();
+			if( info ) info[ 0 ] = st ? 1 : 0;
+			if( st && stereo ) memcpy( stereo, st, (size_t)n * 8 );
+			buf->Release();
+		}
+	}
+	else
+	{
+		iAudioReader* reader = nullptr;
+		std::vector<uint8_t> bytes;
+		if( mode == 1 ) hr = mf->openAudioFile( path, wantStereo != 0, &reader );
+		else
+		{
+			FILE* f = fopen( path, "rb" );
+			if( !f ) { mf->Release(); return E_INVALIDARG; }
+			fseek( f, 0, SEEK_END ); const long sz = ftell( f ); fseek( f, 0, SEEK_SET );
+			bytes.resize( (size_t)sz );
+			const bool ok = fread( bytes.data(), 1, bytes.size(), f ) == bytes.size();
+			fclose( f );
+			if( !ok ) { mf->Release(); return E_FAIL; }
+			hr = mf->loadAudioFileData( bytes.data(), bytes.size(), wantStereo != 0, &reader );
+			bytes.assign( bytes.size(), 0xAB );   // the library must have taken its own copy
+		}
+		if( SUCCEEDED( hr ) )
+		{
+			int64_t ticks = 0;
+			reader->getDuration( ticks );
+			if( info ) { info[ 0 ] = reader->requestedStereo() == S_OK ? 1 : 0; info[ 1 ] = (int32_t)( ticks & 0xFFFFFFFF ); info[ 2 ] = (int32_t)( ticks >> 32 ); }
+			IMFSourceReader* src = nullptr;
+			hr = reader->getReader( &src );
+			while( SUCCEEDED( hr ) && n < cap )
+			{
+				uint32_t got = 0;
+				const uint32_t want = (uint32_t)( cap - n < block ? cap - n : block );
+				hr = src->readPcm( mono + n, want, &got );
+				if( FAILED( hr ) || got == 0 ) break;
+				n += (int32_t)got;
+			}
+			if( src ) src->Release();
+			reader->Release();
+		}
+	}
+	int devices = -1;
+	mf->listCaptureDevices( []( int len, const sCaptureDevice*, void* pv ) -> HRESULT { *static_cast<int*>( pv ) = len; return S_OK; }, &devices );
+	iAudioCapture* cap0 = nullptr;
+	const HRESULT hrCap = mf->openCaptureDevice( "default", sCaptureParams{}, &cap0 );
+	mf->Release();
+	if( devices != 0 || hrCap != E_NOTIMPL ) return E_UNEXPECTED;
+	return FAILED( hr ) ? hr : n;
+}
 void wspc_set_max_len( void* h, int32_t maxLen ) { static_cast<Session*>( h )->maxLen = maxLen; }
 int64_t wspc_token_t0( void* h, int32_t i, int32_t j )
 {

@@ -79,5 +79,10 @@ int main()
 	{ sCaptureParams d; printf( "  sCaptureParams defaults %g %g %g %g %u\n", d.minDuration, d.maxDuration, d.dropStartSilence, d.pauseDuration, d.flags ); }
 	guid( "iAudioCapture", iAudioCapture::iid() );
 	SLOT( iAudioCapture, getReader ); SLOT( iAudioCapture, getParams );
+	// the media layer (iMediaFoundation.cl.h:36-49, MfStructs.h:5-16)
+	SZ( sCaptureDevice ); OFF( sCaptureDevice, displayName ); OFF( sCaptureDevice, endpoint );
+	guid( "iMediaFoundation", iMediaFoundation::iid() );
+	SLOT( iMediaFoundation, loadAudioFile ); SLOT( iMediaFoundation, openAudioFile ); SLOT( iMediaFoundation, loadAudioFileData );
+	SLOT( iMediaFoundation, listCaptureDevices ); SLOT( iMediaFoundation, openCaptureDevice );
 	return 0;
 }

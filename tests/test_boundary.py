@@ -57,31 +57,91 @@ def test_capture_loop_unit():
     assert "capture_test: ok" in _run(exe)
 
 
-def test_cli_streaming_wav_reader(tmp_path):
-    """The CLI's block-wise WAV reader (the pull source it hands to iContext::runStreamed) delivers exactly the samples of its buffered
-    reader: 16-bit mono, 16-bit stereo (down-mixed), 32-bit float with a foreign chunk of odd length in front of the data.  No GPU: the
-    CLI's --verify-stream self-check loads no model."""
+def _wav_cases(tmp_path):
     import struct
     import wave
-    exe = os.path.join(os.path.dirname(HERE), "examples", "main", "whisper_b200_main")
-    if not os.path.exists(exe):
-        pytest.fail("examples/main/whisper_b200_main is missing: run __graft_entry__.build()")
-    rng = np.random.default_rng(5)
-    paths = []
-    for name, ch, n in (("mono.wav", 1, 16000 * 7 + 13), ("stereo.wav", 2, 16000 * 3 + 1)):
+    rng = np.random.default_rng(11)
+    cases = []
+    for name, ch, rate, n in (("mono16k.wav", 1, 16000, 16000 * 3 + 7), ("stereo44k.wav", 2, 44100, 44100 * 2 + 3), ("mono8k.wav", 1, 8000, 8000 * 2 + 1),
+                              ("four48k.wav", 4, 48000, 48000 + 5)):
+        x = rng.integers(-30000, 30000, size=(n, ch)).astype("<i2")
         p = str(tmp_path / name)
         with wave.open(p, "wb") as w:
-            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(16000)
-            w.writeframes(rng.integers(-30000, 30000, size=n * ch).astype("<i2").tobytes())
-        paths.append(p)
-    data = rng.standard_normal(50001).astype("<f4").tobytes()
-    body = (b"WAVE" + b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 3, 1, 16000, 64000, 4, 32)
-            + b"LIST" + struct.pack("<I", 5) + b"abcde\0" + b"data" + struct.pack("<I", len(data)) + data)
-    p = str(tmp_path / "float.wav")
+            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(rate); w.writeframes(x.tobytes())
+        cases.append((p, x.astype(np.float32) / np.float32(32768.0), rate))
+    f = rng.standard_normal((22050 + 9, 2)).astype("<f4")
+    body = (b"WAVE" + b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 3, 2, 22050, 22050 * 8, 8, 32)
+            + b"LIST" + struct.pack("<I", 3) + b"abc\0" + b"data" + struct.pack("<I", f.nbytes) + f.tobytes())
+    p = str(tmp_path / "float22k.wav")
     open(p, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
-    paths.append(p)
-    out = _run(exe, "--verify-stream", *sum((["-f", q] for q in paths), []))
-    assert out.count("streamed reader identical") == 3
+    cases.append((p, f.astype(np.float32), 22050))
+    return cases
+
+
+def _expected_16k(x, rate):
+    """(mono, first two channels) at 16 kHz: channel average, then — for other rates — the linear interpolation wav_reader.h documents."""
+    mono = (x.sum(axis=1, dtype=np.float32) if x.shape[1] <= 2 else np.add.reduce(x, axis=1, dtype=np.float32)) / np.float32(x.shape[1])
+    if x.shape[1] > 2:          # the decoder adds channel by channel in f32
+        acc = np.zeros(x.shape[0], np.float32)
+        for c in range(x.shape[1]):
+            acc = acc + x[:, c]
+        mono = acc / np.float32(x.shape[1])
+    lr = x[:, :2] if x.shape[1] >= 2 else np.repeat(mono[:, None], 2, axis=1)
+    if rate == 16000:
+        return mono, lr
+    n = x.shape[0]
+    m = int(float(n) * 16000.0 / rate)
+    pos = np.arange(m, dtype=np.float64) * rate / 16000.0
+    i0 = pos.astype(np.int64)
+    i1 = np.minimum(i0 + 1, n - 1)
+    t = (pos - i0).astype(np.float32)
+    one = np.float32(1.0)
+    return mono[i0] * (one - t) + mono[i1] * t, lr[i0] * (one - t)[:, None] + lr[i1] * t[:, None]
+
+
+def test_media_layer_decodes_wav_files(tmp_path):
+    """initMediaFoundation -> loadAudioFile / openAudioFile / loadAudioFileData (the calls of the reference CLI, Examples/main/main.cpp:306-318)
+    on RIFF/WAVE input: 16-bit and float, 1 / 2 / 4 channels, 8 - 48 kHz -> 16 kHz mono (+ stereo pairs), the same samples whether the file
+    is loaded whole, streamed from disk or streamed from memory in blocks of any size; announced duration = delivered samples.  No GPU."""
+    import ctypes as C
+    from whisper_b200 import capi
+    capi.lib()
+    shim = os.path.join(BUILD, "libwspc_test.so")
+    if not os.path.exists(shim):
+        pytest.fail("tests/boundary/_build/libwspc_test.so is missing: run __graft_entry__.build()")
+    L = C.CDLL(shim)
+    fp = C.POINTER(C.c_float)
+    L.wspc_media_decode.restype = C.c_int32
+    L.wspc_media_decode.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, fp, fp, C.c_int32, C.POINTER(C.c_int32)]
+    for path, x, rate in _wav_cases(tmp_path):
+        want_mono, want_lr = _expected_16k(x, rate)
+        cap = want_mono.size + 1000
+        mono, stereo, info = np.zeros(cap, np.float32), np.zeros(2 * cap, np.float32), (C.c_int32 * 3)()
+        n = L.wspc_media_decode(path.encode(), 0, 1, 0, mono.ctypes.data_as(fp), stereo.ctypes.data_as(fp), cap, info)
+        assert n == want_mono.size, (path, n)
+        assert np.abs(mono[:n] - want_mono).max() < 1e-6
+        assert info[0] == (1 if x.shape[1] >= 2 else 0)
+        if x.shape[1] >= 2:
+            assert np.abs(stereo[:2 * n].reshape(n, 2) - want_lr).max() < 1e-6
+        # without the stereo request no pairs are kept
+        n0 = L.wspc_media_decode(path.encode(), 0, 0, 0, mono.ctypes.data_as(fp), stereo.ctypes.data_as(fp), cap, info)
+        assert n0 == n and info[0] == 0
+        for mode, block in ((1, 777), (1, 100000), (2, 4096)):
+            got = np.zeros(cap, np.float32)
+            k = L.wspc_media_decode(path.encode(), mode, 1, block, got.ctypes.data_as(fp), None, cap, info)
+            assert k == n and np.array_equal(got[:n], mono[:n]), (path, mode, block)
+            ticks = (info[1] & 0xFFFFFFFF) | (info[2] << 32)
+            assert ticks == n * 625 and info[0] == (1 if x.shape[1] >= 2 else 0)
+    # failures: a missing file, a file that is not RIFF/WAVE, an unsupported sample format
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"definitely not audio")
+    buf = np.zeros(16, np.float32)
+    assert (L.wspc_media_decode(str(tmp_path / "missing.wav").encode(), 0, 0, 0, buf.ctypes.data_as(fp), None, 16, None) & 0xFFFFFFFF) == 0x80070002
+    assert (L.wspc_media_decode(str(bad).encode(), 1, 0, 64, buf.ctypes.data_as(fp), None, 16, None) & 0xFFFFFFFF) == 0x80070057
+    import struct
+    body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 1, 1, 16000, 16000, 1, 8) + b"data" + struct.pack("<I", 4) + b"\0\0\0\0"
+    (tmp_path / "u8.wav").write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    assert (L.wspc_media_decode(str(tmp_path / "u8.wav").encode(), 0, 0, 0, buf.ctypes.data_as(fp), None, 16, None) & 0xFFFFFFFF) == 0x80070057
 
 
 def test_com_exports_include_the_streaming_factory():

@@ -10,6 +10,7 @@
 #include "../../include/whisper_b200_com.h"
 #include "pcm_streamer.h"
 #include "capture_loop.h"
+#include "wav_reader.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -261,6 +262,115 @@ namespace
 			return S_OK;
 		}
 		const sCaptureParams& WSPCALL getParams() const override { return params; }
+	};
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// iMediaFoundation for Linux: RIFF/WAVE in place of Media Foundation (csrc/wav_reader.h)
+	class WavSourceReader : public Object<IMFSourceReader>
+	{
+		std::unique_ptr<wsp::WavDecoder> wav;
+
+	public:
+		explicit WavSourceReader( std::unique_ptr<wsp::WavDecoder> w ) : wav( std::move( w ) ) {}
+		HRESULT WSPCALL readPcm( float* mono, uint32_t capacity, uint32_t* written ) override
+		{
+			if( !mono || !written ) return E_POINTER;
+			*written = (uint32_t)wav->read( mono, nullptr, capacity );
+			if( *written == 0 && !wav->error.empty() )
+			{
+				logMessage( eLogLevel::Error, "audio reader: %s", wav->error.c_str() );
+				return E_FAIL;
+			}
+			return S_OK;
+		}
+	};
+	class WavReaderObj : public Object<iAudioReader>
+	{
+		WavSourceReader* source;
+		int64_t duration;
+		bool stereo;
+		~WavReaderObj() override { source->Release(); }
+
+	public:
+		WavReaderObj( std::unique_ptr<wsp::WavDecoder> w, bool wantStereo ) : duration( (int64_t)w->outputFrames() * 625 ), stereo( wantStereo && w->channels >= 2 )
+		{
+			source = new WavSourceReader( std::move( w ) );
+		}
+		HRESULT WSPCALL getDuration( int64_t& rdi ) const override { rdi = duration; return S_OK; }   // 16 kHz samples * 10^7 / 16000
+		HRESULT WSPCALL getReader( IMFSourceReader** pp ) const override
+		{
+			if( !pp ) return E_POINTER;
+			source->AddRef();
+			*pp = source;
+			return S_OK;
+		}
+		HRESULT WSPCALL requestedStereo() const override { return stereo ? S_OK : S_FALSE; }
+	};
+	class MediaFoundationObj : public Object<iMediaFoundation>
+	{
+		static HRESULT open( std::unique_ptr<wsp::WavDecoder>& w, bool ok, const char* what )
+		{
+			if( ok ) return S_OK;
+			logMessage( eLogLevel::Error, "%s: %s", what, w->error.c_str() );
+			return w->error.compare( 0, 11, "cannot open" ) == 0 ? WSP_HR( 0x80070002 ) : E_INVALIDARG;   // HRESULT_FROM_WIN32( ERROR_FILE_NOT_FOUND )
+		}
+
+	public:
+		HRESULT WSPCALL loadAudioFile( LPCTSTR path, bool stereo, iAudioBuffer** pp ) const override
+		{
+			// Whisper/MF/loadAudioFile.cpp: decode the whole file into an AudioBuffer (mono, and the stereo pairs when asked for and present)
+			if( !path || !pp ) return E_POINTER;
+			*pp = nullptr;
+			auto w = std::make_unique<wsp::WavDecoder>();
+			HR( open( w, w->openFile( path ), path ) );
+			const uint64_t n = w->outputFrames();
+			if( n > 0xFFFFFFFFull ) return E_INVALIDARG;
+			const bool keepStereo = stereo && w->channels >= 2;
+			std::vector<float> mono( (size_t)n ), pairs( keepStereo ? 2 * (size_t)n : 0 );
+			size_t done = 0;
+			while( done < n )
+			{
+				const size_t got = w->read( mono.data() + done, keepStereo ? pairs.data() + 2 * done : nullptr, (size_t)n - done );
+				if( got == 0 ) break;
+				done += got;
+			}
+			if( done != n )
+			{
+				logMessage( eLogLevel::Error, "%s: %s", path, w->error.empty() ? "truncated audio data" : w->error.c_str() );
+				return E_FAIL;
+			}
+			*pp = keepStereo ? new AudioBufferObj( mono.data(), pairs.data(), (uint32_t)n ) : new AudioBufferObj( mono.data(), (uint32_t)n );
+			return S_OK;
+		}
+		HRESULT WSPCALL openAudioFile( LPCTSTR path, bool stereo, iAudioReader** pp ) override
+		{
+			if( !path || !pp ) return E_POINTER;
+			*pp = nullptr;
+			auto w = std::make_unique<wsp::WavDecoder>();
+			HR( open( w, w->openFile( path ), path ) );
+			*pp = new WavReaderObj( std::move( w ), stereo );
+			return S_OK;
+		}
+		HRESULT WSPCALL loadAudioFileData( const void* data, uint64_t size, bool stereo, iAudioReader** pp ) override
+		{
+			if( !data || !pp ) return E_POINTER;
+			*pp = nullptr;
+			auto w = std::make_unique<wsp::WavDecoder>();
+			HR( open( w, w->openMemory( data, size ), "loadAudioFileData" ) );
+			*pp = new WavReaderObj( std::move( w ), stereo );
+			return S_OK;
+		}
+		HRESULT WSPCALL listCaptureDevices( pfnFoundCaptureDevices pfn, void* pv ) override
+		{
+			if( !pfn ) return E_POINTER;
+			return pfn( 0, nullptr, pv );   // no capture devices are enumerated on this platform
+		}
+		HRESULT WSPCALL openCaptureDevice( LPCTSTR, const sCaptureParams&, iAudioCapture** pp ) override
+		{
+			if( pp ) *pp = nullptr;
+			logMessage( eLogLevel::Error, "whisper_b200: no capture devices on this platform; wrap the live source with createAudioCapture" );
+			return E_NOTIMPL;
+		}
 	};
 
 	struct ResultData
@@ -1286,8 +1396,9 @@ namespace Whisper
 	}
 	HRESULT WSPCALL initMediaFoundation( iMediaFoundation** pp )
 	{
-		if( pp ) *pp = nullptr;
-		return E_NOTIMPL;
+		if( !pp ) return E_POINTER;
+		*pp = new MediaFoundationObj();
+		return S_OK;
 	}
 	HRESULT WSPCALL createAudioReader( pfnReadPcm pfn, void* pv, int64_t durationTicks, iAudioReader** pp )
 	{
