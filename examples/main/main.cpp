@@ -2,9 +2,10 @@
 //
 // Same role, option names and output formats as the reference's Examples/main (main.cpp:174-353, params.cpp, textWriter.cpp):
 //   loadModel -> createContext -> fullDefaultParams -> runFull -> getResults -> txt / srt / vtt next to the input file.
-// Media Foundation is replaced by a small RIFF/WAVE reader: 16-bit PCM or 32-bit float, any channel count (mixed down), resampled to
-// 16 kHz by linear interpolation when the file has another rate.  Options of the reference that need its GPU/MF back-ends
-// (-la/-gpu adapters, -di diarize, -owts karaoke script, -su speed-up) are accepted where harmless and rejected otherwise.
+// Inputs are opened through the library's media layer exactly as the reference does (initMediaFoundation -> loadAudioFile, or
+// openAudioFile + runStreamed with -st; main.cpp:304-319); on Linux that layer decodes RIFF/WAVE (16-bit PCM or 32-bit float, any rate
+// and channel count).  -di labels segments with the louder stereo channel (iContext::detectSpeaker).  Options of the reference that
+// have no counterpart here (-owts karaoke script, -su speed-up, colours) are accepted where harmless and rejected otherwise.
 #include "whisper_b200_com.h"
 #include <algorithm>
 #include <math.h>

@@ -57,6 +57,18 @@ def test_capture_loop_unit():
     assert "capture_test: ok" in _run(exe)
 
 
+def test_capture_example_builds_and_parses_its_options():
+    """examples/capture/whisper_b200_capture (live transcription from a pipe over createAudioCapture + runCapture): built, prints its usage,
+    rejects an unknown language before touching the GPU.  (Its transcription path is iContext::runCapture, tested in test_gpu_com.py.)"""
+    exe = os.path.join(os.path.dirname(HERE), "examples", "capture", "whisper_b200_capture")
+    if not os.path.exists(exe):
+        pytest.fail("examples/capture/whisper_b200_capture is missing: run __graft_entry__.build()")
+    r = subprocess.run([exe, "-h"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0 and "s16le 16 kHz mono" in r.stderr
+    r = subprocess.run([exe, "-l", "klingon"], stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 3 and "unknown language" in r.stderr
+
+
 def _wav_cases(tmp_path):
     import struct
     import wave
