@@ -11,7 +11,8 @@
 //   iAudioBuffer             Whisper/API/iMediaFoundation.cl.h:9-17   {013583aa-c9eb-42bc-83db-633c2c317051}
 //   iAudioReader             Whisper/API/iMediaFoundation.cl.h:19-26  {35b988da-04a6-476a-a193-d8891d5dc390}  (input of iContext::runStreamed)
 //   iAudioCapture            Whisper/API/iMediaFoundation.cl.h:28-34  {747752c2-d9fd-40df-8847-583c781bf013}  (input of iContext::runCapture)
-//   sCaptureParams, eCaptureStatus, sCaptureCallbacks   Whisper/API/MfStructs.h:16-52
+//   iMediaFoundation         Whisper/API/iMediaFoundation.cl.h:36-46  {fb9763a5-d77d-4b6e-aff8-f494813cebd8}  (RIFF/WAVE media layer on Linux)
+//   sCaptureParams, eCaptureStatus, sCaptureCallbacks, sCaptureDevice   Whisper/API/MfStructs.h:5-52
 //   sFullParams, flags       Whisper/API/sFullParams.h:5-130
 //   sSegment, sToken, ...    Whisper/API/TranscribeStructs.h:8-137
 //   sModelSetup, callbacks   Whisper/API/sModelSetup.h:6-41, sLoadModelCallbacks.h:5-14, loggerApi.h:7-34, SpecialTokens.h, sLanguageList.h
